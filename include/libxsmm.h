@@ -1,0 +1,128 @@
+/* libxsmm_b200 -- drop-in C API of LIBXSMM's tensor-processing-primitive hot path.
+ *
+ * Every entry point below keeps the name, argument meaning and error behaviour (NULL on
+ * unsupported/failed, library is mute unless libxsmm_verbosity != 0) of the reference API, but the
+ * handle that dispatch returns launches a hand-written sm_100a CUDA kernel instead of JIT'ed x86.
+ * Each declaration cites the reference interface it replaces (file:line in /root/reference).
+ * Additive, GPU-only entry points (batch launch, streams, device memory) live in libxsmm_b200.h.
+ */
+#ifndef LIBXSMM_H
+#define LIBXSMM_H
+
+#include "libxsmm_typedefs.h"
+#include "libxsmm_fsspmdm.h"
+#include "libxsmm_b200.h"
+
+#define LIBXSMM_VERSION_MAJOR 2
+#define LIBXSMM_VERSION_MINOR 0
+#define LIBXSMM_VERSION_UPDATE 0
+#define LIBXSMM_B200 1
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+/* public state words (reference include/libxsmm_generator.h:214-222); LIBXSMM_INIT reads ninit */
+LIBXSMM_APIVAR_PUBLIC(unsigned int libxsmm_ninit);
+LIBXSMM_APIVAR_PUBLIC(int libxsmm_target_archid);
+LIBXSMM_APIVAR_PUBLIC(int libxsmm_verbosity);
+#define LIBXSMM_INIT if (2 > libxsmm_ninit) libxsmm_init();
+
+/* ---- lifetime / environment (reference include/libxsmm.h:62-100) ------------------------------- */
+LIBXSMM_API void libxsmm_init(void);
+LIBXSMM_API void libxsmm_finalize(void);
+LIBXSMM_API int libxsmm_get_target_archid(void);
+LIBXSMM_API void libxsmm_set_target_archid(int id);
+LIBXSMM_API const char* libxsmm_get_target_arch(void);          /* returns "sm_100a" */
+LIBXSMM_API void libxsmm_set_target_arch(const char* arch);     /* accepted and ignored */
+LIBXSMM_API const char* libxsmm_get_typename(libxsmm_datatype datatype);
+LIBXSMM_API int libxsmm_get_verbosity(void);
+LIBXSMM_API void libxsmm_set_verbosity(int level);
+
+/* ---- introspection (reference include/libxsmm.h:102-117) --------------------------------------- */
+LIBXSMM_API int libxsmm_get_mmkernel_info(libxsmm_xmmfunction kernel, libxsmm_mmkernel_info* info);
+LIBXSMM_API int libxsmm_get_meltwkernel_info(libxsmm_xmeltwfunction kernel, libxsmm_meltwkernel_info* info);
+LIBXSMM_API int libxsmm_get_kernel_info(const void* kernel, libxsmm_kernel_info* info);
+LIBXSMM_API int libxsmm_get_registry_info(libxsmm_registry_info* info);
+
+/* ---- shape/config constructors (reference include/libxsmm_generator.h:20-43) ------------------- */
+LIBXSMM_API libxsmm_gemm_shape libxsmm_create_gemm_shape(libxsmm_blasint m, libxsmm_blasint n, libxsmm_blasint k,
+  libxsmm_blasint lda, libxsmm_blasint ldb, libxsmm_blasint ldc,
+  libxsmm_datatype a_in_type, libxsmm_datatype b_in_type, libxsmm_datatype out_type, libxsmm_datatype comp_type);
+LIBXSMM_API libxsmm_gemm_batch_reduce_config libxsmm_create_gemm_batch_reduce_config(
+  libxsmm_gemm_batch_reduce_type br_type, libxsmm_blasint br_stride_a_hint, libxsmm_blasint br_stride_b_hint,
+  unsigned char br_unroll_hint);
+LIBXSMM_API libxsmm_gemm_ext_unary_argops libxsmm_create_gemm_ext_unary_argops(
+  libxsmm_blasint ldap, libxsmm_meltw_unary_type ap_unary_type, libxsmm_bitfield ap_unary_flags, libxsmm_blasint store_ap,
+  libxsmm_blasint ldbp, libxsmm_meltw_unary_type bp_unary_type, libxsmm_bitfield bp_unary_flags, libxsmm_blasint store_bp,
+  libxsmm_blasint ldcp, libxsmm_meltw_unary_type cp_unary_type, libxsmm_bitfield cp_unary_flags, libxsmm_blasint store_cp);
+LIBXSMM_API libxsmm_gemm_ext_binary_postops libxsmm_create_gemm_ext_binary_postops(
+  libxsmm_blasint ldd, libxsmm_datatype d_in_type, libxsmm_meltw_binary_type d_binary_type, libxsmm_bitfield d_binary_flags);
+LIBXSMM_API libxsmm_meltw_unary_shape libxsmm_create_meltw_unary_shape(libxsmm_blasint m, libxsmm_blasint n,
+  libxsmm_blasint ldi, libxsmm_blasint ldo, libxsmm_datatype in0_type, libxsmm_datatype out_type, libxsmm_datatype comp_type);
+LIBXSMM_API libxsmm_meltw_binary_shape libxsmm_create_meltw_binary_shape(libxsmm_blasint m, libxsmm_blasint n,
+  libxsmm_blasint ldi, libxsmm_blasint ldi2, libxsmm_blasint ldo,
+  libxsmm_datatype in0_type, libxsmm_datatype in1_type, libxsmm_datatype out_type, libxsmm_datatype comp_type);
+LIBXSMM_API libxsmm_meltw_ternary_shape libxsmm_create_meltw_ternary_shape(libxsmm_blasint m, libxsmm_blasint n,
+  libxsmm_blasint ldi, libxsmm_blasint ldi2, libxsmm_blasint ldi3, libxsmm_blasint ldo,
+  libxsmm_datatype in0_type, libxsmm_datatype in1_type, libxsmm_datatype in2_type, libxsmm_datatype out_type,
+  libxsmm_datatype comp_type);
+
+/* ---- dense GEMM / BRGEMM dispatch (reference include/libxsmm.h:128-140, src/libxsmm_main.c:3390-3446) -- */
+LIBXSMM_API libxsmm_gemmfunction libxsmm_dispatch_gemm(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags);
+LIBXSMM_API libxsmm_gemmfunction libxsmm_dispatch_brgemm(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags,
+  const libxsmm_gemm_batch_reduce_config brgemm_config);
+LIBXSMM_API libxsmm_gemmfunction_ext libxsmm_dispatch_brgemm_ext(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags,
+  const libxsmm_gemm_batch_reduce_config brgemm_config,
+  const libxsmm_gemm_ext_unary_argops unary_argops, const libxsmm_gemm_ext_binary_postops binary_postops);
+/* AMX tile (re)configuration has no GPU meaning: returns a callable no-op (include/libxsmm.h:139) */
+LIBXSMM_API libxsmm_tilecfgfunction libxsmm_dispatch_tilecfg_gemm(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags);
+
+/* ---- matrix-eltwise dispatch (reference include/libxsmm.h:142-146, src/libxsmm_main.c:3449-3511) -- */
+LIBXSMM_API libxsmm_meltwfunction_unary libxsmm_dispatch_meltw_unary(const libxsmm_meltw_unary_type unary_type,
+  const libxsmm_meltw_unary_shape unary_shape, const libxsmm_bitfield unary_flags);
+LIBXSMM_API libxsmm_meltwfunction_binary libxsmm_dispatch_meltw_binary(const libxsmm_meltw_binary_type binary_type,
+  const libxsmm_meltw_binary_shape binary_shape, const libxsmm_bitfield binary_flags);
+LIBXSMM_API libxsmm_meltwfunction_ternary libxsmm_dispatch_meltw_ternary(const libxsmm_meltw_ternary_type ternary_type,
+  const libxsmm_meltw_ternary_shape ternary_shape, const libxsmm_bitfield ternary_flags);
+
+/* ---- packed sparse GEMM (reference include/libxsmm.h:170-192, src/libxsmm_main.c:3553-3731) ------
+ * which operand is sparse follows the reference's convention: the one whose leading dimension in the
+ * shape is 0 (lda==0: A sparse, ldb==0: B sparse, ldc==0: C sparse). Handles are caller-owned and
+ * freed with libxsmm_release_kernel. */
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csr(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width,
+  const unsigned int* row_ptr, const unsigned int* column_idx, const void* values);
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csc(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width,
+  const unsigned int* column_ptr, const unsigned int* row_idx, const void* values);
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_bcsc(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_spgemm_config spgemm_config);
+LIBXSMM_API libxsmm_tilecfgfunction libxsmm_create_tilecfg_packed_spgemm_bcsc(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_spgemm_config spgemm_config);
+/* sparse A kept on chip, dense row-major B/C (reference include/libxsmm.h:216-223, used by fsspmdm) */
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_spgemm_csr_areg(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_blasint max_N,
+  const unsigned int* row_ptr, const unsigned int* column_idx, const double* values);
+LIBXSMM_API void libxsmm_release_kernel(const void* kernel);      /* reference include/libxsmm.h:229 */
+
+/* ---- memory (reference include/libxsmm_malloc.h:17-31): backed by CUDA managed memory so that
+ * buffers obtained here are valid on host and device ------------------------------------------- */
+LIBXSMM_API void* libxsmm_malloc(size_t size);
+LIBXSMM_API void* libxsmm_aligned_malloc(size_t size, size_t alignment);
+LIBXSMM_API void libxsmm_free(const void* memory);
+
+/* ---- conversions the kernels are bit-compatible with (reference src/libxsmm_math.c:587-830) ---- */
+LIBXSMM_API float libxsmm_convert_bf16_to_f32(libxsmm_bfloat16 in);
+LIBXSMM_API float libxsmm_convert_f16_to_f32(libxsmm_float16 in);
+LIBXSMM_API libxsmm_bfloat16 libxsmm_convert_f32_to_bf16_rne(float in);
+LIBXSMM_API libxsmm_float16 libxsmm_convert_f32_to_f16(float in);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* LIBXSMM_H */

@@ -1,0 +1,370 @@
+// libxsmm_b200 -- batched small-tile GEMM/BRGEMM on the 5th-generation tensor cores (sm_100a).
+//
+//   C_t(m x n) = beta * C_t + sum_{r < br} A_{t,r}(m x k) * B_{t,r}(k x n)      for t < count tiles
+//
+// Replaces the reference's per-ISA GEMM micro-kernels (src/generator_gemm_amx*.c,
+// src/generator_gemm_avx512_microkernel.c) for the 16-bit floating-point dense path; semantics are those
+// of libxsmm_ref_matmul (src/generator_gemm_reference_impl.c:2025-2170, 2367-2419) with f32
+// accumulation in tensor memory instead of a sequential scalar loop (tolerance, not bit-exact).
+//
+// Data flow per CTA (persistent, one CTA per SM, tiles assigned round-robin):
+//   warp 0   TMA producer : cp.async.bulk.tensor.4d of one A k-chunk and one B k-chunk per stage,
+//                           SWIZZLE_128B, ring of STAGES stages guarded by full/empty mbarriers
+//   warp 1   MMA issuer   : one lane issues tcgen05.mma.cta_group::1.kind::f16 (K=16 per instruction)
+//                           accumulating br * ceil(k/16) steps into a TMEM slot; tcgen05.commit frees
+//                           the SMEM stage and finally publishes the slot
+//   warps 2-5 epilogue    : tcgen05.ld 32x32b -> registers -> (convert) -> global stores; frees the slot
+//
+// Operand layouts (libxsmm column-major): A[k*lda+m] is M-contiguous => UMMA "MN-major" A operand,
+// B[n*ldb+k] is K-contiguous => UMMA "K-major" B operand; both land in SMEM in the canonical
+// SWIZZLE_128B layout directly from TMA (box inner extent 64 elements = 128 bytes).
+// For m <= 64 the M=64 instruction shape is used: its accumulator occupies lanes 0-15 of each 32-lane
+// TMEM quadrant, so two tiles share one slot (the second at lane offset 16) and one tcgen05.ld feeds
+// all 32 lanes of an epilogue warp.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "xb_internal.h"
+#include "xb_device.cuh"
+
+namespace {
+
+struct TcParams {
+  int m, n, k;
+  int np;                 // n rounded up to the MMA's N granularity
+  int kchunks;            // ceil(k / 64)
+  int stages, stage_bytes, a_bytes;
+  int nslot, slot_cols;
+  unsigned long long br;
+  long long count;
+  char* c; long long tile_stride_c; long long ldc;
+  int c_type, a_type, beta0;
+  uint32_t idesc;
+  uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // in 16-byte units
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// SMEM matrix descriptor, SWIZZLE_128B, descriptor version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32)
+       | (1ull << 46) | (2ull << 61);
+}
+
+template <int UM>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int TPS = (UM == 64) ? 2 : 1;          // tiles per TMEM slot
+  constexpr int MAX_STAGES = 16, MAX_SLOTS = 8;
+
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  uint64_t* bars = (uint64_t*)(smem + (size_t)P.stages * P.stage_bytes);
+  // barrier map: [0,S) full, [S,2S) empty, [2S,2S+NS) tmem_full, [2S+NS,2S+2NS) tmem_empty, then the TMEM base word
+  const uint32_t bar_base = smem_u32(bars);
+  const int S = P.stages, NS = P.nslot;
+  uint32_t* tmem_word = (uint32_t*)(bars + 2 * MAX_STAGES + 2 * MAX_SLOTS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long G = gridDim.x, b = blockIdx.x;
+  const long long n_local = (b < P.count) ? (P.count - b + G - 1) / G : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
+    for (int i = 0; i < S; ++i) { mbar_init(bar_base + 8 * i, 1); mbar_init(bar_base + 8 * (S + i), 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_base + 8 * (2 * S + i), 1); mbar_init(bar_base + 8 * (2 * S + NS + i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: whole 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_word)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_word;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long i = 0; i < n_local; ++i) {
+        const long long t = b + i * G;
+        for (unsigned long long r = 0; r < P.br; ++r) {
+          for (int kc = 0; kc < P.kchunks; ++kc) {
+            mbar_wait(bar_base + 8 * (S + stage), phase ^ 1);
+            const uint32_t full = bar_base + 8 * stage;
+            const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
+            mbar_expect_tx(full, (uint32_t)P.stage_bytes);
+            tma_load_4d(sa, &map_a, full, 0, kc * 64, (int)r, (int)t);
+            if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, 64, kc * 64, (int)r, (int)t);
+            tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, (int)t);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long i = 0; i < n_local; ++i) {
+        const long long slot_seq = i / TPS; const int half = (int)(i % TPS);
+        const int slot = (int)(slot_seq % NS);
+        if (half == 0) {
+          mbar_wait(bar_base + 8 * (2 * S + NS + slot), (uint32_t)(((slot_seq / NS) & 1) ^ 1));
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * P.slot_cols) + (half ? (16u << 16) : 0u);
+        uint32_t accumulate = 0;
+        for (unsigned long long r = 0; r < P.br; ++r) {
+          for (int kc = 0; kc < P.kchunks; ++kc) {
+            mbar_wait(bar_base + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
+            const int krem = P.k - kc * 64;
+            const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t adesc = make_desc(sa + ks * 2048, P.lbo_a, P.sbo_a);   // 16 k-rows of 128 B
+              const uint64_t bdesc = make_desc(sb + ks * 32, P.lbo_b, P.sbo_b);     // 16 k-elements inside the swizzle row
+              umma_f16(d_tmem, adesc, bdesc, P.idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(bar_base + 8 * (S + stage));     // stage reusable once these MMAs retired
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (half == TPS - 1 || i == n_local - 1) umma_commit(bar_base + 8 * (2 * S + slot));
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                         // TMEM lane quadrant this warp may read
+    const long long n_slots = (n_local + TPS - 1) / TPS;
+    const int half = (UM == 64) ? (lane >> 4) : 0;
+    const int row = (UM == 64) ? (16 * q + (lane & 15)) : (32 * q + lane);
+    for (long long slot_seq = 0; slot_seq < n_slots; ++slot_seq) {
+      const int slot = (int)(slot_seq % NS);
+      mbar_wait(bar_base + 8 * (2 * S + slot), (uint32_t)((slot_seq / NS) & 1));
+      tc_fence_after();
+      const long long i = slot_seq * TPS + half;
+      const bool valid = (i < n_local) && (row < P.m);
+      const long long t = b + i * G;
+      char* ctile = P.c + t * P.tile_stride_c;
+      const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < P.np; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        if (c0 + 32 >= P.np) {                      // last read of this slot: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_base + 8 * (2 * S + NS + slot));
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c0 + j;
+            if (col < P.n) {
+              const long long idx = (long long)col * P.ldc + row;
+              float acc = __uint_as_float(v[j]);
+              if (P.c_type == LIBXSMM_DATATYPE_F32) {
+                float* dst = reinterpret_cast<float*>(ctile) + idx;
+                if (!P.beta0) {
+                  float old = *dst;
+                  if (P.a_type == LIBXSMM_DATATYPE_F16) old = xb_f16_to_f32(xb_f32_to_f16(old));  // reference :2118-2123
+                  acc += old;
+                }
+                *dst = acc;
+              } else if (P.c_type == LIBXSMM_DATATYPE_BF16) {
+                unsigned short* dst = reinterpret_cast<unsigned short*>(ctile) + idx;
+                if (!P.beta0) acc += xb_bf16_to_f32(*dst);
+                *dst = xb_f32_to_bf16_rne(acc);
+              } else {
+                unsigned short* dst = reinterpret_cast<unsigned short*>(ctile) + idx;
+                if (!P.beta0) acc += xb_f16_to_f32(*dst);
+                *dst = xb_f32_to_f16(acc);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+int g_attr_set[2] = {0, 0};
+
+int tc_init_once() {
+  if (g_encode == nullptr) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+      (void)cudaGetLastError(); return 1;
+    }
+    g_encode = (EncodeTiledFn)fn;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return 0;
+}
+
+int env_int(const char* name, int fallback) {
+  const char* e = getenv(name);
+  return (e != nullptr && *e != 0) ? atoi(e) : fallback;
+}
+
+}  // namespace
+
+extern "C" int xb_gemm_tc_supported(const xb_gemm_desc* d) {
+  const unsigned int bad = LIBXSMM_GEMM_FLAG_TRANS_A | LIBXSMM_GEMM_FLAG_TRANS_B | LIBXSMM_GEMM_FLAG_VNNI_A
+                         | LIBXSMM_GEMM_FLAG_VNNI_B | LIBXSMM_GEMM_FLAG_VNNI_C | LIBXSMM_GEMM_FLAG_DECOMPRESS_A_VIA_BITMASK;
+  if ((d->flags & bad) != 0) return 0;
+  if (!(d->ta == d->tb && (d->ta == LIBXSMM_DATATYPE_BF16 || d->ta == LIBXSMM_DATATYPE_F16))) return 0;
+  if (d->tcomp != LIBXSMM_DATATYPE_F32) return 0;
+  if (d->ta == LIBXSMM_DATATYPE_BF16 && !(d->tc == LIBXSMM_DATATYPE_F32 || d->tc == LIBXSMM_DATATYPE_BF16)) return 0;
+  if (d->ta == LIBXSMM_DATATYPE_F16 && !(d->tc == LIBXSMM_DATATYPE_F32 || d->tc == LIBXSMM_DATATYPE_F16)) return 0;
+  if (d->m < 16 || d->n < 16 || d->k < 16 || d->m > 128 || d->n > 256 || d->k > 4096) return 0;
+  if ((d->lda % 8) != 0 || (d->ldb % 8) != 0) return 0;                 // TMA: 16-byte global strides
+  if (!(d->br_type == 0 || d->br_type == 3)) return 0;                  // address/offset modes: SIMT kernel
+  if (d->br_type == 3 && ((d->br_stride_a % 16) != 0 || (d->br_stride_b % 16) != 0 || d->br_stride_a <= 0 || d->br_stride_b <= 0)) return 0;
+  return 1;
+}
+
+extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
+  const xb_gemm_desc& d = L->d;
+  // resolve the uniform strided form (count==1 by-value record included)
+  const char* a = (const char*)L->a; const char* b = (const char*)L->b; char* c = (char*)L->c;
+  long long sa = L->tile_stride_a, sb = L->tile_stride_b, sc = L->tile_stride_c;
+  unsigned long long br = L->br;
+  if (L->recs != nullptr) return xb_gemm_simt_launch(L);
+  if (a == nullptr && c == nullptr) { a = (const char*)L->one.a; b = (const char*)L->one.b; c = (char*)L->one.c; br = L->one.br; sa = sb = sc = 0; }
+  if (d.br_type == 0) br = 1;
+  const int es = 2;
+  const bool aligned = (((uintptr_t)a | (uintptr_t)b) & 15) == 0 && (sa % 16) == 0 && (sb % 16) == 0
+                    && (L->count == 1 || (sa > 0 && sb > 0));
+  if (br == 0 || !aligned || L->count <= 0 || br > 0x7fffffffull || L->count > 0x7fffffffll || tc_init_once() != 0) {
+    return xb_gemm_simt_launch(L);
+  }
+
+  const int UM = (d.m <= 64) ? 64 : 128;
+  TcParams P; memset(&P, 0, sizeof(P));
+  P.m = d.m; P.n = d.n; P.k = d.k;
+  P.np = (UM == 64) ? ((d.n + 7) & ~7) : ((d.n + 15) & ~15);
+  P.kchunks = (d.k + 63) / 64;
+  P.a_bytes = UM * 128; P.stage_bytes = P.a_bytes + P.np * 128;
+  P.stages = (200 * 1024) / P.stage_bytes; if (P.stages > 12) P.stages = 12; if (P.stages < 2) P.stages = 2;
+  P.stages = env_int("LIBXSMM_B200_TC_STAGES", P.stages); if (P.stages > 16) P.stages = 16;
+  P.slot_cols = (P.np + 31) & ~31;
+  P.nslot = 512 / P.slot_cols; if (P.nslot > 4) P.nslot = 4;
+  P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
+  P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0;
+  // instruction descriptor: D=f32, A/B format, A MN-major, B K-major, N>>3, M>>4
+  const uint32_t fmt = (d.ta == LIBXSMM_DATATYPE_BF16) ? 1u : 0u;
+  P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(P.np >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+  P.lbo_a = (uint32_t)env_int("LIBXSMM_B200_TC_LBO_A", 8192 >> 4); P.sbo_a = (uint32_t)env_int("LIBXSMM_B200_TC_SBO_A", 1024 >> 4);
+  P.lbo_b = (uint32_t)env_int("LIBXSMM_B200_TC_LBO_B", 1);         P.sbo_b = (uint32_t)env_int("LIBXSMM_B200_TC_SBO_B", 1024 >> 4);
+
+  const CUtensorMapDataType dt = (d.ta == LIBXSMM_DATATYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const size_t ext_a = ((size_t)(d.k - 1) * d.lda + d.m) * es, ext_b = ((size_t)(d.n - 1) * d.ldb + d.k) * es;
+  const cuuint64_t pad_a = (ext_a + 15) & ~(size_t)15, pad_b = (ext_b + 15) & ~(size_t)15;
+  CUtensorMap map_a, map_b;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d.m, (cuuint64_t)d.k, (cuuint64_t)br, (cuuint64_t)L->count};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.lda * es, (d.br_type == 3) ? (cuuint64_t)d.br_stride_a : pad_a, (L->count > 1) ? (cuuint64_t)sa : pad_a};
+    const cuuint32_t box[4] = {64, 64, 1, 1};
+    const CUresult r = g_encode(&map_a, dt, 4, (void*)a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return xb_gemm_simt_launch(L);
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d.k, (cuuint64_t)d.n, (cuuint64_t)br, (cuuint64_t)L->count};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.ldb * es, (d.br_type == 3) ? (cuuint64_t)d.br_stride_b : pad_b, (L->count > 1) ? (cuuint64_t)sb : pad_b};
+    const cuuint32_t box[4] = {64, (cuuint32_t)P.np, 1, 1};
+    const CUresult r = g_encode(&map_b, dt, 4, (void*)b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return xb_gemm_simt_launch(L);
+  }
+
+  const size_t smem = (size_t)P.stages * P.stage_bytes + 1024 /*align slack*/ + (2 * 16 + 2 * 8) * 8 + 64;
+  const long long tiles_per_cta_unit = (UM == 64) ? 2 : 1;
+  long long grid = (L->count + tiles_per_cta_unit - 1) / tiles_per_cta_unit; if (grid > g_num_sms) grid = g_num_sms; if (grid < 1) grid = 1;
+  cudaStream_t stream = (cudaStream_t)xb_rt_stream();
+  cudaError_t e;
+  if (UM == 64) {
+    if (!g_attr_set[0]) { cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_attr_set[0] = 1; }
+    gemm_tc_kernel<64><<<(unsigned int)grid, 192, smem, stream>>>(map_a, map_b, P);
+  } else {
+    if (!g_attr_set[1]) { cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_attr_set[1] = 1; }
+    gemm_tc_kernel<128><<<(unsigned int)grid, 192, smem, stream>>>(map_a, map_b, P);
+  }
+  xb_rt_count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { xb_rt_note_error((int)e, "gemm_tc"); return (int)e; }
+  return 0;
+}

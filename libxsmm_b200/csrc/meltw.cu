@@ -1,0 +1,499 @@
+// libxsmm_b200 -- matrix-eltwise (TPP) kernels for sm_100a: unary / binary / ternary maps with
+// row/column/scalar broadcast and bitmasks, reductions, layout transforms, gather/scatter and
+// (de)quantisation. All matrices are column-major, element (i,j) at i + j*ld.
+//
+// Semantics follow the reference's portable kernels in src/generator_mateltwise_reference_impl.c:
+//   operand indexing with broadcast ........ :241-272      generic unary ops ........... :76-139, :2470-2498
+//   RELU/LEAKY_RELU/ELU (+bitmask), inverse  :2138-2194    reductions .................. :1065-1443
+//   gather / scatter ........................ :1444-1794    transforms .................. :377-1062
+//   quant / dequant ......................... :2195-2360    binary / ternary ............ :2505-2660
+// Values are loaded to f32 (bf16 loads flush denormals like libxsmm_convert_bf16_to_f32), computed in
+// f32 (f64 only if every type is F64) and stored with round-to-nearest-even. Data-movement kernels
+// (transforms, gather/scatter) are bit-exact. Mapping: one warp per (column, 32-row chunk), so loads
+// and stores are coalesced along i and a bitmask byte is assembled with one __ballot_sync.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include "xb_internal.h"
+#include "xb_device.cuh"
+
+namespace {
+
+enum { FAM_NONE = 0, FAM_MAP, FAM_REDUCE, FAM_SCALAR, FAM_TRANSFORM, FAM_GS, FAM_QUANT };
+
+__host__ __device__ inline bool is_f(int t) { return t == LIBXSMM_DATATYPE_F32 || t == LIBXSMM_DATATYPE_BF16 || t == LIBXSMM_DATATYPE_F16; }
+
+__host__ __device__ inline int family_of(const xb_meltw_desc& d) {
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
+    switch (d.op) {
+      case LIBXSMM_MELTW_TYPE_UNARY_IDENTITY: case LIBXSMM_MELTW_TYPE_UNARY_XOR: case LIBXSMM_MELTW_TYPE_UNARY_X2:
+      case LIBXSMM_MELTW_TYPE_UNARY_SQRT: case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: case LIBXSMM_MELTW_TYPE_UNARY_INC:
+      case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT:
+        if (d.t_in0 == LIBXSMM_DATATYPE_F64 && d.t_out == LIBXSMM_DATATYPE_F64 && d.t_comp == LIBXSMM_DATATYPE_F64) return FAM_MAP;
+        return (is_f(d.t_in0) && is_f(d.t_out)) ? FAM_MAP : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_TANH: case LIBXSMM_MELTW_TYPE_UNARY_TANH_INV: case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID:
+      case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID_INV: case LIBXSMM_MELTW_TYPE_UNARY_GELU: case LIBXSMM_MELTW_TYPE_UNARY_GELU_INV:
+      case LIBXSMM_MELTW_TYPE_UNARY_EXP: case LIBXSMM_MELTW_TYPE_UNARY_REPLICATE_COL_VAR:
+      case LIBXSMM_MELTW_TYPE_UNARY_RELU: case LIBXSMM_MELTW_TYPE_UNARY_RELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU:
+      case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_ELU: case LIBXSMM_MELTW_TYPE_UNARY_ELU_INV:
+        return (is_f(d.t_in0) && is_f(d.t_out)) ? FAM_MAP : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ADD: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD:
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX:
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ABSMAX:
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_ADD: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_MAX:
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_MIN:
+        if (d.t_in0 == LIBXSMM_DATATYPE_F64 && d.t_out == LIBXSMM_DATATYPE_F64) return FAM_REDUCE;
+        return (is_f(d.t_in0) && is_f(d.t_out)) ? FAM_REDUCE : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_TO_SCALAR_OP_ADD:
+        if (d.t_in0 == LIBXSMM_DATATYPE_F64 && d.t_out == LIBXSMM_DATATYPE_F64) return FAM_SCALAR;
+        return (is_f(d.t_in0) && is_f(d.t_out)) ? FAM_SCALAR : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT: return FAM_TRANSFORM;
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2_TO_VNNI2T:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2T_TO_NORM: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4T:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4T_TO_NORM:
+        return (xb_dev_typesize(d.t_in0) == 2) ? FAM_TRANSFORM : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI4T:
+        return (xb_dev_typesize(d.t_in0) <= 2) ? FAM_TRANSFORM : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_NORM:
+        return (xb_dev_typesize(d.t_in0) == 1) ? FAM_TRANSFORM : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_GATHER: case LIBXSMM_MELTW_TYPE_UNARY_SCATTER:
+        return (xb_dev_typesize(d.t_in0) <= 4 && xb_dev_typesize(d.t_in0) >= 1) ? FAM_GS : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_QUANT:
+        return (d.t_in0 == LIBXSMM_DATATYPE_F32 && (d.t_out == LIBXSMM_DATATYPE_I8 || d.t_out == LIBXSMM_DATATYPE_I16 || d.t_out == LIBXSMM_DATATYPE_I32)) ? FAM_QUANT : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT:
+        return (d.t_out == LIBXSMM_DATATYPE_F32 && (d.t_in0 == LIBXSMM_DATATYPE_I8 || d.t_in0 == LIBXSMM_DATATYPE_I16 || d.t_in0 == LIBXSMM_DATATYPE_I32)) ? FAM_QUANT : FAM_NONE;
+      default: return FAM_NONE;
+    }
+  }
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_BINARY) {
+    const bool all64 = d.t_in0 == LIBXSMM_DATATYPE_F64 && d.t_in1 == LIBXSMM_DATATYPE_F64 && d.t_out == LIBXSMM_DATATYPE_F64 && d.t_comp == LIBXSMM_DATATYPE_F64;
+    switch (d.op) {
+      case LIBXSMM_MELTW_TYPE_BINARY_ADD: case LIBXSMM_MELTW_TYPE_BINARY_MUL: case LIBXSMM_MELTW_TYPE_BINARY_SUB:
+      case LIBXSMM_MELTW_TYPE_BINARY_DIV: case LIBXSMM_MELTW_TYPE_BINARY_MULADD: case LIBXSMM_MELTW_TYPE_BINARY_MAX:
+      case LIBXSMM_MELTW_TYPE_BINARY_MIN:
+        return (all64 || (is_f(d.t_in0) && is_f(d.t_in1) && is_f(d.t_out))) ? FAM_MAP : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GT: case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GE: case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_LT:
+      case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_LE: case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_EQ: case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_NE:
+        return (is_f(d.t_in0) && is_f(d.t_in1)) ? FAM_MAP : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_BINARY_ZIP:
+        return (d.t_in0 == LIBXSMM_DATATYPE_U16 || d.t_in0 == LIBXSMM_DATATYPE_BF16 || d.t_in0 == LIBXSMM_DATATYPE_I16) ? FAM_MAP : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_BINARY_MUL_AND_REDUCE_TO_SCALAR_OP_ADD:
+        return (all64 || (is_f(d.t_in0) && is_f(d.t_in1) && is_f(d.t_out))) ? FAM_SCALAR : FAM_NONE;
+      default: return FAM_NONE;
+    }
+  }
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_TERNARY) {
+    const bool all64 = d.t_in0 == LIBXSMM_DATATYPE_F64 && d.t_in1 == LIBXSMM_DATATYPE_F64 && d.t_in2 == LIBXSMM_DATATYPE_F64
+                    && d.t_out == LIBXSMM_DATATYPE_F64 && d.t_comp == LIBXSMM_DATATYPE_F64;
+    switch (d.op) {
+      case LIBXSMM_MELTW_TYPE_TERNARY_SELECT: return (all64 || (is_f(d.t_in0) && is_f(d.t_in1) && is_f(d.t_out))) ? FAM_MAP : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_TERNARY_MULADD: case LIBXSMM_MELTW_TYPE_TERNARY_NMULADD:
+        return (is_f(d.t_in0) && is_f(d.t_in1) && is_f(d.t_in2) && is_f(d.t_out)) ? FAM_MAP : FAM_NONE;
+      default: return FAM_NONE;
+    }
+  }
+  return FAM_NONE;
+}
+
+// ---- typed load/store -----------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_f32(const void* p, long long idx, int t) {
+  if (t == LIBXSMM_DATATYPE_F32) return ((const float*)p)[idx];
+  if (t == LIBXSMM_DATATYPE_BF16) { unsigned short h = ((const unsigned short*)p)[idx]; if ((h & 0x7f80) == 0) h &= 0x8000; return xb_bf16_to_f32(h); }
+  return xb_f16_to_f32(((const unsigned short*)p)[idx]);
+}
+__device__ __forceinline__ void st_f32(void* p, long long idx, int t, float v) {
+  if (t == LIBXSMM_DATATYPE_F32) ((float*)p)[idx] = v;
+  else if (t == LIBXSMM_DATATYPE_BF16) ((unsigned short*)p)[idx] = xb_f32_to_bf16_rne(v);
+  else ((unsigned short*)p)[idx] = xb_f32_to_f16(v);
+}
+// operand index with broadcast flags; which: 0,1,2 = in0,in1,in2
+__device__ __forceinline__ long long bidx(const xb_meltw_desc& d, int which, int i, int j, long long ld) {
+  unsigned int row = 0, col = 0, sca = 0;
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
+    if (which == 0) { row = d.flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_ROW; col = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_COL) | (d.op == LIBXSMM_MELTW_TYPE_UNARY_REPLICATE_COL_VAR); sca = d.flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_SCALAR; }
+  } else if (d.op_class == LIBXSMM_MELTW_OPERATION_BINARY) {
+    row = d.flags & (which == 0 ? LIBXSMM_MELTW_FLAG_BINARY_BCAST_ROW_IN_0 : LIBXSMM_MELTW_FLAG_BINARY_BCAST_ROW_IN_1);
+    col = d.flags & (which == 0 ? LIBXSMM_MELTW_FLAG_BINARY_BCAST_COL_IN_0 : LIBXSMM_MELTW_FLAG_BINARY_BCAST_COL_IN_1);
+    sca = d.flags & (which == 0 ? LIBXSMM_MELTW_FLAG_BINARY_BCAST_SCALAR_IN_0 : LIBXSMM_MELTW_FLAG_BINARY_BCAST_SCALAR_IN_1);
+    if (which > 1) row = col = sca = 0;
+  } else {
+    const unsigned int r[3] = { LIBXSMM_MELTW_FLAG_TERNARY_BCAST_ROW_IN_0, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_ROW_IN_1, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_ROW_IN_2 };
+    const unsigned int c[3] = { LIBXSMM_MELTW_FLAG_TERNARY_BCAST_COL_IN_0, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_COL_IN_1, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_COL_IN_2 };
+    const unsigned int s[3] = { LIBXSMM_MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_0, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_1, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_2 };
+    row = d.flags & r[which]; col = d.flags & c[which]; sca = d.flags & s[which];
+  }
+  if (row) return (long long)j * ld;
+  if (col) return i;
+  if (sca) return 0;
+  return i + (long long)j * ld;
+}
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return (tanhf(x / 2.0f) + 1.0f) / 2.0f; }
+
+__device__ __forceinline__ float unary_f32(float x, int op) {
+  switch (op) {
+    case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: return -1.0f * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_X2: return x * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_XOR: return 0.0f;
+    case LIBXSMM_MELTW_TYPE_UNARY_TANH: return tanhf(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID: return sigmoidf_ref(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_GELU: return (erff(x / sqrtf(2.0f)) + 1.0f) * 0.5f * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_GELU_INV: return 0.5f + 0.5f * erff(x / sqrtf(2.0f)) + x / sqrtf(2.0f * 3.14159265358979323846f) * expf(-0.5f * x * x);
+    case LIBXSMM_MELTW_TYPE_UNARY_TANH_INV: { const float t = tanhf(x); return 1.0f - t * t; }
+    case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID_INV: { const float s = sigmoidf_ref(x); return s * (1.0f - s); }
+    case LIBXSMM_MELTW_TYPE_UNARY_SQRT: return sqrtf(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_INC: return x + 1.0f;
+    case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: return 1.0f / x;
+    case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT: return 1.0f / sqrtf(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_EXP: return expf(x);
+    default: return x;   // IDENTITY, REPLICATE_COL_VAR
+  }
+}
+__device__ __forceinline__ double unary_f64(double x, int op) {
+  switch (op) {
+    case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: return -1.0 * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_X2: return x * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_XOR: return 0.0;
+    case LIBXSMM_MELTW_TYPE_UNARY_SQRT: return sqrt(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_INC: return x + 1.0;
+    case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: return 1.0 / x;
+    case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT: return 1.0 / sqrt(x);
+    default: return x;
+  }
+}
+template <typename T> __device__ __forceinline__ T binary_op(T a, T b, T out, int op) {
+  switch (op) {
+    case LIBXSMM_MELTW_TYPE_BINARY_ADD: return a + b;
+    case LIBXSMM_MELTW_TYPE_BINARY_SUB: return a - b;
+    case LIBXSMM_MELTW_TYPE_BINARY_MUL: return a * b;
+    case LIBXSMM_MELTW_TYPE_BINARY_DIV: return a / b;
+    case LIBXSMM_MELTW_TYPE_BINARY_MULADD: return out + a * b;
+    case LIBXSMM_MELTW_TYPE_BINARY_MAX: return (a > b) ? a : b;
+    case LIBXSMM_MELTW_TYPE_BINARY_MIN: return (a > b) ? b : a;
+    default: return out;
+  }
+}
+__device__ __forceinline__ bool cmp_op(float a, float b, int op) {
+  switch (op) {
+    case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GT: return a > b;
+    case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GE: return a >= b;
+    case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_LT: return a < b;
+    case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_LE: return a <= b;
+    case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_EQ: return a == b;
+    default: return a != b;
+  }
+}
+__device__ __forceinline__ bool mask_bit(const void* mask, int i, int j, long long mask_ld) {
+  return (((const unsigned char*)mask)[i / 8 + (long long)j * (mask_ld / 8)] >> (i % 8)) & 1;
+}
+// a warp holds 32 consecutive rows [i0, i0+32) of column j; lane bit = predicate. Only bits of valid rows change.
+__device__ __forceinline__ void mask_store(void* mask, int i0, int j, long long mask_ld, int m, bool bit, int lane) {
+  const unsigned int word = __ballot_sync(0xffffffffu, bit);
+  if (lane < 4) {
+    const int ib = i0 + lane * 8;
+    if (ib < m) {
+      unsigned char* dst = (unsigned char*)mask + ib / 8 + (long long)j * (mask_ld / 8);
+      const unsigned int valid = (m - ib >= 8) ? 0xffu : ((1u << (m - ib)) - 1u);
+      const unsigned int nb = (word >> (lane * 8)) & 0xffu;
+      *dst = (unsigned char)((valid == 0xffu) ? nb : ((*dst & ~valid) | (nb & valid)));
+    }
+  }
+}
+
+// ---- map kernel: unary / binary / ternary elementwise (with masks) ---------------------------------------------
+__global__ void __launch_bounds__(256) meltw_map_kernel(const xb_meltw_desc d, const xb_meltw_args a, const int n_eff) {
+  const int lane = threadIdx.x & 31;
+  const int chunks = (d.m + 31) / 32;
+  const long long nwork = (long long)chunks * n_eff;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  const bool f64 = (d.t_out == LIBXSMM_DATATYPE_F64);
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nwork; w += wstride) {
+    const int j = (int)(w / chunks), i0 = (int)(w % chunks) * 32, i = i0 + lane;
+    const bool act = i < d.m;
+    const long long oi = i + (long long)j * d.ldo;
+    if (d.op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
+      const int op = d.op;
+      if (f64) { if (act) ((double*)a.out)[oi] = unary_f64(((const double*)a.in0)[bidx(d, 0, i, j, d.ldi)], op); continue; }
+      const float x = act ? ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0) : 0.0f;
+      const bool bitm = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0;
+      if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_ELU) {
+        float y;
+        if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU) y = (x <= 0.0f) ? 0.0f : x;
+        else if (op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU) y = (x <= 0.0f) ? a.alpha * x : x;
+        else y = (x <= 0.0f) ? a.alpha * (expf(x) - 1.0f) : x;
+        if (act) st_f32(a.out, oi, d.t_out, y);
+        if (bitm) mask_store(a.out_aux, i0, j, ((d.ldo + 15) / 16) * 16, d.m, act && !(x <= 0.0f), lane);
+      } else if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU_INV || op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU_INV) {
+        if (act) {
+          const long long mld = bitm ? ((d.ldi + 15) / 16) * 16 : d.ldi;
+          const bool bit = mask_bit(a.in_aux, i, j, mld);
+          st_f32(a.out, oi, d.t_out, bit ? x : ((op == LIBXSMM_MELTW_TYPE_UNARY_RELU_INV) ? 0.0f : a.alpha * x));
+        }
+      } else if (op == LIBXSMM_MELTW_TYPE_UNARY_ELU_INV) {
+        if (act) { const float fwd = ld_f32(a.in_aux, i + (long long)j * d.ldi, d.t_in0); st_f32(a.out, oi, d.t_out, (fwd > 0) ? x : x * (fwd + a.alpha)); }
+      } else if (act) st_f32(a.out, oi, d.t_out, unary_f32(x, op));
+    } else if (d.op_class == LIBXSMM_MELTW_OPERATION_BINARY) {
+      const int op = d.op;
+      if (op == LIBXSMM_MELTW_TYPE_BINARY_ZIP) {
+        if (act) ((unsigned int*)a.out)[oi] = (unsigned int)((const unsigned short*)a.in0)[bidx(d, 0, i, j, d.ldi)]
+                                            | ((unsigned int)((const unsigned short*)a.in1)[bidx(d, 1, i, j, d.ldi2)] << 16);
+        continue;
+      }
+      if (f64 && op < LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GT) {
+        if (act) { double* o = (double*)a.out + oi; *o = binary_op<double>(((const double*)a.in0)[bidx(d, 0, i, j, d.ldi)], ((const double*)a.in1)[bidx(d, 1, i, j, d.ldi2)], *o, op); }
+        continue;
+      }
+      const float x = act ? ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0) : 0.0f;
+      const float y = act ? ld_f32(a.in1, bidx(d, 1, i, j, d.ldi2), d.t_in1) : 0.0f;
+      if (op >= LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GT) mask_store(a.out, i0, j, ((d.ldo + 15) / 16) * 16, d.m, act && cmp_op(x, y, op), lane);
+      else if (act) {
+        const float o = (op == LIBXSMM_MELTW_TYPE_BINARY_MULADD) ? ld_f32(a.out, oi, d.t_out) : 0.0f;
+        st_f32(a.out, oi, d.t_out, binary_op<float>(x, y, o, op));
+      }
+    } else if (act) {
+      if (d.op == LIBXSMM_MELTW_TYPE_TERNARY_SELECT) {
+        const bool bit = mask_bit(a.in2, i, j, ((d.ldi3 + 15) / 16) * 16);
+        if (f64) ((double*)a.out)[oi] = bit ? ((const double*)a.in1)[bidx(d, 1, i, j, d.ldi2)] : ((const double*)a.in0)[bidx(d, 0, i, j, d.ldi)];
+        else st_f32(a.out, oi, d.t_out, bit ? ld_f32(a.in1, bidx(d, 1, i, j, d.ldi2), d.t_in1) : ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0));
+      } else {
+        const float x = ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0), y = ld_f32(a.in1, bidx(d, 1, i, j, d.ldi2), d.t_in1);
+        const float z = ld_f32(a.in2, bidx(d, 2, i, j, d.ldi3), d.t_in2);
+        st_f32(a.out, oi, d.t_out, (d.op == LIBXSMM_MELTW_TYPE_TERNARY_MULADD) ? (z + x * y) : (y - x * z));
+      }
+    }
+  }
+}
+
+// ---- reductions: one warp per result element, lanes stride the reduced dimension, shuffle combine -------------------
+template <typename T> __device__ __forceinline__ T warp_sum(T v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+template <typename T> __device__ __forceinline__ T warp_max(T v) { for (int o = 16; o > 0; o >>= 1) { const T u = __shfl_xor_sync(0xffffffffu, v, o); v = (u > v) ? u : v; } return v; }
+template <typename T> __device__ __forceinline__ T warp_min(T v) { for (int o = 16; o > 0; o >>= 1) { const T u = __shfl_xor_sync(0xffffffffu, v, o); v = (u < v) ? u : v; } return v; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) meltw_reduce_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
+  const int lane = threadIdx.x & 31;
+  const bool rows = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_ROWS) != 0;
+  const bool init_acc = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_INIT_ACC) != 0;
+  const bool argop = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_RECORD_ARGOP) != 0;
+  const bool idx4 = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_IDX_SIZE_4BYTES) != 0;
+  const bool f64 = sizeof(T) == 8;
+  const int op = d.op;
+  const bool by_idx = (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_ADD || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_MAX || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_MIN);
+  const int kind = (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_MAX) ? 1
+                 : (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_MIN) ? 2
+                 : (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ABSMAX) ? 3 : 0;
+  const bool want_x = (op != LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD);
+  const bool want_x2 = (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD);
+  const int nres = rows ? d.n : d.m;
+  const int result_size = rows ? d.n : d.ldo;                 // offset of the x^2 plane (reference :1073-1076)
+  const int len = rows ? d.m : (by_idx ? (int)a.n_rt : d.n);
+  for (int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); o < nres; o += gridDim.x * (blockDim.x >> 5)) {
+    T sx = 0, sx2 = 0, best = (kind == 1) ? (T)-FLT_MAX : ((kind == 2) ? (T)FLT_MAX : (T)0);
+    long long best_j = 0;
+    if (kind != 0 && rows) best = f64 ? (T)((const double*)a.in0)[(long long)o * d.ldi] : (T)ld_f32(a.in0, (long long)o * d.ldi, d.t_in0);
+    if (argop && kind != 0 && !rows) {                        // order-dependent (last extremum wins): one lane scans
+      if (lane == 0) {
+        for (int t = 0; t < len; ++t) {
+          const long long j = by_idx ? (idx4 ? (long long)((const unsigned int*)a.in_aux)[t] : (long long)((const unsigned long long*)a.in_aux)[t]) : t;
+          T v = f64 ? (T)((const double*)a.in0)[o + j * d.ldi] : (T)ld_f32(a.in0, o + j * d.ldi, d.t_in0);
+          if (kind == 3) v = (v < 0) ? -v : v;
+          if ((kind == 2) ? (v <= best) : (v >= best)) { best = v; best_j = j; }
+        }
+        if (idx4) ((unsigned int*)a.out_aux)[o] = (unsigned int)best_j; else ((unsigned long long*)a.out_aux)[o] = (unsigned long long)best_j;
+      }
+      best = __shfl_sync(0xffffffffu, best, 0);
+    } else {
+      for (int t = lane; t < len; t += 32) {
+        long long idx;
+        if (rows) idx = t + (long long)o * d.ldi;
+        else { const long long j = by_idx ? (idx4 ? (long long)((const unsigned int*)a.in_aux)[t] : (long long)((const unsigned long long*)a.in_aux)[t]) : t; idx = o + j * d.ldi; }
+        T v = f64 ? (T)((const double*)a.in0)[idx] : (T)ld_f32(a.in0, idx, d.t_in0);
+        if (kind == 0) { sx += v; sx2 += v * v; }
+        else { if (kind == 3) { v = (v < 0) ? -v : v; best = (best < 0) ? -best : best; } best = (kind == 2) ? ((v < best) ? v : best) : ((v > best) ? v : best); }
+      }
+      if (kind == 0) { sx = warp_sum(sx); sx2 = warp_sum(sx2); } else best = (kind == 2) ? warp_min(best) : warp_max(best);
+    }
+    if (lane == 0) {
+      if (kind == 0) {
+        if (f64) {
+          double* ox = (double*)a.out; double* ox2 = want_x ? ox + result_size : ox;
+          if (want_x) ox[o] = (double)sx + ((init_acc) ? ox[o] : 0.0);
+          if (want_x2) ox2[o] = (double)sx2 + ((init_acc) ? ox2[o] : 0.0);
+        } else {
+          char* base2 = (char*)a.out + (want_x ? (size_t)result_size * xb_dev_typesize(d.t_out) : 0);
+          if (want_x) { float r = (float)sx; if (init_acc && !by_idx) r += ld_f32(a.out, o, d.t_out); st_f32(a.out, o, d.t_out, r); }
+          if (want_x2) { float r = (float)sx2; if (init_acc) r += ld_f32(base2, o, d.t_out); st_f32(base2, o, d.t_out, r); }
+        }
+      } else {
+        if (f64) ((double*)a.out)[o] = (double)best; else st_f32(a.out, o, d.t_out, (float)best);
+      }
+    }
+  }
+}
+
+// whole-matrix reductions to one scalar (single CTA; the tests' sizes are tiny, the large case is a dot product)
+template <typename T>
+__global__ void __launch_bounds__(1024) meltw_scalar_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
+  __shared__ T part[32];
+  const bool f64 = sizeof(T) == 8;
+  const bool dot = (d.op_class == LIBXSMM_MELTW_OPERATION_BINARY);
+  T acc = 0;
+  for (long long e = threadIdx.x; e < (long long)d.m * d.n; e += blockDim.x) {
+    const int i = (int)(e % d.m), j = (int)(e / d.m);
+    T x = f64 ? (T)((const double*)a.in0)[bidx(d, 0, i, j, d.ldi)] : (T)ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0);
+    if (dot) x *= f64 ? (T)((const double*)a.in1)[bidx(d, 1, i, j, d.ldi2)] : (T)ld_f32(a.in1, bidx(d, 1, i, j, d.ldi2), d.t_in1);
+    acc += x;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : (T)0;
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) { if (f64) ((double*)a.out)[0] = (double)acc; else st_f32(a.out, 0, d.t_out, (float)acc); }
+  }
+}
+
+// ---- transforms: one thread per OUTPUT element, pure data movement -------------------------------------------------
+template <typename E>
+__global__ void __launch_bounds__(256) meltw_transform_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
+  const E* in = (const E*)a.in0; E* out = (E*)a.out;
+  const long long M = d.m, N = d.n, ldi = d.ldi, ldo = d.ldo;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  switch (d.op) {
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT:          // out[j*ldo+i] = in[i*ldi+j], i<N, j<M (:390-417)
+      for (long long e = tid; e < M * N; e += nth) { const long long i = e % N, j = e / N; out[j * ldo + i] = in[i * ldi + j]; }
+      break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD:
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD: {
+      // whole ldo x Nn output is defined: zero everywhere except out[(j*ldo*v)+(i*v)+j2] = in[((j*v)+j2)*ldi+i] (:541-553, :690-708, :737-759)
+      const long long v = (d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2 || d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD) ? 2 : 4;
+      const long long Nn = ((N + v - 1) / v) * v;
+      for (long long e = tid; e < ldo * Nn; e += nth) {
+        const long long j = e / (ldo * v), rem = e % (ldo * v), i = rem / v, j2 = rem % v, col = j * v + j2;
+        out[e] = (i < M && col < N) ? in[col * ldi + i] : (E)0;   // rows >= N of the last group are zero padding
+      }
+    } break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4T: {
+      const long long v = (d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2T) ? 2 : 4;   // out[(i*ldo*v)+(j*v)+i2] = in[(j*ldi)+(i*v+i2)]
+      for (long long e = tid; e < (M / v) * N * v; e += nth) { const long long i2 = e % v, j = (e / v) % N, i = e / (v * N); out[i * ldo * v + j * v + i2] = in[j * ldi + i * v + i2]; }
+    } break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2_TO_VNNI2T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI4T: {
+      const long long v = (d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2_TO_VNNI2T) ? 2 : 4;  // out[j*ldo*v+j2+(i*v+i2)*v] = in[i*ldi*v+i2+(j*v+j2)*v]
+      for (long long e = tid; e < (M / v) * (N / v) * v * v; e += nth) {
+        const long long i2 = e % v, j2 = (e / v) % v, i = (e / (v * v)) % (N / v), j = e / (v * v * (N / v));
+        out[j * ldo * v + j2 + (i * v + i2) * v] = in[i * ldi * v + i2 + (j * v + j2) * v];
+      }
+    } break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2T_TO_NORM: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4T_TO_NORM: {
+      const long long v = (d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2T_TO_NORM) ? 2 : 4;   // roles of m/n swapped (:620-660)
+      const long long Mr = d.n, Nr = d.m;                                                          // out[(j*ldo)+(i*v)+i2] = in[(i*ldi*v)+(j*v+i2)]
+      for (long long e = tid; e < (Mr / v) * Nr * v; e += nth) { const long long i2 = e % v, j = (e / v) % Nr, i = e / (v * Nr); out[j * ldo + i * v + i2] = in[i * ldi * v + j * v + i2]; }
+    } break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_NORM:            // out[(i*ldo)+j] = in[((i/4)*ldi*4)+j*4+(i%4)], i<N, j<M (:787-803)
+      for (long long e = tid; e < M * N; e += nth) { const long long j = e % M, i = e / M; out[i * ldo + j] = in[(i / 4) * ldi * 4 + j * 4 + (i % 4)]; }
+      break;
+    default: break;
+  }
+}
+
+// ---- gather / scatter (:1444-1794) ------------------------------------------------------------------------------------
+template <typename E>
+__global__ void __launch_bounds__(256) meltw_gs_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
+  const E* in = (const E*)a.in0; E* out = (E*)a.out;
+  const bool gather = (d.op == LIBXSMM_MELTW_TYPE_UNARY_GATHER);
+  const void* idxp = gather ? a.in_aux : (const void*)a.out_aux;
+  const bool idx8 = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_IDX_SIZE_8BYTES) != 0;
+  const bool cols = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_GS_COLS) != 0, rows = !cols && (d.flags & LIBXSMM_MELTW_FLAG_UNARY_GS_ROWS) != 0;
+  const long long M = d.m, N = d.n, ldi = d.ldi, ldo = d.ldo;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < M * N; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e % M, j = e / M;
+    const long long sel = cols ? j : (rows ? i : (i + j * M));
+    const long long x = idx8 ? (long long)((const unsigned long long*)idxp)[sel] : (long long)((const unsigned int*)idxp)[sel];
+    if (gather) out[i + j * ldo] = cols ? in[i + x * ldi] : (rows ? in[x + j * ldi] : in[x]);
+    else { if (cols) out[i + x * ldo] = in[i + j * ldi]; else if (rows) out[x + j * ldo] = in[i + j * ldi]; else out[x] = in[i + j * ldi]; }
+  }
+}
+
+// ---- quant / dequant (:2195-2360) ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) meltw_quant_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
+  const bool quant = (d.op == LIBXSMM_MELTW_TYPE_UNARY_QUANT);
+  const bool sat = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_SIGN_SAT_QUANT) != 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)d.m * d.n; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % d.m), j = (int)(e / d.m);
+    const long long ii = bidx(d, 0, i, j, d.ldi), oi = i + (long long)j * d.ldo;
+    if (quant) {
+      const float r = nearbyintf(((const float*)a.in0)[ii] * a.alpha);
+      if (d.t_out == LIBXSMM_DATATYPE_I8) ((signed char*)a.out)[oi] = sat ? (signed char)fminf(fmaxf(r, -128.f), 127.f) : (signed char)(0xff & (int)r);
+      else if (d.t_out == LIBXSMM_DATATYPE_I16) ((short*)a.out)[oi] = sat ? (short)fminf(fmaxf(r, -32768.f), 32767.f) : (short)(0xffff & (int)r);
+      else ((int*)a.out)[oi] = (int)r;
+    } else {
+      float v;
+      if (d.t_in0 == LIBXSMM_DATATYPE_I8) v = (float)((const signed char*)a.in0)[ii];
+      else if (d.t_in0 == LIBXSMM_DATATYPE_I16) v = (float)((const short*)a.in0)[ii];
+      else v = (float)((const int*)a.in0)[ii];
+      ((float*)a.out)[oi] = v * a.alpha;
+    }
+  }
+}
+
+int launch_done(const char* where) {
+  xb_rt_count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { xb_rt_note_error((int)e, where); return (int)e; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int xb_meltw_supported(const xb_meltw_desc* d) { return family_of(*d) != FAM_NONE; }
+
+extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
+  cudaStream_t st = (cudaStream_t)xb_rt_stream();
+  const int fam = family_of(*d);
+  if (d->m <= 0 || d->n <= 0) return 0;
+  switch (fam) {
+    case FAM_MAP: {
+      const int n_eff = (d->op_class == LIBXSMM_MELTW_OPERATION_UNARY && d->op == LIBXSMM_MELTW_TYPE_UNARY_REPLICATE_COL_VAR) ? (int)a->n_rt : d->n;
+      const long long warps = (long long)((d->m + 31) / 32) * n_eff;
+      long long grid = (warps + 7) / 8; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) return 0;
+      meltw_map_kernel<<<(unsigned int)grid, 256, 0, st>>>(*d, *a, n_eff);
+      return launch_done("meltw_map");
+    }
+    case FAM_REDUCE: {
+      const int nres = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_ROWS) ? d->n : d->m;
+      int grid = (nres + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
+      if (d->t_in0 == LIBXSMM_DATATYPE_F64) meltw_reduce_kernel<double><<<grid, 256, 0, st>>>(*d, *a);
+      else meltw_reduce_kernel<float><<<grid, 256, 0, st>>>(*d, *a);
+      return launch_done("meltw_reduce");
+    }
+    case FAM_SCALAR:
+      if (d->t_in0 == LIBXSMM_DATATYPE_F64) meltw_scalar_kernel<double><<<1, 1024, 0, st>>>(*d, *a);
+      else meltw_scalar_kernel<float><<<1, 1024, 0, st>>>(*d, *a);
+      return launch_done("meltw_scalar");
+    case FAM_TRANSFORM: case FAM_GS: {
+      const long long work = (long long)(d->ldo > d->m ? d->ldo : d->m) * ((d->n + 3) / 4 * 4);
+      long long grid = (work + 255) / 256; if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+      const int ts = xb_dev_typesize(d->t_in0);
+      if (fam == FAM_TRANSFORM) {
+        if (ts == 8) meltw_transform_kernel<unsigned long long><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+        else if (ts == 4) meltw_transform_kernel<unsigned int><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+        else if (ts == 2) meltw_transform_kernel<unsigned short><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+        else meltw_transform_kernel<unsigned char><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+      } else {
+        if (ts == 4) meltw_gs_kernel<unsigned int><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+        else if (ts == 2) meltw_gs_kernel<unsigned short><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+        else meltw_gs_kernel<unsigned char><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+      }
+      return launch_done("meltw_move");
+    }
+    case FAM_QUANT: {
+      long long grid = ((long long)d->m * d->n + 255) / 256; if (grid > 148 * 16) grid = 148 * 16;
+      meltw_quant_kernel<<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+      return launch_done("meltw_quant");
+    }
+    default: return 1;
+  }
+}

@@ -1,0 +1,343 @@
+// libxsmm_b200 -- sparse kernels of the hot path (sm_100a):
+//   * sreg_kernel      : fsspmdm -- fixed sparse A (CSR, alpha folded in) times dense row-major B,
+//                        N streamed through shared memory in 512-byte column strips with
+//                        cp.async.bulk (TMA 1D) + mbarrier double buffering. HBM-bound.
+//                        Replaces src/generator_spgemm_csr_asparse_reg.c (A kept in registers on x86).
+//   * packed_sp_kernel : SOA-packed sparse x dense with `packed_width` innermost
+//                        (src/generator_packed_spgemm_cs*.c; golds in samples/xgemm_norm_packed/*.c)
+//   * bcsc_simt_kernel : block-sparse B (BCSC) exact-order kernel, every datatype of the reference's
+//                        spmm driver (samples/xgemm_sparse/spmm_kernel.c:74-217); the tensor-core
+//                        version lives in bcsc_tc.cu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "xb_internal.h"
+#include "xb_device.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fsspmdm: C[M x N] (row-major, ldc) = beta*C + A_csr * B[K x N] (row-major, ldb)
+// T = float (V = float4) or double (V = double2): a strip is 32 vectors = 512 bytes of every B row.
+template <typename T> struct Vec;
+template <> struct Vec<float> { typedef float4 type; enum { N = 4 }; };
+template <> struct Vec<double> { typedef double2 type; enum { N = 2 }; };
+
+__device__ __forceinline__ void vfma(float4& acc, float a, const float4& b) {
+  acc.x = fmaf(a, b.x, acc.x); acc.y = fmaf(a, b.y, acc.y); acc.z = fmaf(a, b.z, acc.z); acc.w = fmaf(a, b.w, acc.w);
+}
+__device__ __forceinline__ void vfma(double2& acc, double a, const double2& b) { acc.x = fma(a, b.x, acc.x); acc.y = fma(a, b.y, acc.y); }
+__device__ __forceinline__ void vadd(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void vadd(double2& a, const double2& b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vzero(double2& a) { a = make_double2(0.0, 0.0); }
+
+struct SregParams {
+  int M, K; long long N, ldb, ldc;
+  unsigned int nnz;
+  const unsigned int* rowptr; const unsigned int* colidx; const void* vals;
+  const void* b; void* c;
+  int beta0; int stages;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512, 1) sreg_kernel(const SregParams P) {
+  typedef typename Vec<T>::type V;
+  constexpr int VN = Vec<T>::N;
+  constexpr int STRIP = 32 * VN;                // elements per strip row (512 bytes)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: stages x [K][512 B] | rowptr[M+1] | colidx[nnz] | vals[nnz] | barriers
+  unsigned char* sB = smem_raw;
+  unsigned int* s_rowptr = (unsigned int*)(sB + (size_t)P.stages * P.K * 512);
+  unsigned int* s_col = s_rowptr + (P.M + 1);
+  T* s_val = (T*)(((uintptr_t)(s_col + P.nnz) + 15) & ~(uintptr_t)15);
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(s_val + P.nnz) + 15) & ~(uintptr_t)15);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  for (int i = tid; i <= P.M; i += blockDim.x) s_rowptr[i] = P.rowptr[i];
+  for (unsigned int i = tid; i < P.nnz; i += blockDim.x) { s_col[i] = P.colidx[i]; s_val[i] = ((const T*)P.vals)[i]; }
+  if (tid == 0) {
+    for (int s = 0; s < P.stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long nstrips = (P.N + STRIP - 1) / STRIP;
+  const long long first = blockIdx.x, step = gridDim.x;
+  const T* Bg = (const T*)P.b; T* Cg = (T*)P.c;
+
+  // producer: warp 0 issues one bulk copy per B row of the strip (512 B, or the tail width)
+  auto issue = [&](long long strip, int stage) {
+    const long long n0 = strip * STRIP;
+    const long long w = (P.N - n0 < STRIP) ? (P.N - n0) : STRIP;
+    const uint32_t bytes = (uint32_t)(w * sizeof(T));
+    const uint32_t bar = smem_u32(&bars[stage]);
+    if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)P.K);
+    __syncwarp();
+    for (int k = lane; k < P.K; k += 32) {
+      bulk_g2s(smem_u32(sB + ((size_t)stage * P.K + k) * 512), Bg + (size_t)k * P.ldb + n0, bytes, bar);
+    }
+  };
+
+  long long it = 0;
+  if (warp == 0 && first < nstrips) issue(first, 0);
+  for (long long strip = first; strip < nstrips; strip += step, ++it) {
+    const int stage = (int)(it % P.stages);
+    if (P.stages > 1 && warp == 0 && strip + step < nstrips) issue(strip + step, (int)((it + 1) % P.stages));
+    mbar_wait(smem_u32(&bars[stage]), (uint32_t)((it / P.stages) & 1));
+    const V* Bs = (const V*)(sB + (size_t)stage * P.K * 512);
+    const long long n0 = strip * STRIP;
+    const bool in = (n0 + (long long)lane * VN) < P.N;        // N % VN == 0 is guaranteed by create()
+    for (int row = warp; row < P.M; row += nwarps) {
+      V acc; vzero(acc);
+      const unsigned int e0 = s_rowptr[row], e1 = s_rowptr[row + 1];
+      unsigned int e = e0;
+      for (; e + 1 < e1; e += 2) {                            // two independent LDS in flight
+        const V b0 = Bs[(size_t)s_col[e] * 32 + lane]; const V b1 = Bs[(size_t)s_col[e + 1] * 32 + lane];
+        vfma(acc, s_val[e], b0); vfma(acc, s_val[e + 1], b1);
+      }
+      if (e < e1) vfma(acc, s_val[e], Bs[(size_t)s_col[e] * 32 + lane]);
+      if (in) {
+        V* dst = (V*)(Cg + (size_t)row * P.ldc + n0) + lane;
+        if (!P.beta0) { const V old = *dst; vadd(acc, old); }
+        *dst = acc;
+      }
+    }
+    __syncthreads();                                          // strip consumed: its stage may be refilled
+    if (P.stages == 1 && warp == 0 && strip + step < nstrips) issue(strip + step, 0);
+  }
+}
+
+// fallback without shared-memory staging (very large K, or unaligned leading dimensions)
+template <typename T>
+__global__ void __launch_bounds__(256) sreg_direct_kernel(const SregParams P) {
+  const T* Bg = (const T*)P.b; T* Cg = (T*)P.c; const T* vals = (const T*)P.vals;
+  const long long total = (long long)P.M * P.N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(e / P.N); const long long col = e % P.N;
+    T acc = 0;
+    for (unsigned int z = P.rowptr[row]; z < P.rowptr[row + 1]; ++z) acc += vals[z] * Bg[(size_t)P.colidx[z] * P.ldb + col];
+    T* dst = Cg + (size_t)row * P.ldc + col;
+    *dst = P.beta0 ? acc : (*dst + acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// packed sparse: one CTA per batch item, threads over (n, p)
+struct PackedParams {
+  int kind, M, N, K, P, lda, ldb, ldc, beta0, is_f64;
+  const unsigned int* ptr; const unsigned int* idx;
+  const char* a; const char* b; char* c;
+  long long stride_a, stride_b, stride_c, count;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) packed_sp_kernel(const PackedParams Q) {
+  const int P = Q.P;
+  for (long long item = blockIdx.x; item < Q.count; item += gridDim.x) {
+    const T* A = (const T*)(Q.a + item * Q.stride_a); const T* B = (const T*)(Q.b + item * Q.stride_b);
+    T* C = (T*)(Q.c + item * Q.stride_c);
+    const int work = Q.M * Q.N * P;
+    for (int e = threadIdx.x; e < work; e += blockDim.x) {
+      const int p = e % P, j = (e / P) % Q.N, i = e / (P * Q.N);
+      if (Q.kind == XB_KIND_SP_A_CSR) {           // C[i][j][p] (+)= sum_z a[z] * B[col[z]][j][p]
+        T acc = Q.beta0 ? (T)0 : C[((size_t)i * Q.ldc + j) * P + p];
+        for (unsigned int z = Q.ptr[i]; z < Q.ptr[i + 1]; ++z) acc += A[z] * B[((size_t)Q.idx[z] * Q.ldb + j) * P + p];
+        C[((size_t)i * Q.ldc + j) * P + p] = acc;
+      } else if (Q.kind == XB_KIND_SP_B_CSC) {    // C[i][j][p] (+)= sum_{z in col j} A[i][row[z]][p] * b[z]
+        T acc = Q.beta0 ? (T)0 : C[((size_t)i * Q.ldc + j) * P + p];
+        for (unsigned int z = Q.ptr[j]; z < Q.ptr[j + 1]; ++z) acc += A[((size_t)i * Q.lda + Q.idx[z]) * P + p] * B[z];
+        C[((size_t)i * Q.ldc + j) * P + p] = acc;
+      } else if (Q.kind == XB_KIND_SP_B_CSR) {    // rows of B are k; scan each row for column j
+        T acc = Q.beta0 ? (T)0 : C[((size_t)i * Q.ldc + j) * P + p];
+        for (int k = 0; k < Q.K; ++k) {
+          for (unsigned int z = Q.ptr[k]; z < Q.ptr[k + 1]; ++z) {
+            if ((int)Q.idx[z] == j) acc += A[((size_t)i * Q.lda + k) * P + p] * B[z];
+          }
+        }
+        C[((size_t)i * Q.ldc + j) * P + p] = acc;
+      }
+    }
+  }
+}
+
+// C sparse (CSC pattern): c[z][p] (+)= sum_k A[row[z]][k][p] * B[k][col][p]
+template <typename T>
+__global__ void __launch_bounds__(256) packed_csparse_kernel(const PackedParams Q) {
+  const int P = Q.P;
+  for (long long item = blockIdx.x; item < Q.count; item += gridDim.x) {
+    const T* A = (const T*)(Q.a + item * Q.stride_a); const T* B = (const T*)(Q.b + item * Q.stride_b);
+    T* C = (T*)(Q.c + item * Q.stride_c);
+    for (int j = 0; j < Q.N; ++j) {
+      const unsigned int z0 = Q.ptr[j], z1 = Q.ptr[j + 1];
+      for (int e = threadIdx.x; e < (int)(z1 - z0) * P; e += blockDim.x) {
+        const unsigned int z = z0 + e / P; const int p = e % P; const int i = (int)Q.idx[z];
+        T acc = Q.beta0 ? (T)0 : C[(size_t)z * P + p];
+        for (int k = 0; k < Q.K; ++k) acc += A[((size_t)i * Q.lda + k) * P + p] * B[((size_t)k * Q.ldb + j) * P + p];
+        C[(size_t)z * P + p] = acc;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// BCSC exact-order kernel. One CTA per (m_block, block-column); thread per (m, n_local) element.
+struct BcscParams {
+  int M, K, bk, bn, ta, tb, tc, beta0, trans_a, vnni_a, vnni_b_t;
+  long long N;                  // total columns = n_blocks * bn
+  long long m_blocks;
+  const char* a; const char* bvals; const unsigned int* colptr; const unsigned int* rowidx; char* c;
+};
+
+__device__ __forceinline__ float bcsc_load_f(const char* base, size_t idx, int t) {
+  return (t == LIBXSMM_DATATYPE_F32) ? ((const float*)base)[idx] : xb_bf16_to_f32(((const unsigned short*)base)[idx]);
+}
+
+__global__ void __launch_bounds__(256) bcsc_simt_kernel(const BcscParams Q) {
+  const long long nbc = Q.N / Q.bn;
+  const size_t tsa = xb_dev_typesize(Q.ta), tsc = xb_dev_typesize(Q.tc);
+  const bool is_int = (Q.tc == LIBXSMM_DATATYPE_I32);
+  const int v = (Q.ta == LIBXSMM_DATATYPE_BF16) ? 2 : ((Q.ta == LIBXSMM_DATATYPE_F32) ? 1 : 4);
+  for (long long w = blockIdx.x; w < Q.m_blocks * nbc; w += gridDim.x) {
+    const long long mb = w / nbc, jb = w % nbc;
+    const char* A = Q.a + (size_t)mb * Q.K * Q.M * tsa;
+    char* C = Q.c + (size_t)mb * Q.N * Q.M * tsc;
+    for (int e = threadIdx.x; e < Q.M * Q.bn; e += blockDim.x) {
+      const int i = e % Q.M, nl = e / Q.M;
+      const long long j = jb * Q.bn + nl;
+      const size_t ci = Q.trans_a ? ((size_t)i * Q.N + j) : ((size_t)j * Q.M + i);
+      float facc = 0.f; int iacc = 0;
+      if (!Q.beta0) {
+        if (is_int) iacc = ((const int*)C)[ci];
+        else facc = (Q.tc == LIBXSMM_DATATYPE_F32) ? ((const float*)C)[ci] : xb_bf16_to_f32(((const unsigned short*)C)[ci]);
+      }
+      for (unsigned int z = Q.colptr[jb]; z < Q.colptr[jb + 1]; ++z) {
+        const int kb = (int)Q.rowidx[z];
+        for (int kk = 0; kk < Q.bk; ++kk) {
+          const int k = kb * Q.bk + kk;
+          size_t ai;
+          if (Q.trans_a) ai = (size_t)i * Q.K + k;
+          else if (Q.vnni_a && v > 1) ai = (size_t)(k / v) * Q.M * v + (size_t)i * v + (k % v);
+          else ai = (size_t)k * Q.M + i;
+          size_t bi;
+          if (Q.vnni_b_t) bi = (size_t)z * Q.bk * Q.bn + (size_t)(kk / v) * Q.bn * v + (size_t)nl * v + (kk % v);
+          else bi = (size_t)z * Q.bk * Q.bn + (size_t)nl * Q.bk + kk;
+          if (is_int) {
+            const unsigned char ar = ((const unsigned char*)A)[ai], br = ((const unsigned char*)Q.bvals)[bi];
+            const int av = (Q.ta == LIBXSMM_DATATYPE_U8) ? (int)ar : (int)(signed char)ar;
+            const int bv = (Q.tb == LIBXSMM_DATATYPE_U8) ? (int)br : (int)(signed char)br;
+            iacc += av * bv;
+          } else {
+            facc = __fadd_rn(facc, __fmul_rn(bcsc_load_f(A, ai, Q.ta), bcsc_load_f(Q.bvals, bi, Q.tb)));
+          }
+        }
+      }
+      if (is_int) ((int*)C)[ci] = iacc;
+      else if (Q.tc == LIBXSMM_DATATYPE_F32) ((float*)C)[ci] = facc;
+      else ((unsigned short*)C)[ci] = xb_f32_to_bf16_rne(facc);
+    }
+  }
+}
+
+int g_sms = 0;
+int num_sms() {
+  if (g_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev); if (g_sms <= 0) g_sms = 148; }
+  return g_sms;
+}
+int check_launch(const char* where) {
+  xb_rt_count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { xb_rt_note_error((int)e, where); return (int)e; }
+  return 0;
+}
+int g_sreg_attr[2] = {0, 0};
+
+}  // namespace
+
+extern "C" int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_total) {
+  SregParams P;
+  P.M = d->m; P.K = d->k; P.N = n_total; P.ldb = d->ldb; P.ldc = d->ldc; P.nnz = d->nnz;
+  P.rowptr = d->d_ptr; P.colidx = d->d_idx; P.vals = d->d_val; P.b = b; P.c = c; P.beta0 = d->beta0; P.stages = 2;
+  const bool f64 = (d->ta == LIBXSMM_DATATYPE_F64);
+  const size_t ts = f64 ? 8 : 4;
+  const size_t meta = (size_t)(d->m + 1) * 4 + (size_t)d->nnz * 4 + 16 + (size_t)d->nnz * ts + 16 + 64;
+  const size_t limit = 220 * 1024;
+  cudaStream_t stream = (cudaStream_t)xb_rt_stream();
+  const bool aligned = ((uintptr_t)b % 16 == 0) && ((uintptr_t)c % 16 == 0) && ((d->ldb * ts) % 16 == 0) && ((d->ldc * ts) % 16 == 0)
+                    && ((n_total * ts) % 16 == 0);
+  if (n_total <= 0) return 0;
+  if ((size_t)2 * d->k * 512 + meta > limit) P.stages = 1;
+  if (!aligned || (size_t)P.stages * d->k * 512 + meta > limit) {
+    const long long total = (long long)d->m * n_total;
+    long long grid = (total + 255) / 256; if (grid > num_sms() * 16) grid = num_sms() * 16;
+    if (f64) sreg_direct_kernel<double><<<(unsigned int)grid, 256, 0, stream>>>(P);
+    else sreg_direct_kernel<float><<<(unsigned int)grid, 256, 0, stream>>>(P);
+    return check_launch("sreg_direct");
+  }
+  const size_t smem = (size_t)P.stages * d->k * 512 + meta;
+  const long long strip = f64 ? 64 : 128;
+  long long grid = (n_total + strip - 1) / strip; if (grid > num_sms()) grid = num_sms();
+  if (f64) {
+    if (!g_sreg_attr[1]) { cudaFuncSetAttribute(sreg_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_sreg_attr[1] = 1; }
+    sreg_kernel<double><<<(unsigned int)grid, 512, smem, stream>>>(P);
+  } else {
+    if (!g_sreg_attr[0]) { cudaFuncSetAttribute(sreg_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_sreg_attr[0] = 1; }
+    sreg_kernel<float><<<(unsigned int)grid, 512, smem, stream>>>(P);
+  }
+  return check_launch("sreg");
+}
+
+extern "C" int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const void* b, void* c, long long count,
+                                   long long stride_a, long long stride_b, long long stride_c)
+{
+  PackedParams Q;
+  Q.kind = d->kind; Q.M = d->m; Q.N = d->n; Q.K = d->k; Q.P = d->packed_width; Q.lda = d->lda; Q.ldb = d->ldb; Q.ldc = d->ldc;
+  Q.beta0 = d->beta0; Q.is_f64 = (d->ta == LIBXSMM_DATATYPE_F64); Q.ptr = d->d_ptr; Q.idx = d->d_idx;
+  Q.a = (const char*)a; Q.b = (const char*)b; Q.c = (char*)c; Q.stride_a = stride_a; Q.stride_b = stride_b; Q.stride_c = stride_c; Q.count = count;
+  if (count <= 0) return 0;
+  cudaStream_t stream = (cudaStream_t)xb_rt_stream();
+  const unsigned int grid = (unsigned int)(count < 65535 ? count : 65535);
+  if (d->kind == XB_KIND_SP_C_CSC) {
+    if (Q.is_f64) packed_csparse_kernel<double><<<grid, 256, 0, stream>>>(Q); else packed_csparse_kernel<float><<<grid, 256, 0, stream>>>(Q);
+  } else {
+    if (Q.is_f64) packed_sp_kernel<double><<<grid, 256, 0, stream>>>(Q); else packed_sp_kernel<float><<<grid, 256, 0, stream>>>(Q);
+  }
+  return check_launch("packed_sp");
+}
+
+extern "C" int xb_bcsc_tc_launch(const xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
+                                 const unsigned int* rowidx, unsigned long long n_blocks, void* c);
+
+extern "C" int xb_bcsc_launch(const xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
+                              const unsigned int* rowidx, unsigned long long n_blocks, void* c)
+{
+  BcscParams Q;
+  Q.M = d->packed_width; Q.K = d->k; Q.bk = d->bk; Q.bn = d->bn; Q.ta = d->ta; Q.tb = d->tb; Q.tc = d->tc;
+  Q.beta0 = d->beta0; Q.trans_a = (d->flags & LIBXSMM_GEMM_FLAG_TRANS_A) != 0; Q.vnni_a = (d->flags & LIBXSMM_GEMM_FLAG_VNNI_A) != 0;
+  Q.vnni_b_t = ((d->flags & LIBXSMM_GEMM_FLAG_VNNI_B) != 0) && ((d->flags & LIBXSMM_GEMM_FLAG_TRANS_B) != 0);
+  Q.N = (long long)n_blocks * d->bn; Q.m_blocks = d->m;
+  Q.a = (const char*)a; Q.bvals = (const char*)b_vals; Q.colptr = colptr; Q.rowidx = rowidx; Q.c = (char*)c;
+  if (Q.m_blocks <= 0 || n_blocks == 0) return 0;
+  const long long work = Q.m_blocks * (long long)n_blocks;
+  const unsigned int grid = (unsigned int)(work < (1 << 20) ? work : (1 << 20));
+  bcsc_simt_kernel<<<grid, 256, 0, (cudaStream_t)xb_rt_stream()>>>(Q);
+  return check_launch("bcsc_simt");
+}

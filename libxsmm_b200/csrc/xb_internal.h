@@ -1,0 +1,162 @@
+/* libxsmm_b200 internal interface between the plain-C host runtime (host_*.c) and the CUDA
+ * translation units (*.cu). Everything crossing this boundary is C: plain structs and pointers.
+ * The host side never includes a CUDA header; the .cu side never touches the registry. */
+#ifndef XB_INTERNAL_H
+#define XB_INTERNAL_H
+
+#include "../../include/libxsmm.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define XB_HIDDEN __attribute__((visibility("hidden")))
+
+/* ---- kernel kinds held by a slot --------------------------------------------------------------- */
+enum {
+  XB_KIND_FREE = 0,
+  XB_KIND_GEMM,          /* dense GEMM/BRGEMM (libxsmm_gemm_param) */
+  XB_KIND_GEMM_EXT,      /* dense GEMM/BRGEMM with fused pre/post ops (libxsmm_gemm_ext_param) */
+  XB_KIND_TILECFG,       /* callable no-op */
+  XB_KIND_MELTW,         /* unary/binary/ternary eltwise */
+  XB_KIND_SP_A_CSR,      /* packed: C[M][N][P] += A_csr * B[K][N][P] */
+  XB_KIND_SP_B_CSR,      /* packed: C[M][N][P] += A[M][K][P] * B_csr */
+  XB_KIND_SP_B_CSC,      /* packed: C[M][N][P] += A[M][K][P] * B_csc */
+  XB_KIND_SP_C_CSC,      /* packed: C_csc pattern only */
+  XB_KIND_BCSC,          /* packed block-sparse B */
+  XB_KIND_SREG           /* fsspmdm kernel: sparse A fixed at create time, row-major B/C */
+};
+
+/* normalised dense-GEMM descriptor == registry key for GEMM kinds (memcmp'd, so zero-filled) */
+typedef struct xb_gemm_desc {
+  int m, n, k, lda, ldb, ldc;
+  int ta, tb, tc, tcomp;              /* libxsmm_datatype incl. signedness (I8 vs U8) */
+  unsigned int flags;                 /* libxsmm_gemm_flags as completed by the init functions */
+  int prefetch;
+  int br_type;                        /* 0 none, 1 address, 2 offset, 3 stride */
+  int br_unroll;
+  long long br_stride_a, br_stride_b; /* bytes (stride mode) */
+  /* fused ops (ext ABI): reference src/libxsmm_generator.c:297-321 */
+  int fuse_colbias, d_type, ldd;      /* C += colbias (binary ADD with BCAST_COL) */
+  int cp_op, cp_flags, ldcp;          /* unary on C: RELU (+bitmask) or SIGMOID */
+  int backend;                        /* libxsmm_b200_backend chosen at dispatch */
+  int pad_;
+} xb_gemm_desc;
+
+typedef struct xb_meltw_desc {
+  int op_class;                       /* libxsmm_meltw_operation */
+  int op;                             /* unary/binary/ternary type */
+  unsigned int flags;
+  int m, n, ldi, ldi2, ldi3, ldo;
+  int t_in0, t_in1, t_in2, t_out, t_comp;
+} xb_meltw_desc;
+
+/* sparse kernels: pattern lives in device memory owned by the slot */
+typedef struct xb_sparse_desc {
+  int kind;                           /* XB_KIND_SP_* / BCSC / SREG */
+  int m, n, k, lda, ldb, ldc;
+  int ta, tb, tc, tcomp;
+  unsigned int flags;
+  int packed_width, bk, bn;
+  int max_n;                          /* SREG: loop bound on N */
+  unsigned int nnz, nrows;            /* rows of the pointer array (CSR: rows, CSC: cols) */
+  /* device copies */
+  unsigned int* d_ptr;                /* row_ptr / col_ptr  [nrows+1] */
+  unsigned int* d_idx;                /* column / row indices [nnz] */
+  void* d_val;                        /* SREG: values as the compute type [nnz] */
+  /* SREG column-major twin (built at create): for every k the rows using it */
+  int beta0;
+} xb_sparse_desc;
+
+typedef struct xb_slot {
+  int kind;                           /* XB_KIND_* (FREE when unused) */
+  int registered;                     /* 1: owned by the registry, 0: caller-owned (create_*) */
+  unsigned int nflops;
+  union { xb_gemm_desc gemm; xb_meltw_desc meltw; xb_sparse_desc sp; } u;
+} xb_slot;
+
+/* ---- resolved per-tile record for dense GEMM kernels (device memory when count > 1) ------------ */
+typedef struct xb_gemm_rec {
+  const void* a;        /* base of A (addr mode: device array of br pointers) */
+  const void* b;
+  void* c;
+  const void* a_aux;    /* offset mode: device array of br byte offsets (long long) */
+  const void* b_aux;
+  const void* d;        /* ext: colbias */
+  void* c_aux;          /* ext: relu bitmask out */
+  unsigned long long br;
+  float scf;            /* I8 x I8 -> F32 scalar scale */
+  int pad_;
+} xb_gemm_rec;
+
+/* launch description handed to the CUDA side */
+typedef struct xb_gemm_launch {
+  xb_gemm_desc d;
+  long long count;
+  /* mode 0: uniform strided batch */
+  const void* a; const void* b; void* c;
+  long long tile_stride_a, tile_stride_b, tile_stride_c;   /* bytes */
+  unsigned long long br;
+  /* mode 1: per-tile records (device array of xb_gemm_rec[count]) */
+  const xb_gemm_rec* recs;
+  xb_gemm_rec one;      /* count==1 && !recs: passed by value */
+} xb_gemm_launch;
+
+/* ---- CUDA runtime layer (runtime.cu) ----------------------------------------------------------- */
+int xb_rt_device_count(void);
+int xb_rt_set_device(int ordinal);
+void xb_rt_set_stream(void* stream);
+void* xb_rt_stream(void);
+void xb_rt_set_blocking(int on);
+int xb_rt_blocking(void);
+int xb_rt_sync(void);
+int xb_rt_last_error(void);
+const char* xb_rt_last_error_string(void);
+void xb_rt_note_error(int code, const char* where);
+unsigned long long xb_rt_launch_count(void);
+void xb_rt_count_launch(void);
+void* xb_rt_device_malloc(size_t size);
+void xb_rt_device_free(void* p);
+void* xb_rt_host_malloc(size_t size);
+void xb_rt_host_free(void* p);
+void* xb_rt_managed_malloc(size_t size);
+void xb_rt_managed_free(void* p);
+int xb_rt_memcpy(void* dst, const void* src, size_t size);           /* blocking, any direction */
+int xb_rt_memcpy_async(void* dst, const void* src, size_t size);     /* on the thread's stream */
+int xb_rt_upload(void* dst_dev, const void* src_host, size_t size);  /* stream ordered from pageable */
+/* 0: host (unregistered / pageable), 1: device, 2: managed, 3: pinned host */
+int xb_rt_ptr_kind(const void* p);
+int xb_rt_have_gpu(void);
+/* scratch arena on the device, grown on demand, reset by the caller after sync */
+void* xb_rt_scratch(size_t bytes);
+void xb_rt_scratch_reset(void);
+
+/* ---- kernel launchers (one per .cu file) ------------------------------------------------------- */
+int xb_gemm_simt_launch(const xb_gemm_launch* L);
+int xb_gemm_tc_supported(const xb_gemm_desc* d);          /* pure host logic, no CUDA call */
+int xb_gemm_tc_launch(const xb_gemm_launch* L);
+typedef struct xb_meltw_args {
+  const void* in0; const void* in1; const void* in2; void* out;
+  const void* in_aux;        /* unary in.secondary: bitmask in / index array / fwd output (ELU_INV) */
+  void* out_aux;             /* unary out.secondary: bitmask out / argop indices / scatter index array */
+  float alpha;               /* LEAKY_RELU/ELU alpha, QUANT/DEQUANT scale */
+  unsigned long long n_rt;   /* REPLICATE_COL_VAR: run-time N; COLS_IDX reductions: number of indices */
+} xb_meltw_args;
+int xb_meltw_supported(const xb_meltw_desc* d);                          /* pure host logic */
+int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a);
+int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_total);
+int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const void* b, void* c, long long count,
+                        long long stride_a, long long stride_b, long long stride_c);
+int xb_bcsc_launch(const xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
+                   const unsigned int* rowidx, unsigned long long n_blocks, void* c);
+
+/* ---- host runtime (host_core.c) ---------------------------------------------------------------- */
+xb_slot* xb_slot_of(const void* fnptr);    /* NULL if not one of our thunks */
+void xb_invoke(int slot, const void* param);
+const void* xb_thunk(int slot);
+#define XB_NTHUNKS 8192
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* XB_INTERNAL_H */

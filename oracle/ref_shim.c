@@ -1,0 +1,224 @@
+/* TEST INFRASTRUCTURE -- not part of the product.
+ *
+ * Builds the UNMODIFIED reference (LIBXSMM, /root/reference) in its header-only mode into
+ * oracle/_ref/libxsmm_ref.so and exposes a small plain-C interface ("ref_*") over
+ *   (1) the reference's portable C kernels  libxsmm_reference_gemm / libxsmm_reference_elementwise
+ *       (src/generator_gemm_reference_impl.c:2818, src/generator_mateltwise_reference_impl.c:2663),
+ *   (2) the reference's own JIT path (AMX/AVX-512 on this host) through its public dispatch API,
+ *   (3) OpenMP batch drivers over (2) used as the CPU baseline of bench.py --impl reference.
+ * No reference source is copied: this file only #includes it from where it lies. The recipe is
+ * `make ref` (one gcc call). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load the resulting library.
+ */
+#include <libxsmm_source.h>
+#include <omp.h>
+#include <string.h>
+
+#define REF_API __attribute__((visibility("default")))
+
+REF_API const char* ref_target_arch(void) { libxsmm_init(); return libxsmm_get_target_arch(); }
+REF_API int ref_max_threads(void) { return omp_get_max_threads(); }
+
+static libxsmm_gemm_batch_reduce_config ref_brcfg(int br_type, long long sa, long long sb) {
+  return libxsmm_create_gemm_batch_reduce_config(
+    br_type == 1 ? LIBXSMM_GEMM_BATCH_REDUCE_ADDRESS : (br_type == 2 ? LIBXSMM_GEMM_BATCH_REDUCE_OFFSET
+    : (br_type == 3 ? LIBXSMM_GEMM_BATCH_REDUCE_STRIDE : LIBXSMM_GEMM_BATCH_REDUCE_NONE)), (libxsmm_blasint)sa, (libxsmm_blasint)sb, 0);
+}
+
+static void ref_fill_param(libxsmm_gemm_param* p, unsigned long long* br, void* a, void* b, void* c,
+                           long long* offs_a, long long* offs_b, float* scf) {
+  memset(p, 0, sizeof(*p));
+  p->op.tertiary = br; p->a.primary = a; p->b.primary = b; p->c.primary = c;
+  p->a.secondary = offs_a; p->b.secondary = offs_b; p->c.tertiary = scf;
+}
+
+/* dims = {m,n,k,lda,ldb,ldc}; types = {a,b,comp,c}; mode 0: C reference kernel, 1: JIT kernel.
+ * returns 0 ok, 1 dispatch failed, 2 JIT fell back to the reference kernel (still executed) */
+REF_API int ref_gemm(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a, long long stride_b,
+                     unsigned long long br, void* a, void* b, void* c, long long* offs_a, long long* offs_b, float scf, int mode)
+{
+  const libxsmm_gemm_shape shape = libxsmm_create_gemm_shape(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5],
+    (libxsmm_datatype)types[0], (libxsmm_datatype)types[1], (libxsmm_datatype)types[3], (libxsmm_datatype)types[2]);
+  const libxsmm_gemm_batch_reduce_config cfg = ref_brcfg(br_type, stride_a, stride_b);
+  libxsmm_gemm_param p;
+  unsigned long long brv = br;
+  libxsmm_init();
+  ref_fill_param(&p, &brv, a, b, c, offs_a, offs_b, &scf);
+  if (mode == 0) {
+    libxsmm_descriptor_blob blob;
+    const libxsmm_gemm_descriptor* desc = libxsmm_gemm_descriptor_init_brgemm(&blob, shape, flags, 0, cfg);
+    if (desc == NULL) return 1;
+    libxsmm_reference_gemm(&p, desc);
+    return 0;
+  } else {
+    libxsmm_xmmfunction k; libxsmm_kernel_info info;
+    k.gemm = libxsmm_dispatch_brgemm(shape, flags, 0, cfg);
+    if (k.gemm == NULL) return 1;
+    k.gemm(&p);
+    libxsmm_get_kernel_info(k.ptr_const, &info);
+    return info.is_reference_kernel ? 2 : 0;
+  }
+}
+
+/* desc = {op_class, op, flags, m, n, ldi, ldi2, ldi3, ldo, t_in0, t_in1, t_in2, t_out, t_comp};
+ * param points to a libxsmm_meltw_{unary,binary,ternary}_param image. mode as above. */
+REF_API int ref_meltw(const int* desc, void* param, int mode) {
+  libxsmm_descriptor_blob blob;
+  const libxsmm_meltw_descriptor* d;
+  libxsmm_init();
+  d = libxsmm_meltw_descriptor_init2(&blob, (libxsmm_datatype)desc[9], (libxsmm_datatype)desc[10], (libxsmm_datatype)desc[11],
+        (libxsmm_datatype)desc[13], (libxsmm_datatype)desc[12], desc[3], desc[4], desc[5], desc[8], desc[6], desc[7],
+        (unsigned short)desc[2], (unsigned short)desc[1], (unsigned char)desc[0]);
+  if (mode == 0) { libxsmm_reference_elementwise(param, d); return 0; }
+  else {
+    libxsmm_xmeltwfunction k = libxsmm_dispatch_meltw(d);
+    if (k.xmeltw == NULL) return 1;
+    k.xmeltw(param);
+    return 0;
+  }
+}
+
+REF_API int ref_fsspmdm(int dtype, int M, int N, int K, int lda, int ldb, int ldc, const void* alpha, const void* beta,
+                        const void* a_dense, const void* B, void* C)
+{
+  libxsmm_fsspmdm* h = libxsmm_fsspmdm_create((libxsmm_datatype)dtype, M, N, K, lda, ldb, ldc, alpha, beta, a_dense, 0, NULL);
+  if (h == NULL) return 1;
+  libxsmm_fsspmdm_execute(h, B, C);
+  libxsmm_fsspmdm_destroy(h);
+  return 0;
+}
+
+/* types = {a,b,comp,c}; geometry = {m_blocks, M(packed width), K, N, bk, bn} */
+REF_API int ref_bcsc(const int* types, const int* geo, unsigned int flags, void* A, void* Bvals, unsigned int* colptr,
+                     unsigned int* rowidx, void* C)
+{
+  const libxsmm_gemm_shape shape = libxsmm_create_gemm_shape(geo[0], 0, geo[2], geo[2], 0, geo[3],
+    (libxsmm_datatype)types[0], (libxsmm_datatype)types[1], (libxsmm_datatype)types[3], (libxsmm_datatype)types[2]);
+  libxsmm_spgemm_config cfg; libxsmm_gemm_param p; libxsmm_gemmfunction k;
+  unsigned long long nblk = (unsigned long long)(geo[3] / geo[5]);
+  libxsmm_init();
+  cfg.packed_width = geo[1]; cfg.bk = geo[4]; cfg.bn = geo[5];
+  k = libxsmm_create_packed_spgemm_bcsc(shape, flags, 0, cfg);
+  if (k == NULL) return 1;
+  memset(&p, 0, sizeof(p));
+  p.a.primary = A; p.b.primary = Bvals; p.b.secondary = colptr; p.b.tertiary = rowidx; p.b.quaternary = &nblk; p.c.primary = C;
+  k(&p);
+  libxsmm_release_kernel((const void*)k);
+  return 0;
+}
+
+/* is_csc: 0 -> create_packed_spgemm_csr, 1 -> _csc; dims = {m,n,k,lda,ldb,ldc} */
+REF_API int ref_packed_sp(int is_csc, int dtype, const int* dims, unsigned int flags, int packed_width,
+                          const unsigned int* ptr, const unsigned int* idx, const void* values, void* a, void* b, void* c)
+{
+  const libxsmm_gemm_shape shape = libxsmm_create_gemm_shape(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5],
+    (libxsmm_datatype)dtype, (libxsmm_datatype)dtype, (libxsmm_datatype)dtype, (libxsmm_datatype)dtype);
+  libxsmm_gemm_param p; libxsmm_gemmfunction k;
+  libxsmm_init();
+  k = is_csc ? libxsmm_create_packed_spgemm_csc(shape, flags, 0, packed_width, ptr, idx, values)
+             : libxsmm_create_packed_spgemm_csr(shape, flags, 0, packed_width, ptr, idx, values);
+  if (k == NULL) return 1;
+  memset(&p, 0, sizeof(p));
+  p.a.primary = a; p.b.primary = b; p.c.primary = c;
+  k(&p);
+  libxsmm_release_kernel((const void*)k);
+  return 0;
+}
+
+/* scalar conversions, for pinning the oracle's and the kernels' rounding rules */
+REF_API unsigned short ref_f32_to_bf16(float f) { return libxsmm_convert_f32_to_bf16_rne(f); }
+REF_API unsigned short ref_f32_to_f16(float f) { return libxsmm_convert_f32_to_f16(f); }
+REF_API float ref_f16_to_f32(unsigned short h) { return libxsmm_convert_f16_to_f32(h); }
+REF_API float ref_bf16_to_f32(unsigned short h) { return libxsmm_convert_bf16_to_f32(h); }
+
+/* ---- CPU baseline drivers: the reference's JIT kernel, batch loop over all host cores -------------- */
+/* strided batch of count tiles (same convention as libxsmm_b200_gemm_batch_strided); returns seconds
+ * for `reps` passes, negative on dispatch failure. is_ref[0] tells whether the C fallback was used. */
+REF_API double ref_bench_gemm_batch(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a,
+  long long stride_b, unsigned long long br, char* a, char* b, char* c, long long ta, long long tb, long long tc,
+  long long count, int reps, int* is_ref)
+{
+  const libxsmm_gemm_shape shape = libxsmm_create_gemm_shape(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5],
+    (libxsmm_datatype)types[0], (libxsmm_datatype)types[1], (libxsmm_datatype)types[3], (libxsmm_datatype)types[2]);
+  const libxsmm_gemm_batch_reduce_config cfg = ref_brcfg(br_type, stride_a, stride_b);
+  libxsmm_xmmfunction k; libxsmm_kernel_info info;
+  libxsmm_timer_tickint t0; int rep;
+  libxsmm_init();
+  k.gemm = libxsmm_dispatch_brgemm(shape, flags, 0, cfg);
+  if (k.gemm == NULL) return -1.0;
+  libxsmm_get_kernel_info(k.ptr_const, &info);
+  if (is_ref != NULL) *is_ref = (int)info.is_reference_kernel;
+  t0 = libxsmm_timer_tick();
+  for (rep = 0; rep < reps; ++rep) {
+    long long t;
+#   pragma omp parallel for schedule(static)
+    for (t = 0; t < count; ++t) {
+      libxsmm_gemm_param p; unsigned long long brv = br;
+      memset(&p, 0, sizeof(p));
+      p.op.tertiary = &brv; p.a.primary = a + t * ta; p.b.primary = b + t * tb; p.c.primary = c + t * tc;
+      k.gemm(&p);
+    }
+  }
+  return libxsmm_timer_duration(t0, libxsmm_timer_tick());
+}
+
+/* fsspmdm: N split into one slice per thread like samples/xgemm_sparse_Ainregs/pyfr_driver_asp_reg.c:380-394 */
+REF_API double ref_bench_fsspmdm(int dtype, int M, int N, int K, int lda, const void* alpha, const void* beta,
+                                 const void* a_dense, const char* B, char* C, int reps)
+{
+  const int nthreads = omp_get_max_threads();
+  const int ts = (dtype == LIBXSMM_DATATYPE_F64) ? 8 : 4, vl = 64 / ts;
+  int nslice = (N / vl) / nthreads * vl, rep;
+  libxsmm_fsspmdm *h_main, *h_tail = NULL;
+  libxsmm_timer_tickint t0;
+  libxsmm_init();
+  if (nslice <= 0) nslice = N;
+  h_main = libxsmm_fsspmdm_create((libxsmm_datatype)dtype, M, nslice, K, lda, N, N, alpha, beta, a_dense, 0, NULL);
+  if (h_main == NULL) return -1.0;
+  if (N % nslice != 0) h_tail = libxsmm_fsspmdm_create((libxsmm_datatype)dtype, M, N % nslice, K, lda, N, N, alpha, beta, a_dense, 0, NULL);
+  t0 = libxsmm_timer_tick();
+  for (rep = 0; rep < reps; ++rep) {
+    const int nfull = N / nslice; int s;
+#   pragma omp parallel for schedule(static)
+    for (s = 0; s < nfull; ++s) libxsmm_fsspmdm_execute(h_main, B + (size_t)s * nslice * ts, C + (size_t)s * nslice * ts);
+    if (h_tail != NULL) libxsmm_fsspmdm_execute(h_tail, B + (size_t)nfull * nslice * ts, C + (size_t)nfull * nslice * ts);
+  }
+  {
+    const double dt = libxsmm_timer_duration(t0, libxsmm_timer_tick());
+    libxsmm_fsspmdm_destroy(h_main); if (h_tail != NULL) libxsmm_fsspmdm_destroy(h_tail);
+    return dt;
+  }
+}
+
+/* BCSC: m_blocks split into contiguous ranges, one per thread */
+REF_API double ref_bench_bcsc(const int* types, const int* geo, unsigned int flags, char* A, void* Bvals, unsigned int* colptr,
+                              unsigned int* rowidx, char* C, int reps)
+{
+  const int nthreads = omp_get_max_threads();
+  const int per = (geo[0] + nthreads - 1) / nthreads;
+  const size_t tsa = LIBXSMM_TYPESIZE((libxsmm_datatype)types[0]), tsc = LIBXSMM_TYPESIZE((libxsmm_datatype)types[3]);
+  libxsmm_spgemm_config cfg; libxsmm_gemmfunction k_main, k_tail = NULL;
+  unsigned long long nblk = (unsigned long long)(geo[3] / geo[5]);
+  libxsmm_timer_tickint t0; int rep;
+  const int nfull = geo[0] / per, tail = geo[0] % per;
+  libxsmm_init();
+  cfg.packed_width = geo[1]; cfg.bk = geo[4]; cfg.bn = geo[5];
+  k_main = libxsmm_create_packed_spgemm_bcsc(libxsmm_create_gemm_shape(per, 0, geo[2], geo[2], 0, geo[3],
+    (libxsmm_datatype)types[0], (libxsmm_datatype)types[1], (libxsmm_datatype)types[3], (libxsmm_datatype)types[2]), flags, 0, cfg);
+  if (k_main == NULL) return -1.0;
+  if (tail > 0) k_tail = libxsmm_create_packed_spgemm_bcsc(libxsmm_create_gemm_shape(tail, 0, geo[2], geo[2], 0, geo[3],
+    (libxsmm_datatype)types[0], (libxsmm_datatype)types[1], (libxsmm_datatype)types[3], (libxsmm_datatype)types[2]), flags, 0, cfg);
+  t0 = libxsmm_timer_tick();
+  for (rep = 0; rep < reps; ++rep) {
+    int s;
+#   pragma omp parallel for schedule(static)
+    for (s = 0; s < nfull + (tail > 0 ? 1 : 0); ++s) {
+      libxsmm_gemm_param p; unsigned long long nb = nblk;
+      memset(&p, 0, sizeof(p));
+      p.a.primary = A + (size_t)s * per * geo[2] * geo[1] * tsa; p.b.primary = Bvals; p.b.secondary = colptr; p.b.tertiary = rowidx;
+      p.b.quaternary = &nb; p.c.primary = C + (size_t)s * per * geo[3] * geo[1] * tsc;
+      if (s < nfull) k_main(&p); else k_tail(&p);
+    }
+  }
+  return libxsmm_timer_duration(t0, libxsmm_timer_tick());
+}
