@@ -1,0 +1,134 @@
+"""Dense GEMM/BRGEMM test-case description and seeded operand construction (host side, numpy)."""
+import ctypes as C
+import itertools
+
+import numpy as np
+
+import gen
+
+FLAG_TRANS_A, FLAG_TRANS_B, FLAG_BETA_0, FLAG_VNNI_A, FLAG_VNNI_B = 1, 2, 4, 256, 512
+
+
+class GemmCase:
+    def __init__(self, m, n, k, ta, tb, tcomp, tc, flags=0, br_type=0, br=1, lda=None, ldb=None, ldc=None, pad=0):
+        self.m, self.n, self.k = m, n, k
+        self.ta, self.tb, self.tcomp, self.tc = ta, tb, tcomp, tc
+        self.flags, self.br_type, self.br = flags, br_type, (br if br_type else 1)
+        trans_a, trans_b = bool(flags & FLAG_TRANS_A), bool(flags & FLAG_TRANS_B)
+        honours_a = ta in (gen.F64, gen.F32, gen.BF16)
+        honours_b = tb in (gen.F64, gen.F32, gen.BF16, gen.F16)
+        self.rows_a = k if (trans_a and honours_a) else m          # leading extent
+        self.cols_a = m if (trans_a and honours_a) else k
+        self.rows_b = n if (trans_b and honours_b) else k
+        self.cols_b = k if (trans_b and honours_b) else n
+        self.lda = lda if lda is not None else self.rows_a + pad
+        self.ldb = ldb if ldb is not None else self.rows_b + pad
+        self.ldc = ldc if ldc is not None else m + pad
+        self.size_a, self.size_b, self.size_c = self.cols_a * self.lda, self.cols_b * self.ldb, n * self.ldc
+
+    @property
+    def dims(self):
+        return (self.m, self.n, self.k, self.lda, self.ldb, self.ldc)
+
+    @property
+    def types(self):
+        return (self.ta, self.tb, self.tcomp, self.tc)
+
+    def __repr__(self):
+        return "gemm(m%d n%d k%d ld%d/%d/%d t%s f%d br%d x%d)" % (self.m, self.n, self.k, self.lda, self.ldb, self.ldc,
+                                                                 self.types, self.flags, self.br_type, self.br)
+
+
+class Operands:
+    """Host operands of `count` independent tiles. Stride mode lays the br blocks of a tile out back to back."""
+
+    def __init__(self, case, seed=555, count=1):
+        rng = np.random.default_rng(seed)
+        c = case
+        nblk = c.br if c.br_type in (2, 3) else 1
+        self.blk_a, self.blk_b = c.size_a * gen.TS[c.ta], c.size_b * gen.TS[c.tb]       # bytes per block
+        if c.br_type == 1:   # address mode: blocks live in a pool, per-tile pointer arrays select them
+            self.pool_a = gen.values(rng, c.size_a * c.br * count, c.ta)
+            self.pool_b = gen.values(rng, c.size_b * c.br * count, c.tb)
+            self.a, self.b = self.pool_a, self.pool_b
+        else:
+            self.a = gen.values(rng, c.size_a * nblk * count, c.ta)
+            self.b = gen.values(rng, c.size_b * nblk * count, c.tb)
+        self.c0 = gen.values(rng, c.size_c * count, c.tc)                                 # initial C (beta=1 input)
+        self.tile_a, self.tile_b = self.blk_a * (c.br if c.br_type else 1), self.blk_b * (c.br if c.br_type else 1)
+        self.tile_c = c.size_c * gen.TS[c.tc]
+        self.stride_a = self.blk_a if c.br_type == 3 else 0
+        self.stride_b = self.blk_b if c.br_type == 3 else 0
+        self.offs_a = self.offs_b = None
+        if c.br_type == 2:   # shuffled block order to make the offsets non-trivial
+            perm = rng.permutation(c.br)
+            self.offs_a = (perm * self.blk_a).astype(np.int64)
+            self.offs_b = (perm[::-1] * self.blk_b).astype(np.int64)
+        self.scf = 0.125 if (c.tc == gen.F32 and c.ta in (gen.I8, gen.U8)) else 0.0
+        self.count = count
+
+    def addr_arrays(self, base_a, base_b, tile):
+        """ctypes void*[br] arrays for tile `tile` given the base addresses of the pools."""
+        c = self.case_br
+        arr_a = (C.c_void_p * c)(*[base_a + (tile * c + r) * self.blk_a for r in range(c)])
+        arr_b = (C.c_void_p * c)(*[base_b + (tile * c + (c - 1 - r)) * self.blk_b for r in range(c)])
+        return arr_a, arr_b
+
+
+def ref_result(side, case, ops, run_gemm):
+    """C after one invocation per tile computed by `side` (oracle/ref dict); returns a numpy copy."""
+    c = ops.c0.copy()
+    ops.case_br = case.br
+    for t in range(ops.count):
+        cv = c[t * case.size_c:(t + 1) * case.size_c]
+        if case.br_type == 1:
+            aa, ab = ops.addr_arrays(ops.a.ctypes.data, ops.b.ctypes.data, t)
+            rc = run_gemm(side, case.dims, case.types, case.flags, 1, 0, 0, case.br, aa, ab, cv, scf=ops.scf)
+        else:
+            av = ops.a[t * (ops.tile_a // gen.TS[case.ta]):]
+            bv = ops.b[t * (ops.tile_b // gen.TS[case.tb]):]
+            rc = run_gemm(side, case.dims, case.types, case.flags, case.br_type, ops.stride_a, ops.stride_b, case.br, av, bv, cv,
+                          offs_a=ops.offs_a, offs_b=ops.offs_b, scf=ops.scf)
+        assert rc == 0, (case, rc)
+    return c
+
+
+# precision tuples (A, B, COMP, C) required by the first bar (bold entries)
+TUPLES = [
+    (gen.F64, gen.F64, gen.F64, gen.F64), (gen.F32, gen.F32, gen.F32, gen.F32),
+    (gen.BF16, gen.BF16, gen.F32, gen.F32), (gen.BF16, gen.BF16, gen.F32, gen.BF16),
+    (gen.F16, gen.F16, gen.F32, gen.F16), (gen.F16, gen.F16, gen.F32, gen.F32),
+    (gen.U8, gen.I8, gen.I32, gen.I32), (gen.I8, gen.U8, gen.I32, gen.I32), (gen.U8, gen.U8, gen.I32, gen.I32),
+    (gen.I8, gen.I8, gen.I32, gen.I32), (gen.I8, gen.I8, gen.I32, gen.F32), (gen.U8, gen.I8, gen.I32, gen.F32),
+    (gen.I16, gen.I16, gen.I32, gen.I32),
+]
+
+
+def flag_variants(t):
+    ta = t[0]
+    out = [0]
+    if ta in (gen.F64, gen.F32):
+        out += [FLAG_TRANS_A, FLAG_TRANS_B, FLAG_TRANS_A | FLAG_TRANS_B]
+    elif ta == gen.BF16:
+        out += [FLAG_VNNI_A, FLAG_TRANS_A, FLAG_TRANS_B, FLAG_VNNI_A | FLAG_TRANS_B]
+    elif ta == gen.F16:
+        out += [FLAG_VNNI_A, FLAG_TRANS_B]
+    elif ta in (gen.I8, gen.U8):
+        out = [FLAG_VNNI_A] if t[3] == gen.F32 else [FLAG_VNNI_A, 0]
+    elif ta == gen.I16:
+        out += [FLAG_VNNI_A]
+    return out
+
+
+def small_cases(seed=7):
+    """The reference's own test matrix in miniature (samples/xgemm/kernel_test/*.tpl): random m,n,k, eqld/gtld,
+    beta 0/1, the four batch-reduce modes, per-precision layout flags."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for t in TUPLES:
+        for fl, br_type, beta0, pad in itertools.product(flag_variants(t), (0, 1, 2, 3), (0, 1), (0, 3)):
+            m, n = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+            k = int(rng.integers(1, 10)) * 4
+            flags = fl | (FLAG_BETA_0 if beta0 else 0)
+            cases.append(GemmCase(m, n, k, *t, flags=flags, br_type=br_type, br=5, pad=pad))
+    return cases

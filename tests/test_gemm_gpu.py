@@ -1,0 +1,135 @@
+"""GPU parity of the dense GEMM/BRGEMM path through the C ABI.
+
+ * exact-order CUDA-core kernel: bit-identical to the oracle (and to the reference itself where
+   oracle/_ref is present) for every precision tuple / layout flag / batch-reduce mode of the first bar;
+ * tcgen05 kernel: within the reference's acceptance norms (samples/xgemm/gemm_kernel.c:5312-5414:
+   f32 out < 1.2e-5, bf16/f16 out < 5e-3 relative Frobenius error)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import gen
+import libxsmm_b200 as X
+from gpu_util import dev, dispatch, host, run_single_calls
+from oracle_ffi import oracle, ref, run_gemm
+
+pytestmark = pytest.mark.gpu
+
+
+def test_simt_every_tuple_bit_exact():
+    X.libxsmm_b200_set_force_simt(1)
+    try:
+        n = 0
+        for case in cases.small_cases():
+            ops = cases.Operands(case, seed=100 + n)
+            kernel = dispatch(case, ops)
+            assert kernel, case
+            assert X.libxsmm_b200_kernel_backend(kernel) == X.BACKEND_SIMT
+            d_a, d_b, d_c = dev(ops.a), dev(ops.b), dev(ops.c0)
+            run_single_calls(kernel, case, ops, d_a, d_b, d_c)
+            got = host(d_c, gen.NP_OF[case.tc])
+            want = cases.ref_result(oracle, case, ops, run_gemm)
+            assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), case
+            if ref is not None and n % 7 == 0:
+                assert np.array_equal(got.view(np.uint8), cases.ref_result(ref, case, ops, run_gemm).view(np.uint8)), case
+            n += 1
+    finally:
+        X.libxsmm_b200_set_force_simt(0)
+
+
+def test_hello_host_pointers_f64_and_f32():
+    """samples/hello/hello.c: plain host memory, 1000 calls C += A_i * B_i of a 13x5x7 kernel"""
+    for t in (gen.F64, gen.F32):
+        case = cases.GemmCase(13, 5, 7, t, t, t, t)
+        ops = cases.Operands(case, count=50)
+        kernel = dispatch(case, ops)
+        assert kernel
+        c = np.zeros(case.size_c, dtype=gen.NP_OF[t]); want = c.copy()
+        fn = X.GEMMFUNCTION(kernel)
+        for i in range(ops.count):
+            p = X.GemmParam()
+            p.a.primary = ops.a.ctypes.data + i * ops.tile_a; p.b.primary = ops.b.ctypes.data + i * ops.tile_b; p.c.primary = c.ctypes.data
+            fn(C.byref(p))
+            run_gemm(oracle, case.dims, case.types, 0, 0, 0, 0, 1, ops.a[i * case.size_a:], ops.b[i * case.size_b:], want)
+        X.check()
+        assert np.array_equal(c, want)
+
+
+TC_SHAPES = [(64, 64, 64), (64, 64, 32), (32, 64, 64), (64, 32, 64), (48, 40, 80), (128, 64, 64), (96, 128, 64),
+             (128, 128, 128), (16, 16, 16), (64, 256, 64), (64, 64, 128), (24, 72, 200)]
+
+
+@pytest.mark.parametrize("ta,tc", [(gen.BF16, gen.F32), (gen.BF16, gen.BF16), (gen.F16, gen.F32), (gen.F16, gen.F16)])
+def test_tcgen05_brgemm_within_reference_norm(ta, tc):
+    thr = 1.2e-5 if tc == gen.F32 else 5e-3
+    n = 0
+    for (m, n_, k) in TC_SHAPES:
+        for br_type, br, beta0, count in ((3, 8, 1, 37), (3, 3, 0, 5), (0, 1, 1, 300), (3, 1, 0, 2)):
+            if m * n_ * k >= 128 ** 3 and count > 40:
+                count = 40
+            case = cases.GemmCase(m, n_, k, ta, ta, gen.F32, tc, flags=(cases.FLAG_BETA_0 if beta0 else 0), br_type=br_type, br=br,
+                                  lda=(m + 7) // 8 * 8, ldb=(k + 7) // 8 * 8, ldc=m + (3 if n % 2 else 0))
+            ops = cases.Operands(case, seed=900 + n, count=count)
+            kernel = dispatch(case, ops)
+            assert kernel and X.libxsmm_b200_kernel_backend(kernel) == X.BACKEND_TCGEN05, case
+            d_a, d_b, d_c = dev(ops.a), dev(ops.b), dev(ops.c0)
+            rc = X.libxsmm_b200_gemm_batch_strided(kernel, d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(),
+                                                   ops.tile_a, ops.tile_b, ops.tile_c, case.br, count)
+            assert rc == 0, (case, X.libxsmm_b200_last_error_string())
+            got = host(d_c, gen.NP_OF[tc])
+            want = cases.ref_result(oracle, case, ops, run_gemm)
+            err = gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc))
+            assert err <= thr, (case, count, err)
+            # untouched padding of C (ldc > m) must be preserved
+            if case.ldc > case.m:
+                g = got.reshape(count, case.n, case.ldc)[:, :, case.m:]; w = ops.c0.reshape(count, case.n, case.ldc)[:, :, case.m:]
+                assert np.array_equal(g, w), case
+            n += 1
+
+
+def test_tcgen05_single_call_matches_batch():
+    case = cases.GemmCase(64, 64, 64, gen.BF16, gen.BF16, gen.F32, gen.F32, flags=cases.FLAG_BETA_0, br_type=3, br=8)
+    ops = cases.Operands(case, count=3)
+    kernel = dispatch(case, ops)
+    d_a, d_b, d_c = dev(ops.a), dev(ops.b), dev(ops.c0)
+    run_single_calls(kernel, case, ops, d_a, d_b, d_c)
+    got = host(d_c, np.float32)
+    want = cases.ref_result(oracle, case, ops, run_gemm)
+    assert gen.normf_rel(want, got) <= 1.2e-5
+
+
+def test_batch_plan_address_mode():
+    """general batch entry point: one reference argument struct per tile, address batch-reduce"""
+    case = cases.GemmCase(32, 24, 16, gen.F32, gen.F32, gen.F32, gen.F32, flags=0, br_type=1, br=4)
+    ops = cases.Operands(case, count=9); ops.case_br = case.br
+    kernel = dispatch(case, ops)
+    d_a, d_b, d_c = dev(ops.a), dev(ops.b), dev(ops.c0)
+    params = (X.GemmParam * ops.count)(); keep = []
+    for t in range(ops.count):
+        aa, ab = ops.addr_arrays(d_a.data_ptr(), d_b.data_ptr(), t); br = C.c_ulonglong(case.br); keep += [aa, ab, br]
+        params[t].op.tertiary = C.addressof(br)
+        params[t].a.primary, params[t].b.primary = C.addressof(aa), C.addressof(ab)
+        params[t].c.primary = d_c.data_ptr() + t * ops.tile_c
+    assert X.libxsmm_b200_gemm_batch(kernel, params, ops.count) == 0
+    X.check()
+    assert np.array_equal(host(d_c, np.float32), cases.ref_result(oracle, case, ops, run_gemm))
+
+
+def test_int8_full_size_linearity_property():
+    """size-independent property at a BASELINE size (int8 128^3, batch 4096): C(A, B1+B2) == C(A,B1) + C(A,B2) exactly"""
+    case = cases.GemmCase(128, 128, 128, gen.I8, gen.I8, gen.I32, gen.I32, flags=cases.FLAG_BETA_0 | cases.FLAG_VNNI_A)
+    count = 4096
+    rng = np.random.default_rng(11)
+    a = rng.integers(-20, 20, size=case.size_a * count, dtype=np.int8)
+    b1 = rng.integers(-20, 20, size=case.size_b * count, dtype=np.int8); b2 = rng.integers(-20, 20, size=case.size_b * count, dtype=np.int8)
+    ops = cases.Operands(case, count=1)
+    kernel = dispatch(case, ops)
+    outs = []
+    for b in (b1, b2, (b1 + b2).astype(np.int8)):
+        d_a, d_b = dev(a), dev(b); d_c = torch.zeros(case.size_c * count * 4, dtype=torch.uint8, device="cuda")
+        assert X.libxsmm_b200_gemm_batch_strided(kernel, d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(), case.size_a, case.size_b, case.size_c * 4, 1, count) == 0
+        outs.append(host(d_c, np.int32))
+    assert np.array_equal(outs[0] + outs[1], outs[2])

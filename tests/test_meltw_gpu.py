@@ -1,0 +1,314 @@
+"""GPU parity of the matrix-eltwise (TPP) kernels against the reference's portable C kernels
+(libxsmm_reference_elementwise, via oracle/_ref) on seeded inputs; sizes like the reference's own
+eltwise suite (m, n in 1..100, eqld and gtld). Data movement, masks, integer outputs and IEEE-exact
+ops are compared bit for bit; transcendental ops with the bounds of samples/eltwise/eltwise_unary_simple.c:569-591."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import gen
+import libxsmm_b200 as X
+from gpu_util import dev, host
+from oracle_ffi import iarr, ref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref is None, reason="oracle/_ref/libxsmm_ref.so missing")]
+
+UNS = gen.F64 + 26   # LIBXSMM_DATATYPE_UNSUPPORTED
+EXACT_UNARY = ["IDENTITY", "XOR", "X2", "SQRT", "NEGATE", "INC", "RECIPROCAL", "RECIPROCAL_SQRT"]
+APPROX_UNARY = ["TANH", "TANH_INV", "SIGMOID", "SIGMOID_INV", "GELU", "GELU_INV", "EXP"]
+
+
+def _rand(rng, n, t, positive=False):
+    x = rng.standard_normal(n).astype(np.float32)
+    if positive:
+        x = np.abs(x) + 0.1
+    if t == gen.F32:
+        return x
+    if t == gen.F64:
+        return x.astype(np.float64)
+    if t == gen.BF16:
+        return gen.f32_to_bf16_bits(x)
+    return x.astype(np.float16).view(np.uint16)
+
+
+def _ref_call(desc, param):
+    assert ref["meltw"](iarr(*desc), C.addressof(param), 0) == 0
+
+
+def _desc(op_class, op, flags, m, n, ldi, ldi2, ldi3, ldo, t0, t1, t2, to, tcomp):
+    return (op_class, op, flags, m, n, ldi, ldi2, ldi3, ldo, t0, t1, t2, to, tcomp)
+
+
+def _cmp(got, want, t, exact, tol):
+    if exact:
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    else:
+        g, w = gen.to_f64(got, t), gen.to_f64(want, t)
+        ok = np.isfinite(w)
+        assert np.allclose(g[ok], w[ok], rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("tin,tout", [(gen.F32, gen.F32), (gen.BF16, gen.BF16), (gen.F16, gen.F32), (gen.F32, gen.BF16), (gen.F64, gen.F64)])
+def test_unary_generic_ops(tin, tout):
+    rng = np.random.default_rng(51)
+    names = EXACT_UNARY + ([] if tin == gen.F64 else APPROX_UNARY)
+    for name in names:
+        op = getattr(X, "MELTW_TYPE_UNARY_" + name)
+        for (m, n, pad, bc) in ((33, 17, 0, 0), (100, 3, 5, 0), (1, 64, 2, 0), (40, 9, 0, X.MELTW_FLAG_UNARY_BCAST_ROW),
+                                (40, 9, 0, X.MELTW_FLAG_UNARY_BCAST_COL), (7, 7, 1, X.MELTW_FLAG_UNARY_BCAST_SCALAR)):
+            ldi, ldo = m + pad, m + 2 * pad
+            x = _rand(rng, ldi * n, tin, positive=name in ("SQRT", "RECIPROCAL", "RECIPROCAL_SQRT"))
+            y0 = _rand(rng, ldo * n, tout)
+            tcomp = gen.F64 if tin == gen.F64 else gen.F32
+            k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, tin, tout, tcomp), bc)
+            assert k, (name, tin, tout)
+            d_x, d_y = dev(x), dev(y0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_y.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want = y0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+            _ref_call(_desc(1, op, bc, m, n, ldi, 0, 0, ldo, tin, UNS, UNS, tout, tcomp), q)
+            tol = 7e-4 if tout == gen.F32 else 7e-3
+            _cmp(host(d_y, gen.NP_OF[tout]), want, tout, name in EXACT_UNARY, tol)
+
+
+@pytest.mark.parametrize("t", [gen.F32, gen.BF16])
+def test_relu_family_with_bitmask(t):
+    rng = np.random.default_rng(52)
+    for fwd, inv in (("RELU", "RELU_INV"), ("LEAKY_RELU", "LEAKY_RELU_INV"), ("ELU", "ELU_INV")):
+        for (m, n, pad) in ((35, 11, 0), (64, 5, 3), (9, 40, 7)):
+            for bitm in ((1, 0) if fwd != "ELU" else (0,)):
+                ld = m + pad
+                flags = X.MELTW_FLAG_UNARY_BITMASK_2BYTEMULT if bitm else 0
+                x = _rand(rng, ld * n, t); y0 = _rand(rng, ld * n, t)
+                alpha = C.c_float(0.3)
+                mask_ld = (ld + 15) // 16 * 16
+                mask0 = rng.integers(0, 256, size=mask_ld // 8 * n, dtype=np.uint8)
+                op = getattr(X, "MELTW_TYPE_UNARY_" + fwd)
+                k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, t, t, gen.F32), flags)
+                assert k
+                d_x, d_y, d_m = dev(x), dev(y0), dev(mask0)
+                p = X.MeltwUnaryParam(); p.op.primary = C.addressof(alpha)
+                p.inp.primary, p.out.primary, p.out.secondary = d_x.data_ptr(), d_y.data_ptr(), d_m.data_ptr()
+                X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+                want = y0.copy(); wmask = mask0.copy()
+                q = X.MeltwUnaryParam(); q.op.primary = C.addressof(alpha)
+                q.inp.primary, q.out.primary, q.out.secondary = x.ctypes.data, want.ctypes.data, wmask.ctypes.data
+                _ref_call(_desc(1, op, flags, m, n, ld, 0, 0, ld, t, UNS, UNS, t, gen.F32), q)
+                _cmp(host(d_y, gen.NP_OF[t]), want, t, fwd != "ELU", 7e-3 if t == gen.BF16 else 7e-4)
+                if bitm:
+                    assert np.array_equal(host(d_m, np.uint8), wmask), (fwd, m, n)
+                # backward: needs the mask (relu/leaky) or the forward output (elu)
+                if fwd == "ELU" or bitm:
+                    g = _rand(rng, ld * n, t); o0 = _rand(rng, ld * n, t)
+                    opi = getattr(X, "MELTW_TYPE_UNARY_" + inv)
+                    ki = X.libxsmm_dispatch_meltw_unary(opi, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, t, t, gen.F32), flags)
+                    assert ki
+                    aux_h = want if fwd == "ELU" else wmask
+                    d_g, d_o, d_aux = dev(g), dev(o0), dev(aux_h)
+                    p = X.MeltwUnaryParam(); p.op.primary = C.addressof(alpha)
+                    p.inp.primary, p.inp.secondary, p.out.primary = d_g.data_ptr(), d_aux.data_ptr(), d_o.data_ptr()
+                    X.MELTW_UNARY_FN(ki)(C.byref(p)); X.check()
+                    wo = o0.copy(); q = X.MeltwUnaryParam(); q.op.primary = C.addressof(alpha)
+                    q.inp.primary, q.inp.secondary, q.out.primary = g.ctypes.data, aux_h.ctypes.data, wo.ctypes.data
+                    _ref_call(_desc(1, opi, flags, m, n, ld, 0, 0, ld, t, UNS, UNS, t, gen.F32), q)
+                    _cmp(host(d_o, gen.NP_OF[t]), wo, t, True, 0)
+
+
+@pytest.mark.parametrize("t", [gen.F32, gen.BF16, gen.F64])
+def test_binary_and_ternary(t):
+    rng = np.random.default_rng(53)
+    tcomp = gen.F64 if t == gen.F64 else gen.F32
+    for name in ("ADD", "MUL", "SUB", "DIV", "MULADD", "MAX", "MIN"):
+        op = getattr(X, "MELTW_TYPE_BINARY_" + name)
+        for (m, n, pad, fl) in ((33, 17, 0, 0), (50, 4, 3, X.MELTW_FLAG_BINARY_BCAST_COL_IN_0), (20, 20, 0, X.MELTW_FLAG_BINARY_BCAST_ROW_IN_1),
+                                (8, 3, 1, X.MELTW_FLAG_BINARY_BCAST_SCALAR_IN_1)):
+            ld = m + pad
+            a, b, o0 = _rand(rng, ld * n, t), _rand(rng, ld * n, t, positive=(name == "DIV")), _rand(rng, ld * n, t)
+            k = X.libxsmm_dispatch_meltw_binary(op, X.libxsmm_create_meltw_binary_shape(m, n, ld, ld, ld, t, t, t, tcomp), fl)
+            assert k, name
+            d_a, d_b, d_o = dev(a), dev(b), dev(o0)
+            p = X.MeltwBinaryParam(); p.in0.primary, p.in1.primary, p.out.primary = d_a.data_ptr(), d_b.data_ptr(), d_o.data_ptr()
+            X.MELTW_BINARY_FN(k)(C.byref(p)); X.check()
+            want = o0.copy(); q = X.MeltwBinaryParam(); q.in0.primary, q.in1.primary, q.out.primary = a.ctypes.data, b.ctypes.data, want.ctypes.data
+            _ref_call(_desc(2, op, fl, m, n, ld, ld, 0, ld, t, t, UNS, t, tcomp), q)
+            _cmp(host(d_o, gen.NP_OF[t]), want, t, True, 0)
+    if t == gen.F64:
+        return
+    # compare -> bitmask, then select by that bitmask
+    for name in ("GT", "GE", "LT", "LE", "EQ", "NE"):
+        op = getattr(X, "MELTW_TYPE_BINARY_CMP_OP_" + name)
+        m, n, ld = 37, 9, 40
+        a, b = _rand(rng, ld * n, t), _rand(rng, ld * n, t)
+        b[::5] = a[::5]
+        mask_ld = (ld + 15) // 16 * 16
+        mask0 = rng.integers(0, 256, size=mask_ld // 8 * n, dtype=np.uint8)
+        k = X.libxsmm_dispatch_meltw_binary(op, X.libxsmm_create_meltw_binary_shape(m, n, ld, ld, ld, t, t, t, gen.F32), X.MELTW_FLAG_BINARY_BITMASK_2BYTEMULT)
+        assert k
+        d_a, d_b, d_m = dev(a), dev(b), dev(mask0)
+        p = X.MeltwBinaryParam(); p.in0.primary, p.in1.primary, p.out.primary = d_a.data_ptr(), d_b.data_ptr(), d_m.data_ptr()
+        X.MELTW_BINARY_FN(k)(C.byref(p)); X.check()
+        wmask = mask0.copy(); q = X.MeltwBinaryParam(); q.in0.primary, q.in1.primary, q.out.primary = a.ctypes.data, b.ctypes.data, wmask.ctypes.data
+        _ref_call(_desc(2, op, X.MELTW_FLAG_BINARY_BITMASK_2BYTEMULT, m, n, ld, ld, 0, ld, t, t, UNS, t, gen.F32), q)
+        assert np.array_equal(host(d_m, np.uint8), wmask), name
+        ks = X.libxsmm_dispatch_meltw_ternary(X.MELTW_TYPE_TERNARY_SELECT, X.libxsmm_create_meltw_ternary_shape(m, n, ld, ld, ld, ld, t, t, gen.F32 + 99 if False else t, t, gen.F32),
+                                              X.MELTW_FLAG_TERNARY_BITMASK_2BYTEMULT)
+        assert ks
+        o0 = _rand(rng, ld * n, t); d_o = dev(o0)
+        p = X.MeltwTernaryParam(); p.in0.primary, p.in1.primary, p.in2.primary, p.out.primary = d_a.data_ptr(), d_b.data_ptr(), d_m.data_ptr(), d_o.data_ptr()
+        X.MELTW_TERNARY_FN(ks)(C.byref(p)); X.check()
+        want = o0.copy(); q = X.MeltwTernaryParam()
+        q.in0.primary, q.in1.primary, q.in2.primary, q.out.primary = a.ctypes.data, b.ctypes.data, wmask.ctypes.data, want.ctypes.data
+        _ref_call(_desc(3, X.MELTW_TYPE_TERNARY_SELECT, X.MELTW_FLAG_TERNARY_BITMASK_2BYTEMULT, m, n, ld, ld, ld, ld, t, t, t, t, gen.F32), q)
+        _cmp(host(d_o, gen.NP_OF[t]), want, t, True, 0)
+    for op in (X.MELTW_TYPE_TERNARY_MULADD, X.MELTW_TYPE_TERNARY_NMULADD):
+        m, n, ld = 21, 13, 24
+        a, b, c_, o0 = (_rand(rng, ld * n, t) for _ in range(4))
+        k = X.libxsmm_dispatch_meltw_ternary(op, X.libxsmm_create_meltw_ternary_shape(m, n, ld, ld, ld, ld, t, t, t, t, gen.F32), 0)
+        assert k
+        d_a, d_b, d_c, d_o = dev(a), dev(b), dev(c_), dev(o0)
+        p = X.MeltwTernaryParam(); p.in0.primary, p.in1.primary, p.in2.primary, p.out.primary = d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(), d_o.data_ptr()
+        X.MELTW_TERNARY_FN(k)(C.byref(p)); X.check()
+        want = o0.copy(); q = X.MeltwTernaryParam()
+        q.in0.primary, q.in1.primary, q.in2.primary, q.out.primary = a.ctypes.data, b.ctypes.data, c_.ctypes.data, want.ctypes.data
+        _ref_call(_desc(3, op, 0, m, n, ld, ld, ld, ld, t, t, t, t, gen.F32), q)
+        _cmp(host(d_o, gen.NP_OF[t]), want, t, True, 0)
+
+
+@pytest.mark.parametrize("t", [gen.F32, gen.BF16, gen.F64])
+def test_reductions(t):
+    rng = np.random.default_rng(54)
+    tcomp = gen.F64 if t == gen.F64 else gen.F32
+    for name in ("REDUCE_X_OP_ADD", "REDUCE_X2_OP_ADD", "REDUCE_X_X2_OP_ADD", "REDUCE_X_OP_MAX", "REDUCE_X_OP_MIN", "REDUCE_X_OP_ABSMAX"):
+        op = getattr(X, "MELTW_TYPE_UNARY_" + name)
+        for rows in (1, 0):
+            for (m, n, pad) in ((33, 17, 0), (100, 40, 4), (5, 77, 1)):
+                ldi = m + pad
+                nres = n if rows else m
+                ldo = nres
+                flags = X.MELTW_FLAG_UNARY_REDUCE_ROWS if rows else X.MELTW_FLAG_UNARY_REDUCE_COLS
+                x = _rand(rng, ldi * n, t); o0 = _rand(rng, 2 * ldo, t)
+                k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, t, t, tcomp), flags)
+                assert k, name
+                d_x, d_o = dev(x), dev(o0)
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_o.data_ptr()
+                X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+                want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+                _ref_call(_desc(1, op, flags, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, tcomp), q)
+                got = host(d_o, gen.NP_OF[t])
+                nvalid = nres * (2 if name == "REDUCE_X_X2_OP_ADD" else 1)
+                exact = "ADD" not in name
+                if name == "REDUCE_X2_OP_ADD" and t == gen.F64:
+                    continue   # the reference's f64 x^2 path stores nothing (generator_mateltwise_reference_impl.c:1297)
+                g, w = got[:nvalid], want[:nvalid]
+                if name == "REDUCE_X_X2_OP_ADD" and t == gen.F64:
+                    g, w = got[:nres], want[:nres]
+                _cmp(g, w, t, exact, 1e-2 if t == gen.BF16 else 1e-4)
+
+
+def test_transforms_and_gather_scatter_bit_exact():
+    rng = np.random.default_rng(55)
+    # --- transposes of every element size ---
+    for t in (gen.F64, gen.F32, gen.BF16, gen.I8):
+        for (m, n, pi, po) in ((33, 17, 0, 0), (64, 64, 2, 5), (1, 9, 0, 0)):
+            ldi, ldo = m + pi, n + po
+            x = rng.integers(0, 256, size=ldi * n * gen.TS[t], dtype=np.uint8); o0 = rng.integers(0, 256, size=ldo * m * gen.TS[t], dtype=np.uint8)
+            op = X.MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT
+            k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, t, t, t), 0)
+            assert k
+            d_x, d_o = dev(x), dev(o0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_o.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+            _ref_call(_desc(1, op, 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), q)
+            assert np.array_equal(host(d_o, np.uint8), want), ("normt", t, m, n)
+    # --- VNNI packers (even / multiple-of-4 n so that the reference does not read past the matrix) ---
+    for name, t, v in (("NORM_TO_VNNI2", gen.BF16, 2), ("NORM_TO_VNNI4", gen.I8, 4), ("NORM_TO_VNNI4", gen.BF16, 4), ("NORM_TO_VNNI2T", gen.BF16, 2),
+                       ("NORM_TO_VNNI4T", gen.BF16, 4), ("VNNI2_TO_VNNI2T", gen.BF16, 2), ("VNNI4_TO_VNNI4T", gen.I8, 4), ("VNNI4_TO_VNNI4T", gen.BF16, 4),
+                       ("VNNI2T_TO_NORM", gen.BF16, 2), ("VNNI4T_TO_NORM", gen.BF16, 4), ("VNNI4_TO_NORM", gen.I8, 4)):
+        op = getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_" + name)
+        for (m, n, pad) in ((32, 16, 0), (64, 8, 4), (8, 64, 0), (40, 12, 8)):
+            ldi = m + pad
+            ldo = (n if name in ("VNNI2_TO_VNNI2T", "VNNI4_TO_VNNI4T", "NORM_TO_VNNI2T", "NORM_TO_VNNI4T") else
+                   (n if name in ("VNNI2T_TO_NORM", "VNNI4T_TO_NORM") else m)) + pad
+            x = rng.integers(0, 256, size=(ldi + 8) * (n + 8) * 4 * gen.TS[t], dtype=np.uint8)
+            o0 = rng.integers(0, 256, size=(ldo + 8) * (max(m, n) + 8) * 4 * gen.TS[t], dtype=np.uint8)
+            k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, t, t, t), 0)
+            assert k, name
+            d_x, d_o = dev(x), dev(o0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_o.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+            _ref_call(_desc(1, op, 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), q)
+            assert np.array_equal(host(d_o, np.uint8), want), (name, t, m, n, pad)
+    # --- gather / scatter ---
+    for t in (gen.F32, gen.BF16, gen.I8):
+        for mode, fl in (("cols", X.MELTW_FLAG_UNARY_GS_COLS), ("rows", X.MELTW_FLAG_UNARY_GS_ROWS), ("offs", X.MELTW_FLAG_UNARY_GS_OFFS)):
+            for idx8 in (0, 1):
+                m, n, big = 24, 10, 50
+                it = np.uint64 if idx8 else np.uint32
+                flags = fl | (X.MELTW_FLAG_UNARY_IDX_SIZE_8BYTES if idx8 else X.MELTW_FLAG_UNARY_IDX_SIZE_4BYTES)
+                for op in (X.MELTW_TYPE_UNARY_GATHER, X.MELTW_TYPE_UNARY_SCATTER):
+                    gather = op == X.MELTW_TYPE_UNARY_GATHER
+                    if mode == "cols":
+                        idx = rng.permutation(big)[:n].astype(it); ldi, ldo = m, m; in_n, out_n = (big, n) if gather else (n, big); in_m = out_m = m
+                    elif mode == "rows":
+                        idx = rng.permutation(big)[:m].astype(it); ldi, ldo = (big, m) if gather else (m, big); in_n = out_n = n
+                    else:
+                        idx = rng.permutation(big * big)[:m * n].astype(it); ldi, ldo = (big, m) if gather else (m, big); in_n, out_n = (big, n) if gather else (n, big)
+                    x = rng.integers(0, 256, size=big * big * gen.TS[t], dtype=np.uint8); o0 = rng.integers(0, 256, size=big * big * gen.TS[t], dtype=np.uint8)
+                    k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, t, t, t), flags)
+                    assert k
+                    d_x, d_o, d_i = dev(x), dev(o0), dev(idx)
+                    p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_o.data_ptr()
+                    q = X.MeltwUnaryParam(); want = o0.copy(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+                    if gather:
+                        p.inp.secondary, q.inp.secondary = d_i.data_ptr(), idx.ctypes.data
+                    else:
+                        p.out.secondary, q.out.secondary = d_i.data_ptr(), idx.ctypes.data
+                    X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+                    _ref_call(_desc(1, op, flags, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), q)
+                    assert np.array_equal(host(d_o, np.uint8), want), (t, mode, idx8, gather)
+
+
+def test_quant_dequant_and_scalar_reductions():
+    rng = np.random.default_rng(56)
+    m, n, ld = 37, 11, 40
+    scf = C.c_float(12.5)
+    x = (rng.standard_normal(ld * n) * 8).astype(np.float32)
+    for tout, npdt in ((gen.I8, np.int8), (gen.I16, np.int16), (gen.I32, np.int32)):
+        for fl in (0, X.MELTW_FLAG_UNARY_SIGN_SAT_QUANT):
+            if tout == gen.I32 and fl:
+                continue
+            o0 = rng.integers(-100, 100, size=ld * n).astype(npdt)
+            k = X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_QUANT, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, gen.F32, tout, gen.F32), fl)
+            assert k
+            d_x, d_o = dev(x), dev(o0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.inp.secondary, p.out.primary = d_x.data_ptr(), C.addressof(scf), d_o.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.inp.secondary, q.out.primary = x.ctypes.data, C.addressof(scf), want.ctypes.data
+            _ref_call(_desc(1, X.MELTW_TYPE_UNARY_QUANT, fl, m, n, ld, 0, 0, ld, gen.F32, UNS, UNS, tout, gen.F32), q)
+            assert np.array_equal(host(d_o, npdt), want), (tout, fl)
+            # and back
+            kd = X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_DEQUANT, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, tout, gen.F32, gen.F32), 0)
+            assert kd
+            f0 = rng.standard_normal(ld * n).astype(np.float32); d_f = dev(f0); d_q = dev(want)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.inp.secondary, p.out.primary = d_q.data_ptr(), C.addressof(scf), d_f.data_ptr()
+            X.MELTW_UNARY_FN(kd)(C.byref(p)); X.check()
+            wf = f0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.inp.secondary, q.out.primary = want.ctypes.data, C.addressof(scf), wf.ctypes.data
+            _ref_call(_desc(1, X.MELTW_TYPE_UNARY_DEQUANT, 0, m, n, ld, 0, 0, ld, tout, UNS, UNS, gen.F32, gen.F32), q)
+            assert np.array_equal(host(d_f, np.float32), wf)
+    # reduce-to-scalar and dot product (order of summation differs: tolerance)
+    a, b = rng.standard_normal(ld * n).astype(np.float32), rng.standard_normal(ld * n).astype(np.float32)
+    k = X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_REDUCE_TO_SCALAR_OP_ADD, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, gen.F32, gen.F32, gen.F32), 0)
+    d_a, d_o = dev(a), dev(np.zeros(4, dtype=np.float32))
+    p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_a.data_ptr(), d_o.data_ptr()
+    X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+    assert abs(float(host(d_o, np.float32)[0]) - float(a.reshape(n, ld)[:, :m].sum(dtype=np.float64))) < 1e-3
+    k = X.libxsmm_dispatch_meltw_binary(X.MELTW_TYPE_BINARY_MUL_AND_REDUCE_TO_SCALAR_OP_ADD, X.libxsmm_create_meltw_binary_shape(m, n, ld, ld, ld, gen.F32, gen.F32, gen.F32, gen.F32), 0)
+    d_b = dev(b)
+    p = X.MeltwBinaryParam(); p.in0.primary, p.in1.primary, p.out.primary = d_a.data_ptr(), d_b.data_ptr(), d_o.data_ptr()
+    X.MELTW_BINARY_FN(k)(C.byref(p)); X.check()
+    want = float((a.reshape(n, ld)[:, :m].astype(np.float64) * b.reshape(n, ld)[:, :m]).sum())
+    assert abs(float(host(d_o, np.float32)[0]) - want) < 1e-3

@@ -1,0 +1,124 @@
+"""CPU-only: pins oracle/oracle.c (the restatement) against the UNMODIFIED reference built from
+/root/reference (oracle/_ref/libxsmm_ref.so) on seeded inputs -- bit for bit -- and against the
+reference's JIT path (AMX/AVX-512 on this host) within the reference's own acceptance norms."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import gen
+from oracle_ffi import oracle, ref, run_gemm
+
+needs_ref = pytest.mark.skipif(ref is None, reason="oracle/_ref/libxsmm_ref.so not built (no /root/reference here)")
+
+
+@needs_ref
+def test_conversions_match_reference():
+    rng = np.random.default_rng(1)
+    bits = np.concatenate([rng.integers(0, 2**32, size=20000, dtype=np.uint64).astype(np.uint32),
+                           np.array([0, 0x80000000, 0x7f800000, 0xff800000, 0x7fc00000, 0x7f800001, 0x00000001, 0x007fffff,
+                                     0x38800000, 0x387fffff, 0x33000000, 0x33000001, 0x477fe000, 0x477ff000, 0x47800000], dtype=np.uint32)])
+    for u in bits:
+        f = float(np.array([u], dtype=np.uint32).view(np.float32)[0])
+        assert oracle["f32_to_bf16"](f) == ref["f32_to_bf16"](f), hex(u)
+        assert oracle["f32_to_f16"](f) == ref["f32_to_f16"](f), hex(u)
+    for h in range(0, 65536, 7):
+        a, b = oracle["f16_to_f32"](h), ref["f16_to_f32"](h)
+        assert (a == b) or (a != a and b != b), h
+        a, b = oracle["bf16_to_f32"](h), ref["bf16_to_f32"](h)
+        assert (a == b) or (a != a and b != b), h
+
+
+@needs_ref
+def test_gemm_restatement_is_bit_exact():
+    n = 0
+    for case in cases.small_cases():
+        ops = cases.Operands(case, seed=555 + n)
+        want = cases.ref_result(ref, case, ops, run_gemm)
+        got = cases.ref_result(oracle, case, ops, run_gemm)
+        assert np.array_equal(want.view(np.uint8), got.view(np.uint8)), case
+        n += 1
+    assert n > 300
+
+
+@needs_ref
+def test_reference_jit_agrees_with_reference_kernel():
+    """the JIT'ed x86 kernels (the CPU baseline) against the C kernel, reference thresholds (gemm_kernel.c:5312-5414)"""
+    for t, thr in (((gen.F32, gen.F32, gen.F32, gen.F32), 1.2e-5), ((gen.BF16, gen.BF16, gen.F32, gen.F32), 1.2e-5),
+                   ((gen.BF16, gen.BF16, gen.F32, gen.BF16), 5e-3), ((gen.U8, gen.I8, gen.I32, gen.I32), 0.0)):
+        flags = cases.FLAG_BETA_0 | (cases.FLAG_VNNI_A if t[0] != gen.F32 else 0)
+        case = cases.GemmCase(64, 64, 64, *t, flags=flags, br_type=3, br=8)
+        ops = cases.Operands(case)
+        c_ref = ops.c0.copy(); c_jit = ops.c0.copy()
+        assert run_gemm(ref, case.dims, case.types, case.flags, 3, ops.stride_a, ops.stride_b, 8, ops.a, ops.b, c_ref, mode=0) == 0
+        rc = run_gemm(ref, case.dims, case.types, case.flags, 3, ops.stride_a, ops.stride_b, 8, ops.a, ops.b, c_jit, mode=1)
+        assert rc in (0, 2)
+        assert gen.normf_rel(gen.to_f64(c_ref, t[3]), gen.to_f64(c_jit, t[3])) <= thr
+
+
+def _bcsc_inputs(rng, ta, tb, tc, mblocks, M, K, N, bk, bn, density, vnni_a=True, trans_a=False):
+    nbr, nbc = K // bk, N // bn
+    keep = rng.random((nbc, nbr)) < density
+    colptr = np.zeros(nbc + 1, dtype=np.uint32); rowidx = []
+    for j in range(nbc):
+        rows = np.nonzero(keep[j])[0]
+        rowidx.extend(rows.tolist()); colptr[j + 1] = len(rowidx)
+    rowidx = np.array(rowidx if rowidx else [0], dtype=np.uint32)
+    nnzb = int(colptr[-1])
+    bvals = gen.values(rng, max(nnzb, 1) * bk * bn, tb)
+    a = gen.values(rng, mblocks * K * M, ta)
+    c0 = gen.values(rng, mblocks * N * M, tc)
+    return a, bvals, colptr, rowidx, c0
+
+
+def _run_bcsc(side, types, geo, flags, a, bvals, colptr, rowidx, c):
+    from oracle_ffi import iarr
+    return side["bcsc"](iarr(*types), iarr(*geo), flags, a.ctypes.data, bvals.ctypes.data, colptr.ctypes.data, rowidx.ctypes.data, c.ctypes.data)
+
+
+@needs_ref
+def test_bcsc_oracle_matches_reference_jit():
+    """no portable C kernel exists for BCSC in the reference (no fallback for this build kind): the x86 JIT is
+    the second opinion; f32 and bf16 accumulate in a different order, integer paths must agree exactly."""
+    rng = np.random.default_rng(3)
+    for (ta, tb, tcomp, tc), thr in (((gen.F32, gen.F32, gen.F32, gen.F32), 1e-4), ((gen.BF16, gen.BF16, gen.F32, gen.BF16), 5e-3),
+                                      ((gen.U8, gen.I8, gen.I32, gen.I32), 0.0), ((gen.I8, gen.U8, gen.I32, gen.I32), 0.0)):
+        for beta0 in (1, 0):
+            mblocks, M, K, N, bk, bn = 3, 32, 128, 64, 32 if ta != gen.F32 else 16, 16
+            flags = (cases.FLAG_BETA_0 if beta0 else 0) | (cases.FLAG_VNNI_A if ta != gen.F32 else 0)
+            a, bvals, colptr, rowidx, c0 = _bcsc_inputs(rng, ta, tb, tc, mblocks, M, K, N, bk, bn, 0.5)
+            geo = (mblocks, M, K, N, bk, bn)
+            c_o, c_r = c0.copy(), c0.copy()
+            assert _run_bcsc(oracle, (ta, tb, tcomp, tc), geo, flags, a, bvals, colptr, rowidx, c_o) == 0
+            rc = _run_bcsc(ref, (ta, tb, tcomp, tc), geo, flags, a, bvals, colptr, rowidx, c_r)
+            if rc != 0:
+                pytest.skip("reference JIT cannot build BCSC for this host ISA")
+            err = gen.normf_rel(gen.to_f64(c_r, tc), gen.to_f64(c_o, tc))
+            assert err <= thr, ((ta, tb, tc), beta0, err)
+
+
+@needs_ref
+def test_fsspmdm_oracle_matches_reference():
+    rng = np.random.default_rng(4)
+    for dtype, eps in ((gen.F32, 1e-4), (gen.F64, 1e-8)):
+        for beta in (0.0, 1.0):
+            M, K, N = 24, 40, 96
+            npdt = gen.NP_OF[dtype]
+            a = (gen.values(rng, M * K, gen.F64) * (rng.random(M * K) < 0.2)).astype(npdt)
+            b = gen.values(rng, K * N, dtype); c0 = gen.values(rng, M * N, dtype)
+            alpha = np.array([1.5], dtype=npdt); bt = np.array([beta], dtype=npdt)
+            c_o, c_r = c0.copy(), c0.copy()
+            args = (dtype, M, N, K, K, N, N, alpha.ctypes.data, bt.ctypes.data, a.ctypes.data, b.ctypes.data)
+            assert oracle["fsspmdm"](*args, c_o.ctypes.data) == 0
+            assert ref["fsspmdm"](*args, c_r.ctypes.data) == 0
+            assert gen.normf_rel(c_r, c_o) <= eps
+    # invalid inputs answer "no handle" on both sides (N not a multiple of the vector length, beta=2, empty A)
+    M, K, N = 8, 8, 24
+    a = np.ones(M * K, dtype=np.float32); b = np.ones(K * N, dtype=np.float32); c = np.zeros(M * N, dtype=np.float32)
+    one = np.array([1.0], dtype=np.float32); two = np.array([2.0], dtype=np.float32)
+    for side in (oracle, ref):
+        assert side["fsspmdm"](gen.F32, M, N, K, K, N, N, one.ctypes.data, one.ctypes.data, a.ctypes.data, b.ctypes.data, c.ctypes.data) != 0
+        assert side["fsspmdm"](gen.F32, M, 32, K, K, 32, 32, one.ctypes.data, two.ctypes.data, a.ctypes.data, b.ctypes.data, c.ctypes.data) != 0
+        z = np.zeros(M * K, dtype=np.float32)
+        assert side["fsspmdm"](gen.F32, M, 32, K, K, 32, 32, one.ctypes.data, one.ctypes.data, z.ctypes.data, b.ctypes.data, c.ctypes.data) != 0

@@ -1,0 +1,155 @@
+"""GPU parity of the sparse kernels through the C ABI: fsspmdm, BCSC, packed CSR/CSC."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import gen
+import libxsmm_b200 as X
+from gpu_util import dev, host
+from oracle_ffi import iarr, oracle, ref
+from test_oracle_vs_ref import _bcsc_inputs, _run_bcsc
+
+pytestmark = pytest.mark.gpu
+
+
+def _fsspmdm_case(rng, dtype, M, K, N, density, lda=None, ldb=None, ldc=None, uniq=True):
+    npdt = gen.NP_OF[dtype]
+    lda, ldb, ldc = lda or K, ldb or N, ldc or N
+    a = np.zeros(M * lda, dtype=npdt)
+    vals = gen.values(rng, M * K, gen.F64) if uniq else rng.standard_normal(M * K)
+    a.reshape(M, lda)[:, :K] = (vals * (rng.random(M * K) < density)).reshape(M, K).astype(npdt)
+    b = rng.standard_normal(K * ldb).astype(npdt); c0 = rng.standard_normal(M * ldc).astype(npdt)
+    return a, b, c0, lda, ldb, ldc
+
+
+@pytest.mark.parametrize("dtype,eps", [(gen.F32, 1e-4), (gen.F64, 1e-8)])
+def test_fsspmdm_matches_oracle(dtype, eps):
+    """thresholds of samples/xgemm_sparse_Ainregs/pyfr_driver_asp_reg.c:18-20 (matdiff epsilon)"""
+    rng = np.random.default_rng(21)
+    for (M, K, N, dens, pad) in ((32, 128, 4096, 0.15, 0), (192, 96, 1024, 0.02, 0), (7, 5, 64, 0.6, 16), (48, 200, 2048 + 64, 0.1, 0),
+                                 (33, 300, 512, 0.05, 0), (64, 700, 256, 0.03, 0)):
+        for beta in (0.0, 1.0):
+            a, b, c0, lda, ldb, ldc = _fsspmdm_case(rng, dtype, M, K, N, dens, ldb=N + pad, ldc=N + pad)
+            npdt = gen.NP_OF[dtype]
+            alpha = np.array([0.5], dtype=npdt); bt = np.array([beta], dtype=npdt)
+            h = X.libxsmm_fsspmdm_create(dtype, M, N, K, lda, ldb, ldc, alpha.ctypes.data, bt.ctypes.data, a.ctypes.data, 0, None)
+            assert h, (M, K, N)
+            d_b, d_c = dev(b), dev(c0)
+            X.libxsmm_fsspmdm_execute(h, d_b.data_ptr(), d_c.data_ptr()); X.check()
+            got = host(d_c, npdt)
+            want = c0.copy()
+            assert oracle["fsspmdm"](dtype, M, N, K, lda, ldb, ldc, alpha.ctypes.data, bt.ctypes.data, a.ctypes.data, b.ctypes.data, want.ctypes.data) == 0
+            g, w = got.reshape(M, ldc), want.reshape(M, ldc)
+            assert gen.normf_rel(w[:, :N], g[:, :N]) <= eps, (M, K, N, beta)
+            assert np.array_equal(g[:, N:], c0.reshape(M, ldc)[:, N:])
+            # host-pointer execution (the reference calling convention) gives the same result
+            c_h = c0.copy()
+            X.libxsmm_fsspmdm_execute(h, b.ctypes.data, c_h.ctypes.data); X.check()
+            assert np.array_equal(c_h, got)
+            X.libxsmm_fsspmdm_destroy(h)
+
+
+def test_fsspmdm_invalid_inputs_return_null():
+    a = np.ones(64, dtype=np.float32); one = np.array([1.0], dtype=np.float32); two = np.array([2.0], dtype=np.float32)
+    assert not X.libxsmm_fsspmdm_create(gen.F32, 8, 24, 8, 8, 24, 24, one.ctypes.data, one.ctypes.data, a.ctypes.data, 0, None)   # N % 16
+    assert not X.libxsmm_fsspmdm_create(gen.F32, 8, 32, 8, 8, 32, 32, one.ctypes.data, two.ctypes.data, a.ctypes.data, 0, None)   # beta = 2
+    assert not X.libxsmm_fsspmdm_create(gen.F32, 8, 32, 8, 4, 32, 32, one.ctypes.data, one.ctypes.data, a.ctypes.data, 0, None)   # lda < K
+    z = np.zeros(64, dtype=np.float32)
+    assert not X.libxsmm_fsspmdm_create(gen.F32, 8, 32, 8, 8, 32, 32, one.ctypes.data, one.ctypes.data, z.ctypes.data, 0, None)   # empty A
+    assert not X.libxsmm_fsspmdm_create(gen.F32, 8, 32, 8, 8, 32, 32, one.ctypes.data, one.ctypes.data, None, 0, None)
+
+
+def test_fsspmdm_full_size_linearity_property():
+    """BASELINE size (M=32, K=128, N=1e6 padded to 16): op(B1 + B2) == op(B1) + op(B2) within f32 rounding"""
+    rng = np.random.default_rng(5)
+    M, K, N = 32, 128, 1000000
+    a = (gen.values(rng, M * K, gen.F32) * (rng.random(M * K) < 0.15)).astype(np.float32)
+    one = np.array([1.0], dtype=np.float32); zero = np.array([0.0], dtype=np.float32)
+    h = X.libxsmm_fsspmdm_create(gen.F32, M, N, K, K, N, N, one.ctypes.data, zero.ctypes.data, a.ctypes.data, 0, None)
+    assert h
+    b1 = torch.randn(K * N, device="cuda"); b2 = torch.randn(K * N, device="cuda")
+    outs = []
+    for b in (b1, b2, b1 + b2):
+        c = torch.full((M * N,), float("nan"), device="cuda")
+        X.libxsmm_fsspmdm_execute(h, b.data_ptr(), c.data_ptr()); X.check()
+        outs.append(c)
+    err = (outs[0] + outs[1] - outs[2]).norm() / outs[2].norm()
+    assert float(err) < 1e-5
+    X.libxsmm_fsspmdm_destroy(h)
+
+
+@pytest.mark.parametrize("types", [(gen.F32, gen.F32, gen.F32, gen.F32), (gen.BF16, gen.BF16, gen.F32, gen.BF16),
+                                   (gen.U8, gen.I8, gen.I32, gen.I32), (gen.I8, gen.U8, gen.I32, gen.I32)])
+def test_bcsc_bit_exact_vs_oracle(types):
+    rng = np.random.default_rng(31)
+    ta, tb, tcomp, tc = types
+    for (mblocks, M, K, N, bk, bn, dens) in ((5, 32, 128, 64, 32, 16, 0.5), (3, 16, 64, 96, 16, 32, 0.3), (2, 64, 256, 128, 32, 32, 0.5), (4, 8, 32, 32, 8, 8, 0.9)):
+        if ta != gen.F32 and bk % (2 if ta == gen.BF16 else 4):
+            continue
+        for beta0, trans_a in ((1, 0), (0, 0), (1, 1)):
+            flags = (cases.FLAG_BETA_0 if beta0 else 0) | (cases.FLAG_VNNI_A if (ta != gen.F32 and not trans_a) else 0) | (cases.FLAG_TRANS_A if trans_a else 0)
+            a, bvals, colptr, rowidx, c0 = _bcsc_inputs(rng, ta, tb, tc, mblocks, M, K, N, bk, bn, dens)
+            sh = X.libxsmm_create_gemm_shape(mblocks, 0, K, K, 0, N, ta, tb, tc, tcomp)
+            cfg = X.SpgemmConfig(M, bk, bn)
+            kernel = X.libxsmm_create_packed_spgemm_bcsc(sh, flags, 0, cfg)
+            assert kernel
+            d_a, d_b, d_cp, d_ri, d_c = dev(a), dev(bvals), dev(colptr), dev(rowidx), dev(c0)
+            X.call_gemm(kernel, d_a, d_b, d_c, colptr=d_cp, rowidx=d_ri, nblocks=N // bn); X.check()
+            got = host(d_c, gen.NP_OF[tc])
+            want = c0.copy()
+            assert _run_bcsc(oracle, types, (mblocks, M, K, N, bk, bn), flags, a, bvals, colptr, rowidx, want) == 0
+            if X.libxsmm_b200_kernel_backend(kernel) == X.BACKEND_STREAM and tc != gen.I32 and False:
+                pass
+            if tc == gen.I32:
+                assert np.array_equal(got, want), (types, mblocks, M, K, N)
+            else:
+                thr = 5e-3 if tc == gen.BF16 else 1e-4          # spmm_kernel.c:1019-1029
+                assert gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc)) <= thr, (types, mblocks, M, K, N, beta0, trans_a)
+            X.libxsmm_release_kernel(kernel)
+
+
+@pytest.mark.parametrize("dtype", [gen.F32, gen.F64])
+def test_packed_csr_csc_bit_exact(dtype):
+    """SOA-packed sparse x dense (EDGE/SeisSol sizes): A-sparse CSR, B-sparse CSC, B-sparse CSR, C-sparse CSC"""
+    rng = np.random.default_rng(41)
+    npdt = gen.NP_OF[dtype]
+    for (M, N, K, P) in ((9, 9, 9, 8), (20, 9, 35, 16), (56, 9, 56, 64), (4, 3, 5, 1)):
+        for beta0 in (0, 1):
+            flags = cases.FLAG_BETA_0 if beta0 else 0
+            # --- A sparse (CSR over M rows) ---
+            dense = (rng.random((M, K)) < 0.3)
+            rowptr = np.concatenate([[0], np.cumsum(dense.sum(1))]).astype(np.uint32); colidx = np.nonzero(dense)[1].astype(np.uint32)
+            if len(colidx) == 0:
+                continue
+            avals = gen.values(rng, len(colidx), dtype); b = gen.values(rng, K * N * P, dtype); c0 = gen.values(rng, M * N * P, dtype)
+            dims = (M, N, K, 0, N, N)
+            k1 = X.libxsmm_create_packed_spgemm_csr(X.libxsmm_create_gemm_shape(*dims, dtype, dtype, dtype, dtype), flags, 0, P,
+                                                    rowptr.ctypes.data, colidx.ctypes.data, avals.ctypes.data)
+            assert k1
+            d_a, d_b, d_c = dev(avals), dev(b), dev(c0)
+            X.call_gemm(k1, d_a, d_b, d_c); X.check()
+            want = c0.copy()
+            assert oracle["packed_sp"](0, dtype, iarr(*dims), flags, P, rowptr.ctypes.data, colidx.ctypes.data, avals.ctypes.data,
+                                       avals.ctypes.data, b.ctypes.data, want.ctypes.data) == 0
+            assert np.array_equal(host(d_c, npdt), want), ("asparse", M, N, K, P)
+            X.libxsmm_release_kernel(k1)
+            # --- B sparse (CSC over N columns) ---
+            dense = (rng.random((K, N)) < 0.3)
+            colptr = np.concatenate([[0], np.cumsum(dense.sum(0))]).astype(np.uint32); rowidx = np.nonzero(dense.T)[1].astype(np.uint32)
+            if len(rowidx) == 0:
+                continue
+            bvals = gen.values(rng, len(rowidx), dtype); a = gen.values(rng, M * K * P, dtype)
+            dims = (M, N, K, K, 0, N)
+            k2 = X.libxsmm_create_packed_spgemm_csc(X.libxsmm_create_gemm_shape(*dims, dtype, dtype, dtype, dtype), flags, 0, P,
+                                                    colptr.ctypes.data, rowidx.ctypes.data, bvals.ctypes.data)
+            assert k2
+            d_a, d_b, d_c = dev(a), dev(bvals), dev(c0)
+            X.call_gemm(k2, d_a, d_b, d_c); X.check()
+            want = c0.copy()
+            assert oracle["packed_sp"](1, dtype, iarr(*dims), flags, P, colptr.ctypes.data, rowidx.ctypes.data, bvals.ctypes.data,
+                                       a.ctypes.data, bvals.ctypes.data, want.ctypes.data) == 0
+            assert np.array_equal(host(d_c, npdt), want), ("bsparse_csc", M, N, K, P)
+            X.libxsmm_release_kernel(k2)
