@@ -42,7 +42,7 @@ ref: oracle/_ref/libxsmm_ref.so
 oracle/_ref/libxsmm_ref.so: oracle/ref_shim.c
 	@mkdir -p oracle/_ref
 	@if [ -d $(REFDIR)/include ]; then \
-	  $(CC) -O2 -fPIC -shared -fopenmp -ffp-contract=off -I$(REFDIR)/include -I$(REFDIR)/src -o $@ $< -lm -lpthread -ldl; \
+	  $(CC) -O2 -fPIC -shared -fvisibility=hidden -Wl,-Bsymbolic -fopenmp -ffp-contract=off -I$(REFDIR)/include -I$(REFDIR)/src -o $@ $< -lm -lpthread -ldl; \
 	else echo "reference tree not present: keeping prebuilt $@"; fi
 
 clean:

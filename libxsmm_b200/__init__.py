@@ -16,7 +16,7 @@ if not os.path.exists(LIB_PATH):
     raise ImportError(
         "libxsmm_b200: %s is missing -- build it with `make lib` (or __graft_entry__.build()); "
         "there is no CPU fallback" % LIB_PATH)
-lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL if hasattr(C, "RTLD_GLOBAL") else 0)
+lib = C.CDLL(LIB_PATH)   # RTLD_LOCAL: the reference build used by the tests has same-named symbols
 
 # ---- enumerations (include/libxsmm_typedefs.h) -------------------------------------------------------
 _DT = ("F64 F32 BF16 F16 BF8 HF8 I64 U64 I32 U32 I16 U16 I8 U8 MXBF8 MXHF8 MXBF6 MXHF6 I4X2 U4X2 "
