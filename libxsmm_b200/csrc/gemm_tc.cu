@@ -37,7 +37,7 @@ struct TcParams {
   int np;                 // n rounded up to the MMA's N granularity
   int kchunks;            // ceil(k / 64)
   int stages, stage_bytes, a_bytes;
-  int nslot, slot_cols;
+  int nslot, slot_cols, tmem_cols, evict_first;
   unsigned long long br;
   long long count;
   char* c; long long tile_stride_c; long long ldc;
@@ -70,6 +70,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+               :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -100,7 +104,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16
 }
 
 template <int UM>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int TPS = (UM == 64) ? 2 : 1;          // tiles per TMEM slot
@@ -126,7 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM: whole 512 columns (one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_word)), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_word)), "r"((uint32_t)P.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -138,6 +142,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      uint64_t policy = 0;
+      if (P.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       for (long long i = 0; i < n_local; ++i) {
         const long long t = b + i * G;
         for (unsigned long long r = 0; r < P.br; ++r) {
@@ -146,9 +152,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t full = bar_base + 8 * stage;
             const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
             mbar_expect_tx(full, (uint32_t)P.stage_bytes);
-            tma_load_4d(sa, &map_a, full, 0, kc * 64, (int)r, (int)t);
-            if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, 64, kc * 64, (int)r, (int)t);
-            tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, (int)t);
+            if (P.evict_first) {
+              tma_load_4d_hint(sa, &map_a, full, 0, kc * 64, (int)r, (int)t, policy);
+              if (UM == 128) tma_load_4d_hint(sa + 8192, &map_a, full, 64, kc * 64, (int)r, (int)t, policy);
+              tma_load_4d_hint(sb, &map_b, full, kc * 64, 0, (int)r, (int)t, policy);
+            } else {
+              tma_load_4d(sa, &map_a, full, 0, kc * 64, (int)r, (int)t);
+              if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, 64, kc * 64, (int)r, (int)t);
+              tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, (int)t);
+            }
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -245,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
   }
 }
 
@@ -317,10 +329,16 @@ extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
   P.np = (UM == 64) ? ((d.n + 7) & ~7) : ((d.n + 15) & ~15);
   P.kchunks = (d.k + 63) / 64;
   P.a_bytes = UM * 128; P.stage_bytes = P.a_bytes + P.np * 128;
-  P.stages = (200 * 1024) / P.stage_bytes; if (P.stages > 12) P.stages = 12; if (P.stages < 2) P.stages = 2;
-  P.stages = env_int("LIBXSMM_B200_TC_STAGES", P.stages); if (P.stages > 16) P.stages = 16;
+  // several independent (producer, MMA, epilogue) pipelines per SM hide each other's serial phases: measured on
+  // B200 (64^3 x 8 bf16, streaming): 1 CTA/SM 77%, 2 CTAs/SM 105% of the copy-measured HBM peak.
+  int ctas = env_int("LIBXSMM_B200_TC_CTAS", 2); if (ctas < 1) ctas = 1; if (ctas > 4) ctas = 4;
   P.slot_cols = (P.np + 31) & ~31;
-  P.nslot = 512 / P.slot_cols; if (P.nslot > 4) P.nslot = 4;
+  while (ctas > 1 && (2 * P.stage_bytes + 2048 > (224 * 1024) / ctas || P.slot_cols > 512 / (ctas == 3 ? 4 : ctas))) --ctas;
+  P.stages = ((224 * 1024) / ctas - 2048) / P.stage_bytes; if (P.stages > 12) P.stages = 12; if (P.stages < 2) P.stages = 2;
+  { const int st = env_int("LIBXSMM_B200_TC_STAGES", ctas > 1 ? 4 : P.stages); if (st >= 2 && st <= P.stages) P.stages = st; }
+  P.tmem_cols = (ctas == 3) ? 128 : 512 / ctas;
+  P.nslot = P.tmem_cols / P.slot_cols; if (P.nslot > 4) P.nslot = 4;
+  P.evict_first = env_int("LIBXSMM_B200_TC_EVICT_FIRST", 0);
   P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
   P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0;
   // instruction descriptor: D=f32, A/B format, A MN-major, B K-major, N>>3, M>>4
@@ -353,7 +371,7 @@ extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
 
   const size_t smem = (size_t)P.stages * P.stage_bytes + 1024 /*align slack*/ + (2 * 16 + 2 * 8) * 8 + 64;
   const long long tiles_per_cta_unit = (UM == 64) ? 2 : 1;
-  long long grid = (L->count + tiles_per_cta_unit - 1) / tiles_per_cta_unit; if (grid > g_num_sms) grid = g_num_sms; if (grid < 1) grid = 1;
+  long long grid = (L->count + tiles_per_cta_unit - 1) / tiles_per_cta_unit; if (grid > (long long)g_num_sms * ctas) grid = (long long)g_num_sms * ctas; if (grid < 1) grid = 1;
   cudaStream_t stream = (cudaStream_t)xb_rt_stream();
   cudaError_t e;
   if (UM == 64) {

@@ -162,12 +162,18 @@ LIBXSMM_API libxsmm_gemmfunction libxsmm_create_spgemm_csr_areg(const libxsmm_ge
   xb_fill_sparse_common(&s->u.sp, XB_KIND_SREG, &gemm_shape, gemm_flags);
   s->u.sp.max_n = max_N;
   failed = xb_upload_pattern(&s->u.sp, row_ptr, (unsigned int)gemm_shape.m, column_idx, nnz);
-  /* values arrive as double (reference src/libxsmm_fsspmdm.c:163,225) and are narrowed to the compute type */
+  /* values arrive as double (reference src/libxsmm_fsspmdm.c:163,225) and are narrowed to the compute type; each
+   * non-zero is stored as {value, byte offset of its B row inside a shared-memory stage} for the streaming kernel */
+  ts = (ts == 8) ? 16 : 8;
   tmp = malloc((size_t)nnz * ts);
   s->u.sp.d_val = xb_rt_device_malloc((size_t)nnz * ts);
   if (tmp == NULL || s->u.sp.d_val == NULL) failed = 1;
   else {
-    for (i = 0; i < nnz; ++i) { if (ts == 8) ((double*)tmp)[i] = values[i]; else ((float*)tmp)[i] = (float)values[i]; }
+    memset(tmp, 0, (size_t)nnz * ts);
+    for (i = 0; i < nnz; ++i) {
+      if (ts == 16) { *(double*)((char*)tmp + (size_t)i * 16) = values[i]; *(unsigned int*)((char*)tmp + (size_t)i * 16 + 8) = column_idx[i] * 512u; }
+      else { *(float*)((char*)tmp + (size_t)i * 8) = (float)values[i]; *(unsigned int*)((char*)tmp + (size_t)i * 8 + 4) = column_idx[i] * 512u; }
+    }
     if (0 != xb_rt_memcpy(s->u.sp.d_val, tmp, (size_t)nnz * ts)) failed = 1;
   }
   free(tmp);

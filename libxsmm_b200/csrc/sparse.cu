@@ -10,8 +10,10 @@
 //                        version lives in bcsc_tc.cu.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "xb_internal.h"
 #include "xb_device.cuh"
+#include "xb_tma.cuh"
 
 namespace {
 
@@ -53,27 +55,32 @@ __device__ __forceinline__ void vzero(double2& a) { a = make_double2(0.0, 0.0); 
 struct SregParams {
   int M, K; long long N, ldb, ldc;
   unsigned int nnz;
-  const unsigned int* rowptr; const unsigned int* colidx; const void* vals;
+  const unsigned int* rowptr; const void* entries;      // entries: packed {value, byte offset of the B row in a stage}
   const void* b; void* c;
   int beta0; int stages;
 };
 
+template <typename T> struct SregEntry;
+template <> struct SregEntry<float> { float v; unsigned int off; };
+template <> struct SregEntry<double> { double v; unsigned int off; unsigned int pad; };
+
+// shared memory: [barriers 1 KB][stages x K x 512 B of B][nnz entries][M+1 row pointers]
 template <typename T>
-__global__ void __launch_bounds__(512, 1) sreg_kernel(const SregParams P) {
+__global__ void __launch_bounds__(1024, 1) sreg_kernel(const __grid_constant__ CUtensorMap map_b, const SregParams P) {
   typedef typename Vec<T>::type V;
+  typedef SregEntry<T> E;
   constexpr int VN = Vec<T>::N;
   constexpr int STRIP = 32 * VN;                // elements per strip row (512 bytes)
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: stages x [K][512 B] | rowptr[M+1] | colidx[nnz] | vals[nnz] | barriers
-  unsigned char* sB = smem_raw;
-  unsigned int* s_rowptr = (unsigned int*)(sB + (size_t)P.stages * P.K * 512);
-  unsigned int* s_col = s_rowptr + (P.M + 1);
-  T* s_val = (T*)(((uintptr_t)(s_col + P.nnz) + 15) & ~(uintptr_t)15);
-  uint64_t* bars = (uint64_t*)(((uintptr_t)(s_val + P.nnz) + 15) & ~(uintptr_t)15);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned char* sB = smem_raw + 1024;       // TMA tensor destinations: keep stage bases 1 KB aligned
+  const size_t stage_bytes = (size_t)P.K * 512;
+  E* s_ent = reinterpret_cast<E*>(sB + (size_t)P.stages * stage_bytes);
+  unsigned int* s_rowptr = reinterpret_cast<unsigned int*>(s_ent + P.nnz);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   for (int i = tid; i <= P.M; i += blockDim.x) s_rowptr[i] = P.rowptr[i];
-  for (unsigned int i = tid; i < P.nnz; i += blockDim.x) { s_col[i] = P.colidx[i]; s_val[i] = ((const T*)P.vals)[i]; }
+  for (unsigned int i = tid; i < P.nnz; i += blockDim.x) s_ent[i] = reinterpret_cast<const E*>(P.entries)[i];
   if (tid == 0) {
     for (int s = 0; s < P.stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -82,59 +89,69 @@ __global__ void __launch_bounds__(512, 1) sreg_kernel(const SregParams P) {
 
   const long long nstrips = (P.N + STRIP - 1) / STRIP;
   const long long first = blockIdx.x, step = gridDim.x;
-  const T* Bg = (const T*)P.b; T* Cg = (T*)P.c;
+  T* Cg = (T*)P.c;
+  const int S = P.stages;
 
-  // producer: warp 0 issues one bulk copy per B row of the strip (512 B, or the tail width)
+  // producer: one TMA tensor copy per strip (box = 512 bytes x min(K,256) rows; columns past N are zero-filled)
   auto issue = [&](long long strip, int stage) {
-    const long long n0 = strip * STRIP;
-    const long long w = (P.N - n0 < STRIP) ? (P.N - n0) : STRIP;
-    const uint32_t bytes = (uint32_t)(w * sizeof(T));
-    const uint32_t bar = smem_u32(&bars[stage]);
-    if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)P.K);
-    __syncwarp();
-    for (int k = lane; k < P.K; k += 32) {
-      bulk_g2s(smem_u32(sB + ((size_t)stage * P.K + k) * 512), Bg + (size_t)k * P.ldb + n0, bytes, bar);
+    if (lane == 0) {
+      const uint32_t bar = smem_u32(&bars[stage]);
+      mbar_expect_tx(bar, (uint32_t)stage_bytes);
+      for (int k0 = 0; k0 < P.K; k0 += 256) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     :: "r"(smem_u32(sB + (size_t)stage * stage_bytes + (size_t)k0 * 512)), "l"(&map_b), "r"((int)(strip * STRIP)), "r"(k0), "r"(bar) : "memory");
+      }
     }
   };
 
+  // prologue: fill S-1 stages
+  if (warp == 0) {
+    if (S == 1) { if (first < nstrips) issue(first, 0); }
+    else for (int s = 0; s < S - 1; ++s) if (first + (long long)s * step < nstrips) issue(first + (long long)s * step, s);
+  }
   long long it = 0;
-  if (warp == 0 && first < nstrips) issue(first, 0);
   for (long long strip = first; strip < nstrips; strip += step, ++it) {
-    const int stage = (int)(it % P.stages);
-    if (P.stages > 1 && warp == 0 && strip + step < nstrips) issue(strip + step, (int)((it + 1) % P.stages));
-    mbar_wait(smem_u32(&bars[stage]), (uint32_t)((it / P.stages) & 1));
-    const V* Bs = (const V*)(sB + (size_t)stage * P.K * 512);
+    const int stage = (int)(it % S);
+    if (S > 1 && warp == 0) {             // keep S-1 strips in flight: the stage being refilled was released by the barrier below
+      const long long nxt = strip + (long long)(S - 1) * step;
+      if (nxt < nstrips) issue(nxt, (int)((it + S - 1) % S));
+    }
+    mbar_wait(smem_u32(&bars[stage]), (uint32_t)((it / S) & 1));
+    const unsigned char* Bs = sB + (size_t)stage * stage_bytes + (size_t)lane * sizeof(V);
     const long long n0 = strip * STRIP;
     const bool in = (n0 + (long long)lane * VN) < P.N;        // N % VN == 0 is guaranteed by create()
     for (int row = warp; row < P.M; row += nwarps) {
-      V acc; vzero(acc);
-      const unsigned int e0 = s_rowptr[row], e1 = s_rowptr[row + 1];
-      unsigned int e = e0;
-      for (; e + 1 < e1; e += 2) {                            // two independent LDS in flight
-        const V b0 = Bs[(size_t)s_col[e] * 32 + lane]; const V b1 = Bs[(size_t)s_col[e + 1] * 32 + lane];
-        vfma(acc, s_val[e], b0); vfma(acc, s_val[e + 1], b1);
+      V acc0, acc1; vzero(acc0); vzero(acc1);
+      unsigned int e = s_rowptr[row];
+      const unsigned int e1 = s_rowptr[row + 1];
+      for (; e + 4 <= e1; e += 4) {                           // 4 independent B loads in flight
+        const E t0 = s_ent[e], t1 = s_ent[e + 1], t2 = s_ent[e + 2], t3 = s_ent[e + 3];
+        const V b0 = *reinterpret_cast<const V*>(Bs + t0.off), b1 = *reinterpret_cast<const V*>(Bs + t1.off);
+        const V b2 = *reinterpret_cast<const V*>(Bs + t2.off), b3 = *reinterpret_cast<const V*>(Bs + t3.off);
+        vfma(acc0, t0.v, b0); vfma(acc1, t1.v, b1); vfma(acc0, t2.v, b2); vfma(acc1, t3.v, b3);
       }
-      if (e < e1) vfma(acc, s_val[e], Bs[(size_t)s_col[e] * 32 + lane]);
+      for (; e < e1; ++e) { const E t = s_ent[e]; vfma(acc0, t.v, *reinterpret_cast<const V*>(Bs + t.off)); }
+      vadd(acc0, acc1);
       if (in) {
-        V* dst = (V*)(Cg + (size_t)row * P.ldc + n0) + lane;
-        if (!P.beta0) { const V old = *dst; vadd(acc, old); }
-        *dst = acc;
+        V* dst = reinterpret_cast<V*>(Cg + (size_t)row * P.ldc + n0) + lane;
+        if (!P.beta0) { const V old = *dst; vadd(acc0, old); }
+        *dst = acc0;
       }
     }
     __syncthreads();                                          // strip consumed: its stage may be refilled
-    if (P.stages == 1 && warp == 0 && strip + step < nstrips) issue(strip + step, 0);
+    if (S == 1 && warp == 0 && strip + step < nstrips) issue(strip + step, 0);
   }
 }
 
 // fallback without shared-memory staging (very large K, or unaligned leading dimensions)
 template <typename T>
 __global__ void __launch_bounds__(256) sreg_direct_kernel(const SregParams P) {
-  const T* Bg = (const T*)P.b; T* Cg = (T*)P.c; const T* vals = (const T*)P.vals;
+  const T* Bg = (const T*)P.b; T* Cg = (T*)P.c; const SregEntry<T>* ent = (const SregEntry<T>*)P.entries;
   const long long total = (long long)P.M * P.N;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(e / P.N); const long long col = e % P.N;
     T acc = 0;
-    for (unsigned int z = P.rowptr[row]; z < P.rowptr[row + 1]; ++z) acc += vals[z] * Bg[(size_t)P.colidx[z] * P.ldb + col];
+    for (unsigned int z = P.rowptr[row]; z < P.rowptr[row + 1]; ++z) acc += ent[z].v * Bg[(size_t)(ent[z].off >> 9) * P.ldb + col];
     T* dst = Cg + (size_t)row * P.ldc + col;
     *dst = P.beta0 ? acc : (*dst + acc);
   }
@@ -275,16 +292,17 @@ int g_sreg_attr[2] = {0, 0};
 extern "C" int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_total) {
   SregParams P;
   P.M = d->m; P.K = d->k; P.N = n_total; P.ldb = d->ldb; P.ldc = d->ldc; P.nnz = d->nnz;
-  P.rowptr = d->d_ptr; P.colidx = d->d_idx; P.vals = d->d_val; P.b = b; P.c = c; P.beta0 = d->beta0; P.stages = 2;
+  P.rowptr = d->d_ptr; P.entries = d->d_val; P.b = b; P.c = c; P.beta0 = d->beta0; P.stages = 3;
   const bool f64 = (d->ta == LIBXSMM_DATATYPE_F64);
-  const size_t ts = f64 ? 8 : 4;
-  const size_t meta = (size_t)(d->m + 1) * 4 + (size_t)d->nnz * 4 + 16 + (size_t)d->nnz * ts + 16 + 64;
-  const size_t limit = 220 * 1024;
+  const size_t ts = f64 ? 8 : 4, es = f64 ? 16 : 8;
+  const size_t meta = 1024 + (size_t)d->nnz * es + (size_t)(d->m + 1) * 4 + 16;
+  const size_t limit = 226 * 1024;
   cudaStream_t stream = (cudaStream_t)xb_rt_stream();
   const bool aligned = ((uintptr_t)b % 16 == 0) && ((uintptr_t)c % 16 == 0) && ((d->ldb * ts) % 16 == 0) && ((d->ldc * ts) % 16 == 0)
                     && ((n_total * ts) % 16 == 0);
   if (n_total <= 0) return 0;
-  if ((size_t)2 * d->k * 512 + meta > limit) P.stages = 1;
+  { const char* e = getenv("LIBXSMM_B200_SREG_STAGES"); if (e != nullptr && *e) P.stages = atoi(e); }
+  while (P.stages > 1 && (size_t)P.stages * d->k * 512 + meta > limit) --P.stages;
   if (!aligned || (size_t)P.stages * d->k * 512 + meta > limit) {
     const long long total = (long long)d->m * n_total;
     long long grid = (total + 255) / 256; if (grid > num_sms() * 16) grid = num_sms() * 16;
@@ -295,12 +313,30 @@ extern "C" int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, l
   const size_t smem = (size_t)P.stages * d->k * 512 + meta;
   const long long strip = f64 ? 64 : 128;
   long long grid = (n_total + strip - 1) / strip; if (grid > num_sms()) grid = num_sms();
+  int warps = d->m < 4 ? 4 : (d->m > 32 ? 32 : d->m);      // one row per warp and pass
+  { const char* e = getenv("LIBXSMM_B200_SREG_WARPS"); if (e != nullptr && *e) warps = atoi(e); }
+  const int threads = warps * 32;
+  CUtensorMap map_b;
+  {
+    xb_encode_tiled_fn enc = xb_tma_encoder();
+    const cuuint64_t dims[2] = {(cuuint64_t)n_total, (cuuint64_t)d->k};
+    const cuuint64_t strides[1] = {(cuuint64_t)d->ldb * ts};
+    const cuuint32_t box[2] = {(cuuint32_t)strip, (cuuint32_t)(d->k < 256 ? d->k : 256)};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc == nullptr || (d->k > 256 && (d->k % 256) != 0) || CUDA_SUCCESS != enc(&map_b, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)b,
+          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) {
+      const long long total = (long long)d->m * n_total;
+      long long g2 = (total + 255) / 256; if (g2 > num_sms() * 16) g2 = num_sms() * 16;
+      if (f64) sreg_direct_kernel<double><<<(unsigned int)g2, 256, 0, stream>>>(P); else sreg_direct_kernel<float><<<(unsigned int)g2, 256, 0, stream>>>(P);
+      return check_launch("sreg_direct");
+    }
+  }
   if (f64) {
     if (!g_sreg_attr[1]) { cudaFuncSetAttribute(sreg_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_sreg_attr[1] = 1; }
-    sreg_kernel<double><<<(unsigned int)grid, 512, smem, stream>>>(P);
+    sreg_kernel<double><<<(unsigned int)grid, threads, smem, stream>>>(map_b, P);
   } else {
     if (!g_sreg_attr[0]) { cudaFuncSetAttribute(sreg_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_sreg_attr[0] = 1; }
-    sreg_kernel<float><<<(unsigned int)grid, 512, smem, stream>>>(P);
+    sreg_kernel<float><<<(unsigned int)grid, threads, smem, stream>>>(map_b, P);
   }
   return check_launch("sreg");
 }
