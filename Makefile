@@ -12,7 +12,7 @@ CSRC      := libxsmm_b200/csrc
 OBJDIR    := build/obj
 LIB       := libxsmm_b200/lib/libxsmm_b200.so
 HOST_C    := host_core.c host_thunks.c host_sparse.c host_meltw.c
-DEVICE_CU := runtime.cu gemm_simt.cu gemm_tc.cu sparse.cu meltw.cu
+DEVICE_CU := runtime.cu gemm_simt.cu gemm_tc.cu sparse.cu bcsc_tc.cu meltw.cu
 OBJS      := $(addprefix $(OBJDIR)/,$(HOST_C:.c=.o) $(DEVICE_CU:.cu=.o))
 REFDIR    ?= /root/reference
 
@@ -25,7 +25,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.c $(CSRC)/xb_internal.h $(CSRC)/xb_device.cuh include/l
 	@mkdir -p $(OBJDIR)
 	$(CC) $(CFLAGS) -Iinclude -x c -c $< -o $@
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/xb_internal.h $(CSRC)/xb_device.cuh include/libxsmm.h include/libxsmm_typedefs.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/xb_internal.h $(CSRC)/xb_device.cuh $(CSRC)/xb_tma.cuh include/libxsmm.h include/libxsmm_typedefs.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -Iinclude -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 

@@ -266,9 +266,9 @@ def also_fsspmdm(X, torch, pk, args, full=False):
             "config": {"workload": "configs[2]: fsspmdm f32 M=32 K=128 N=1e6 15% nnz beta=0; B+C = 640 MB per step (> L2)"}}
 
 
-def also_bcsc(X, torch, pk, args, full=False):
+def also_bcsc(X, torch, pk, args, full=False, mblocks=8192):
     import numpy as np
-    Mb, Kb, Nb, bk, bn, mblocks = 32, 512, 512, 32, 32, 8192
+    Mb, Kb, Nb, bk, bn = 32, 512, 512, 32, 32
     rng = np.random.default_rng(555)
     nbr, nbc = Kb // bk, Nb // bn
     keep = np.zeros(nbr * nbc, dtype=bool); keep[rng.permutation(nbr * nbc)[:nbr * nbc // 2]] = True

@@ -218,17 +218,16 @@ void xb_invoke_sparse(const xb_slot* s, const libxsmm_gemm_param* p) {
       unsigned int nnzb = 0;
       const void *a, *bv, *cp, *ri;
       if (nbc == 0 || colptr_h == NULL) break;
-      if (xb_rt_ptr_kind(colptr_h) == 1) { rc = xb_rt_memcpy(&nnzb, colptr_h + nbc, sizeof(nnzb)); }
-      else nnzb = colptr_h[nbc];
+      if (xb_rt_ptr_kind(colptr_h) != 1) nnzb = colptr_h[nbc];   /* device-resident pattern: count stays on the device (0 = unknown) */
       c_bytes = (size_t)d->m * nbc * d->bn * d->packed_width * tsc;
       a = xb_dev_in(p->a.primary, (size_t)d->m * d->k * d->packed_width * ts, &staged);
-      bv = xb_dev_in(p->b.primary, (size_t)nnzb * d->bk * d->bn * libxsmm_typesize((libxsmm_datatype)d->tb), &staged);
+      bv = (nnzb == 0) ? p->b.primary : xb_dev_in(p->b.primary, (size_t)nnzb * d->bk * d->bn * libxsmm_typesize((libxsmm_datatype)d->tb), &staged);
       cp = xb_dev_in(colptr_h, (size_t)(nbc + 1) * sizeof(unsigned int), &staged);
-      ri = xb_dev_in(p->b.tertiary, (size_t)(nnzb ? nnzb : 1) * sizeof(unsigned int), &staged);
+      ri = (nnzb == 0) ? p->b.tertiary : xb_dev_in(p->b.tertiary, (size_t)nnzb * sizeof(unsigned int), &staged);
       c_dev = p->c.primary;
       if (xb_rt_ptr_kind(p->c.primary) == 0) { c_host = p->c.primary; c_dev = xb_rt_scratch(c_bytes); if (c_dev && !d->beta0) xb_rt_upload(c_dev, c_host, c_bytes); staged = 1; }
       if (a == NULL || bv == NULL || cp == NULL || ri == NULL || c_dev == NULL) { rc = 2; break; }
-      rc = xb_bcsc_launch(d, a, bv, (const unsigned int*)cp, (const unsigned int*)ri, nbc, c_dev);
+      rc = xb_bcsc_launch(d, a, bv, (const unsigned int*)cp, (const unsigned int*)ri, nbc, nnzb, c_dev);
     } break;
     default: break;
   }

@@ -359,12 +359,16 @@ extern "C" int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const
   return check_launch("packed_sp");
 }
 
-extern "C" int xb_bcsc_tc_launch(const xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
-                                 const unsigned int* rowidx, unsigned long long n_blocks, void* c);
+extern "C" int xb_bcsc_tc_launch(xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
+                                 const unsigned int* rowidx, unsigned long long n_blocks, unsigned int nnzb, void* c);
 
 extern "C" int xb_bcsc_launch(const xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
-                              const unsigned int* rowidx, unsigned long long n_blocks, void* c)
+                              const unsigned int* rowidx, unsigned long long n_blocks, unsigned int nnzb, void* c)
 {
+  if (d->m > 0 && n_blocks > 0) {   // tensor-core kernel for the bf16 VNNI case; everything else: exact-order kernel below
+    const int rc = xb_bcsc_tc_launch(const_cast<xb_sparse_desc*>(d), a, b_vals, colptr, rowidx, n_blocks, nnzb, c);
+    if (rc >= 0) return rc;
+  }
   BcscParams Q;
   Q.M = d->packed_width; Q.K = d->k; Q.bk = d->bk; Q.bn = d->bn; Q.ta = d->ta; Q.tb = d->tb; Q.tc = d->tc;
   Q.beta0 = d->beta0; Q.trans_a = (d->flags & LIBXSMM_GEMM_FLAG_TRANS_A) != 0; Q.vnni_a = (d->flags & LIBXSMM_GEMM_FLAG_VNNI_A) != 0;

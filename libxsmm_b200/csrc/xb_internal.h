@@ -148,7 +148,7 @@ int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_
 int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const void* b, void* c, long long count,
                         long long stride_a, long long stride_b, long long stride_c);
 int xb_bcsc_launch(const xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
-                   const unsigned int* rowidx, unsigned long long n_blocks, void* c);
+                   const unsigned int* rowidx, unsigned long long n_blocks, unsigned int nnzb, void* c);
 
 /* ---- host runtime (host_core.c) ---------------------------------------------------------------- */
 xb_slot* xb_slot_of(const void* fnptr);    /* NULL if not one of our thunks */
