@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the LIBXSMM hot path on B200 (contract: one JSON line on stdout).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload brgemm|fsspmdm|bcsc]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload brgemm|fsspmdm|bcsc|sweep]
 
 Workload (BASELINE.json configs[1]): batched BRGEMM bf16 x bf16 -> f32, m=n=k=64, br=8 (stride mode),
 batch = 65536 independent tiles PER GPU with all operands unique ("mode S" of SURVEY.md 8d). One step is
@@ -35,6 +35,17 @@ BR = 8
 BATCH = 65536
 BF16, F32 = 2, 1
 FLAG_BETA_0 = 4
+WORKLOAD = ("configs[1]: batched BRGEMM bf16->f32 m=n=k=64 brcount=8 batch=65536 per GPU, stride-BR, beta=0, "
+            "mode S (all operands unique)")
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` captures (bytes)
+NCU_TRAFFIC = {"gemm_tc_kernel<64>": (9652.8e6, "profiles/r01_ncu_gemm_tc.txt"),
+               "sreg_kernel<float>": (622.2e6, "profiles/r01_ncu_sreg.txt"),
+               "bcsc_tc_kernel<32>": (None, "profiles/r01_ncu_bcsc_tc.txt")}
+
+
+def traffic(kernel):
+    t = NCU_TRAFFIC.get(kernel, (None, None))
+    return t[0]
 
 
 def peaks():
@@ -182,18 +193,21 @@ def run_ours(args):
             total_ms, per = time_steps(torch, step, args.steps, args.warmup, dist)
         launches = X.libxsmm_b200_launch_count() - launches0 - args.warmup
         X.check()
-        flops = 2.0 * M * N * K * BR * BATCH
+        from libxsmm_b200.shard import weak_batch
+        per_gpu, job_tiles = weak_batch(BATCH, world)      # batch is the only shard axis: every rank owns BATCH tiles, no collective
+        flops = 2.0 * M * N * K * BR * per_gpu
         bytes_alg = float(BATCH) * (sa + sb + sc)
         ms = total_ms / args.steps
         kern_ms = sorted(per)[len(per) // 2]
-        value = world * flops / (ms * 1e-3) / 1e9
+        value = (2.0 * M * N * K * BR * job_tiles) / (ms * 1e-3) / 1e9     # whole job; ms is the max over ranks
         ach = bytes_alg / (kern_ms * 1e-3) / 1e9
         out = {"metric": "batched BRGEMM GFLOP/s (bf16, m=n=k=64, br=8, batch=65536/GPU, unique operands)", "value": value, "unit": "GFLOP/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": "configs[1]: batched BRGEMM bf16->f32 m=n=k=64 brcount=8 batch=65536 per GPU, stride-BR, beta=0, mode S (all operands unique)",
+               "config": {"workload": WORKLOAD,
                           "batch_per_gpu": BATCH, "parallelism": "batch sharded, no collective", "l2_policy": "inputs (8.6 GB) larger than L2, no flush"},
-               "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic("gemm_tc_kernel<64>"),
+                            "traffic_src": NCU_TRAFFIC["gemm_tc_kernel<64>"][1], "algorithmic_bytes": bytes_alg,
                             "peak_src": pk["src"], "kernel": "gemm_tc_kernel<64>", "kernel_ms": kern_ms,
                             "tensor_frac_of_measured_bf16_peak": (flops / (kern_ms * 1e-3) / 1e12) / pk["bf16_tflops"]},
                "gpu_launches": int(launches), "clocks": clocks.summary()}
@@ -212,6 +226,8 @@ def run_ours(args):
         out = also_fsspmdm(X, torch, pk, args, full=True)
     elif args.workload == "bcsc":
         out = also_bcsc(X, torch, pk, args, full=True)
+    elif args.workload == "sweep":
+        out = sweep(X, torch, pk, args)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -262,7 +278,7 @@ def also_fsspmdm(X, torch, pk, args, full=False):
     X.libxsmm_fsspmdm_destroy(h)
     return {"metric": "fsspmdm GFLOP/s (f32 M=32 K=128 N=1e6, 15% nnz)", "value": 2.0 * nnz * Nf / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (sparse)",
             "dense_equiv_gflops": 2.0 * Mf * Kf * Nf / (ms * 1e-3) / 1e9, "ms_per_step": ms, "nnz": nnz,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel": "sreg_kernel<float>"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic("sreg_kernel<float>"), "algorithmic_bytes": bytes_alg, "kernel": "sreg_kernel<float>"},
             "config": {"workload": "configs[2]: fsspmdm f32 M=32 K=128 N=1e6 15% nnz beta=0; B+C = 640 MB per step (> L2)"}}
 
 
@@ -298,8 +314,44 @@ def also_bcsc(X, torch, pk, args, full=False, mblocks=8192):
     return {"metric": "BCSC spmm GFLOP/s dense-equivalent (bf16, M=32 N=K=512, 32x32 blocks, 50%, m_blocks=8192)",
             "value": 2.0 * Mb * mblocks * Nb * Kb / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (dense-equivalent)",
             "effective_gflops": 2.0 * Mb * mblocks * nnzb * bk * bn / (ms * 1e-3) / 1e9, "ms_per_step": ms,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel": "bcsc kernel"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic("bcsc_tc_kernel<32>"), "algorithmic_bytes": bytes_alg,
+                         "kernel": "bcsc_tc_kernel<32> (+ bcsc_prep_kernel, bcsc_pack_b_kernel: the timed call is all three launches)"},
             "config": {"workload": "configs[3] on one GPU: BCSC bf16 M=32 N=K=512 bk=bn=32 50% m_blocks=8192; A+C = 537 MB per step (> L2)"}}
+
+
+def sweep(X, torch, pk, args, batch=32768):
+    """configs[4]: int8 x int8 -> int32 (U8 x I8, VNNI4 A) and F16 x F16 -> F32, m=n=k in {8..128}, br=1, unique operands"""
+    I8, U8, I32, F16 = 12, 13, 8, 3
+    pts = []
+    for name, ta, tb, tcc, tcomp, flags, esz, csz in (("u8*i8->i32", U8, I8, I32, I32, FLAG_BETA_0 | X.GEMM_FLAG_VNNI_A, 1, 4),
+                                                       ("f16*f16->f32", F16, F16, F32, F32, FLAG_BETA_0, 2, 4)):
+        for m in (8, 16, 32, 64, 128):
+            shape = X.libxsmm_create_gemm_shape(m, m, m, m, m, m, ta, tb, tcc, tcomp)
+            kernel = X.libxsmm_dispatch_gemm(shape, flags, 0)
+            if not kernel:
+                pts.append({"type": name, "m": m, "error": "dispatch returned NULL"}); continue
+            a = torch.randint(0, 5, (batch * m * m * esz,), dtype=torch.uint8, device="cuda")
+            b = torch.randint(0, 5, (batch * m * m * esz,), dtype=torch.uint8, device="cuda")
+            if esz == 2:
+                a = (torch.randint(-5, 6, (batch * m * m,), device="cuda").float() / 10).half(); b = a.roll(7)
+            c = torch.empty(batch * m * m * csz, dtype=torch.uint8, device="cuda")
+            sa = sb = m * m * esz; sc = m * m * csz
+
+            def step():
+                rc = X.libxsmm_b200_gemm_batch_strided(kernel, a.data_ptr(), b.data_ptr(), c.data_ptr(), sa, sb, sc, 1, batch)
+                assert rc == 0, X.libxsmm_b200_last_error_string()
+            total_ms, per = time_steps(torch, step, max(5, args.steps // 2), 3)
+            X.check()
+            ms = sorted(per)[len(per) // 2]
+            bytes_alg = float(batch) * (sa + sb + sc)
+            ach = bytes_alg / (ms * 1e-3) / 1e9
+            pts.append({"type": name, "m": m, "gflops": 2.0 * m * m * m * batch / (ms * 1e-3) / 1e9, "ms": ms, "gbs": ach, "hbm_frac": ach / pk["hbm_gbs"],
+                        "backend": int(X.libxsmm_b200_kernel_backend(kernel)), "l2_note": "operands %.0f MB%s" % (bytes_alg / 1e6, "" if bytes_alg > 2.5e8 else " (fits L2: not an HBM number)")})
+    best = max((p for p in pts if "gflops" in p), key=lambda p: p["gflops"])
+    return {"metric": "mixed-precision sweep GFLOP/s (configs[4], diagonal m=n=k)", "value": best["gflops"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": 3, "higher_is_better": True, "dtype": "u8/i8->i32, f16->f32", "data": "synthetic",
+            "config": {"workload": "configs[4]: int8 and f16 GEMM m=n=k in {8,16,32,64,128}, batch=32768, br=1, beta=0, unique operands"},
+            "points": pts, "roofline": {"bound": "hbm", "achieved": best["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": best["hbm_frac"], "traffic": None}}
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
@@ -350,7 +402,8 @@ def run_reference(args):
                       "value": v, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": dt / (args.warmup + args.steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "bf16", "data": "synthetic",
-                      "config": {"workload": "configs[1] on the host CPU: each step a bounded sample (2048 tiles) of the batch, LIBXSMM JIT, OpenMP over tiles"},
+                      "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH,
+                                 "reference_arm": "host CPU: each step a bounded sample (2048 tiles) of the batch, LIBXSMM JIT through libxsmm_dispatch_brgemm, OpenMP over tiles"},
                       "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": base["cores"], "kind": "reference", "sample": base["sample"]},
                       "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
@@ -361,7 +414,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="brgemm", choices=["brgemm", "fsspmdm", "bcsc"])
+    ap.add_argument("--workload", default="brgemm", choices=["brgemm", "fsspmdm", "bcsc", "sweep"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

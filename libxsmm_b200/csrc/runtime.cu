@@ -54,10 +54,13 @@ int xb_rt_blocking(void) { return tls.blocking; }
 
 void xb_rt_note_error(int code, const char* where) {
   int expected = 0;
+  bool first = false;
   if (g_last_error.compare_exchange_strong(expected, code)) {
     snprintf(g_error_where, sizeof(g_error_where), "%s", where ? where : "?");
+    first = true;
   }
-  if (libxsmm_verbosity != 0) {
+  // handles return void (reference ABI): the first failure is always reported, there is no CPU path to fall back to
+  if (first || libxsmm_verbosity != 0) {
     fprintf(stderr, "LIBXSMM-B200 ERROR (%s): %s\n", where ? where : "?", cudaGetErrorString((cudaError_t)code));
   }
 }
