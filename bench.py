@@ -355,9 +355,22 @@ def sweep(X, torch, pk, args, batch=32768):
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core this process may run on.
+    Must run before the OpenMP runtime of oracle/_ref is loaded."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.setdefault("OMP_PROC_BIND", "false")
+    return n
+
+
 def cpu_baseline_brgemm(sample_tiles=4096, budget_s=12.0):
     """the reference's own JIT BRGEMM kernel over a bounded sample of the same batch, all host cores (OpenMP)"""
     import numpy as np
+    use_all_host_threads()
     from oracle_ffi import ref_lib, iarr
     if ref_lib is None:
         return {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libxsmm_ref.so missing"}

@@ -16,6 +16,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "xb_internal.h"
 #include "xb_device.cuh"
 
@@ -207,6 +208,165 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const xb_gemm_launch L, 
   }
 }
 
+
+// ---- 8-bit integer tiles: dp4a kernel ------------------------------------------------------------------------------
+// Integer sums wrap modulo 2^32 and are therefore exact in ANY order: the int8 paths need not follow the reference's
+// loop order to stay bit-identical (reference :1452-1683). One WARP per tile: the VNNI4 A words [k/4][m] and the
+// k-contiguous B words [n][k/4] of a 64-wide k chunk are staged in shared memory with coalesced 4-byte loads, every
+// lane keeps a TM x TN block of accumulators and issues one dp4a per (m, n, 4 k). HBM-bound by construction
+// (m*k + k*n + 4*m*n bytes per tile); 8 warps per CTA and several CTAs per SM hide the load latency.
+template <bool UA, bool UB> __device__ __forceinline__ unsigned int dp4a_x(unsigned int a, unsigned int b, unsigned int c) {
+  unsigned int d;
+  if (UA && UB) asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  else if (UA && !UB) asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  else if (!UA && UB) asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  else asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+constexpr int I8_WARPS = 16, I8_KC = 64;   // warps per CTA, k bytes per staged chunk
+
+__device__ __forceinline__ void group_sync(int wpt, int group) {
+  if (wpt == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "r"(wpt * 32) : "memory");
+}
+
+// WPT warps share one tile: each owns one (LM*TM) x (LN*TN) block of C and keeps it in registers over the whole k loop;
+// the group stages the operand chunk once. 16/WPT tiles are in flight per CTA.
+template <int TM, int TN, bool UA, bool UB>
+__global__ void __launch_bounds__(I8_WARPS * 32, 2) gemm_i8_kernel(const xb_gemm_launch L, const int to_f32, const int wpt, const int smem_words_per_group) {
+  constexpr int LM = 8, LN = 4;                       // lanes along m and n
+  extern __shared__ unsigned int smem_i8[];
+  const xb_gemm_desc& d = L.d;
+  const int m = d.m, n = d.n, kq_all = d.k >> 2;
+  const long long lda = d.lda, ldb = d.ldb, ldc = d.ldc;
+  const bool beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = I8_WARPS / wpt, group = warp / wpt, wg = warp % wpt, gtid = wg * 32 + lane, gsize = wpt * 32;
+  const int lm = lane % LM, ln = lane / LM;
+  const int passes_m = (m + LM * TM - 1) / (LM * TM);
+  const int m0 = (wg % passes_m) * (LM * TM), n0 = (wg / passes_m) * (LN * TN);   // this warp's block (may be empty: n0 >= n)
+  const int kcq = (kq_all < I8_KC / 4) ? kq_all : I8_KC / 4;      // words of k per chunk
+  // both panels are stored k-group-major ([q][m] and [q][n]) so that a lane's TM / TN operands are contiguous (128-bit shared
+  // loads); row strides are 4 * odd words: 16-byte aligned, and the transposing B fill spreads over the banks
+  const int ms = (((m + 3) >> 2) | 1) << 2, ns = (((n + 3) >> 2) | 1) << 2;
+  unsigned int* sa = smem_i8 + (size_t)group * smem_words_per_group;   // [kcq][ms]
+  unsigned int* sb = sa + (size_t)kcq * ms;                            // [kcq][ns]
+  const long long ntiles_rounded = ((L.count + (long long)gridDim.x * groups - 1) / ((long long)gridDim.x * groups)) * ((long long)gridDim.x * groups);
+  for (long long t = (long long)blockIdx.x * groups + group; t < ntiles_rounded; t += (long long)gridDim.x * groups) {
+    const bool live = t < L.count;                    // dead iterations only keep the group barriers balanced
+    TileCtx x; if (live) resolve_tile(L, t, x); else { x.br = 0; }
+    unsigned int acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0u;
+    if (live) for (unsigned long long r = 0; r < x.br; ++r) {
+      const char *pa, *pb; br_ptrs(d, x, r, 1, 1, pa, pb);
+      for (int q0 = 0; q0 < kq_all; q0 += kcq) {
+        const int qn = (kq_all - q0 < kcq) ? (kq_all - q0) : kcq;
+        group_sync(wpt, group);                        // previous chunk fully consumed
+        for (int e = gtid; e < qn * m; e += gsize) {   // A words: rows of m contiguous words
+          const int q = e / m, i = e - q * m;
+          sa[q * ms + i] = reinterpret_cast<const unsigned int*>(pa + ((long long)(q0 + q) * lda) * 4)[i];
+        }
+        for (int e = gtid; e < n * qn; e += gsize) {   // B words: rows of qn contiguous words
+          const int jn = e / qn, q = e - jn * qn;
+          sb[q * ns + jn] = reinterpret_cast<const unsigned int*>(pb + (long long)jn * ldb + (long long)q0 * 4)[q];
+        }
+        group_sync(wpt, group);
+        if (n0 < n) for (int q = 0; q < qn; ++q) {
+          unsigned int av[TM], bv[TN];
+          if (TM == 4) {   // operands beyond m / n are padding words of the row (never stored to C)
+            const uint4 a4 = *reinterpret_cast<const uint4*>(sa + q * ms + m0 + lm * 4);
+            const uint4 b0 = *reinterpret_cast<const uint4*>(sb + q * ns + n0 + ln * 8), b1 = *reinterpret_cast<const uint4*>(sb + q * ns + n0 + ln * 8 + 4);
+            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3 % TM] = a4.w;
+            bv[0] = b0.x; bv[1] = b0.y; bv[2 % TN] = b0.z; bv[3 % TN] = b0.w; bv[4 % TN] = b1.x; bv[5 % TN] = b1.y; bv[6 % TN] = b1.z; bv[7 % TN] = b1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < TM; ++i) { const int mi = m0 + lm * TM + i; av[i] = (mi < m) ? sa[q * ms + mi] : 0u; }
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { const int nj = n0 + ln * TN + j; bv[j] = (nj < n) ? sb[q * ns + nj] : 0u; }
+          }
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = dp4a_x<UA, UB>(av[i], bv[j], acc[i][j]);
+        }
+      }
+    }
+    if (live && TM == 4 && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(x.c) & 15) == 0 && m0 + lm * 4 + 3 < m) {
+      // four consecutive rows per lane: 16-byte accesses, 8 lanes cover 128 contiguous bytes of a C column
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int nj = n0 + ln * TN + j;
+        if (nj < n) {
+          const long long ci = (long long)nj * ldc + m0 + lm * 4;
+          if (!to_f32) {
+            uint4 v = make_uint4(acc[0][j], acc[1 % TM][j], acc[2 % TM][j], acc[3 % TM][j]);
+            if (!beta0) { const uint4 o = *reinterpret_cast<const uint4*>(reinterpret_cast<const int*>(x.c) + ci); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *reinterpret_cast<uint4*>(reinterpret_cast<int*>(x.c) + ci) = v;
+          } else {
+            float4 f = make_float4(__fmul_rn((float)(int)acc[0][j], x.scf), __fmul_rn((float)(int)acc[1 % TM][j], x.scf),
+                                   __fmul_rn((float)(int)acc[2 % TM][j], x.scf), __fmul_rn((float)(int)acc[3 % TM][j], x.scf));
+            if (!beta0) { const float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x.c) + ci);
+                          f.x = __fadd_rn(f.x, o.x); f.y = __fadd_rn(f.y, o.y); f.z = __fadd_rn(f.z, o.z); f.w = __fadd_rn(f.w, o.w); }
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(x.c) + ci) = f;
+          }
+        }
+      }
+    } else if (live) {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int nj = n0 + ln * TN + j;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          const int mi = m0 + lm * TM + i;
+          if (mi < m && nj < n) {
+            const long long ci = (long long)nj * ldc + mi;
+            if (!to_f32) {
+              unsigned int v = acc[i][j];
+              if (!beta0) v += (unsigned int)reinterpret_cast<const int*>(x.c)[ci];
+              reinterpret_cast<int*>(x.c)[ci] = (int)v;
+            } else {                                               // reference :1579-1585
+              float f = __fmul_rn((float)(int)acc[i][j], x.scf);
+              if (!beta0) f = __fadd_rn(f, reinterpret_cast<const float*>(x.c)[ci]);
+              reinterpret_cast<float*>(x.c)[ci] = f;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// host side: is the dp4a kernel applicable? (VNNI4 A, whole words everywhere, strided or single-tile launch)
+bool i8_fast_ok(const xb_gemm_launch& L, int path) {
+  const xb_gemm_desc& d = L.d;
+  if (path != P_I8_I32 && path != P_I8_F32) return false;
+  if (path == P_I8_I32 && (d.flags & LIBXSMM_GEMM_FLAG_VNNI_A) == 0) return false;    // flat A: bytes of 4 different rows per word
+  if ((d.k & 3) != 0 || (d.ldb & 3) != 0 || d.m > 1024 || d.n > 1024) return false;
+  if (L.recs != nullptr || d.br_type == 1 || d.br_type == 2) return false;            // per-tile pointers are not checkable on the host
+  const bool single = (L.a == nullptr && L.c == nullptr);
+  const uintptr_t a = (uintptr_t)(single ? L.one.a : L.a), b = (uintptr_t)(single ? L.one.b : L.b), c = (uintptr_t)(single ? L.one.c : L.c);
+  if (((a | b | c) & 3) != 0) return false;
+  if (!single && (((L.tile_stride_a | L.tile_stride_b | L.tile_stride_c) & 3) != 0)) return false;
+  if (d.br_type == 3 && (((d.br_stride_a | d.br_stride_b) & 3) != 0)) return false;
+  return true;
+}
+
+template <int TM, int TN>
+cudaError_t launch_i8(const xb_gemm_launch& L, int path, int wpt, int words_per_group, size_t smem, unsigned int grid, cudaStream_t st) {
+  const bool ua = (L.d.ta == LIBXSMM_DATATYPE_U8), ub = (L.d.tb == LIBXSMM_DATATYPE_U8);
+  const int to_f32 = (path == P_I8_F32);
+#define XB_I8_CASE(A, B) do { \
+    static int attr_set = 0; \
+    if (!attr_set) { cudaFuncSetAttribute(gemm_i8_kernel<TM, TN, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = 1; } \
+    gemm_i8_kernel<TM, TN, A, B><<<grid, I8_WARPS * 32, smem, st>>>(L, to_f32, wpt, words_per_group); } while (0)
+  if (ua && ub) XB_I8_CASE(true, true); else if (ua) XB_I8_CASE(true, false); else if (ub) XB_I8_CASE(false, true); else XB_I8_CASE(false, false);
+#undef XB_I8_CASE
+  return cudaGetLastError();
+}
 }  // namespace
 
 extern "C" int xb_gemm_simt_supported(const xb_gemm_desc* d) { return xb_path_of(*d) != P_NONE; }
@@ -215,6 +375,33 @@ extern "C" int xb_gemm_simt_launch(const xb_gemm_launch* L) {
   const int path = xb_path_of(L->d);
   if (path == P_NONE) return 1;
   if (L->count <= 0) return 0;
+  if (i8_fast_ok(*L, path) && getenv("LIBXSMM_B200_I8_EXACT_ORDER") == nullptr) {
+    const int small = (L->d.m < L->d.n) ? L->d.m : L->d.n;
+    const int tm = (small >= 32) ? 4 : ((small >= 16) ? 2 : 1), tn = 2 * tm;           // lane block; a warp covers 8*tm x 4*tn of C
+    const int passes = ((L->d.m + 8 * tm - 1) / (8 * tm)) * ((L->d.n + 4 * tn - 1) / (4 * tn));
+    int wpt = 1; while (wpt < passes) wpt *= 2;                                        // warps per tile: 1, 2, 4, 8 or 16
+    const int kcq = (L->d.k / 4 < I8_KC / 4) ? L->d.k / 4 : I8_KC / 4;
+    // panels [kcq][ms] + [kcq][ns] (+ slack: a 4x8 lane block may read up to 31 padding words past the last row)
+    const int words = kcq * (((((L->d.m + 3) >> 2) | 1) << 2) + ((((L->d.n + 3) >> 2) | 1) << 2)) + 64;
+    const int groups = I8_WARPS / (wpt > I8_WARPS ? I8_WARPS : wpt);
+    const size_t smem = (size_t)words * 4 * groups;
+    if (wpt <= I8_WARPS && smem <= 200 * 1024) {
+      static int sms = 0;
+      if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+      const long long ctas_needed = (L->count + groups - 1) / groups;
+      long long per_sm = (long long)((220 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 2) per_sm = 2;   // 64 registers x 512 threads: two CTAs per SM
+      long long grid = (long long)sms * per_sm;
+      if (grid > ctas_needed) grid = ctas_needed;
+      cudaStream_t st = (cudaStream_t)xb_rt_stream();
+      cudaError_t e;
+      if (tm == 4) e = launch_i8<4, 8>(*L, path, wpt, words, smem, (unsigned int)grid, st);
+      else if (tm == 2) e = launch_i8<2, 4>(*L, path, wpt, words, smem, (unsigned int)grid, st);
+      else e = launch_i8<1, 2>(*L, path, wpt, words, smem, (unsigned int)grid, st);
+      xb_rt_count_launch();
+      if (e != cudaSuccess) { xb_rt_note_error((int)e, "gemm_i8"); return (int)e; }
+      return 0;
+    }
+  }
   const long long grid = L->count < (1 << 20) ? L->count : (1 << 20);
   gemm_simt_kernel<<<(unsigned int)grid, 256, 0, (cudaStream_t)xb_rt_stream()>>>(*L, path);
   xb_rt_count_launch();

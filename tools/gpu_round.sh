@@ -2,7 +2,7 @@
 # executed on the GPU box through gpurun; everything interesting lands in gpurun_out/
 mkdir -p gpurun_out
 echo "=== smoke"; timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
-for f in test_gemm_gpu test_sparse_gpu test_meltw_gpu; do
+for f in test_gemm_gpu test_sparse_gpu test_meltw_gpu test_golden; do
   echo "=== $f"; timeout -s KILL 600 python -m pytest tests/$f.py -m gpu -q -x > gpurun_out/$f.log 2>&1; echo "$f rc=$?"; tail -6 gpurun_out/$f.log
 done
 echo "=== bench"; timeout -s KILL 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
