@@ -480,8 +480,17 @@ LIBXSMM_API int libxsmm_b200_gemm_batch_strided(libxsmm_gemmfunction kernel, con
   if (s == NULL || count < 0) return -1;
   if (s->u.gemm.br_type == 1) return -2;   /* address mode needs per-tile arrays: use libxsmm_b200_gemm_batch */
   if (count == 0) return 0;
-  if (xb_rt_ptr_kind(a) == 0 || xb_rt_ptr_kind(b) == 0 || xb_rt_ptr_kind(c) == 0) {
-    return xb_gemm_batch_strided_host(s, a, b, c, stride_a, stride_b, stride_c, br_count, count);
+  {
+    const int ka = xb_rt_ptr_kind(a), kb = xb_rt_ptr_kind(b), kc = xb_rt_ptr_kind(c);
+    const char* zc = getenv("LIBXSMM_B200_ZEROCOPY");
+    const int zero_copy = (zc != NULL && zc[0] == '1');       /* pinned memory is device-accessible: optional in-place access */
+    const int host = (ka == 0 || kb == 0 || kc == 0) || (!zero_copy && (ka == 3 || kb == 3 || kc == 3));
+    if (host) {
+      if ((ka == 0 || ka == 3) && (kb == 0 || kb == 3) && (kc == 0 || kc == 3)) {
+        return xb_gemm_batch_strided_host(s, a, b, c, stride_a, stride_b, stride_c, br_count, count);
+      }
+      if (ka == 0 || kb == 0 || kc == 0) return -4;            /* mixed pageable-host / device operands: not supported in one call */
+    }
   }
   memset(&L, 0, sizeof(L));
   L.d = s->u.gemm; L.count = count;
@@ -492,46 +501,59 @@ LIBXSMM_API int libxsmm_b200_gemm_batch_strided(libxsmm_gemmfunction kernel, con
   return rc;
 }
 
+typedef struct xb_hostbatch {
+  const xb_gemm_desc* d; const char* a; const char* b; char* c;
+  long long sa, sb, sc, chunk, count; unsigned long long br;
+  size_t fa, fb, fc; int copy_c_in;
+} xb_hostbatch;
+
+static void xb_hostbatch_describe(void* ctx, long long i, xb_pipe_chunk* ch) {
+  const xb_hostbatch* h = (const xb_hostbatch*)ctx;
+  const long long t0 = i * h->chunk, nt = (h->count - t0 < h->chunk) ? (h->count - t0) : h->chunk;
+  ch->first = t0; ch->count = nt;
+  ch->host_a = h->a + t0 * h->sa; ch->host_b = h->b + t0 * h->sb; ch->host_c = h->c + t0 * h->sc;
+  ch->bytes_a = (size_t)(nt - 1) * (size_t)h->sa + h->fa; ch->bytes_b = (size_t)(nt - 1) * (size_t)h->sb + h->fb;
+  ch->bytes_c = (size_t)(nt - 1) * (size_t)h->sc + h->fc; ch->copy_c_in = h->copy_c_in;
+}
+
+static int xb_hostbatch_launch(void* ctx, const xb_pipe_chunk* ch, void* da, void* db, void* dc) {
+  const xb_hostbatch* h = (const xb_hostbatch*)ctx;
+  xb_gemm_launch L;
+  memset(&L, 0, sizeof(L));
+  L.d = *h->d; L.count = ch->count; L.a = da; L.b = db; L.c = dc;
+  L.tile_stride_a = h->sa; L.tile_stride_b = h->sb; L.tile_stride_c = h->sc; L.br = (h->d->br_type == 0) ? 1ull : h->br;
+  return xb_run_gemm_launch(&L);
+}
+
 static int xb_gemm_batch_strided_host(const xb_slot* s, const void* a, const void* b, void* c,
   long long sa, long long sb, long long sc, unsigned long long br, long long count)
 {
-  /* the batch is cut into chunks so that copies of chunk i+1 overlap the kernel of chunk i on the
-   * device's copy engines; every chunk is a dense range of tiles, which requires the tile strides to
-   * cover the tile footprint (checked: positive strides). */
+  /* the batch is cut into chunks that flow through xb_rt_pipeline: the copies of chunk i+1 (H2D) and of chunk i-1 (D2H)
+   * overlap the kernel of chunk i. Every chunk is a dense range of tiles, which requires the tile strides to cover the
+   * tile footprint (checked: positive strides). Returns when C is valid in host memory. */
   const xb_gemm_desc* d = &s->u.gemm;
   const size_t tsa = libxsmm_typesize((libxsmm_datatype)d->ta), tsb = libxsmm_typesize((libxsmm_datatype)d->tb);
   const size_t tsc = libxsmm_typesize((libxsmm_datatype)d->tc);
-  size_t fa = xb_extent_a(d) * tsa, fb = xb_extent_b(d) * tsb;
-  const size_t fc = ((size_t)(d->n - 1) * d->ldc + d->m) * tsc;
-  long long chunk, t0;
-  int rc = 0;
+  xb_hostbatch h;
+  long long nchunks;
   if (sa <= 0 || sb <= 0 || sc <= 0 || d->br_type == 2) return -3;
-  if (d->br_type == 3 && br > 0) { fa += (size_t)(br - 1) * (size_t)d->br_stride_a; fb += (size_t)(br - 1) * (size_t)d->br_stride_b; }
+  memset(&h, 0, sizeof(h));
+  h.d = d; h.a = (const char*)a; h.b = (const char*)b; h.c = (char*)c; h.sa = sa; h.sb = sb; h.sc = sc; h.br = br; h.count = count;
+  h.fa = xb_extent_a(d) * tsa; h.fb = xb_extent_b(d) * tsb; h.fc = ((size_t)(d->n - 1) * d->ldc + d->m) * tsc;
+  if (d->br_type == 3 && br > 0) { h.fa += (size_t)(br - 1) * (size_t)d->br_stride_a; h.fb += (size_t)(br - 1) * (size_t)d->br_stride_b; }
+  h.copy_c_in = ((d->flags & LIBXSMM_GEMM_FLAG_BETA_0) == 0 || (size_t)sc != h.fc) ? 1 : 0;
   {
     const size_t per_tile = (size_t)sa + (size_t)sb + (size_t)sc;
-    const size_t budget = (size_t)768 << 20;      /* device staging budget per chunk */
-    chunk = (long long)(budget / (per_tile ? per_tile : 1));
-    if (chunk < 1) chunk = 1;
-    if (chunk > count) chunk = count;
+    size_t budget = (size_t)128 << 20;            /* staging bytes per chunk: small enough to overlap, large enough to amortise launches */
+    const char* e = getenv("LIBXSMM_B200_CHUNK_MB");
+    if (e != NULL && atoi(e) > 0) budget = (size_t)atoi(e) << 20;
+    h.chunk = (long long)(budget / (per_tile ? per_tile : 1));
+    if (h.chunk < 1) h.chunk = 1;
+    if (h.chunk > count) h.chunk = count;
   }
-  for (t0 = 0; t0 < count && rc == 0; t0 += chunk) {
-    const long long nt = (count - t0 < chunk) ? (count - t0) : chunk;
-    const size_t ba = (size_t)(nt - 1) * (size_t)sa + fa, bb = (size_t)(nt - 1) * (size_t)sb + fb, bc = (size_t)(nt - 1) * (size_t)sc + fc;
-    void* da = xb_rt_scratch(ba); void* db = xb_rt_scratch(bb); void* dc = xb_rt_scratch(bc);
-    xb_gemm_launch L;
-    if (da == NULL || db == NULL || dc == NULL) { rc = 2; break; }
-    xb_rt_memcpy_async(da, (const char*)a + t0 * sa, ba);
-    xb_rt_memcpy_async(db, (const char*)b + t0 * sb, bb);
-    if ((d->flags & LIBXSMM_GEMM_FLAG_BETA_0) == 0 || (size_t)sc != fc) xb_rt_memcpy_async(dc, (const char*)c + t0 * sc, bc);
-    memset(&L, 0, sizeof(L));
-    L.d = *d; L.count = nt; L.a = da; L.b = db; L.c = dc;
-    L.tile_stride_a = sa; L.tile_stride_b = sb; L.tile_stride_c = sc; L.br = (d->br_type == 0) ? 1ull : br;
-    rc = xb_run_gemm_launch(&L);
-    if (rc == 0) rc = xb_rt_memcpy_async((char*)c + t0 * sc, dc, bc);
-    if (rc == 0) rc = xb_rt_sync();
-    xb_rt_scratch_reset();
-  }
-  return rc;
+  nchunks = (count + h.chunk - 1) / h.chunk;
+  return xb_rt_pipeline(nchunks, (size_t)(h.chunk - 1) * (size_t)sa + h.fa, (size_t)(h.chunk - 1) * (size_t)sb + h.fb,
+                        (size_t)(h.chunk - 1) * (size_t)sc + h.fc, xb_hostbatch_describe, xb_hostbatch_launch, &h);
 }
 
 struct libxsmm_b200_gemm_plan {

@@ -133,6 +133,74 @@ int xb_rt_ptr_kind(const void* p) {
   }
 }
 
+// ---- chunked host <-> device pipeline ------------------------------------------------------------------------------
+// Host-resident batches are cut into chunks that flow through three streams (H2D copy, kernel, D2H copy) over two sets
+// of staging buffers, so that the copy engines run in both PCIe directions while the kernel of the previous chunk executes.
+namespace {
+struct Pipe {
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t in_done[2] = {nullptr, nullptr}, k_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+  char* buf[2] = {nullptr, nullptr}; size_t cap = 0;
+  int device = -1;
+};
+thread_local Pipe xb_pipe_state;
+bool xb_pipe_setup(size_t bytes_per_slot) {
+  int dev = 0; cudaGetDevice(&dev);
+  if (xb_pipe_state.device != dev) {             // first use on this thread / device change: (re)create streams and events
+    xb_pipe_state = Pipe(); xb_pipe_state.device = dev;
+    if (cudaStreamCreateWithFlags(&xb_pipe_state.s_in, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&xb_pipe_state.s_k, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&xb_pipe_state.s_out, cudaStreamNonBlocking) != cudaSuccess) return false;
+    for (int i = 0; i < 2; ++i) {
+      if (cudaEventCreateWithFlags(&xb_pipe_state.in_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&xb_pipe_state.k_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&xb_pipe_state.out_done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+  }
+  if (xb_pipe_state.cap < bytes_per_slot) {
+    for (int i = 0; i < 2; ++i) { if (xb_pipe_state.buf[i]) cudaFree(xb_pipe_state.buf[i]); xb_pipe_state.buf[i] = nullptr; }
+    xb_pipe_state.cap = 0;
+    for (int i = 0; i < 2; ++i) if (cudaMalloc((void**)&xb_pipe_state.buf[i], bytes_per_slot) != cudaSuccess) return false;
+    xb_pipe_state.cap = bytes_per_slot;
+  }
+  return true;
+}
+}  // namespace
+
+int xb_rt_pipeline(long long nchunks, size_t max_a, size_t max_b, size_t max_c, xb_pipe_describe_fn describe, xb_pipe_launch_fn launch, void* ctx) {
+  const size_t oa = 0, ob = (max_a + 255) & ~(size_t)255, oc = ob + ((max_b + 255) & ~(size_t)255);
+  const size_t per_slot = oc + ((max_c + 255) & ~(size_t)255);
+  if (!xb_pipe_setup(per_slot)) { xb_rt_note_error((int)cudaGetLastError(), "pipeline"); return 2; }
+  cudaStream_t user = tls.stream;
+  cudaError_t e = cudaStreamSynchronize(user);         // everything the caller queued before this call
+  int rc = 0;
+  for (long long i = 0; i < nchunks && e == cudaSuccess && rc == 0; ++i) {
+    const int s = (int)(i & 1);
+    xb_pipe_chunk ch; describe(ctx, i, &ch);
+    char* da = xb_pipe_state.buf[s] + oa; char* db = xb_pipe_state.buf[s] + ob; char* dc = xb_pipe_state.buf[s] + oc;
+    if (i >= 2) e = cudaStreamWaitEvent(xb_pipe_state.s_in, xb_pipe_state.out_done[s], 0);     // slot free again (its result left the device)
+    if (e == cudaSuccess && ch.bytes_a) e = cudaMemcpyAsync(da, ch.host_a, ch.bytes_a, cudaMemcpyHostToDevice, xb_pipe_state.s_in);
+    if (e == cudaSuccess && ch.bytes_b) e = cudaMemcpyAsync(db, ch.host_b, ch.bytes_b, cudaMemcpyHostToDevice, xb_pipe_state.s_in);
+    if (e == cudaSuccess && ch.copy_c_in && ch.bytes_c) e = cudaMemcpyAsync(dc, ch.host_c, ch.bytes_c, cudaMemcpyHostToDevice, xb_pipe_state.s_in);
+    if (e == cudaSuccess) e = cudaEventRecord(xb_pipe_state.in_done[s], xb_pipe_state.s_in);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(xb_pipe_state.s_k, xb_pipe_state.in_done[s], 0);
+    if (e != cudaSuccess) break;
+    tls.stream = xb_pipe_state.s_k;
+    rc = launch(ctx, &ch, da, db, dc);
+    tls.stream = user;
+    if (rc != 0) break;
+    e = cudaEventRecord(xb_pipe_state.k_done[s], xb_pipe_state.s_k);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(xb_pipe_state.s_out, xb_pipe_state.k_done[s], 0);
+    if (e == cudaSuccess && ch.bytes_c) e = cudaMemcpyAsync(ch.host_c, dc, ch.bytes_c, cudaMemcpyDeviceToHost, xb_pipe_state.s_out);
+    if (e == cudaSuccess) e = cudaEventRecord(xb_pipe_state.out_done[s], xb_pipe_state.s_out);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(xb_pipe_state.s_in); if (e == cudaSuccess) e = e2;
+  e2 = cudaStreamSynchronize(xb_pipe_state.s_k); if (e == cudaSuccess) e = e2;
+  e2 = cudaStreamSynchronize(xb_pipe_state.s_out); if (e == cudaSuccess) e = e2;
+  if (e != cudaSuccess) { xb_rt_note_error((int)e, "pipeline"); return (int)e; }
+  return rc;
+}
+
 void* xb_rt_scratch(size_t bytes) {
   bytes = (bytes + 255) & ~(size_t)255;
   if (tls.scratch_used + bytes <= tls.scratch_cap) {

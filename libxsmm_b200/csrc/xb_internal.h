@@ -123,6 +123,17 @@ void* xb_rt_managed_malloc(size_t size);
 void xb_rt_managed_free(void* p);
 int xb_rt_memcpy(void* dst, const void* src, size_t size);           /* blocking, any direction */
 int xb_rt_memcpy_async(void* dst, const void* src, size_t size);     /* on the thread's stream */
+/* chunked host<->device pipeline (three streams, two staging slots); `launch` runs with the thread's stream switched
+ * to the pipeline's compute stream and must only enqueue work */
+typedef struct xb_pipe_chunk {
+  const void* host_a; const void* host_b; void* host_c;
+  size_t bytes_a, bytes_b, bytes_c;
+  int copy_c_in;               /* C is read by the kernel (beta = 1, or gaps between tiles that must survive) */
+  long long first, count;      /* units of the batch in this chunk */
+} xb_pipe_chunk;
+typedef void (*xb_pipe_describe_fn)(void* ctx, long long index, xb_pipe_chunk* out);
+typedef int (*xb_pipe_launch_fn)(void* ctx, const xb_pipe_chunk* chunk, void* dev_a, void* dev_b, void* dev_c);
+int xb_rt_pipeline(long long nchunks, size_t max_a, size_t max_b, size_t max_c, xb_pipe_describe_fn describe, xb_pipe_launch_fn launch, void* ctx);
 int xb_rt_upload(void* dst_dev, const void* src_host, size_t size);  /* stream ordered from pageable */
 /* 0: host (unregistered / pageable), 1: device, 2: managed, 3: pinned host */
 int xb_rt_ptr_kind(const void* p);

@@ -133,3 +133,32 @@ def test_int8_full_size_linearity_property():
         assert X.libxsmm_b200_gemm_batch_strided(kernel, d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(), case.size_a, case.size_b, case.size_c * 4, 1, count) == 0
         outs.append(host(d_c, np.int32))
     assert np.array_equal(outs[0] + outs[1], outs[2])
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_resident_batch_goes_through_the_copy_pipeline(pinned, monkeypatch):
+    """libxsmm_b200_gemm_batch_strided with HOST buffers (the e2e path of bench.py): chunks of the batch are staged through
+    three streams; many small chunks (1 MB) exercise slot reuse; beta=1 needs C copied in as well."""
+    monkeypatch.setenv("LIBXSMM_B200_CHUNK_MB", "1")
+    for (t, beta0, count) in (((gen.BF16, gen.BF16, gen.F32, gen.F32), 1, 150), ((gen.BF16, gen.BF16, gen.F32, gen.BF16), 0, 90),
+                              ((gen.U8, gen.I8, gen.I32, gen.I32), 0, 70)):
+        flags = (cases.FLAG_BETA_0 if beta0 else 0) | (cases.FLAG_VNNI_A if t[0] == gen.U8 else 0)
+        case = cases.GemmCase(64, 64, 64, *t, flags=flags, br_type=3, br=4)
+        ops = cases.Operands(case, seed=31, count=count)
+        kernel = dispatch(case, ops)
+        assert kernel
+        want = cases.ref_result(oracle, case, ops, run_gemm)
+        if pinned:
+            ha, hb, hc = (torch.from_numpy(x.view(np.uint8).copy()).pin_memory() for x in (ops.a, ops.b, ops.c0))
+            pa, pb, pc = ha.data_ptr(), hb.data_ptr(), hc.data_ptr()
+        else:
+            ha, hb, hc = ops.a.copy(), ops.b.copy(), ops.c0.copy()
+            pa, pb, pc = ha.ctypes.data, hb.ctypes.data, hc.ctypes.data
+        rc = X.libxsmm_b200_gemm_batch_strided(kernel, pa, pb, pc, ops.tile_a, ops.tile_b, ops.tile_c, case.br, count)
+        assert rc == 0, X.libxsmm_b200_last_error_string()
+        X.check()
+        got = hc.numpy().view(gen.NP_OF[case.tc]) if pinned else hc
+        if case.tc == gen.I32:
+            assert np.array_equal(got, want)
+        else:
+            assert gen.normf_rel(gen.to_f64(want, case.tc), gen.to_f64(got, case.tc)) <= (1.2e-5 if case.tc == gen.F32 else 5e-3)
