@@ -329,14 +329,20 @@ extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
   P.np = (UM == 64) ? ((d.n + 7) & ~7) : ((d.n + 15) & ~15);
   P.kchunks = (d.k + 63) / 64;
   P.a_bytes = UM * 128; P.stage_bytes = P.a_bytes + P.np * 128;
-  // several independent (producer, MMA, epilogue) pipelines per SM hide each other's serial phases: measured on
-  // B200 (64^3 x 8 bf16, streaming): 1 CTA/SM 77%, 2 CTAs/SM 105% of the copy-measured HBM peak.
-  int ctas = env_int("LIBXSMM_B200_TC_CTAS", 2); if (ctas < 1) ctas = 1; if (ctas > 4) ctas = 4;
+  // several independent (producer, MMA, epilogue) pipelines per SM hide each other's serial phases. Measured on B200:
+  // 64^3 x 8 bf16 streaming: 1 CTA/SM 77%, 2 CTAs/SM 105% of the copy-measured HBM peak (4 CTAs: 102%);
+  // f16 64^3 br=1: 2 CTAs 43%, 4 CTAs 83%; 128^3 br=1: 41% -> 60%. Tiles with few stage loads are latency-bound per
+  // tile, so they get more co-resident CTAs (registers cap this at 6 x 192 threads).
+  const long long loads_per_tile = (long long)P.kchunks * (long long)br;
   P.slot_cols = (P.np + 31) & ~31;
-  while (ctas > 1 && (2 * P.stage_bytes + 2048 > (224 * 1024) / ctas || P.slot_cols > 512 / (ctas == 3 ? 4 : ctas))) --ctas;
+  // six CTAs leave 64 TMEM columns each: worth it only while that still holds two accumulator slots (f16 64^3: 4 CTAs 83%, 6 CTAs 77%)
+  int ctas = env_int("LIBXSMM_B200_TC_CTAS", loads_per_tile <= 2 ? ((2 * P.slot_cols <= 64) ? 6 : 4) : (loads_per_tile <= 4 ? 4 : 2));
+  if (ctas < 1) ctas = 1; if (ctas > 6) ctas = 6;
+  auto tmem_for = [](int c) { return c == 1 ? 512 : (c == 2 ? 256 : (c <= 4 ? 128 : 64)); };   // power-of-two allocations that sum to <= 512
+  while (ctas > 1 && (2 * P.stage_bytes + 2048 > (224 * 1024) / ctas || P.slot_cols > tmem_for(ctas))) --ctas;
   P.stages = ((224 * 1024) / ctas - 2048) / P.stage_bytes; if (P.stages > 12) P.stages = 12; if (P.stages < 2) P.stages = 2;
   { const int st = env_int("LIBXSMM_B200_TC_STAGES", ctas > 1 ? 4 : P.stages); if (st >= 2 && st <= P.stages) P.stages = st; }
-  P.tmem_cols = (ctas == 3) ? 128 : 512 / ctas;
+  P.tmem_cols = tmem_for(ctas);
   P.nslot = P.tmem_cols / P.slot_cols; if (P.nslot > 4) P.nslot = 4;
   P.evict_first = env_int("LIBXSMM_B200_TC_EVICT_FIRST", 0);
   P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
