@@ -435,8 +435,11 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
     if (DBG && P.dbg != nullptr && bid == 0 && warp == 4 && lane == 0) { P.dbg[8] = w0; P.dbg[9] = XB_CLOCK() - tstart; }
   } else if (warp >= 12 && warp < 12 + kConvWarps) {
     // ========================================= converters =======================================
-    const int ctid = (warp - 12) * 32 + lane;             // 0..255
-    constexpr int MG = M / 8, KPS = 32, NTASKS = G * KPS * MG;   // one task = 8 m-values of one k-pair (two 16-byte rows out); 512 per k-step
+    // One work unit = 4 consecutive rows (m) of one k-pair: a 16-byte read of VNNI words, two 8-byte writes (rows k, k+1 of
+    // the canonical operand). Lanes 0-15 of a half-warp take the 16 units of ONE (k-pair, 64-row atom): their reads are
+    // two contiguous 128-byte runs and their writes fill one whole 128-byte row each -- no shared-memory bank conflicts
+    // (the first version's 32-byte lane stride made every access 2-way conflicted: 18M of 30M wavefronts in ncu).
+    const int cw = warp - 12, q = lane & 15, kp_lo = lane >> 4;
     int rs = 0, cs = 0; uint32_t rph = 0, cph = 0; long long w_r = 0, w_c = 0; const long long tstart = XB_CLOCK();
     for (long long i = 0; i < n_local; ++i) {
       for (int ks = 0; ks < NKS; ++ks) {
@@ -444,19 +447,21 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
         XB_READY(w_c, can_empty + 8 * cs, cph ^ 1); XB_TWAIT(w_c, mbar_wait_x(can_empty + 8 * cs, cph ^ 1, P.spin & 4));
         const uint8_t* src = s_raw + (size_t)rs * A_STAGE;
         uint8_t* dst = s_can + (size_t)cs * A_STAGE;
+        if (!(P.skip & 1)) {
 #pragma unroll
-        for (int t = ctid; t < ((P.skip & 1) ? 0 : NTASKS); t += kConvWarps * 32) {
-          const int mg = t % MG, kp = (t / MG) % KPS, g = t / (MG * KPS);
-          const uint4* s = reinterpret_cast<const uint4*>(src + ((size_t)(g * KPS + kp) * M + mg * 8) * 4);
-          const uint4 w0 = s[0], w1 = s[1];
-          uint4 ev, od;
-          ev.x = __byte_perm(w0.x, w0.y, 0x5410); ev.y = __byte_perm(w0.z, w0.w, 0x5410); ev.z = __byte_perm(w1.x, w1.y, 0x5410); ev.w = __byte_perm(w1.z, w1.w, 0x5410);
-          od.x = __byte_perm(w0.x, w0.y, 0x7632); od.y = __byte_perm(w0.z, w0.w, 0x7632); od.z = __byte_perm(w1.x, w1.y, 0x7632); od.w = __byte_perm(w1.z, w1.w, 0x7632);
-          const int mrow = g * M + mg * 8, atom = mrow >> 6, ch = (mrow & 63) >> 3;
-          uint8_t* base = dst + (size_t)atom * (64 * 128);
-          const int k0 = 2 * kp, k1 = 2 * kp + 1;
-          *reinterpret_cast<uint4*>(base + k0 * 128 + ((ch ^ (k0 & 7)) << 4)) = ev;
-          *reinterpret_cast<uint4*>(base + k1 * 128 + ((ch ^ (k1 & 7)) << 4)) = od;
+          for (int it = 0; it < 32 / kConvWarps; ++it) {
+            const int idx = cw * (32 / kConvWarps) + it;          // 0..31: (atom, pair of k-pairs)
+            const int atom = idx & 1, kp = (idx >> 1) * 2 + kp_lo;
+            const int mrow = atom * 64 + 4 * q, g = mrow / M, mm = mrow % M;
+            const uint4 w = *reinterpret_cast<const uint4*>(src + ((size_t)(g * 32 + kp) * M + mm) * 4);
+            uint2 ev, od;
+            ev.x = __byte_perm(w.x, w.y, 0x5410); ev.y = __byte_perm(w.z, w.w, 0x5410);
+            od.x = __byte_perm(w.x, w.y, 0x7632); od.y = __byte_perm(w.z, w.w, 0x7632);
+            uint8_t* base = dst + (size_t)atom * (64 * 128);
+            const int k0 = 2 * kp, k1 = 2 * kp + 1, ch = q >> 1, sub = (q & 1) << 3;
+            *reinterpret_cast<uint2*>(base + k0 * 128 + ((ch ^ (k0 & 7)) << 4) + sub) = ev;
+            *reinterpret_cast<uint2*>(base + k1 * 128 + ((ch ^ (k1 & 7)) << 4) + sub) = od;
+          }
         }
         if (!(P.skip & 128)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -465,7 +470,7 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
         if (++cs == CS) { cs = 0; cph ^= 1; }
       }
     }
-    if (DBG && P.dbg != nullptr && bid == 0 && ctid == 0) { P.dbg[10] = w_r; P.dbg[11] = w_c; P.dbg[12] = XB_CLOCK() - tstart; }
+    if (DBG && P.dbg != nullptr && bid == 0 && cw == 0 && lane == 0) { P.dbg[10] = w_r; P.dbg[11] = w_c; P.dbg[12] = XB_CLOCK() - tstart; }
   }
 
   tc_fence_before();
