@@ -292,7 +292,10 @@ def also_fsspmdm(X, torch, pk, args, full=False):
     bytes_alg = 4.0 * (Kf * Nf + Mf * Nf)
     ach = bytes_alg / (ms * 1e-3) / 1e9
     X.libxsmm_fsspmdm_destroy(h)
-    return {"metric": "fsspmdm GFLOP/s (f32 M=32 K=128 N=1e6, 15% nnz)", "value": 2.0 * nnz * Nf / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (sparse)",
+    cpu = None
+    if full or not getattr(args, "no_cpu", False):
+        cpu = cpu_baseline_fsspmdm(a, Mf, Kf, nnz)
+    return {"cpu_baseline": cpu, "metric": "fsspmdm GFLOP/s (f32 M=32 K=128 N=1e6, 15% nnz)", "value": 2.0 * nnz * Nf / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (sparse)",
             "dense_equiv_gflops": 2.0 * Mf * Kf * Nf / (ms * 1e-3) / 1e9, "ms_per_step": ms, "nnz": nnz,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic("sreg_kernel<float>"), "algorithmic_bytes": bytes_alg, "kernel": "sreg_kernel<float>"},
             "config": {"workload": "configs[2]: fsspmdm f32 M=32 K=128 N=1e6 15% nnz beta=0; B+C = 640 MB per step (> L2)"}}
@@ -327,7 +330,10 @@ def also_bcsc(X, torch, pk, args, full=False, mblocks=8192):
     bytes_alg = 2.0 * (mblocks * Kb * Mb + mblocks * Nb * Mb) + 2.0 * nnzb * bk * bn
     ach = bytes_alg / (ms * 1e-3) / 1e9
     X.libxsmm_release_kernel(kernel)
-    return {"metric": "BCSC spmm GFLOP/s dense-equivalent (bf16, M=32 N=K=512, 32x32 blocks, 50%, m_blocks=8192)",
+    cpu = None
+    if mblocks == 8192 and (full or not getattr(args, "no_cpu", False)):
+        cpu = cpu_baseline_bcsc(colptr, rowidx, nnzb, (Mb, Kb, Nb, bk, bn))
+    return {"cpu_baseline": cpu, "metric": "BCSC spmm GFLOP/s dense-equivalent (bf16, M=32 N=K=512, 32x32 blocks, 50%, m_blocks=8192)",
             "value": 2.0 * Mb * mblocks * Nb * Kb / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (dense-equivalent)",
             "effective_gflops": 2.0 * Mb * mblocks * nnzb * bk * bn / (ms * 1e-3) / 1e9, "ms_per_step": ms,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic("bcsc_tc_kernel<32>"), "algorithmic_bytes": bytes_alg,
@@ -409,6 +415,51 @@ def cpu_baseline_brgemm(sample_tiles=4096, budget_s=12.0):
     return {"value": fl / t / 1e9, "unit": "GFLOP/s", "cores": int(ref_lib.ref_max_threads()), "kind": "reference",
             "sample": "%d tiles (%.0f MB of A+B, streamed) x %d passes, LIBXSMM JIT target %s%s, VNNI_A layout" % (
                 sample_tiles, (2.0 * na * 2) / 1e6, reps, ref_lib.ref_target_arch().decode(), " [C reference kernel!]" if is_ref.value else "")}
+
+
+def cpu_baseline_fsspmdm(a_dense, Mf, Kf, nnz, n_sample=200000, budget_s=4.0):
+    """the reference's fsspmdm JIT on a bounded N-slice of the same operator, all host cores (slices of N per thread)"""
+    import numpy as np
+    use_all_host_threads()
+    from oracle_ffi import ref_lib
+    if ref_lib is None:
+        return {"value": None, "unit": "GFLOP/s (sparse)", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    rng = np.random.default_rng(7)
+    b = rng.standard_normal(Kf * n_sample).astype(np.float32); c = np.zeros(Mf * n_sample, dtype=np.float32)
+    one = np.array([1.0], dtype=np.float32); zero = np.array([0.0], dtype=np.float32)
+    args = (F32, Mf, n_sample, Kf, Kf, one.ctypes.data, zero.ctypes.data, a_dense.ctypes.data, b.ctypes.data, c.ctypes.data)
+    t1 = ref_lib.ref_bench_fsspmdm(*args, 1)
+    if t1 < 0:
+        return {"value": None, "unit": "GFLOP/s (sparse)", "cores": int(ref_lib.ref_max_threads()), "kind": "reference", "sample": "create returned NULL"}
+    reps = max(1, min(500, int(budget_s / max(t1, 1e-4))))
+    t = ref_lib.ref_bench_fsspmdm(*args, reps)
+    return {"value": 2.0 * nnz * n_sample * reps / t / 1e9, "unit": "GFLOP/s (sparse)", "gbs": 4.0 * (Kf + Mf) * n_sample * reps / t / 1e9,
+            "cores": int(ref_lib.ref_max_threads()), "kind": "reference", "sample": "N=%d columns (%.0f MB of B+C) x %d passes, LIBXSMM JIT" % (n_sample, 4.0 * (Kf + Mf) * n_sample / 1e6, reps)}
+
+
+def cpu_baseline_bcsc(colptr, rowidx, nnzb, geo, mblocks=1024, budget_s=4.0):
+    """the reference's BCSC JIT (AMX on SPR) on a bounded number of m_blocks, contiguous ranges per thread"""
+    import numpy as np
+    use_all_host_threads()
+    from oracle_ffi import ref_lib, iarr
+    Mb, Kb, Nb, bk, bn = geo
+    if ref_lib is None:
+        return {"value": None, "unit": "GFLOP/s (dense-equivalent)", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    rng = np.random.default_rng(8)
+
+    def bf16(n):
+        x = (rng.integers(-5, 6, size=n).astype(np.float32) / 10).view(np.uint32)
+        return ((x + 0x7FFF + ((x >> 16) & 1)) >> 16).astype(np.uint16)
+    a = bf16(mblocks * Kb * Mb); bv = bf16(nnzb * bk * bn); c = np.zeros(mblocks * Nb * Mb, dtype=np.uint16)
+    cp = colptr.copy(); ri = rowidx.copy()
+    args = (iarr(BF16, BF16, F32, BF16), iarr(mblocks, Mb, Kb, Nb, bk, bn), FLAG_BETA_0 | 256, a.ctypes.data, bv.ctypes.data, cp.ctypes.data, ri.ctypes.data, c.ctypes.data)
+    t1 = ref_lib.ref_bench_bcsc(*args, 1)
+    if t1 < 0:
+        return {"value": None, "unit": "GFLOP/s (dense-equivalent)", "cores": int(ref_lib.ref_max_threads()), "kind": "reference", "sample": "JIT returned NULL on this host"}
+    reps = max(1, min(500, int(budget_s / max(t1, 1e-4))))
+    t = ref_lib.ref_bench_bcsc(*args, reps)
+    return {"value": 2.0 * Mb * mblocks * Nb * Kb * reps / t / 1e9, "unit": "GFLOP/s (dense-equivalent)", "cores": int(ref_lib.ref_max_threads()), "kind": "reference",
+            "sample": "%d m_blocks (%.0f MB of A+C) x %d passes, LIBXSMM JIT target %s" % (mblocks, 4.0 * mblocks * Mb * (Kb + Nb) / 2 / 1e6, reps, ref_lib.ref_target_arch().decode())}
 
 
 def run_reference(args):
