@@ -35,8 +35,8 @@ $(LIB): $(OBJS)
 	ln -sf libxsmm_b200.so libxsmm_b200/lib/libxsmm.so
 
 oracle: oracle/liboracle.so
-oracle/liboracle.so: oracle/oracle.c
-	$(CC) -O2 -std=gnu99 -fPIC -shared -ffp-contract=off -fopenmp -o $@ $< -lm
+oracle/liboracle.so: oracle/oracle.c oracle/oracle_meltw.c
+	$(CC) -O2 -std=gnu99 -fPIC -shared -ffp-contract=off -fopenmp -Iinclude -o $@ oracle/oracle.c oracle/oracle_meltw.c -lm
 
 ref: oracle/_ref/libxsmm_ref.so
 oracle/_ref/libxsmm_ref.so: oracle/ref_shim.c

@@ -1,0 +1,324 @@
+/* TEST INFRASTRUCTURE -- not part of the product; nothing under libxsmm_b200/ may call into this file.
+ *
+ * CPU restatement (plain C, written from the algorithm) of the reference's portable matrix-eltwise kernels,
+ * src/generator_mateltwise_reference_impl.c, for the operations of SURVEY.md 8a (rows a5, a6) that the CUDA
+ * library dispatches most: element-wise unary / binary / ternary maps with broadcast, the ReLU family with
+ * bitmasks, compare / select / zip, row and column reductions (sum, sum of squares, max, min), the norm ->
+ * transposed / VNNI2 / VNNI4 layout transforms, quantise / dequantise. Operations that are not restated return 2
+ * and stay pinned by the reference itself (oracle/_ref). Pinned bit for bit against libxsmm_reference_elementwise
+ * in tests/test_oracle_vs_ref.py (transcendental ops: same libm calls, so equal on the same host).
+ *
+ * Interface mirrors ref_meltw (oracle/ref_shim.c): desc = {op_class, op, flags, m, n, ldi, ldi2, ldi3, ldo,
+ * t_in0, t_in1, t_in2, t_out, t_comp}, param = the reference's libxsmm_meltw_{unary,binary,ternary}_param.
+ * All matrices are column-major: element (i, j) at i + j*ld.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include "libxsmm_typedefs.h"      /* this repository's own ABI header: enumerators and argument structs */
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+float oracle_bf16_to_f32(uint16_t h);
+uint16_t oracle_f32_to_bf16(float f);
+float oracle_f16_to_f32(uint16_t h);
+uint16_t oracle_f32_to_f16(float f);
+
+typedef struct mdesc { int op_class, op; unsigned int flags; int m, n; long long ldi, ldi2, ldi3, ldo; int t0, t1, t2, to, tc; } mdesc;
+
+static int is_f(int t) { return t == LIBXSMM_DATATYPE_F32 || t == LIBXSMM_DATATYPE_BF16 || t == LIBXSMM_DATATYPE_F16; }
+static int tsz(int t) {
+  switch (t) { case LIBXSMM_DATATYPE_F64: case LIBXSMM_DATATYPE_I64: case LIBXSMM_DATATYPE_U64: return 8;
+               case LIBXSMM_DATATYPE_F32: case LIBXSMM_DATATYPE_I32: case LIBXSMM_DATATYPE_U32: return 4;
+               case LIBXSMM_DATATYPE_BF16: case LIBXSMM_DATATYPE_F16: case LIBXSMM_DATATYPE_I16: case LIBXSMM_DATATYPE_U16: return 2;
+               default: return 1; }
+}
+/* load to f32 / store with RNE: reference :2470-2498 (load via libxsmm_convert_*_to_f32, store via *_rne) */
+static float ldf(const void* p, long long i, int t) {
+  if (t == LIBXSMM_DATATYPE_F32) return ((const float*)p)[i];
+  if (t == LIBXSMM_DATATYPE_BF16) return oracle_bf16_to_f32(((const uint16_t*)p)[i]);
+  return oracle_f16_to_f32(((const uint16_t*)p)[i]);
+}
+static void stf(void* p, long long i, int t, float v) {
+  if (t == LIBXSMM_DATATYPE_F32) ((float*)p)[i] = v;
+  else if (t == LIBXSMM_DATATYPE_BF16) ((uint16_t*)p)[i] = oracle_f32_to_bf16(v);
+  else ((uint16_t*)p)[i] = oracle_f32_to_f16(v);
+}
+/* operand index under the broadcast flags: reference :241-272 (row-bcast -> j*ld, col-bcast -> i, scalar -> 0) */
+static long long bidx(const mdesc* d, int which, int i, int j, long long ld) {
+  unsigned int row = 0, col = 0, sca = 0;
+  if (d->op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
+    row = d->flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_ROW; col = d->flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_COL; sca = d->flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_SCALAR;
+  } else if (d->op_class == LIBXSMM_MELTW_OPERATION_BINARY) {
+    row = d->flags & (which == 0 ? LIBXSMM_MELTW_FLAG_BINARY_BCAST_ROW_IN_0 : LIBXSMM_MELTW_FLAG_BINARY_BCAST_ROW_IN_1);
+    col = d->flags & (which == 0 ? LIBXSMM_MELTW_FLAG_BINARY_BCAST_COL_IN_0 : LIBXSMM_MELTW_FLAG_BINARY_BCAST_COL_IN_1);
+    sca = d->flags & (which == 0 ? LIBXSMM_MELTW_FLAG_BINARY_BCAST_SCALAR_IN_0 : LIBXSMM_MELTW_FLAG_BINARY_BCAST_SCALAR_IN_1);
+  } else {
+    const unsigned int r[3] = { LIBXSMM_MELTW_FLAG_TERNARY_BCAST_ROW_IN_0, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_ROW_IN_1, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_ROW_IN_2 };
+    const unsigned int c[3] = { LIBXSMM_MELTW_FLAG_TERNARY_BCAST_COL_IN_0, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_COL_IN_1, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_COL_IN_2 };
+    const unsigned int s[3] = { LIBXSMM_MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_0, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_1, LIBXSMM_MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_2 };
+    row = d->flags & r[which]; col = d->flags & c[which]; sca = d->flags & s[which];
+  }
+  if (row) return (long long)j * ld;
+  if (col) return i;
+  if (sca) return 0;
+  return i + (long long)j * ld;
+}
+/* bitmask addressing: bit (i, j) at byte i/8 + j*(mask_ld/8), mask_ld = UPDIV(ld,16)*16 bits (reference :2142) */
+static long long mask_ld_of(long long ld) { return ((ld + 15) / 16) * 16; }
+static int mask_get(const void* mask, int i, int j, long long mld) { return (((const uint8_t*)mask)[i / 8 + (long long)j * (mld / 8)] >> (i % 8)) & 1; }
+static void mask_put(void* mask, int i, int j, long long mld, int bit) {
+  uint8_t* b = (uint8_t*)mask + i / 8 + (long long)j * (mld / 8);
+  *b = (uint8_t)((*b & ~(1u << (i % 8))) | ((unsigned int)(bit != 0) << (i % 8)));
+}
+
+/* generic f32 unary ops: reference :76-113 (sigmoid defined through tanh, gelu through erff: :18-40) */
+static float sigm(float x) { return (tanhf(x / 2.0f) + 1.0f) / 2.0f; }
+static float unary_f32(float x, int op) {
+  switch (op) {
+    case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: return -1.0f * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_X2: return x * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_XOR: return 0.0f;
+    case LIBXSMM_MELTW_TYPE_UNARY_TANH: return tanhf(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID: return sigm(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_GELU: return (erff(x / sqrtf(2.0f)) + 1.0f) * 0.5f * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_GELU_INV: return 0.5f + 0.5f * erff(x / sqrtf(2.0f)) + x / sqrtf(2.0f * 3.14159265358979323846f) * expf(-0.5f * x * x);
+    case LIBXSMM_MELTW_TYPE_UNARY_TANH_INV: { const float t = tanhf(x); return 1.0f - t * t; }
+    case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID_INV: { const float s = sigm(x); return s * (1.0f - s); }
+    case LIBXSMM_MELTW_TYPE_UNARY_SQRT: return sqrtf(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_INC: return x + 1.0f;
+    case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: return 1.0f / x;
+    case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT: return 1.0f / sqrtf(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_EXP: return expf(x);
+    default: return x;
+  }
+}
+static double unary_f64(double x, int op) {   /* reference :116-139 */
+  switch (op) {
+    case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: return -1.0 * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_X2: return x * x;
+    case LIBXSMM_MELTW_TYPE_UNARY_XOR: return 0.0;
+    case LIBXSMM_MELTW_TYPE_UNARY_SQRT: return sqrt(x);
+    case LIBXSMM_MELTW_TYPE_UNARY_INC: return x + 1.0;
+    case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: return 1.0 / x;
+    case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT: return 1.0 / sqrt(x);
+    default: return x;
+  }
+}
+
+static int unary_map(const mdesc* d, const libxsmm_meltw_unary_param* p) {
+  const int op = d->op, f64 = (d->t0 == LIBXSMM_DATATYPE_F64 && d->to == LIBXSMM_DATATYPE_F64);
+  const int bitm = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0;
+  const float alpha = (p->op.primary != NULL && (op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU_INV
+                       || op == LIBXSMM_MELTW_TYPE_UNARY_ELU || op == LIBXSMM_MELTW_TYPE_UNARY_ELU_INV)) ? *(const float*)p->op.primary : 0.0f;
+  int i, j;
+  if (!f64 && !(is_f(d->t0) && is_f(d->to))) return 2;
+  for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+    const long long oi = i + (long long)j * d->ldo;
+    if (f64) { ((double*)p->out.primary)[oi] = unary_f64(((const double*)p->in.primary)[bidx(d, 0, i, j, d->ldi)], op); continue; }
+    {
+      const float x = ldf(p->in.primary, bidx(d, 0, i, j, d->ldi), d->t0);
+      switch (op) {
+        case LIBXSMM_MELTW_TYPE_UNARY_RELU: case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU: case LIBXSMM_MELTW_TYPE_UNARY_ELU: {   /* :2138-2167: test is in <= 0 */
+          float y = x;
+          if (x <= 0.0f) y = (op == LIBXSMM_MELTW_TYPE_UNARY_RELU) ? 0.0f : ((op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU) ? alpha * x : alpha * (expf(x) - 1.0f));
+          stf(p->out.primary, oi, d->to, y);
+          if (bitm) mask_put(p->out.secondary, i, j, mask_ld_of(d->ldo), !(x <= 0.0f));
+        } break;
+        case LIBXSMM_MELTW_TYPE_UNARY_RELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU_INV: {                           /* :2168-2194 */
+          const int bit = mask_get(p->in.secondary, i, j, bitm ? mask_ld_of(d->ldi) : d->ldi);
+          stf(p->out.primary, oi, d->to, bit ? x : ((op == LIBXSMM_MELTW_TYPE_UNARY_RELU_INV) ? 0.0f : alpha * x));
+        } break;
+        case LIBXSMM_MELTW_TYPE_UNARY_ELU_INV: {
+          const float fwd = ldf(p->in.secondary, i + (long long)j * d->ldi, d->t0);
+          stf(p->out.primary, oi, d->to, (fwd > 0) ? x : x * (fwd + alpha));
+        } break;
+        default: stf(p->out.primary, oi, d->to, unary_f32(x, op));
+      }
+    }
+  }
+  return 0;
+}
+
+/* reductions: reference :1065-1443. REDUCE_ROWS collapses i (n results), otherwise j (m results, buffer pitch ldo);
+ * X_X2 stores the sums, then the sums of squares at element offset result_size (:1073-1076); INIT_ACC adds the old output */
+static int unary_reduce(const mdesc* d, const libxsmm_meltw_unary_param* p) {
+  const int op = d->op, rows = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_ROWS) != 0, init = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_INIT_ACC) != 0;
+  const int f64 = (d->t0 == LIBXSMM_DATATYPE_F64 && d->to == LIBXSMM_DATATYPE_F64);
+  const int kind = (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX) ? 1 : ((op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN) ? 2 : 0);
+  const int want_x = (op != LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD), want_x2 = (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD);
+  const int nres = rows ? d->n : d->m, len = rows ? d->m : d->n;
+  const long long result_size = rows ? d->n : d->ldo;
+  int o, t;
+  if (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_RECORD_ARGOP) return 2;
+  if (!f64 && !(is_f(d->t0) && is_f(d->to))) return 2;
+  for (o = 0; o < nres; ++o) {
+    double sx = 0.0, sx2 = 0.0, best = 0.0; float fsx = 0.0f, fsx2 = 0.0f, fbest = 0.0f;
+    for (t = 0; t < len; ++t) {
+      const long long idx = rows ? (t + (long long)o * d->ldi) : (o + (long long)t * d->ldi);
+      if (f64) { const double v = ((const double*)p->in.primary)[idx]; sx += v; sx2 += v * v; if (t == 0 || (kind == 1 ? v > best : v < best)) best = v; }
+      else { const float v = ldf(p->in.primary, idx, d->t0); fsx += v; fsx2 += v * v; if (t == 0 || (kind == 1 ? v > fbest : v < fbest)) fbest = v; }
+    }
+    if (kind != 0) {
+      if (f64) ((double*)p->out.primary)[o] = best; else stf(p->out.primary, o, d->to, fbest);
+    } else if (f64) {
+      double* ox = (double*)p->out.primary; double* ox2 = want_x ? ox + result_size : ox;
+      if (want_x) ox[o] = sx + (init ? ox[o] : 0.0);
+      if (want_x2) ox2[o] = sx2 + (init ? ox2[o] : 0.0);
+    } else {
+      char* base2 = (char*)p->out.primary + (want_x ? (size_t)result_size * tsz(d->to) : 0);
+      if (want_x) { float r = fsx; if (init) r += ldf(p->out.primary, o, d->to); stf(p->out.primary, o, d->to, r); }
+      if (want_x2) { float r = fsx2; if (init) r += ldf(base2, o, d->to); stf(base2, o, d->to, r); }
+    }
+  }
+  return 0;
+}
+
+/* layout transforms, pure data movement: reference :390-417 (NORM_TO_NORMT), :541-553 (NORM_TO_VNNI2, N padded to even
+ * with zeros in the _PAD variant), the VNNI4 analogue */
+static int unary_transform(const mdesc* d, const libxsmm_meltw_unary_param* p) {
+  const int ts = tsz(d->t0), op = d->op;
+  const char* in = (const char*)p->in.primary; char* out = (char*)p->out.primary;
+  int i, j;
+  if (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT) {
+    for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) memcpy(out + ((long long)i * d->ldo + j) * ts, in + ((long long)j * d->ldi + i) * ts, (size_t)ts);
+    return 0;
+  }
+  {
+    const int v = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2 || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD) ? 2
+                : ((op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4 || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD) ? 4 : 0);
+    const int pad = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD);
+    const int nv = pad ? (d->n + v - 1) / v : d->n / v;
+    int j2;
+    if (v == 0) return 2;
+    /* out[(j*ldo*v) + (i*v) + j2] = in[((v*j + j2)*ldi) + i] */
+    for (j = 0; j < nv; ++j) for (i = 0; i < d->m; ++i) for (j2 = 0; j2 < v; ++j2) {
+      char* dst = out + (((long long)j * d->ldo * v) + ((long long)i * v) + j2) * ts;
+      if (v * j + j2 < d->n) memcpy(dst, in + (((long long)(v * j + j2) * d->ldi) + i) * ts, (size_t)ts); else memset(dst, 0, (size_t)ts);
+    }
+  }
+  return 0;
+}
+
+/* quantise / dequantise: reference :2195-2360 */
+static int unary_quant(const mdesc* d, const libxsmm_meltw_unary_param* p) {
+  int i, j;
+  if (d->op == LIBXSMM_MELTW_TYPE_UNARY_DEQUANT) {
+    const float scf = *(const float*)p->in.secondary;
+    if (d->to != LIBXSMM_DATATYPE_F32) return 2;
+    for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+      const long long ii = i + (long long)j * d->ldi; float v;
+      if (d->t0 == LIBXSMM_DATATYPE_I8) v = (float)((const int8_t*)p->in.primary)[ii];
+      else if (d->t0 == LIBXSMM_DATATYPE_I16) v = (float)((const int16_t*)p->in.primary)[ii];
+      else if (d->t0 == LIBXSMM_DATATYPE_I32) v = (float)((const int32_t*)p->in.primary)[ii];
+      else return 2;
+      ((float*)p->out.primary)[i + (long long)j * d->ldo] = v * scf;
+    }
+    return 0;
+  }
+  return 2;   /* QUANT variants (saturating / non-saturating, MX block formats) stay with the reference */
+}
+
+static int binary_map(const mdesc* d, const libxsmm_meltw_binary_param* p) {
+  const int op = d->op;
+  const int f64 = d->t0 == LIBXSMM_DATATYPE_F64 && d->t1 == LIBXSMM_DATATYPE_F64 && d->to == LIBXSMM_DATATYPE_F64;
+  int i, j;
+  if (op == LIBXSMM_MELTW_TYPE_BINARY_ZIP) {   /* :2547-2559: two 16-bit planes -> one 32-bit word (in1 is the high half) */
+    for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i)
+      ((uint32_t*)p->out.primary)[i + (long long)j * d->ldo] = (uint32_t)((const uint16_t*)p->in0.primary)[bidx(d, 0, i, j, d->ldi)]
+                                                            | ((uint32_t)((const uint16_t*)p->in1.primary)[bidx(d, 1, i, j, d->ldi2)] << 16);
+    return 0;
+  }
+  if (op == LIBXSMM_MELTW_TYPE_BINARY_MUL_AND_REDUCE_TO_SCALAR_OP_ADD) return 2;
+  if (!f64 && !(is_f(d->t0) && is_f(d->t1))) return 2;
+  for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+    const long long oi = i + (long long)j * d->ldo;
+    if (f64) {
+      const double a = ((const double*)p->in0.primary)[bidx(d, 0, i, j, d->ldi)], b = ((const double*)p->in1.primary)[bidx(d, 1, i, j, d->ldi2)];
+      double* o = (double*)p->out.primary + oi;
+      switch (op) {
+        case LIBXSMM_MELTW_TYPE_BINARY_ADD: *o = a + b; break; case LIBXSMM_MELTW_TYPE_BINARY_SUB: *o = a - b; break;
+        case LIBXSMM_MELTW_TYPE_BINARY_MUL: *o = a * b; break; case LIBXSMM_MELTW_TYPE_BINARY_DIV: *o = a / b; break;
+        case LIBXSMM_MELTW_TYPE_BINARY_MULADD: *o = *o + a * b; break;
+        case LIBXSMM_MELTW_TYPE_BINARY_MAX: *o = (a > b) ? a : b; break; case LIBXSMM_MELTW_TYPE_BINARY_MIN: *o = (a > b) ? b : a; break;
+        default: return 2;
+      }
+    } else {
+      const float a = ldf(p->in0.primary, bidx(d, 0, i, j, d->ldi), d->t0), b = ldf(p->in1.primary, bidx(d, 1, i, j, d->ldi2), d->t1);
+      float r;
+      switch (op) {
+        case LIBXSMM_MELTW_TYPE_BINARY_ADD: r = a + b; break; case LIBXSMM_MELTW_TYPE_BINARY_SUB: r = a - b; break;
+        case LIBXSMM_MELTW_TYPE_BINARY_MUL: r = a * b; break; case LIBXSMM_MELTW_TYPE_BINARY_DIV: r = a / b; break;
+        case LIBXSMM_MELTW_TYPE_BINARY_MULADD: r = ldf(p->out.primary, oi, d->to) + a * b; break;       /* :2505-2593: out += a*b, reads out */
+        case LIBXSMM_MELTW_TYPE_BINARY_MAX: r = (a > b) ? a : b; break; case LIBXSMM_MELTW_TYPE_BINARY_MIN: r = (a > b) ? b : a; break;
+        case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GT: case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GE: case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_LT:
+        case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_LE: case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_EQ: case LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_NE: {   /* :2573-2581 */
+          const int bit = (op == LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GT) ? (a > b) : (op == LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GE) ? (a >= b)
+                        : (op == LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_LT) ? (a < b) : (op == LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_LE) ? (a <= b)
+                        : (op == LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_EQ) ? (a == b) : (a != b);
+          mask_put(p->out.primary, i, j, mask_ld_of(d->ldo), bit);
+          continue;
+        }
+        default: return 2;
+      }
+      if (!is_f(d->to)) return 2;
+      stf(p->out.primary, oi, d->to, r);
+    }
+  }
+  return 0;
+}
+
+static int ternary_map(const mdesc* d, const libxsmm_meltw_ternary_param* p) {   /* reference :2596-2660 */
+  const int f64 = d->t0 == LIBXSMM_DATATYPE_F64 && d->t1 == LIBXSMM_DATATYPE_F64 && d->to == LIBXSMM_DATATYPE_F64;
+  int i, j;
+  for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+    const long long oi = i + (long long)j * d->ldo;
+    if (d->op == LIBXSMM_MELTW_TYPE_TERNARY_SELECT) {          /* bit 0 -> in0, bit 1 -> in1; mask pitch rounded up to 16 bits (:2620) */
+      const int bit = mask_get(p->in2.primary, i, j, mask_ld_of(d->ldi3));
+      if (f64) ((double*)p->out.primary)[oi] = bit ? ((const double*)p->in1.primary)[bidx(d, 1, i, j, d->ldi2)] : ((const double*)p->in0.primary)[bidx(d, 0, i, j, d->ldi)];
+      else if (is_f(d->t0) && is_f(d->t1) && is_f(d->to))
+        stf(p->out.primary, oi, d->to, bit ? ldf(p->in1.primary, bidx(d, 1, i, j, d->ldi2), d->t1) : ldf(p->in0.primary, bidx(d, 0, i, j, d->ldi), d->t0));
+      else return 2;
+    } else if (d->op == LIBXSMM_MELTW_TYPE_TERNARY_MULADD || d->op == LIBXSMM_MELTW_TYPE_TERNARY_NMULADD) {
+      float x, y, z;
+      if (!(is_f(d->t0) && is_f(d->t1) && is_f(d->t2) && is_f(d->to))) return 2;
+      x = ldf(p->in0.primary, bidx(d, 0, i, j, d->ldi), d->t0); y = ldf(p->in1.primary, bidx(d, 1, i, j, d->ldi2), d->t1);
+      z = ldf(p->in2.primary, bidx(d, 2, i, j, d->ldi3), d->t2);
+      stf(p->out.primary, oi, d->to, (d->op == LIBXSMM_MELTW_TYPE_TERNARY_MULADD) ? (z + x * y) : (y - x * z));   /* in2 + in0*in1 ; in1 - in0*in2 */
+    } else return 2;
+  }
+  return 0;
+}
+
+/* returns 0 = computed, 2 = operation not restated here (use the reference), 1 = invalid */
+ORACLE_API int oracle_meltw(const int* desc, void* param, int mode) {
+  mdesc d;
+  (void)mode;
+  d.op_class = desc[0]; d.op = desc[1]; d.flags = (unsigned int)desc[2]; d.m = desc[3]; d.n = desc[4];
+  d.ldi = desc[5]; d.ldi2 = desc[6]; d.ldi3 = desc[7]; d.ldo = desc[8]; d.t0 = desc[9]; d.t1 = desc[10]; d.t2 = desc[11]; d.to = desc[12]; d.tc = desc[13];
+  if (d.m <= 0 || d.n <= 0 || param == NULL) return 1;
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
+    switch (d.op) {
+      case LIBXSMM_MELTW_TYPE_UNARY_IDENTITY: case LIBXSMM_MELTW_TYPE_UNARY_XOR: case LIBXSMM_MELTW_TYPE_UNARY_X2: case LIBXSMM_MELTW_TYPE_UNARY_SQRT:
+      case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: case LIBXSMM_MELTW_TYPE_UNARY_INC: case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT:
+      case LIBXSMM_MELTW_TYPE_UNARY_TANH: case LIBXSMM_MELTW_TYPE_UNARY_TANH_INV: case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID: case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID_INV:
+      case LIBXSMM_MELTW_TYPE_UNARY_GELU: case LIBXSMM_MELTW_TYPE_UNARY_GELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_EXP:
+      case LIBXSMM_MELTW_TYPE_UNARY_RELU: case LIBXSMM_MELTW_TYPE_UNARY_RELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU: case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU_INV:
+      case LIBXSMM_MELTW_TYPE_UNARY_ELU: case LIBXSMM_MELTW_TYPE_UNARY_ELU_INV:
+        return unary_map(&d, (const libxsmm_meltw_unary_param*)param);
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ADD: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD:
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN:
+        return unary_reduce(&d, (const libxsmm_meltw_unary_param*)param);
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD:
+        return unary_transform(&d, (const libxsmm_meltw_unary_param*)param);
+      case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT: case LIBXSMM_MELTW_TYPE_UNARY_QUANT:
+        return unary_quant(&d, (const libxsmm_meltw_unary_param*)param);
+      default: return 2;
+    }
+  }
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_BINARY) return binary_map(&d, (const libxsmm_meltw_binary_param*)param);
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_TERNARY) return ternary_map(&d, (const libxsmm_meltw_ternary_param*)param);
+  return 1;
+}

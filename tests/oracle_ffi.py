@@ -19,7 +19,8 @@ _I, _U, _P, _LL, _ULL, _F = C.c_int, C.c_uint, C.c_void_p, C.c_longlong, C.c_ulo
 
 
 def _build_if_needed():
-    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ROOT, "oracle", "oracle.c")):
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("oracle.c", "oracle_meltw.c")]
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", ROOT, "oracle"], stdout=subprocess.DEVNULL)
     if not os.path.exists(REF_SO) and os.path.isdir("/root/reference/include"):
         subprocess.check_call(["make", "-C", ROOT, "ref"], stdout=subprocess.DEVNULL)
@@ -48,6 +49,8 @@ for _n, _r, _a in (("f32_to_bf16", C.c_ushort, [_F]), ("f32_to_f16", C.c_ushort,
     _fn = getattr(oracle_lib, "oracle_" + _n)
     _fn.restype, _fn.argtypes = _r, _a
     oracle[_n] = _fn
+oracle_lib.oracle_meltw.restype, oracle_lib.oracle_meltw.argtypes = _I, [_P, _P, _I]
+oracle["meltw"] = oracle_lib.oracle_meltw          # 0 = computed, 2 = op not restated (the reference stays the only checker)
 _fn = oracle_lib.oracle_gemm_batch
 _fn.restype, _fn.argtypes = _I, [_P, _P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _LL, _LL, _LL, _LL]
 oracle["gemm_batch"] = _fn

@@ -11,9 +11,9 @@ import torch
 import gen
 import libxsmm_b200 as X
 from gpu_util import dev, host
-from oracle_ffi import iarr, ref
+from oracle_ffi import iarr, oracle, ref
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref is None, reason="oracle/_ref/libxsmm_ref.so missing")]
+pytestmark = [pytest.mark.gpu]
 
 UNS = gen.F64 + 26   # LIBXSMM_DATATYPE_UNSUPPORTED
 EXACT_UNARY = ["IDENTITY", "XOR", "X2", "SQRT", "NEGATE", "INC", "RECIPROCAL", "RECIPROCAL_SQRT"]
@@ -34,7 +34,15 @@ def _rand(rng, n, t, positive=False):
 
 
 def _ref_call(desc, param):
-    assert ref["meltw"](iarr(*desc), C.addressof(param), 0) == 0
+    """expected result: the reference itself where oracle/_ref travelled with the snapshot, else the pinned restatement
+    (oracle/oracle_meltw.c; it answers 2 for the operations it does not restate)"""
+    if ref is not None:
+        assert ref["meltw"](iarr(*desc), C.addressof(param), 0) == 0
+        return
+    rc = oracle["meltw"](iarr(*desc), C.addressof(param), 0)
+    if rc == 2:
+        pytest.skip("operation not restated in oracle/oracle_meltw.c and oracle/_ref is absent")
+    assert rc == 0
 
 
 def _desc(op_class, op, flags, m, n, ldi, ldi2, ldi3, ldo, t0, t1, t2, to, tcomp):

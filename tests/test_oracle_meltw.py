@@ -1,0 +1,177 @@
+"""CPU-only: pins the mateltwise restatement (oracle/oracle_meltw.c) against libxsmm_reference_elementwise of the
+UNMODIFIED reference (oracle/_ref) on seeded inputs, bit for bit -- including the transcendental ops, which call the
+same libm functions in the same order on the same host."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import gen
+import libxsmm_b200 as X     # only for the enumerators and argument structs (no kernel is launched)
+from oracle_ffi import iarr, oracle, ref
+
+pytestmark = pytest.mark.skipif(ref is None, reason="oracle/_ref/libxsmm_ref.so not built (no /root/reference here)")
+UNS = gen.F64 + 26
+
+
+def rnd(rng, n, t, positive=False):
+    x = rng.standard_normal(n).astype(np.float32)
+    if positive:
+        x = np.abs(x) + 0.1
+    if t == gen.F32:
+        return x
+    if t == gen.F64:
+        return x.astype(np.float64)
+    if t == gen.BF16:
+        return gen.f32_to_bf16_bits(x)
+    return x.astype(np.float16).view(np.uint16)
+
+
+def both(desc, make_param, outs):
+    """run reference and restatement on identical copies; `outs` lists the output arrays (copied per side)"""
+    res = []
+    for side in (ref, oracle):
+        bufs = [o.copy() for o in outs]
+        keep = []
+        p = make_param(bufs, keep)
+        rc = side["meltw"](iarr(*desc), C.addressof(p), 0)
+        assert rc == 0, (desc, rc)
+        res.append(bufs)
+    for a, b in zip(*res):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), desc
+
+
+UNARY = ["IDENTITY", "XOR", "X2", "SQRT", "NEGATE", "INC", "RECIPROCAL", "RECIPROCAL_SQRT", "TANH", "TANH_INV", "SIGMOID", "SIGMOID_INV", "GELU", "GELU_INV", "EXP"]
+
+
+@pytest.mark.parametrize("tin,tout", [(gen.F32, gen.F32), (gen.BF16, gen.BF16), (gen.F16, gen.F32), (gen.F32, gen.BF16), (gen.BF16, gen.F16), (gen.F64, gen.F64)])
+def test_unary_map_ops(tin, tout):
+    rng = np.random.default_rng(61)
+    for name in (UNARY[:8] if tin == gen.F64 else UNARY):
+        op = getattr(X, "MELTW_TYPE_UNARY_" + name)
+        for (m, n, pad, bc) in ((33, 17, 0, 0), (100, 3, 5, 0), (1, 64, 2, 0), (40, 9, 0, X.MELTW_FLAG_UNARY_BCAST_ROW),
+                                (40, 9, 0, X.MELTW_FLAG_UNARY_BCAST_COL), (7, 7, 1, X.MELTW_FLAG_UNARY_BCAST_SCALAR)):
+            ldi, ldo = m + pad, m + 2 * pad
+            x = rnd(rng, ldi * n, tin, positive=name in ("SQRT", "RECIPROCAL", "RECIPROCAL_SQRT")); y0 = rnd(rng, ldo * n, tout)
+            tcomp = gen.F64 if tin == gen.F64 else gen.F32
+
+            def mk(bufs, keep):
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
+                return p
+            both((1, op, bc, m, n, ldi, 0, 0, ldo, tin, UNS, UNS, tout, tcomp), mk, [y0])
+
+
+@pytest.mark.parametrize("t", [gen.F32, gen.BF16, gen.F16])
+def test_relu_family_and_masks(t):
+    rng = np.random.default_rng(62)
+    for fwd, inv in (("RELU", "RELU_INV"), ("LEAKY_RELU", "LEAKY_RELU_INV"), ("ELU", "ELU_INV")):
+        for (m, n, pad) in ((35, 11, 0), (64, 5, 3), (9, 40, 7)):
+            for bitm in ((1, 0) if fwd != "ELU" else (0,)):
+                ld = m + pad
+                flags = X.MELTW_FLAG_UNARY_BITMASK_2BYTEMULT if bitm else 0
+                x = rnd(rng, ld * n, t); y0 = rnd(rng, ld * n, t); alpha = C.c_float(0.3)
+                mask0 = rng.integers(0, 256, size=(ld + 15) // 16 * 2 * n, dtype=np.uint8)
+                op = getattr(X, "MELTW_TYPE_UNARY_" + fwd)
+
+                def mk(bufs, keep):
+                    p = X.MeltwUnaryParam(); p.op.primary = C.addressof(alpha)
+                    p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, bufs[0].ctypes.data, bufs[1].ctypes.data
+                    return p
+                both((1, op, flags, m, n, ld, 0, 0, ld, t, UNS, UNS, t, gen.F32), mk, [y0, mask0])
+                if fwd == "ELU" or bitm:
+                    g = rnd(rng, ld * n, t); o0 = rnd(rng, ld * n, t)
+                    aux = rnd(rng, ld * n, t) if fwd == "ELU" else mask0
+                    opi = getattr(X, "MELTW_TYPE_UNARY_" + inv)
+
+                    def mki(bufs, keep):
+                        p = X.MeltwUnaryParam(); p.op.primary = C.addressof(alpha)
+                        p.inp.primary, p.inp.secondary, p.out.primary = g.ctypes.data, aux.ctypes.data, bufs[0].ctypes.data
+                        return p
+                    both((1, opi, flags, m, n, ld, 0, 0, ld, t, UNS, UNS, t, gen.F32), mki, [o0])
+
+
+@pytest.mark.parametrize("t", [gen.F32, gen.BF16, gen.F64])
+def test_binary_ternary_compare_select(t):
+    rng = np.random.default_rng(63)
+    tcomp = gen.F64 if t == gen.F64 else gen.F32
+    for (m, n, pad) in ((33, 9, 0), (16, 20, 4)):
+        ld = m + pad
+        a, b, c3, y0 = (rnd(rng, ld * n, t) for _ in range(4))
+        for name in ("ADD", "MUL", "SUB", "DIV", "MULADD", "MAX", "MIN"):
+            for bc in (0, X.MELTW_FLAG_BINARY_BCAST_COL_IN_0, X.MELTW_FLAG_BINARY_BCAST_ROW_IN_1, X.MELTW_FLAG_BINARY_BCAST_SCALAR_IN_1):
+                def mk(bufs, keep):
+                    p = X.MeltwBinaryParam(); p.in0.primary, p.in1.primary, p.out.primary = a.ctypes.data, b.ctypes.data, bufs[0].ctypes.data
+                    return p
+                both((2, getattr(X, "MELTW_TYPE_BINARY_" + name), bc, m, n, ld, ld, 0, ld, t, t, UNS, t, tcomp), mk, [y0])
+        if t != gen.F64:
+            mask0 = rng.integers(0, 256, size=(ld + 15) // 16 * 2 * n, dtype=np.uint8)
+            for name in ("GT", "GE", "LT", "LE", "EQ", "NE"):
+                def mkc(bufs, keep):
+                    p = X.MeltwBinaryParam(); p.in0.primary, p.in1.primary, p.out.primary = a.ctypes.data, b.ctypes.data, bufs[0].ctypes.data
+                    return p
+                both((2, getattr(X, "MELTW_TYPE_BINARY_CMP_OP_" + name), X.MELTW_FLAG_BINARY_BITMASK_2BYTEMULT if hasattr(X, "MELTW_FLAG_BINARY_BITMASK_2BYTEMULT") else 0,
+                      m, n, ld, ld, 0, ld, t, t, UNS, gen.F32 if False else t, tcomp), mkc, [mask0])
+            for name in ("MULADD", "NMULADD"):
+                def mkt(bufs, keep):
+                    p = X.MeltwTernaryParam(); p.in0.primary, p.in1.primary, p.in2.primary, p.out.primary = a.ctypes.data, b.ctypes.data, c3.ctypes.data, bufs[0].ctypes.data
+                    return p
+                both((3, getattr(X, "MELTW_TYPE_TERNARY_" + name), 0, m, n, ld, ld, ld, ld, t, t, t, t, tcomp), mkt, [y0])
+        sel = rng.integers(0, 256, size=(ld + 15) // 16 * 2 * n, dtype=np.uint8)
+
+        def mks(bufs, keep):
+            p = X.MeltwTernaryParam(); p.in0.primary, p.in1.primary, p.in2.primary, p.out.primary = a.ctypes.data, b.ctypes.data, sel.ctypes.data, bufs[0].ctypes.data
+            return p
+        both((3, X.MELTW_TYPE_TERNARY_SELECT, X.MELTW_FLAG_TERNARY_BITMASK_2BYTEMULT if hasattr(X, "MELTW_FLAG_TERNARY_BITMASK_2BYTEMULT") else 0,
+              m, n, ld, ld, ld, ld, t, t, gen.F32 if False else UNS + 0 if False else t, t, tcomp), mks, [y0])
+
+
+@pytest.mark.parametrize("t", [gen.F32, gen.BF16, gen.F64])
+def test_reductions(t):
+    rng = np.random.default_rng(64)
+    for (m, n, pad) in ((33, 17, 0), (8, 70, 3)):
+        ldi = m + pad
+        x = rnd(rng, ldi * n, t)
+        for name in ("X_OP_ADD", "X2_OP_ADD", "X_X2_OP_ADD", "X_OP_MAX", "X_OP_MIN"):
+            if t == gen.F64 and "X2" in name:
+                continue    # the reference's F64 path never stores the sums of squares (it zeroes the plane, :1150-1153 and :1282): not restated
+            for rows in (1, 0):
+                for init in ((0, 1) if "ADD" in name else (0,)):
+                    flags = (X.MELTW_FLAG_UNARY_REDUCE_ROWS if rows else X.MELTW_FLAG_UNARY_REDUCE_COLS) | (X.MELTW_FLAG_UNARY_REDUCE_INIT_ACC if init else 0)
+                    ldo = n if rows else m      # ldo > m: the reference also stores its (uninitialised) scratch for rows m..ldo-1 (:1425-1430): not part of the contract
+                    y0 = rnd(rng, 2 * max(ldo, n, m) + 8, t)
+
+                    def mk(bufs, keep):
+                        p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
+                        return p
+                    both((1, getattr(X, "MELTW_TYPE_UNARY_REDUCE_" + name), flags, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, gen.F64 if t == gen.F64 else gen.F32), mk, [y0])
+
+
+def test_layout_transforms_and_dequant():
+    rng = np.random.default_rng(65)
+    for (m, n, pad) in ((32, 16, 0), (17, 9, 3), (8, 4, 0)):
+        ldi = m + pad
+        for t, npdt in ((gen.BF16, np.uint16), (gen.F32, np.float32), (gen.I8, np.uint8)):
+            x = rng.integers(0, 250, size=ldi * n).astype(npdt)
+            for name, ldo, osize in (("NORM_TO_NORMT", n + 2, (n + 2) * m),):
+                y0 = np.zeros(osize, dtype=npdt)
+
+                def mk(bufs, keep):
+                    p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
+                    return p
+                both((1, getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_" + name), 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), mk, [y0])
+        for t, npdt, v, nn in ((gen.BF16, np.uint16, 2, 16), (gen.BF16, np.uint16, 4, 16), (gen.I8, np.uint8, 4, 16)):
+            x = rng.integers(0, 250, size=ldi * nn).astype(npdt)
+            y0 = np.zeros((m + 1) * nn, dtype=npdt)
+
+            def mkv(bufs, keep):
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
+                return p
+            both((1, getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI%d" % v), 0, m, nn, ldi, 0, 0, m + 1, t, UNS, UNS, t, t), mkv, [y0])
+    for t, npdt in ((gen.I8, np.int8), (gen.I16, np.int16), (gen.I32, np.int32)):
+        m, n, ld = 20, 7, 23
+        x = rng.integers(-100, 100, size=ld * n).astype(npdt); y0 = np.zeros(ld * n, dtype=np.float32); scf = C.c_float(0.0625)
+
+        def mkd(bufs, keep):
+            p = X.MeltwUnaryParam(); p.inp.primary, p.inp.secondary, p.out.primary = x.ctypes.data, C.addressof(scf), bufs[0].ctypes.data
+            return p
+        both((1, X.MELTW_TYPE_UNARY_DEQUANT, 0, m, n, ld, 0, 0, ld, t, UNS, UNS, gen.F32, gen.F32), mkd, [y0])
