@@ -52,7 +52,7 @@ struct BcscTcParams {
   const uint4* ops;                         // {d col | A row offset/16 << 16, B offset/16, idesc N bits, accumulate}
   const unsigned int* col_any;              // [nbc] column has at least one block
   const char* b_packed;                     // B blocks in visiting order, pre-swizzled (bcsc_pack_b_kernel)
-  int mma_warps;
+  int mma_warps, ops_cap;                   // ops_cap: operations that fit the shared-memory copy (variant 2)
   char* c; int beta0;
   uint32_t idesc, b_layout, b_sbo16;        // UMMA descriptor pieces
   int spin;                                 // bit mask: roles polling with test_wait (1 MMA, 2 epilogue, 4 converters, 8 producers)
@@ -481,6 +481,235 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
   }
 }
 
+
+// ---- variant 2: two CTAs per SM -------------------------------------------------------------------------------------------
+// The pipeline above is bound by hand-over LATENCY (a stage is occupied from the start of its conversion until its MMAs
+// retire, ~2000+ cycles, while the HBM budget is ~670 cycles per k-step), not by any throughput: the cure that worked for the
+// dense kernel is a second, independent pipeline on the same SM. To make two CTAs fit (<= ~112 KB of shared memory, 256 TMEM
+// columns, <= 85 registers x 384 threads each) the VNNI -> canonical conversion is done IN PLACE (every converter thread pulls
+// its 8 x 16 bytes into registers, the 128 converter threads meet at a named barrier, then write), which removes the second A
+// ring, and each CTA keeps a single 256-column accumulator: while its epilogue drains, the sibling CTA computes.
+//   warp 0 A producer | warp 2 B producer | warps 1,3 MMA issuers (column ownership as above) | warps 4-7 epilogue | warps 8-11 converters
+constexpr int kThreads2 = 384;
+
+template <int M>
+__global__ void __launch_bounds__(kThreads2, 2)
+bcsc_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) {
+  constexpr int G = 128 / M;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int AS = P.raw_stages, BS = P.b_stages;
+  const int NP = P.nparts, NKS = P.nks, NL = P.nparts * P.nks;
+  uint8_t* s_a = smem;
+  uint8_t* s_b = s_a + (size_t)AS * A_STAGE;
+  uint4* s_ops = (uint4*)(s_b + (size_t)BS * P.b_stage_bytes);
+  unsigned int* s_lp = (unsigned int*)(s_ops + P.ops_cap + 1);
+  unsigned int* s_wr = s_lp + NL + 1;
+  unsigned char* s_any = (unsigned char*)(s_wr + 4 * NL);
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(s_any + P.nbc) + 15) & ~(uintptr_t)15);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t a_full = bar0, a_conv = a_full + 8 * 8, a_empty = a_conv + 8 * 8, b_full = a_empty + 8 * 8, b_empty = b_full + 8 * 8;
+  const uint32_t t_full = b_empty + 8 * 8, t_empty = t_full + 8;
+  uint32_t* tmem_word = (uint32_t*)(bars + 5 * 8 + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long Gd = gridDim.x, bid = blockIdx.x;
+  const long long n_local = ((bid < P.ngroups) ? (P.ngroups - bid + Gd - 1) / Gd : 0) * NP;
+  const uint32_t blk_bytes = (uint32_t)P.bn * P.bk * 2;
+  {
+    const unsigned int nnzb = P.list_ptr[NL];
+    for (unsigned int i = threadIdx.x; i < nnzb && i < (unsigned int)P.ops_cap; i += blockDim.x) s_ops[i] = P.ops[i];
+    for (int i = threadIdx.x; i < 4 * NL; i += blockDim.x) s_wr[i] = P.wranges[i];
+    for (int i = threadIdx.x; i <= NL; i += blockDim.x) s_lp[i] = P.list_ptr[i];
+    for (int i = threadIdx.x; i < P.nbc; i += blockDim.x) s_any[i] = (unsigned char)P.col_any[i];
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
+    for (int i = 0; i < AS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_conv + 8 * i, 4); mbar_init(a_empty + 8 * i, 2); }
+    for (int i = 0; i < BS; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 2); }
+    mbar_init(t_full, 2); mbar_init(t_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_word)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_word;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0; uint32_t aph = 0;
+      for (long long i = 0; i < n_local; ++i) {
+        const long long grp = bid + (i / NP) * Gd;
+        for (int ks = 0; ks < NKS; ++ks) {
+          mbar_wait(a_empty + 8 * as, aph ^ 1);
+          mbar_expect_tx(a_full + 8 * as, (uint32_t)A_STAGE);
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                       :: "r"(smem_u32(s_a + (size_t)as * A_STAGE)), "l"(&map_a), "r"(0), "r"(ks * 32), "r"((int)(grp * G)), "r"(a_full + 8 * as) : "memory");
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      int bs = 0; uint32_t bph = 0;
+      for (long long i = 0; i < n_local; ++i) {
+        const int l0 = (int)(i % NP) * NKS;
+        for (int ks = 0; ks < NKS; ++ks) {
+          const unsigned int e0 = s_lp[l0 + ks], e1 = s_lp[l0 + ks + 1];
+          mbar_wait(b_empty + 8 * bs, bph ^ 1);
+          mbar_expect_tx(b_full + 8 * bs, (e1 - e0) * blk_bytes);
+          if (e1 > e0) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(s_b + (size_t)bs * P.b_stage_bytes)), "l"(P.b_packed + (size_t)e0 * blk_bytes), "r"((e1 - e0) * blk_bytes),
+                            "r"(b_full + 8 * bs) : "memory");
+          }
+          if (++bs == BS) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    const int mw = (warp == 1) ? 0 : 1;
+    int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+    const uint32_t a_hi = desc_hi(1024 >> 4, 2), b_hi = desc_hi(P.b_sbo16, P.b_layout);
+    const uint32_t a_lo0 = desc_lo(smem_u32(s_a), (uint32_t)(64 * 128) >> 4);
+    const uint32_t b_lo0 = desc_lo(smem_u32(s_b), 1);
+    const int ksteps = P.ksteps;
+    for (long long i = 0; i < n_local; ++i) {
+      mbar_wait(t_empty, (uint32_t)((i & 1) ^ 1));
+      tc_fence_after();
+      const int l0 = (int)(i % NP) * NKS;
+      for (int ks = 0; ks < NKS; ++ks) {
+        const unsigned int rng = s_wr[4 * (l0 + ks) + mw], ob = rng & 0xFFFFu, on = rng >> 16;
+        uint4 op = s_ops[ob];
+        mbar_wait(a_conv + 8 * as, aph);
+        mbar_wait(b_full + 8 * bs, bph);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + (uint32_t)as * (A_STAGE >> 4);
+        const uint32_t b_stage_lo = b_lo0 + (uint32_t)bs * ((uint32_t)P.b_stage_bytes >> 4);
+        for (unsigned int o = 0; o < on; ++o) {
+          const uint4 nxt = s_ops[ob + o + 1];
+          const uint32_t d = tmem_base + (op.x & 0xFFFFu), a_op = a_lo + (op.x >> 16), b_lo = b_stage_lo + op.y, idesc = P.idesc | op.z;
+          uint32_t accumulate = op.w;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            if (leader) umma_f16(d, desc64(a_hi, a_op + kk * (2048 >> 4)), desc64(b_hi, b_lo + kk * (32 >> 4)), idesc, accumulate);
+            accumulate = 1;
+          }
+          op = nxt;
+        }
+        if (leader) { umma_commit(a_empty + 8 * as); umma_commit(b_empty + 8 * bs); }
+        __syncwarp();
+        if (++as == AS) { as = 0; aph ^= 1; }
+        if (++bs == BS) { bs = 0; bph ^= 1; }
+      }
+      if (leader) umma_commit(t_full);
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const int mbl = row / M, m = row % M;
+    const bool bn32 = (P.bn % 32) == 0;
+    for (long long i = 0; i < n_local; ++i) {
+      const long long grp = bid + (i / NP) * Gd;
+      const long long mb = grp * G + mbl;
+      const bool valid = mb < P.m_blocks;
+      const int part = (int)(i % NP), pc0 = part * P.part_cols;
+      const int pcols = (P.ncols - pc0 < P.part_cols) ? (P.ncols - pc0) : P.part_cols;
+      const int nchunks = (pcols + 31) / 32;
+      __nv_bfloat16* cblk = reinterpret_cast<__nv_bfloat16*>(P.c) + ((size_t)mb * P.ncols + pc0) * M + m;
+      mbar_wait(t_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * 32;
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        if (ch + 1 == nchunks) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty); }
+        __nv_bfloat16* dst = cblk + (size_t)c0 * M;
+        const int ncol = (pcols - c0 < 32) ? (pcols - c0) : 32;
+        const int jb = (pc0 + c0) / P.bn;
+        const bool any0 = s_any[jb] != 0, any1 = bn32 ? any0 : (s_any[(pc0 + c0 + 16) / P.bn < P.nbc ? (pc0 + c0 + 16) / P.bn : jb] != 0);
+        if (P.beta0 && (M % 2) == 0) {
+          const bool odd = lane & 1;
+          unsigned int* dst32 = reinterpret_cast<unsigned int*>(dst - (odd ? 1 : 0));
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 2) {
+            const bool anyc = (jj < 16) ? any0 : any1;
+            const float mine_c0 = anyc ? __uint_as_float(v[jj]) : 0.0f, mine_c1 = anyc ? __uint_as_float(v[jj + 1]) : 0.0f;
+            const float send = odd ? mine_c0 : mine_c1;
+            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+            const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(got, mine_c1) : __floats2bfloat162_rn(mine_c0, got);
+            if (valid && (jj < 16 || ncol == 32)) dst32[((jj + (odd ? 1 : 0)) * M) >> 1] = *reinterpret_cast<const unsigned int*>(&pk);
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            if (jj < 16 || ncol == 32) {
+              float acc = ((jj < 16) ? any0 : any1) ? __uint_as_float(v[jj]) : 0.0f;
+              if (!P.beta0) acc += __bfloat162float(dst[jj * M]);
+              dst[jj * M] = __float2bfloat16_rn(acc);
+            }
+          }
+        }
+      }
+      if (nchunks == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty); }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // in-place conversion: 1024 units (4 rows x 1 k-pair) per stage, 8 per thread; same lane mapping as above (conflict-free)
+    const int cw = warp - 8, q = lane & 15, kp_lo = lane >> 4;
+    int as = 0; uint32_t aph = 0;
+    for (long long i = 0; i < n_local; ++i) {
+      for (int ks = 0; ks < NKS; ++ks) {
+        mbar_wait(a_full + 8 * as, aph);
+        uint8_t* buf = s_a + (size_t)as * A_STAGE;
+        uint4 w[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int idx = cw * 8 + it, atom = idx & 1, kp = (idx >> 1) * 2 + kp_lo;
+          const int mrow = atom * 64 + 4 * q, g = mrow / M, mm = mrow % M;
+          w[it] = *reinterpret_cast<const uint4*>(buf + ((size_t)(g * 32 + kp) * M + mm) * 4);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // every converter thread holds its share of the raw stage
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int idx = cw * 8 + it, atom = idx & 1, kp = (idx >> 1) * 2 + kp_lo;
+          uint2 ev, od;
+          ev.x = __byte_perm(w[it].x, w[it].y, 0x5410); ev.y = __byte_perm(w[it].z, w[it].w, 0x5410);
+          od.x = __byte_perm(w[it].x, w[it].y, 0x7632); od.y = __byte_perm(w[it].z, w[it].w, 0x7632);
+          uint8_t* base = buf + (size_t)atom * (64 * 128);
+          const int k0 = 2 * kp, k1 = 2 * kp + 1, ch = q >> 1, sub = (q & 1) << 3;
+          *reinterpret_cast<uint2*>(base + k0 * 128 + ((ch ^ (k0 & 7)) << 4) + sub) = ev;
+          *reinterpret_cast<uint2*>(base + k1 * 128 + ((ch ^ (k1 & 7)) << 4) + sub) = od;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_conv + 8 * as);
+        if (++as == AS) { as = 0; aph ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+template <int M>
+cudaError_t launch_two(long long grid, size_t smem, cudaStream_t stream, const CUtensorMap& ma, const BcscTcParams& P) {
+  static int attr_set = 0;
+  if (!attr_set) { cudaFuncSetAttribute(bcsc_tc2_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); attr_set = 1; }
+  bcsc_tc2_kernel<M><<<(unsigned int)grid, kThreads2, smem, stream>>>(ma, P);
+  return cudaGetLastError();
+}
+
 int g_sms = 0;
 
 template <int M, bool DBG>
@@ -547,6 +776,14 @@ extern "C" int xb_bcsc_tc_launch(xb_sparse_desc* d, const void* a, const void* b
   if (P.raw_stages > 8) P.raw_stages = 8;
   P.raw_stages = env_int("LIBXSMM_B200_BCSC_RAW", 2, P.raw_stages, P.raw_stages);
   P.mma_warps = env_int("LIBXSMM_B200_BCSC_MMAW", 1, 4, 4);
+  // variant 2 (two CTAs per SM): one 256-column accumulator, two stages per ring, everything within 112 KB
+  P.ops_cap = (int)nnzb;
+  const size_t meta2 = ((size_t)P.ops_cap + 1) * 16 + ((size_t)5 * nl + 8) * 4 + (size_t)n_blocks + 16 + (5 * 8 + 2) * 8 + 64 + 1024;
+  const int a2 = env_int("LIBXSMM_B200_BCSC_V2_AST", 2, 4, 2), b2 = env_int("LIBXSMM_B200_BCSC_V2_BST", 2, 4, 2);
+  const size_t smem2 = meta2 + (size_t)a2 * A_STAGE + (size_t)b2 * P.b_stage_bytes;
+  // measured (BASELINE size): variant 2 0.226 ms, variant 1 0.221 ms -- co-residency does not help here, so it stays opt-in
+  const bool v2 = env_int("LIBXSMM_B200_BCSC_V2", 0, 1, 0) == 1 && P.slot_cols <= 256 && smem2 <= 112 * 1024;
+  if (v2) { P.mma_warps = 2; P.raw_stages = a2; P.b_stages = b2; }
   const int cpw = (bpp + P.mma_warps - 1) / P.mma_warps;
 
   // per-handle device buffer: cached pattern + visiting order (the handle is caller-owned; reused across calls)
@@ -594,10 +831,14 @@ extern "C" int xb_bcsc_tc_launch(xb_sparse_desc* d, const void* a, const void* b
     if (CUDA_SUCCESS != enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) return -1;
   }
-  const size_t smem = meta + (size_t)(P.raw_stages + P.can_stages) * A_STAGE + (size_t)P.b_stages * P.b_stage_bytes;
-  const long long grid = P.ngroups < g_sms ? P.ngroups : g_sms;
+  const size_t smem = v2 ? smem2 : meta + (size_t)(P.raw_stages + P.can_stages) * A_STAGE + (size_t)P.b_stages * P.b_stage_bytes;
+  const long long grid = v2 ? (P.ngroups < 2ll * g_sms ? P.ngroups : 2ll * g_sms) : (P.ngroups < g_sms ? P.ngroups : g_sms);
   cudaError_t e = cudaErrorInvalidValue;
-  if (P.dbg != nullptr && M == 32) e = launch_one<32, true>(grid, smem, stream, map_a, P);
+  if (v2 && M == 16) e = launch_two<16>(grid, smem, stream, map_a, P);
+  else if (v2 && M == 32) e = launch_two<32>(grid, smem, stream, map_a, P);
+  else if (v2 && M == 64) e = launch_two<64>(grid, smem, stream, map_a, P);
+  else if (v2 && M == 128) e = launch_two<128>(grid, smem, stream, map_a, P);
+  else if (P.dbg != nullptr && M == 32) e = launch_one<32, true>(grid, smem, stream, map_a, P);
   else if (M == 16) e = launch_one<16, false>(grid, smem, stream, map_a, P);
   else if (M == 32) e = launch_one<32, false>(grid, smem, stream, map_a, P);
   else if (M == 64) e = launch_one<64, false>(grid, smem, stream, map_a, P);
