@@ -710,6 +710,240 @@ cudaError_t launch_two(long long grid, size_t smem, cudaStream_t stream, const C
   return cudaGetLastError();
 }
 
+// ---- variant 3 (opt-in, LIBXSMM_B200_BCSC_V3=1): the A operand lives in TENSOR MEMORY ---------------------------------------
+// For kind::f16 a 32-bit TMEM cell of the A operand holds two consecutive k of one row -- which is exactly one VNNI2 word.
+// So the "conversion" degenerates to a transposing copy: thread = row m reads its 32 words of a k-step from the raw TMA
+// stage (conflict-free) and writes them with ONE tcgen05.st.32x32b.x32 into an A ring in TMEM; the MMAs then take A from
+// TMEM (no 4 KB shared-memory read of A per instruction, no canonical ring, no PRMT, no proxy fence). TMEM plan: two
+// accumulator slots of 192 columns (column parts of <= 192) + four A stages of 32 columns = 512.
+constexpr int kA3Stages = 4, kD3Cols = 192;
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+               "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+               "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                  "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                  "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads, 1)
+bcsc_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) {
+  constexpr int G = 128 / M;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int RS = P.raw_stages, BS = P.b_stages, TS = kA3Stages;
+  const int NP = P.nparts, NKS = P.nks, NL = P.nparts * P.nks;
+  uint8_t* s_raw = smem;
+  uint8_t* s_b = s_raw + (size_t)RS * A_STAGE;
+  uint4* s_ops = (uint4*)(s_b + (size_t)BS * P.b_stage_bytes);
+  unsigned int* s_lp = (unsigned int*)(s_ops + P.ops_cap + 1);
+  unsigned int* s_wr = s_lp + NL + 1;
+  unsigned char* s_any = (unsigned char*)(s_wr + 4 * NL);
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(s_any + P.nbc) + 15) & ~(uintptr_t)15);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t raw_full = bar0, raw_empty = raw_full + 8 * 16, ta_full = raw_empty + 8 * 16, ta_empty = ta_full + 8 * 8;
+  const uint32_t b_full = ta_empty + 8 * 8, b_empty = b_full + 8 * 16, t_full = b_empty + 8 * 16, t_empty = t_full + 8 * 2;
+  uint32_t* tmem_word = (uint32_t*)(bars + 4 * 16 + 2 * 8 + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long Gd = gridDim.x, bid = blockIdx.x;
+  const long long n_local = ((bid < P.ngroups) ? (P.ngroups - bid + Gd - 1) / Gd : 0) * NP;
+  const uint32_t blk_bytes = (uint32_t)P.bn * P.bk * 2;
+  {
+    const unsigned int nnzb = P.list_ptr[NL];
+    for (unsigned int i = threadIdx.x; i < nnzb && i < (unsigned int)P.ops_cap; i += blockDim.x) s_ops[i] = P.ops[i];
+    for (int i = threadIdx.x; i < 4 * NL; i += blockDim.x) s_wr[i] = P.wranges[i];
+    for (int i = threadIdx.x; i <= NL; i += blockDim.x) s_lp[i] = P.list_ptr[i];
+    for (int i = threadIdx.x; i < P.nbc; i += blockDim.x) s_any[i] = (unsigned char)P.col_any[i];
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
+    for (int i = 0; i < RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
+    for (int i = 0; i < TS; ++i) { mbar_init(ta_full + 8 * i, 4); mbar_init(ta_empty + 8 * i, (uint32_t)P.mma_warps); }
+    for (int i = 0; i < BS; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, (uint32_t)P.mma_warps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, (uint32_t)P.mma_warps); mbar_init(t_empty + 8 * i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_word)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_word;
+  const uint32_t tmem_a = tmem_base + 2u * kD3Cols;          // A ring: columns 384..511
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int rs = 0; uint32_t rph = 0;
+      for (long long i = 0; i < n_local; ++i) {
+        const long long grp = bid + (i / NP) * Gd;
+        for (int ks = 0; ks < NKS; ++ks) {
+          mbar_wait(raw_empty + 8 * rs, rph ^ 1);
+          mbar_expect_tx(raw_full + 8 * rs, (uint32_t)A_STAGE);
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                       :: "r"(smem_u32(s_raw + (size_t)rs * A_STAGE)), "l"(&map_a), "r"(0), "r"(ks * 32), "r"((int)(grp * G)), "r"(raw_full + 8 * rs) : "memory");
+          if (++rs == RS) { rs = 0; rph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      int bs = 0; uint32_t bph = 0;
+      for (long long i = 0; i < n_local; ++i) {
+        const int l0 = (int)(i % NP) * NKS;
+        for (int ks = 0; ks < NKS; ++ks) {
+          const unsigned int e0 = s_lp[l0 + ks], e1 = s_lp[l0 + ks + 1];
+          mbar_wait(b_empty + 8 * bs, bph ^ 1);
+          mbar_expect_tx(b_full + 8 * bs, (e1 - e0) * blk_bytes);
+          if (e1 > e0) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(s_b + (size_t)bs * P.b_stage_bytes)), "l"(P.b_packed + (size_t)e0 * blk_bytes), "r"((e1 - e0) * blk_bytes),
+                            "r"(b_full + 8 * bs) : "memory");
+          }
+          if (++bs == BS) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 || (warp == 3 && P.mma_warps >= 2) || (warp >= 20 && warp - 18 < P.mma_warps)) {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    const int mw = (warp == 1) ? 0 : ((warp == 3) ? 1 : warp - 18);
+    int ts = 0, bs = 0; uint32_t tph = 0, bph = 0;
+    const uint32_t b_hi = desc_hi(P.b_sbo16, P.b_layout);
+    const uint32_t b_lo0 = desc_lo(smem_u32(s_b), 1);
+    const uint32_t idesc0 = P.idesc & ~(1u << 15);           // A from TMEM: rows in lanes, k along the columns (K-major)
+    const int ksteps = P.ksteps;
+    for (long long i = 0; i < n_local; ++i) {
+      const int slot = (int)(i & 1);
+      mbar_wait(t_empty + 8 * slot, (uint32_t)(((i >> 1) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)(slot * kD3Cols);
+      const int l0 = (int)(i % NP) * NKS;
+      for (int ks = 0; ks < NKS; ++ks) {
+        const unsigned int rng = s_wr[4 * (l0 + ks) + mw], ob = rng & 0xFFFFu, on = rng >> 16;
+        uint4 op = s_ops[ob];
+        mbar_wait(ta_full + 8 * ts, tph);
+        mbar_wait(b_full + 8 * bs, bph);
+        tc_fence_after();
+        const uint32_t a_stage = tmem_a + (uint32_t)ts * 32u;
+        const uint32_t b_stage_lo = b_lo0 + (uint32_t)bs * ((uint32_t)P.b_stage_bytes >> 4);
+        for (unsigned int o = 0; o < on; ++o) {
+          const uint4 nxt = s_ops[ob + o + 1];
+          const uint32_t d = d_base + (op.x & 0xFFFFu), a_col = a_stage + ((op.x >> 16) >> 4), b_lo = b_stage_lo + op.y, idesc = idesc0 | op.z;
+          uint32_t accumulate = op.w;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            if (leader) umma_f16_ts(d, a_col + (uint32_t)kk * 8u, desc64(b_hi, b_lo + kk * (32 >> 4)), idesc, accumulate);
+            accumulate = 1;
+          }
+          op = nxt;
+        }
+        if (leader) { umma_commit(ta_empty + 8 * ts); umma_commit(b_empty + 8 * bs); }
+        __syncwarp();
+        if (++ts == TS) { ts = 0; tph ^= 1; }
+        if (++bs == BS) { bs = 0; bph ^= 1; }
+      }
+      if (leader) umma_commit(t_full + 8 * slot);
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 12) {
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int row = 32 * q + lane;
+    const int mbl = row / M, m = row % M;
+    const bool bn32 = (P.bn % 32) == 0;
+    for (long long i = 0; i < n_local; ++i) {
+      const int slot = (int)(i & 1);
+      const long long grp = bid + (i / NP) * Gd;
+      const long long mb = grp * G + mbl;
+      const bool valid = mb < P.m_blocks;
+      const int part = (int)(i % NP), pc0 = part * P.part_cols;
+      const int pcols = (P.ncols - pc0 < P.part_cols) ? (P.ncols - pc0) : P.part_cols;
+      const int nchunks = (pcols + 31) / 32, cbeg = half ? (nchunks + 1) / 2 : 0, cend = half ? nchunks : (nchunks + 1) / 2;
+      __nv_bfloat16* cblk = reinterpret_cast<__nv_bfloat16*>(P.c) + ((size_t)mb * P.ncols + pc0) * M + m;
+      mbar_wait(t_full + 8 * slot, (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(slot * kD3Cols) + ((uint32_t)(q * 32) << 16);
+      if (cbeg == cend) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
+      for (int ch = cbeg; ch < cend; ++ch) {
+        const int c0 = ch * 32;
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        if (ch + 1 == cend) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
+        __nv_bfloat16* dst = cblk + (size_t)c0 * M;
+        const int ncol = (pcols - c0 < 32) ? (pcols - c0) : 32;
+        const int jb = (pc0 + c0) / P.bn;
+        const bool any0 = s_any[jb] != 0, any1 = bn32 ? any0 : (s_any[(pc0 + c0 + 16) / P.bn < P.nbc ? (pc0 + c0 + 16) / P.bn : jb] != 0);
+        if (P.beta0 && (M % 2) == 0) {
+          const bool odd = lane & 1;
+          unsigned int* dst32 = reinterpret_cast<unsigned int*>(dst - (odd ? 1 : 0));
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 2) {
+            const bool anyc = (jj < 16) ? any0 : any1;
+            const float mine_c0 = anyc ? __uint_as_float(v[jj]) : 0.0f, mine_c1 = anyc ? __uint_as_float(v[jj + 1]) : 0.0f;
+            const float send = odd ? mine_c0 : mine_c1;
+            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+            const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(got, mine_c1) : __floats2bfloat162_rn(mine_c0, got);
+            if (valid && (jj < 16 || ncol == 32)) dst32[((jj + (odd ? 1 : 0)) * M) >> 1] = *reinterpret_cast<const unsigned int*>(&pk);
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            if (jj < 16 || ncol == 32) {
+              float acc = ((jj < 16) ? any0 : any1) ? __uint_as_float(v[jj]) : 0.0f;
+              if (!P.beta0) acc += __bfloat162float(dst[jj * M]);
+              dst[jj * M] = __float2bfloat16_rn(acc);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 12 && warp < 16) {
+    // transposing copy raw VNNI words -> TMEM A stage: this warp owns rows 32q .. 32q+31 (its TMEM lane quadrant)
+    const int q = warp & 3, mrow = 32 * q + lane, g = mrow / M, mm = mrow % M;
+    int rs = 0, ts = 0; uint32_t rph = 0, tph = 0;
+    for (long long i = 0; i < n_local; ++i) {
+      for (int ks = 0; ks < NKS; ++ks) {
+        mbar_wait(raw_full + 8 * rs, rph);
+        mbar_wait(ta_empty + 8 * ts, tph ^ 1);
+        tc_fence_after();
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(s_raw + (size_t)rs * A_STAGE) + (size_t)g * 32 * M + mm;
+        uint32_t w[32];
+#pragma unroll
+        for (int kp = 0; kp < 32; ++kp) w[kp] = src[(size_t)kp * M];
+        tmem_st32(tmem_a + (uint32_t)ts * 32u + ((uint32_t)(q * 32) << 16), w);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(ta_full + 8 * ts); mbar_arrive(raw_empty + 8 * rs); }
+        if (++rs == RS) { rs = 0; rph ^= 1; }
+        if (++ts == TS) { ts = 0; tph ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int M>
+cudaError_t launch_three(long long grid, size_t smem, cudaStream_t stream, const CUtensorMap& ma, const BcscTcParams& P) {
+  static int attr_set = 0;
+  if (!attr_set) { cudaFuncSetAttribute(bcsc_tc3_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = 1; }
+  bcsc_tc3_kernel<M><<<(unsigned int)grid, kThreads, smem, stream>>>(ma, P);
+  return cudaGetLastError();
+}
+
 int g_sms = 0;
 
 template <int M, bool DBG>
@@ -749,7 +983,9 @@ extern "C" int xb_bcsc_tc_launch(xb_sparse_desc* d, const void* a, const void* b
   // column parts: an accumulator of <= 256 columns leaves room for a second one in TMEM, so the epilogue of one work item
   // overlaps the MMAs of the next (a single 512-column accumulator serialises the two phases)
   int bpp = (int)n_blocks, nparts = 1;
-  if (ncols > 256) { bpp = 256 / bn; nparts = ((int)n_blocks + bpp - 1) / bpp; }
+  const bool v3 = env_int("LIBXSMM_B200_BCSC_V3", 0, 1, 0) == 1 && bn <= kD3Cols;      // opt-in: A operand in tensor memory
+  if (v3) { bpp = kD3Cols / bn; if (bpp > (int)n_blocks) bpp = (int)n_blocks; nparts = ((int)n_blocks + bpp - 1) / bpp; }
+  else if (ncols > 256) { bpp = 256 / bn; nparts = ((int)n_blocks + bpp - 1) / bpp; }
   if (env_int("LIBXSMM_B200_BCSC_PARTS", 1, 1, 0) == 1) { bpp = (int)n_blocks; nparts = 1; }
   const int nl = nparts * nks;
   if (nl > kMaxLists - 1) return -1;
@@ -782,7 +1018,16 @@ extern "C" int xb_bcsc_tc_launch(xb_sparse_desc* d, const void* a, const void* b
   const int a2 = env_int("LIBXSMM_B200_BCSC_V2_AST", 2, 4, 2), b2 = env_int("LIBXSMM_B200_BCSC_V2_BST", 2, 4, 2);
   const size_t smem2 = meta2 + (size_t)a2 * A_STAGE + (size_t)b2 * P.b_stage_bytes;
   // measured (BASELINE size): variant 2 0.226 ms, variant 1 0.221 ms -- co-residency does not help here, so it stays opt-in
-  const bool v2 = env_int("LIBXSMM_B200_BCSC_V2", 0, 1, 0) == 1 && P.slot_cols <= 256 && smem2 <= 112 * 1024;
+  const bool v2 = !v3 && env_int("LIBXSMM_B200_BCSC_V2", 0, 1, 0) == 1 && P.slot_cols <= 256 && smem2 <= 112 * 1024;
+  const size_t meta3 = ((size_t)P.ops_cap + 1) * 16 + ((size_t)5 * nl + 8) * 4 + (size_t)n_blocks + 16 + (4 * 16 + 2 * 8 + 4) * 8 + 64 + 1024;
+  size_t smem3 = 0;
+  if (v3) {
+    P.mma_warps = env_int("LIBXSMM_B200_BCSC_MMAW", 1, 4, 4);
+    P.raw_stages = env_int("LIBXSMM_B200_BCSC_V3_RAW", 2, 8, 4); P.b_stages = env_int("LIBXSMM_B200_BCSC_V3_BST", 2, 8, 5);
+    while (P.b_stages > 2 && meta3 + (size_t)P.raw_stages * A_STAGE + (size_t)P.b_stages * P.b_stage_bytes > 224 * 1024) --P.b_stages;
+    smem3 = meta3 + (size_t)P.raw_stages * A_STAGE + (size_t)P.b_stages * P.b_stage_bytes;
+    if (smem3 > 224 * 1024) return -1;
+  }
   if (v2) { P.mma_warps = 2; P.raw_stages = a2; P.b_stages = b2; }
   const int cpw = (bpp + P.mma_warps - 1) / P.mma_warps;
 
@@ -834,7 +1079,11 @@ extern "C" int xb_bcsc_tc_launch(xb_sparse_desc* d, const void* a, const void* b
   const size_t smem = v2 ? smem2 : meta + (size_t)(P.raw_stages + P.can_stages) * A_STAGE + (size_t)P.b_stages * P.b_stage_bytes;
   const long long grid = v2 ? (P.ngroups < 2ll * g_sms ? P.ngroups : 2ll * g_sms) : (P.ngroups < g_sms ? P.ngroups : g_sms);
   cudaError_t e = cudaErrorInvalidValue;
-  if (v2 && M == 16) e = launch_two<16>(grid, smem, stream, map_a, P);
+  if (v3 && M == 16) e = launch_three<16>(grid, smem3, stream, map_a, P);
+  else if (v3 && M == 32) e = launch_three<32>(grid, smem3, stream, map_a, P);
+  else if (v3 && M == 64) e = launch_three<64>(grid, smem3, stream, map_a, P);
+  else if (v3 && M == 128) e = launch_three<128>(grid, smem3, stream, map_a, P);
+  else if (v2 && M == 16) e = launch_two<16>(grid, smem, stream, map_a, P);
   else if (v2 && M == 32) e = launch_two<32>(grid, smem, stream, map_a, P);
   else if (v2 && M == 64) e = launch_two<64>(grid, smem, stream, map_a, P);
   else if (v2 && M == 128) e = launch_two<128>(grid, smem, stream, map_a, P);
