@@ -4,7 +4,7 @@
  * src/generator_mateltwise_reference_impl.c, for the operations of SURVEY.md 8a (rows a5, a6) that the CUDA
  * library dispatches most: element-wise unary / binary / ternary maps with broadcast, the ReLU family with
  * bitmasks, compare / select / zip, row and column reductions (sum, sum of squares, max, min), the norm ->
- * transposed / VNNI2 / VNNI4 layout transforms, quantise / dequantise. Operations that are not restated return 2
+ * transposed / VNNI2 / VNNI4 layout transforms, gather / scatter, quantise / dequantise. Operations that are not restated return 2
  * and stay pinned by the reference itself (oracle/_ref). Pinned bit for bit against libxsmm_reference_elementwise
  * in tests/test_oracle_vs_ref.py (transcendental ops: same libm calls, so equal on the same host).
  *
@@ -217,7 +217,44 @@ static int unary_quant(const mdesc* d, const libxsmm_meltw_unary_param* p) {
     }
     return 0;
   }
-  return 2;   /* QUANT variants (saturating / non-saturating, MX block formats) stay with the reference */
+  if (d->op == LIBXSMM_MELTW_TYPE_UNARY_QUANT && d->t0 == LIBXSMM_DATATYPE_F32 && p->in.secondary != NULL
+      && (d->flags & LIBXSMM_MELTW_FLAG_UNARY_NO_SCF_QUANT) == 0) {
+    /* :2206-2217: nearbyintf(x * scf), then wrap to the low bits or saturate (SIGN_SAT_QUANT) */
+    const float scf = *(const float*)p->in.secondary;
+    const int sat = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_SIGN_SAT_QUANT) != 0;
+    if (!(d->to == LIBXSMM_DATATYPE_I8 || d->to == LIBXSMM_DATATYPE_I16 || d->to == LIBXSMM_DATATYPE_I32)) return 2;
+    for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+      const float r = nearbyintf(((const float*)p->in.primary)[bidx(d, 0, i, j, d->ldi)] * scf);
+      const long long oi = i + (long long)j * d->ldo;
+      if (d->to == LIBXSMM_DATATYPE_I8) ((int8_t*)p->out.primary)[oi] = sat ? (int8_t)fminf(fmaxf(r, -128.f), 127.f) : (int8_t)(0xff & (int)r);
+      else if (d->to == LIBXSMM_DATATYPE_I16) ((int16_t*)p->out.primary)[oi] = sat ? (int16_t)fminf(fmaxf(r, -32768.f), 32767.f) : (int16_t)(0xffff & (int)r);
+      else ((int32_t*)p->out.primary)[oi] = (int32_t)r;
+    }
+    return 0;
+  }
+  return 2;   /* MX / NV block formats stay with the reference */
+}
+
+/* gather / scatter, pure data movement: reference :1444-1794. Index array in in.secondary (gather) or out.secondary
+ * (scatter), 4-byte entries unless IDX_SIZE_8BYTES; GS_COLS moves whole columns, GS_ROWS whole rows, otherwise one
+ * linear offset per element of the m x n index matrix */
+static int unary_gs(const mdesc* d, const libxsmm_meltw_unary_param* p) {
+  const int ts = tsz(d->t0), gather = (d->op == LIBXSMM_MELTW_TYPE_UNARY_GATHER);
+  const int idx8 = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_IDX_SIZE_8BYTES) != 0;
+  const int cols = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_GS_COLS) != 0, rows = !cols && (d->flags & LIBXSMM_MELTW_FLAG_UNARY_GS_ROWS) != 0;
+  const void* idxp = gather ? p->in.secondary : p->out.secondary;
+  const char* in = (const char*)p->in.primary; char* out = (char*)p->out.primary;
+  long long i, j;
+  if (ts > 4 || idxp == NULL) return 2;
+  for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+    const long long sel = cols ? j : (rows ? i : (i + j * d->m));
+    const long long x = idx8 ? (long long)((const uint64_t*)idxp)[sel] : (long long)((const uint32_t*)idxp)[sel];
+    long long src, dst;
+    if (gather) { dst = i + j * d->ldo; src = cols ? (i + x * d->ldi) : (rows ? (x + j * d->ldi) : x); }
+    else { src = i + j * d->ldi; dst = cols ? (i + x * d->ldo) : (rows ? (x + j * d->ldo) : x); }
+    memcpy(out + dst * ts, in + src * ts, (size_t)ts);
+  }
+  return 0;
 }
 
 static int binary_map(const mdesc* d, const libxsmm_meltw_binary_param* p) {
@@ -315,6 +352,8 @@ ORACLE_API int oracle_meltw(const int* desc, void* param, int mode) {
         return unary_transform(&d, (const libxsmm_meltw_unary_param*)param);
       case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT: case LIBXSMM_MELTW_TYPE_UNARY_QUANT:
         return unary_quant(&d, (const libxsmm_meltw_unary_param*)param);
+      case LIBXSMM_MELTW_TYPE_UNARY_GATHER: case LIBXSMM_MELTW_TYPE_UNARY_SCATTER:
+        return unary_gs(&d, (const libxsmm_meltw_unary_param*)param);
       default: return 2;
     }
   }

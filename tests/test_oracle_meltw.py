@@ -175,3 +175,41 @@ def test_layout_transforms_and_dequant():
             p = X.MeltwUnaryParam(); p.inp.primary, p.inp.secondary, p.out.primary = x.ctypes.data, C.addressof(scf), bufs[0].ctypes.data
             return p
         both((1, X.MELTW_TYPE_UNARY_DEQUANT, 0, m, n, ld, 0, 0, ld, t, UNS, UNS, gen.F32, gen.F32), mkd, [y0])
+
+
+def test_gather_scatter_and_quant():
+    rng = np.random.default_rng(66)
+    for t, npdt in ((gen.F32, np.float32), (gen.BF16, np.uint16), (gen.I8, np.uint8)):
+        for idx8 in (0, 1):
+            idt = np.uint64 if idx8 else np.uint32
+            f8 = X.MELTW_FLAG_UNARY_IDX_SIZE_8BYTES if idx8 else X.MELTW_FLAG_UNARY_IDX_SIZE_4BYTES
+            m, n, big = 19, 11, 40
+            # gather columns / rows / offsets out of a big x big source
+            src = rng.integers(0, 250, size=big * big).astype(npdt)
+            for mode, idx in ((X.MELTW_FLAG_UNARY_GS_COLS, rng.integers(0, big, size=n)), (X.MELTW_FLAG_UNARY_GS_ROWS, rng.integers(0, big, size=m)),
+                              (X.MELTW_FLAG_UNARY_GS_OFFS, rng.integers(0, big * big, size=m * n))):
+                ia = idx.astype(idt); y0 = np.zeros((m + 2) * n, dtype=npdt)
+
+                def mk(bufs, keep):
+                    p = X.MeltwUnaryParam(); p.inp.primary, p.inp.secondary, p.out.primary = src.ctypes.data, ia.ctypes.data, bufs[0].ctypes.data
+                    return p
+                both((1, X.MELTW_TYPE_UNARY_GATHER, mode | f8, m, n, big, 0, 0, m + 2, t, UNS, UNS, t, t), mk, [y0])
+            # scatter with unique targets (the result must not depend on the visiting order)
+            x = rng.integers(0, 250, size=(m + 1) * n).astype(npdt)
+            for mode, idx in ((X.MELTW_FLAG_UNARY_GS_COLS, rng.permutation(big)[:n]), (X.MELTW_FLAG_UNARY_GS_ROWS, rng.permutation(big)[:m]),
+                              (X.MELTW_FLAG_UNARY_GS_OFFS, rng.permutation(big * big)[:m * n])):
+                ia = idx.astype(idt); y0 = rng.integers(0, 250, size=big * big).astype(npdt)
+
+                def mks(bufs, keep):
+                    p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, bufs[0].ctypes.data, ia.ctypes.data
+                    return p
+                both((1, X.MELTW_TYPE_UNARY_SCATTER, mode | f8, m, n, m + 1, 0, 0, big, t, UNS, UNS, t, t), mks, [y0])
+    for tout, npdt in ((gen.I8, np.int8), (gen.I16, np.int16), (gen.I32, np.int32)):
+        for sat in (0, X.MELTW_FLAG_UNARY_SIGN_SAT_QUANT):
+            m, n, ld = 23, 9, 25
+            x = (rng.standard_normal(ld * n) * 90).astype(np.float32); y0 = np.zeros(ld * n, dtype=npdt); scf = C.c_float(1.75)
+
+            def mkq(bufs, keep):
+                p = X.MeltwUnaryParam(); p.inp.primary, p.inp.secondary, p.out.primary = x.ctypes.data, C.addressof(scf), bufs[0].ctypes.data
+                return p
+            both((1, X.MELTW_TYPE_UNARY_QUANT, sat, m, n, ld, 0, 0, ld, gen.F32, UNS, UNS, tout, gen.F32), mkq, [y0])
