@@ -56,6 +56,7 @@ struct BcscTcParams {
   char* c; int beta0;
   uint32_t idesc, b_layout, b_sbo16;        // UMMA descriptor pieces
   int spin;                                 // bit mask: roles polling with test_wait (1 MMA, 2 epilogue, 4 converters, 8 producers)
+  int b_cpasync;                            // experiment (LIBXSMM_B200_BCSC_BCPASYNC=1): B through per-thread cp.async instead of the TMA engine
   int sleep;                                // producers/converters/epilogue back off with nanosleep between polls (LIBXSMM_B200_BCSC_SLEEP)
   int skip;                                 // diagnostic ablation mask (LIBXSMM_B200_BCSC_SKIP): 1 conv, 2 B loads, 4 A loads, 8 stores, 16 MMAs
   long long* dbg;                           // optional per-role cycle counters (CTA 0), see tools/bcsc_probe.py
@@ -274,7 +275,7 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
     for (int i = 0; i < RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, kConvWarps); }
     for (int i = 0; i < CS; ++i) { mbar_init(can_full + 8 * i, kConvWarps); mbar_init(can_empty + 8 * i, (uint32_t)P.mma_warps); }
-    for (int i = 0; i < BS; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, (uint32_t)P.mma_warps); }
+    for (int i = 0; i < BS; ++i) { mbar_init(b_full + 8 * i, P.b_cpasync ? 32u : 1u); mbar_init(b_empty + 8 * i, (uint32_t)P.mma_warps); }
     for (int i = 0; i < NS; ++i) { mbar_init(t_full + 8 * i, (uint32_t)P.mma_warps); mbar_init(t_empty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -306,7 +307,25 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
     }
   } else if (warp == 2) {
     // ========================================= B producer =======================================
-    if (lane == 0) {
+    if (P.b_cpasync) {
+      // experiment: B is L2-resident, so it can bypass the TMA engine: every lane copies 16-byte chunks with cp.async and
+      // arrives on the stage barrier when its own copies have landed (cp.async.mbarrier.arrive.noinc)
+      int bs = 0; uint32_t bph = 0;
+      for (long long i = 0; i < n_local; ++i) {
+        const int l0 = (int)(i % NP) * NKS;
+        for (int ks = 0; ks < NKS; ++ks) {
+          const unsigned int e0 = s_lp[l0 + ks], e1 = s_lp[l0 + ks + 1];
+          mbar_wait(b_empty + 8 * bs, bph ^ 1);
+          const uint32_t dst = smem_u32(s_b + (size_t)bs * P.b_stage_bytes);
+          const char* src = P.b_packed + (size_t)e0 * blk_bytes;
+          const unsigned int nchunk = ((e1 - e0) * blk_bytes) >> 4;
+          for (unsigned int c = (unsigned int)lane; c < nchunk; c += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + c * 16u), "l"(src + (size_t)c * 16) : "memory");
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(b_full + 8 * bs) : "memory");
+          if (++bs == BS) { bs = 0; bph ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int bs = 0; uint32_t bph = 0; long long w0 = 0; const long long tstart = XB_CLOCK();
       for (long long i = 0; i < n_local; ++i) {
         const int l0 = (int)(i % NP) * NKS;
@@ -348,6 +367,7 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
           uint4 op = s_ops[ob];                                          // fetched ahead of the waits (a stale/unused slot is harmless)
           XB_READY(w_c, can_full + 8 * cs, cph); XB_TWAIT(w_c, mbar_wait_x(can_full + 8 * cs, cph, P.spin & 1));
           XB_READY(w_b, b_full + 8 * bs, bph); XB_TWAIT(w_b, mbar_wait_x(b_full + 8 * bs, bph, P.spin & 1));
+          if (P.b_cpasync) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async wrote through the generic proxy
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + (uint32_t)cs * (A_STAGE >> 4);
           const uint32_t b_stage_lo = b_lo0 + (uint32_t)bs * ((uint32_t)P.b_stage_bytes >> 4);
@@ -1064,6 +1084,7 @@ extern "C" int xb_bcsc_tc_launch(xb_sparse_desc* d, const void* a, const void* b
   P.b_sbo16 = (uint32_t)(8 * bk * 2) >> 4;
   P.sleep = env_int("LIBXSMM_B200_BCSC_SLEEP", 0, 1, 1); P.spin = env_int("LIBXSMM_B200_BCSC_SPIN", 0, 15, 0);
   P.skip = env_int("LIBXSMM_B200_BCSC_SKIP", 0, 255, 0);
+  P.b_cpasync = env_int("LIBXSMM_B200_BCSC_BCPASYNC", 0, 1, 0);
   P.dbg = nullptr;
   { const char* e = getenv("LIBXSMM_B200_BCSC_DEBUG"); if (e && *e) P.dbg = (long long*)(uintptr_t)strtoull(e, nullptr, 0); }
 
