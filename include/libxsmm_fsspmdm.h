@@ -1,42 +1,55 @@
-/* libxsmm_b200 -- fixed-size sparse (A) x dense (B) multiplication, row-major:
- *   C(M x N, ldc) = beta * C + alpha * A(M x K, lda; given dense, zeros dropped) * B(K x N, ldb)
- * API and semantics follow the reference include/libxsmm_fsspmdm.h:26-45 and
- * src/libxsmm_fsspmdm.c:24-560: beta in {0,1}, F32/F64, N % (64/sizeof(T)) == 0, lda >= K,
- * ldb >= N, ldc >= N, NULL for an all-zero A. The sparsity pattern and alpha-scaled values are
- * frozen at create time and kept in device memory; execute() launches one streaming kernel.
+/* libxsmm_b200 -- fixed sparse operator times dense matrix ("fsspmdm"), row-major:
+ *
+ *     C[rows x cols] = beta * C + alpha * A[rows x inner] * B[inner x cols]
+ *
+ * A is handed over as a DENSE array once, at create time; entries with alpha*a == 0 are dropped and
+ * the remaining pattern plus alpha-scaled values are frozen in device memory, execute() launches one
+ * streaming kernel over B and C. Constraints (as in the reference, src/libxsmm_fsspmdm.c:24-140):
+ * beta is 0 or 1, F32 or F64 only, cols % (64/sizeof(T)) == 0, ld_a >= inner, ld_b >= cols,
+ * ld_c >= cols; an all-zero operator yields NULL.
+ *
+ * ABI-compatible with the reference's include/libxsmm_fsspmdm.h:26-45 (same symbols, same argument
+ * order and types); the two trailing create arguments are accepted and ignored: `c_is_nt` (streaming
+ * store hint) and `timer_tick` (the reference benchmarks alternative x86 kernels with it).
  */
 #ifndef LIBXSMM_FSSPMDM_H
 #define LIBXSMM_FSSPMDM_H
 
 #include "libxsmm_typedefs.h"
 
-#define libxsmm_dfsspmdm libxsmm_fsspmdm
-#define libxsmm_sfsspmdm libxsmm_fsspmdm
 typedef struct libxsmm_fsspmdm libxsmm_fsspmdm;
+/* the typed front ends share the one opaque handle type */
+#define libxsmm_sfsspmdm libxsmm_fsspmdm
+#define libxsmm_dfsspmdm libxsmm_fsspmdm
 
 #if defined(__cplusplus)
 extern "C" {
 #endif
-LIBXSMM_API libxsmm_fsspmdm* libxsmm_fsspmdm_create(libxsmm_datatype datatype,
-  libxsmm_blasint M, libxsmm_blasint N, libxsmm_blasint K, libxsmm_blasint lda, libxsmm_blasint ldb, libxsmm_blasint ldc,
-  const void* alpha, const void* beta, const void* a_dense, int LIBXSMM_ARGDEF(c_is_nt, 0),
-  libxsmm_timer_tickint LIBXSMM_ARGDEF((*timer_tick)(void), NULL));
-LIBXSMM_API libxsmm_dfsspmdm* libxsmm_dfsspmdm_create(
-  libxsmm_blasint M, libxsmm_blasint N, libxsmm_blasint K, libxsmm_blasint lda, libxsmm_blasint ldb, libxsmm_blasint ldc,
-  double alpha, double beta, const double* a_dense, int LIBXSMM_ARGDEF(c_is_nt, 0),
-  libxsmm_timer_tickint LIBXSMM_ARGDEF((*timer_tick)(void), NULL));
-LIBXSMM_API libxsmm_sfsspmdm* libxsmm_sfsspmdm_create(
-  libxsmm_blasint M, libxsmm_blasint N, libxsmm_blasint K, libxsmm_blasint lda, libxsmm_blasint ldb, libxsmm_blasint ldc,
-  float alpha, float beta, const float* a_dense, int LIBXSMM_ARGDEF(c_is_nt, 0),
-  libxsmm_timer_tickint LIBXSMM_ARGDEF((*timer_tick)(void), NULL));
 
-LIBXSMM_API void libxsmm_fsspmdm_execute(const libxsmm_fsspmdm* handle, const void* B, void* C);
-LIBXSMM_API void libxsmm_dfsspmdm_execute(const libxsmm_dfsspmdm* handle, const double* B, double* C);
-LIBXSMM_API void libxsmm_sfsspmdm_execute(const libxsmm_sfsspmdm* handle, const float* B, float* C);
+/* ---- type-erased: alpha/beta/dense_a point to values of `precision` (F32 or F64) ---------------- */
+LIBXSMM_API libxsmm_fsspmdm* libxsmm_fsspmdm_create(libxsmm_datatype precision, libxsmm_blasint rows, libxsmm_blasint cols,
+                                                    libxsmm_blasint inner, libxsmm_blasint ld_a, libxsmm_blasint ld_b, libxsmm_blasint ld_c,
+                                                    const void* alpha, const void* beta, const void* dense_a,
+                                                    int LIBXSMM_ARGDEF(c_is_nt, 0), libxsmm_timer_tickint LIBXSMM_ARGDEF((*timer_tick)(void), NULL));
+LIBXSMM_API void libxsmm_fsspmdm_execute(const libxsmm_fsspmdm* op, const void* b, void* c);
+LIBXSMM_API void libxsmm_fsspmdm_destroy(libxsmm_fsspmdm* op);
 
-LIBXSMM_API void libxsmm_fsspmdm_destroy(libxsmm_fsspmdm* handle);
-LIBXSMM_API void libxsmm_dfsspmdm_destroy(libxsmm_dfsspmdm* handle);
-LIBXSMM_API void libxsmm_sfsspmdm_destroy(libxsmm_sfsspmdm* handle);
+/* ---- single precision --------------------------------------------------------------------------- */
+LIBXSMM_API libxsmm_sfsspmdm* libxsmm_sfsspmdm_create(libxsmm_blasint rows, libxsmm_blasint cols, libxsmm_blasint inner,
+                                                      libxsmm_blasint ld_a, libxsmm_blasint ld_b, libxsmm_blasint ld_c,
+                                                      float alpha, float beta, const float* dense_a,
+                                                      int LIBXSMM_ARGDEF(c_is_nt, 0), libxsmm_timer_tickint LIBXSMM_ARGDEF((*timer_tick)(void), NULL));
+LIBXSMM_API void libxsmm_sfsspmdm_execute(const libxsmm_sfsspmdm* op, const float* b, float* c);
+LIBXSMM_API void libxsmm_sfsspmdm_destroy(libxsmm_sfsspmdm* op);
+
+/* ---- double precision --------------------------------------------------------------------------- */
+LIBXSMM_API libxsmm_dfsspmdm* libxsmm_dfsspmdm_create(libxsmm_blasint rows, libxsmm_blasint cols, libxsmm_blasint inner,
+                                                      libxsmm_blasint ld_a, libxsmm_blasint ld_b, libxsmm_blasint ld_c,
+                                                      double alpha, double beta, const double* dense_a,
+                                                      int LIBXSMM_ARGDEF(c_is_nt, 0), libxsmm_timer_tickint LIBXSMM_ARGDEF((*timer_tick)(void), NULL));
+LIBXSMM_API void libxsmm_dfsspmdm_execute(const libxsmm_dfsspmdm* op, const double* b, double* c);
+LIBXSMM_API void libxsmm_dfsspmdm_destroy(libxsmm_dfsspmdm* op);
+
 #if defined(__cplusplus)
 }
 #endif
