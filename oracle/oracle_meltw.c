@@ -3,8 +3,8 @@
  * CPU restatement (plain C, written from the algorithm) of the reference's portable matrix-eltwise kernels,
  * src/generator_mateltwise_reference_impl.c, for the operations of SURVEY.md 8a (rows a5, a6) that the CUDA
  * library dispatches most: element-wise unary / binary / ternary maps with broadcast, the ReLU family with
- * bitmasks, compare / select / zip, row and column reductions (sum, sum of squares, max, min), the norm ->
- * transposed / VNNI2 / VNNI4 layout transforms, gather / scatter, quantise / dequantise. Operations that are not restated return 2
+ * bitmasks, compare / select / zip, row / column / to-scalar reductions (sum, sum of squares, max, min, absmax), all
+ * layout transforms, gather / scatter, quantise / dequantise. Operations that are not restated return 2
  * and stay pinned by the reference itself (oracle/_ref). Pinned bit for bit against libxsmm_reference_elementwise
  * in tests/test_oracle_vs_ref.py (transcendental ops: same libm calls, so equal on the same host).
  *
@@ -146,7 +146,8 @@ static int unary_map(const mdesc* d, const libxsmm_meltw_unary_param* p) {
 static int unary_reduce(const mdesc* d, const libxsmm_meltw_unary_param* p) {
   const int op = d->op, rows = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_ROWS) != 0, init = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_INIT_ACC) != 0;
   const int f64 = (d->t0 == LIBXSMM_DATATYPE_F64 && d->to == LIBXSMM_DATATYPE_F64);
-  const int kind = (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX) ? 1 : ((op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN) ? 2 : 0);
+  const int kind = (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX) ? 1 : ((op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN) ? 2
+                 : ((op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ABSMAX) ? 3 : 0));   /* ABSMAX: max over |x| */
   const int want_x = (op != LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD), want_x2 = (op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD);
   const int nres = rows ? d->n : d->m, len = rows ? d->m : d->n;
   const long long result_size = rows ? d->n : d->ldo;
@@ -157,8 +158,8 @@ static int unary_reduce(const mdesc* d, const libxsmm_meltw_unary_param* p) {
     double sx = 0.0, sx2 = 0.0, best = 0.0; float fsx = 0.0f, fsx2 = 0.0f, fbest = 0.0f;
     for (t = 0; t < len; ++t) {
       const long long idx = rows ? (t + (long long)o * d->ldi) : (o + (long long)t * d->ldi);
-      if (f64) { const double v = ((const double*)p->in.primary)[idx]; sx += v; sx2 += v * v; if (t == 0 || (kind == 1 ? v > best : v < best)) best = v; }
-      else { const float v = ldf(p->in.primary, idx, d->t0); fsx += v; fsx2 += v * v; if (t == 0 || (kind == 1 ? v > fbest : v < fbest)) fbest = v; }
+      if (f64) { double v = ((const double*)p->in.primary)[idx]; sx += v; sx2 += v * v; if (kind == 3) v = fabs(v); if (t == 0 || (kind == 2 ? v < best : v > best)) best = v; }
+      else { float v = ldf(p->in.primary, idx, d->t0); fsx += v; fsx2 += v * v; if (kind == 3) v = fabsf(v); if (t == 0 || (kind == 2 ? v < fbest : v > fbest)) fbest = v; }
     }
     if (kind != 0) {
       if (f64) ((double*)p->out.primary)[o] = best; else stf(p->out.primary, o, d->to, fbest);
@@ -175,31 +176,56 @@ static int unary_reduce(const mdesc* d, const libxsmm_meltw_unary_param* p) {
   return 0;
 }
 
-/* layout transforms, pure data movement: reference :390-417 (NORM_TO_NORMT), :541-553 (NORM_TO_VNNI2, N padded to even
- * with zeros in the _PAD variant), the VNNI4 analogue */
+/* layout transforms, pure data movement: reference :377-1062. Formulas (elements, E = element of 1/2/4/8 bytes):
+ *   NORM_TO_NORMT      out[j*ldo + i] = in[i*ldi + j]                      i < n, j < m               (:390-417)
+ *   NORM_TO_VNNIv(_PAD) the WHOLE ldo x ceil(n/v)*v output is defined: zero, except
+ *                      out[j*ldo*v + i*v + j2] = in[(j*v + j2)*ldi + i]     i < m, j*v + j2 < n        (:541-553, :690-759)
+ *   NORM_TO_VNNIvT     out[i*ldo*v + j*v + i2] = in[j*ldi + i*v + i2]       i < m/v, j < n
+ *   VNNIv_TO_VNNIvT    out[j*ldo*v + j2 + (i*v + i2)*v] = in[i*ldi*v + i2 + (j*v + j2)*v]   i < n/v, j < m/v (:433-441)
+ *   VNNIvT_TO_NORM     roles of m and n swapped: out[j*ldo + i*v + i2] = in[i*ldi*v + j*v + i2]   i < n/v, j < m  (:620-660)
+ *   VNNI4_TO_NORM      out[i*ldo + j] = in[(i/4)*ldi*4 + j*4 + i%4]         i < n, j < m               (:787-803) */
+#define CP(dst_idx, src_idx) memcpy(out + (dst_idx) * ts, in + (src_idx) * ts, (size_t)ts)
 static int unary_transform(const mdesc* d, const libxsmm_meltw_unary_param* p) {
   const int ts = tsz(d->t0), op = d->op;
   const char* in = (const char*)p->in.primary; char* out = (char*)p->out.primary;
-  int i, j;
-  if (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT) {
-    for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) memcpy(out + ((long long)i * d->ldo + j) * ts, in + ((long long)j * d->ldi + i) * ts, (size_t)ts);
-    return 0;
-  }
-  {
-    const int v = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2 || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD) ? 2
-                : ((op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4 || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD) ? 4 : 0);
-    const int pad = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD);
-    const int nv = pad ? (d->n + v - 1) / v : d->n / v;
-    int j2;
-    if (v == 0) return 2;
-    /* out[(j*ldo*v) + (i*v) + j2] = in[((v*j + j2)*ldi) + i] */
-    for (j = 0; j < nv; ++j) for (i = 0; i < d->m; ++i) for (j2 = 0; j2 < v; ++j2) {
-      char* dst = out + (((long long)j * d->ldo * v) + ((long long)i * v) + j2) * ts;
-      if (v * j + j2 < d->n) memcpy(dst, in + (((long long)(v * j + j2) * d->ldi) + i) * ts, (size_t)ts); else memset(dst, 0, (size_t)ts);
+  const long long M = d->m, N = d->n, ldi = d->ldi, ldo = d->ldo;
+  long long i, j, i2, j2, v;
+  switch (op) {
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT:
+      for (j = 0; j < M; ++j) for (i = 0; i < N; ++i) CP(j * ldo + i, i * ldi + j);
+      return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD:
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD: {
+      long long e; const long long Nn = 0;
+      v = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2 || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD) ? 2 : 4;
+      (void)Nn;
+      for (e = 0; e < ldo * (((N + v - 1) / v) * v); ++e) {
+        const long long jj = e / (ldo * v), rem = e % (ldo * v), col = jj * v + rem % v;
+        i = rem / v;
+        if (i < M && col < N) CP(e, col * ldi + i); else memset(out + e * ts, 0, (size_t)ts);
+      }
+      return 0;
     }
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4T:
+      v = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2T) ? 2 : 4;
+      for (i = 0; i < M / v; ++i) for (j = 0; j < N; ++j) for (i2 = 0; i2 < v; ++i2) CP(i * ldo * v + j * v + i2, j * ldi + i * v + i2);
+      return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2_TO_VNNI2T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI4T:
+      v = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2_TO_VNNI2T) ? 2 : 4;
+      for (j = 0; j < M / v; ++j) for (i = 0; i < N / v; ++i) for (j2 = 0; j2 < v; ++j2) for (i2 = 0; i2 < v; ++i2)
+        CP(j * ldo * v + j2 + (i * v + i2) * v, i * ldi * v + i2 + (j * v + j2) * v);
+      return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2T_TO_NORM: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4T_TO_NORM:
+      v = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2T_TO_NORM) ? 2 : 4;
+      for (i = 0; i < N / v; ++i) for (j = 0; j < M; ++j) for (i2 = 0; i2 < v; ++i2) CP(j * ldo + i * v + i2, i * ldi * v + j * v + i2);
+      return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_NORM:
+      for (i = 0; i < N; ++i) for (j = 0; j < M; ++j) CP(i * ldo + j, (i / 4) * ldi * 4 + j * 4 + (i % 4));
+      return 0;
+    default: return 2;
   }
-  return 0;
 }
+#undef CP
 
 /* quantise / dequantise: reference :2195-2360 */
 static int unary_quant(const mdesc* d, const libxsmm_meltw_unary_param* p) {
@@ -257,6 +283,21 @@ static int unary_gs(const mdesc* d, const libxsmm_meltw_unary_param* p) {
   return 0;
 }
 
+/* sum of all elements (unary) / of the element-wise product (binary) into one scalar, sequential over j then i in the
+ * compute type: reference :2097-2117 and :2523-2546 */
+static int reduce_to_scalar(const mdesc* d, const void* in0, const void* in1, void* out) {
+  const int f64 = d->t0 == LIBXSMM_DATATYPE_F64 && d->to == LIBXSMM_DATATYPE_F64 && d->tc == LIBXSMM_DATATYPE_F64 && (in1 == NULL || d->t1 == LIBXSMM_DATATYPE_F64);
+  float acc = 0.0f; double acc64 = 0.0;
+  int i, j;
+  if (!f64 && !(is_f(d->t0) && is_f(d->to) && (in1 == NULL || is_f(d->t1)))) return 2;
+  for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+    if (f64) { double v = ((const double*)in0)[bidx(d, 0, i, j, d->ldi)]; if (in1 != NULL) v *= ((const double*)in1)[bidx(d, 1, i, j, d->ldi2)]; acc64 += v; }
+    else { float v = ldf(in0, bidx(d, 0, i, j, d->ldi), d->t0); if (in1 != NULL) v = v * ldf(in1, bidx(d, 1, i, j, d->ldi2), d->t1); acc += v; }
+  }
+  if (f64) ((double*)out)[0] = acc64; else stf(out, 0, d->to, acc);
+  return 0;
+}
+
 static int binary_map(const mdesc* d, const libxsmm_meltw_binary_param* p) {
   const int op = d->op;
   const int f64 = d->t0 == LIBXSMM_DATATYPE_F64 && d->t1 == LIBXSMM_DATATYPE_F64 && d->to == LIBXSMM_DATATYPE_F64;
@@ -267,7 +308,7 @@ static int binary_map(const mdesc* d, const libxsmm_meltw_binary_param* p) {
                                                             | ((uint32_t)((const uint16_t*)p->in1.primary)[bidx(d, 1, i, j, d->ldi2)] << 16);
     return 0;
   }
-  if (op == LIBXSMM_MELTW_TYPE_BINARY_MUL_AND_REDUCE_TO_SCALAR_OP_ADD) return 2;
+  if (op == LIBXSMM_MELTW_TYPE_BINARY_MUL_AND_REDUCE_TO_SCALAR_OP_ADD) return reduce_to_scalar(d, p->in0.primary, p->in1.primary, p->out.primary);
   if (!f64 && !(is_f(d->t0) && is_f(d->t1))) return 2;
   for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
     const long long oi = i + (long long)j * d->ldo;
@@ -345,11 +386,17 @@ ORACLE_API int oracle_meltw(const int* desc, void* param, int mode) {
       case LIBXSMM_MELTW_TYPE_UNARY_ELU: case LIBXSMM_MELTW_TYPE_UNARY_ELU_INV:
         return unary_map(&d, (const libxsmm_meltw_unary_param*)param);
       case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ADD: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD:
-      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN:
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ABSMAX:
         return unary_reduce(&d, (const libxsmm_meltw_unary_param*)param);
       case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD:
       case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4T:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2_TO_VNNI2T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI4T:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2T_TO_NORM: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4T_TO_NORM:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_NORM:
         return unary_transform(&d, (const libxsmm_meltw_unary_param*)param);
+      case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_TO_SCALAR_OP_ADD:
+        return reduce_to_scalar(&d, ((const libxsmm_meltw_unary_param*)param)->in.primary, NULL, ((const libxsmm_meltw_unary_param*)param)->out.primary);
       case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT: case LIBXSMM_MELTW_TYPE_UNARY_QUANT:
         return unary_quant(&d, (const libxsmm_meltw_unary_param*)param);
       case LIBXSMM_MELTW_TYPE_UNARY_GATHER: case LIBXSMM_MELTW_TYPE_UNARY_SCATTER:

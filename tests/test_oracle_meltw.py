@@ -131,7 +131,7 @@ def test_reductions(t):
     for (m, n, pad) in ((33, 17, 0), (8, 70, 3)):
         ldi = m + pad
         x = rnd(rng, ldi * n, t)
-        for name in ("X_OP_ADD", "X2_OP_ADD", "X_X2_OP_ADD", "X_OP_MAX", "X_OP_MIN"):
+        for name in ("X_OP_ADD", "X2_OP_ADD", "X_X2_OP_ADD", "X_OP_MAX", "X_OP_MIN", "X_OP_ABSMAX"):
             if t == gen.F64 and "X2" in name:
                 continue    # the reference's F64 path never stores the sums of squares (it zeroes the plane, :1150-1153 and :1282): not restated
             for rows in (1, 0):
@@ -147,26 +147,33 @@ def test_reductions(t):
 
 
 def test_layout_transforms_and_dequant():
+    """same matrix of transforms as tests/test_meltw_gpu.py, output buffers pre-filled with random bytes so that every byte
+    the reference defines (including the zero padding of the VNNI packers) is compared"""
     rng = np.random.default_rng(65)
-    for (m, n, pad) in ((32, 16, 0), (17, 9, 3), (8, 4, 0)):
-        ldi = m + pad
-        for t, npdt in ((gen.BF16, np.uint16), (gen.F32, np.float32), (gen.I8, np.uint8)):
-            x = rng.integers(0, 250, size=ldi * n).astype(npdt)
-            for name, ldo, osize in (("NORM_TO_NORMT", n + 2, (n + 2) * m),):
-                y0 = np.zeros(osize, dtype=npdt)
+    for t in (gen.F64, gen.F32, gen.BF16, gen.I8):
+        for (m, n, pi, po) in ((33, 17, 0, 0), (64, 64, 2, 5), (1, 9, 0, 0)):
+            ldi, ldo = m + pi, n + po
+            x = rng.integers(0, 256, size=ldi * n * gen.TS[t], dtype=np.uint8); o0 = rng.integers(0, 256, size=ldo * m * gen.TS[t], dtype=np.uint8)
 
-                def mk(bufs, keep):
-                    p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
-                    return p
-                both((1, getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_" + name), 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), mk, [y0])
-        for t, npdt, v, nn in ((gen.BF16, np.uint16, 2, 16), (gen.BF16, np.uint16, 4, 16), (gen.I8, np.uint8, 4, 16)):
-            x = rng.integers(0, 250, size=ldi * nn).astype(npdt)
-            y0 = np.zeros((m + 1) * nn, dtype=npdt)
+            def mk(bufs, keep):
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
+                return p
+            both((1, X.MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT, 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), mk, [o0])
+    for name, t, v in (("NORM_TO_VNNI2", gen.BF16, 2), ("NORM_TO_VNNI4", gen.I8, 4), ("NORM_TO_VNNI4", gen.BF16, 4), ("NORM_TO_VNNI2T", gen.BF16, 2),
+                       ("NORM_TO_VNNI4T", gen.BF16, 4), ("VNNI2_TO_VNNI2T", gen.BF16, 2), ("VNNI4_TO_VNNI4T", gen.I8, 4), ("VNNI4_TO_VNNI4T", gen.BF16, 4),
+                       ("VNNI2T_TO_NORM", gen.BF16, 2), ("VNNI4T_TO_NORM", gen.BF16, 4), ("VNNI4_TO_NORM", gen.I8, 4)):
+        op = getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_" + name)
+        for (m, n, pad) in ((32, 16, 0), (64, 8, 4), (8, 64, 0), (40, 12, 8)):
+            ldi = m + pad
+            ldo = (n if name in ("VNNI2_TO_VNNI2T", "VNNI4_TO_VNNI4T", "NORM_TO_VNNI2T", "NORM_TO_VNNI4T") else
+                   (n if name in ("VNNI2T_TO_NORM", "VNNI4T_TO_NORM") else m)) + pad
+            x = rng.integers(0, 256, size=(ldi + 8) * (n + 8) * 4 * gen.TS[t], dtype=np.uint8)
+            o0 = rng.integers(0, 256, size=(ldo + 8) * (max(m, n) + 8) * 4 * gen.TS[t], dtype=np.uint8)
 
             def mkv(bufs, keep):
                 p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
                 return p
-            both((1, getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI%d" % v), 0, m, nn, ldi, 0, 0, m + 1, t, UNS, UNS, t, t), mkv, [y0])
+            both((1, op, 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), mkv, [o0])
     for t, npdt in ((gen.I8, np.int8), (gen.I16, np.int16), (gen.I32, np.int32)):
         m, n, ld = 20, 7, 23
         x = rng.integers(-100, 100, size=ld * n).astype(npdt); y0 = np.zeros(ld * n, dtype=np.float32); scf = C.c_float(0.0625)
@@ -213,3 +220,22 @@ def test_gather_scatter_and_quant():
                 p = X.MeltwUnaryParam(); p.inp.primary, p.inp.secondary, p.out.primary = x.ctypes.data, C.addressof(scf), bufs[0].ctypes.data
                 return p
             both((1, X.MELTW_TYPE_UNARY_QUANT, sat, m, n, ld, 0, 0, ld, gen.F32, UNS, UNS, tout, gen.F32), mkq, [y0])
+
+
+@pytest.mark.parametrize("t", [gen.F32, gen.BF16, gen.F64])
+def test_reductions_to_scalar(t):
+    rng = np.random.default_rng(67)
+    tcomp = gen.F64 if t == gen.F64 else gen.F32
+    m, n, ld = 37, 11, 40
+    a, b = rnd(rng, ld * n, t), rnd(rng, ld * n, t)
+    y0 = rnd(rng, 4, t)
+
+    def mku(bufs, keep):
+        p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = a.ctypes.data, bufs[0].ctypes.data
+        return p
+    both((1, X.MELTW_TYPE_UNARY_REDUCE_TO_SCALAR_OP_ADD, 0, m, n, ld, 0, 0, ld, t, UNS, UNS, t, tcomp), mku, [y0])
+
+    def mkb(bufs, keep):
+        p = X.MeltwBinaryParam(); p.in0.primary, p.in1.primary, p.out.primary = a.ctypes.data, b.ctypes.data, bufs[0].ctypes.data
+        return p
+    both((2, X.MELTW_TYPE_BINARY_MUL_AND_REDUCE_TO_SCALAR_OP_ADD, 0, m, n, ld, ld, 0, ld, t, t, UNS, t, tcomp), mkb, [y0])
