@@ -11,7 +11,7 @@ CFLAGS    := -O2 -std=gnu99 -fPIC -fvisibility=hidden -Wall -Wno-unused-function
 CSRC      := libxsmm_b200/csrc
 OBJDIR    := build/obj
 LIB       := libxsmm_b200/lib/libxsmm_b200.so
-HOST_C    := host_core.c host_thunks.c host_sparse.c host_meltw.c
+HOST_C    := host_core.c host_thunks.c host_sparse.c host_meltw.c host_utils.c
 DEVICE_CU := runtime.cu gemm_simt.cu gemm_tc.cu sparse.cu bcsc_tc.cu meltw.cu
 OBJS      := $(addprefix $(OBJDIR)/,$(HOST_C:.c=.o) $(DEVICE_CU:.cu=.o))
 REFDIR    ?= /root/reference
@@ -21,7 +21,7 @@ all: lib oracle
 
 lib: $(LIB)
 
-$(OBJDIR)/%.o: $(CSRC)/%.c $(CSRC)/xb_internal.h $(CSRC)/xb_device.cuh include/libxsmm.h include/libxsmm_typedefs.h include/libxsmm_b200.h
+$(OBJDIR)/%.o: $(CSRC)/%.c $(CSRC)/xb_internal.h $(CSRC)/xb_device.cuh include/libxsmm.h include/libxsmm_typedefs.h include/libxsmm_b200.h include/libxsmm_utils.h
 	@mkdir -p $(OBJDIR)
 	$(CC) $(CFLAGS) -Iinclude -x c -c $< -o $@
 

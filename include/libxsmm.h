@@ -89,6 +89,16 @@ LIBXSMM_API libxsmm_meltwfunction_binary libxsmm_dispatch_meltw_binary(const lib
   const libxsmm_meltw_binary_shape binary_shape, const libxsmm_bitfield binary_flags);
 LIBXSMM_API libxsmm_meltwfunction_ternary libxsmm_dispatch_meltw_ternary(const libxsmm_meltw_ternary_type ternary_type,
   const libxsmm_meltw_ternary_shape ternary_shape, const libxsmm_bitfield ternary_flags);
+/* descriptor route (reference include/libxsmm.h:143, include/libxsmm_generator.h:48-57): the blob is filled by one of the two
+ * init helpers; dispatch returns the same handle the typed dispatcher above returns for the same operation */
+LIBXSMM_API libxsmm_meltw_descriptor* libxsmm_meltw_descriptor_init(libxsmm_descriptor_blob* blob,
+  libxsmm_datatype in_type, libxsmm_datatype out_type, libxsmm_blasint m, libxsmm_blasint n, libxsmm_blasint ldi, libxsmm_blasint ldo,
+  unsigned short flags, unsigned short param, unsigned char operation);
+LIBXSMM_API libxsmm_meltw_descriptor* libxsmm_meltw_descriptor_init2(libxsmm_descriptor_blob* blob,
+  libxsmm_datatype in0_type, libxsmm_datatype in1_type, libxsmm_datatype in2_type, libxsmm_datatype comp_type, libxsmm_datatype out_type,
+  libxsmm_blasint m, libxsmm_blasint n, libxsmm_blasint ldi, libxsmm_blasint ldo, libxsmm_blasint ldi2, libxsmm_blasint ldi3,
+  unsigned short flags, unsigned short param, unsigned char operation);
+LIBXSMM_API libxsmm_xmeltwfunction libxsmm_dispatch_meltw(const libxsmm_meltw_descriptor* descriptor);
 
 /* ---- packed sparse GEMM (reference include/libxsmm.h:170-192, src/libxsmm_main.c:3553-3731) ------
  * which operand is sparse follows the reference's convention: the one whose leading dimension in the

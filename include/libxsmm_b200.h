@@ -40,6 +40,9 @@ LIBXSMM_API int libxsmm_b200_last_error(void);
 LIBXSMM_API const char* libxsmm_b200_last_error_string(void);
 LIBXSMM_API unsigned long long libxsmm_b200_launch_count(void); /* kernels launched by this library */
 LIBXSMM_API int libxsmm_b200_kernel_backend(const void* kernel);
+/* BCSC handles (libxsmm_create_packed_spgemm_bcsc): the kernel a call with `n_block_columns` (= *b.quaternary) takes:
+ * 0 exact-order CUDA-core kernel, 1 tcgen05 with A converted in shared memory, 2 tcgen05 with A in tensor memory; -1: not BCSC */
+LIBXSMM_API int libxsmm_b200_bcsc_variant(const void* kernel, unsigned long long n_block_columns);
 /* force the SIMT kernel for dense GEMM handles dispatched afterwards (debug / parity checking) */
 LIBXSMM_API void libxsmm_b200_set_force_simt(int on);
 

@@ -98,7 +98,8 @@ static void xb_sparse_release(xb_sparse_desc* sp) {
   if (sp->d_ptr) xb_rt_device_free(sp->d_ptr);
   if (sp->d_idx) xb_rt_device_free(sp->d_idx);
   if (sp->d_val) xb_rt_device_free(sp->d_val);
-  sp->d_ptr = NULL; sp->d_idx = NULL; sp->d_val = NULL;
+  if (sp->work) xb_bcsc_state_free(sp->work);
+  sp->d_ptr = NULL; sp->d_idx = NULL; sp->d_val = NULL; sp->work = NULL;
 }
 
 /* ---- lifetime ---------------------------------------------------------------------------------- */
@@ -478,7 +479,7 @@ LIBXSMM_API int libxsmm_b200_gemm_batch_strided(libxsmm_gemmfunction kernel, con
   xb_gemm_launch L;
   int rc;
   if (s == NULL || count < 0) return -1;
-  if (s->u.gemm.br_type == 1) return -2;   /* address mode needs per-tile arrays: use libxsmm_b200_gemm_batch */
+  if (s->u.gemm.br_type == 1 || s->u.gemm.br_type == 2) return -2;   /* address / offset mode need per-tile arrays: use libxsmm_b200_gemm_batch */
   if (count == 0) return 0;
   {
     const int ka = xb_rt_ptr_kind(a), kb = xb_rt_ptr_kind(b), kc = xb_rt_ptr_kind(c);
@@ -718,8 +719,16 @@ LIBXSMM_API int libxsmm_b200_kernel_backend(const void* kernel) {
     case XB_KIND_GEMM: case XB_KIND_GEMM_EXT: return s->u.gemm.backend;
     case XB_KIND_TILECFG: return LIBXSMM_B200_BACKEND_NOOP;
     case XB_KIND_FREE: return LIBXSMM_B200_BACKEND_NONE;
+    /* BCSC: which kernel runs also depends on the call-time column count; this is the handle's eligibility (one block-column) */
+    case XB_KIND_BCSC: return (xb_bcsc_tc_variant(&s->u.sp, 1) != 0) ? LIBXSMM_B200_BACKEND_TCGEN05 : LIBXSMM_B200_BACKEND_SIMT;
     default: return LIBXSMM_B200_BACKEND_STREAM;
   }
+}
+
+LIBXSMM_API int libxsmm_b200_bcsc_variant(const void* kernel, unsigned long long n_block_columns) {
+  const xb_slot* s = xb_slot_of(kernel);
+  if (s == NULL || s->kind != XB_KIND_BCSC) return -1;
+  return xb_bcsc_tc_variant(&s->u.sp, n_block_columns);
 }
 
 LIBXSMM_API void libxsmm_release_kernel(const void* kernel) {

@@ -85,6 +85,65 @@ LIBXSMM_API libxsmm_meltwfunction_ternary libxsmm_dispatch_meltw_ternary(const l
   return (libxsmm_meltwfunction_ternary)xb_dispatch_meltw(&d);
 }
 
+/* ---- descriptor-based dispatch (reference include/libxsmm.h:143, include/libxsmm_generator.h:48-57) ---------------
+ * libxsmm_dispatch_meltw takes the library's packed descriptor (reference src/libxsmm_main.h:292-302): six 32-bit
+ * extents, the five datatypes in 6-bit fields (IN0 [5:0], IN1 [11:6], IN2 [17:12], OUT [23:18], COMP [29:24]), the
+ * flags and the operation class (bits 2:0) / operation type (bits 15:3). Callers fill it through the two init helpers. */
+struct libxsmm_meltw_descriptor {
+  unsigned int m, n, ldi, ldo, ldi2, ldi3;
+  unsigned int datatypes;
+  unsigned short flags;
+  unsigned short param_operation;
+} __attribute__((packed));
+
+static unsigned int xb_meltw_pack_types(int in0, int in1, int in2, int out, int comp) {
+  return ((unsigned int)in0 & 0x3fu) | (((unsigned int)in1 & 0x3fu) << 6) | (((unsigned int)in2 & 0x3fu) << 12)
+       | (((unsigned int)out & 0x3fu) << 18) | (((unsigned int)comp & 0x3fu) << 24);
+}
+
+LIBXSMM_API libxsmm_meltw_descriptor* libxsmm_meltw_descriptor_init2(libxsmm_descriptor_blob* blob,
+  libxsmm_datatype in0_type, libxsmm_datatype in1_type, libxsmm_datatype in2_type, libxsmm_datatype comp_type, libxsmm_datatype out_type,
+  libxsmm_blasint m, libxsmm_blasint n, libxsmm_blasint ldi, libxsmm_blasint ldo, libxsmm_blasint ldi2, libxsmm_blasint ldi3,
+  unsigned short flags, unsigned short param, unsigned char operation)
+{
+  libxsmm_meltw_descriptor* d = (libxsmm_meltw_descriptor*)blob;
+  if (blob == NULL) return NULL;
+  memset(blob, 0, sizeof(*blob));
+  d->m = (unsigned int)m; d->n = (unsigned int)n; d->ldi = (unsigned int)ldi; d->ldo = (unsigned int)ldo; d->ldi2 = (unsigned int)ldi2; d->ldi3 = (unsigned int)ldi3;
+  d->datatypes = xb_meltw_pack_types((int)in0_type, (int)in1_type, (int)in2_type, (int)out_type, (int)comp_type);
+  d->flags = flags;
+  d->param_operation = (unsigned short)((operation & 0x7u) | ((unsigned int)param << 3));
+  return d;
+}
+
+LIBXSMM_API libxsmm_meltw_descriptor* libxsmm_meltw_descriptor_init(libxsmm_descriptor_blob* blob,
+  libxsmm_datatype in_type, libxsmm_datatype out_type, libxsmm_blasint m, libxsmm_blasint n, libxsmm_blasint ldi, libxsmm_blasint ldo,
+  unsigned short flags, unsigned short param, unsigned char operation)
+{
+  return libxsmm_meltw_descriptor_init2(blob, in_type, LIBXSMM_DATATYPE_IMPLICIT, LIBXSMM_DATATYPE_IMPLICIT, LIBXSMM_DATATYPE_IMPLICIT, out_type,
+                                        m, n, ldi, ldo, 0, 0, flags, param, operation);
+}
+
+LIBXSMM_API libxsmm_xmeltwfunction libxsmm_dispatch_meltw(const libxsmm_meltw_descriptor* descriptor) {
+  libxsmm_xmeltwfunction result;
+  xb_meltw_desc d;
+  result.xmeltw = NULL;
+  if (descriptor == NULL) return result;
+  memset(&d, 0, sizeof(d));
+  d.op_class = (int)(descriptor->param_operation & 0x7u); d.op = (int)(descriptor->param_operation >> 3); d.flags = descriptor->flags;
+  d.m = (int)descriptor->m; d.n = (int)descriptor->n; d.ldi = (int)descriptor->ldi; d.ldo = (int)descriptor->ldo;
+  d.t_in0 = (int)(descriptor->datatypes & 0x3fu); d.t_out = (int)((descriptor->datatypes >> 18) & 0x3fu); d.t_comp = (int)((descriptor->datatypes >> 24) & 0x3fu);
+  /* the registry key is the one the typed dispatchers build, so both routes return the identical handle */
+  d.t_in1 = d.t_in2 = LIBXSMM_DATATYPE_UNSUPPORTED;
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_BINARY || d.op_class == LIBXSMM_MELTW_OPERATION_TERNARY) {
+    d.ldi2 = (int)descriptor->ldi2; d.t_in1 = (int)((descriptor->datatypes >> 6) & 0x3fu);
+  }
+  if (d.op_class == LIBXSMM_MELTW_OPERATION_TERNARY) { d.ldi3 = (int)descriptor->ldi3; d.t_in2 = (int)((descriptor->datatypes >> 12) & 0x3fu); }
+  if (d.op_class != LIBXSMM_MELTW_OPERATION_UNARY && d.op_class != LIBXSMM_MELTW_OPERATION_BINARY && d.op_class != LIBXSMM_MELTW_OPERATION_TERNARY) return result;
+  result.xmeltw = (void (*)(const void*))(uintptr_t)xb_dispatch_meltw(&d);
+  return result;
+}
+
 /* ---- invocation -------------------------------------------------------------------------------------------- */
 typedef struct xb_stage { void* host; void* dev; size_t bytes; } xb_stage;
 typedef struct xb_stager { xb_stage out[4]; int nout; int staged; int failed; } xb_stager;
@@ -179,6 +238,14 @@ void xb_invoke_meltw(const xb_slot* s, const void* param) {
         const size_t mld = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) ? mask_ld_i : (size_t)d->ldi;
         a.in_aux = stage_in(&st, p->in.secondary, (mld / 8) * (size_t)d->n + 1);
       } else if (op == LIBXSMM_MELTW_TYPE_UNARY_ELU_INV) a.in_aux = stage_in(&st, p->in.secondary, ((size_t)(d->n - 1) * d->ldi + d->m) * ts_in);
+      else if ((op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MAX || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_MIN || op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ABSMAX)
+            && (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_RECORD_ARGOP) != 0) {
+        /* arg-max/min column indices land in out.secondary (reference :1243-1268); only the column reduction records them */
+        if ((d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_ROWS) == 0) {
+          a.out_aux = stage_inout(&st, p->out.secondary, (size_t)d->m * ((d->flags & LIBXSMM_MELTW_FLAG_UNARY_IDX_SIZE_4BYTES) ? 4 : 8));
+          if (a.out_aux == NULL) st.failed = 1;
+        }
+      }
     }
   } else if (d->op_class == LIBXSMM_MELTW_OPERATION_BINARY) {
     const libxsmm_meltw_binary_param* p = (const libxsmm_meltw_binary_param*)param;

@@ -227,7 +227,7 @@ void xb_invoke_sparse(const xb_slot* s, const libxsmm_gemm_param* p) {
       c_dev = p->c.primary;
       if (xb_rt_ptr_kind(p->c.primary) == 0) { c_host = p->c.primary; c_dev = xb_rt_scratch(c_bytes); if (c_dev && !d->beta0) xb_rt_upload(c_dev, c_host, c_bytes); staged = 1; }
       if (a == NULL || bv == NULL || cp == NULL || ri == NULL || c_dev == NULL) { rc = 2; break; }
-      rc = xb_bcsc_launch(d, a, bv, (const unsigned int*)cp, (const unsigned int*)ri, nbc, nnzb, c_dev);
+      rc = xb_bcsc_launch((xb_sparse_desc*)(uintptr_t)d /* only the handle's scratch cache (d->work) is touched, under its own lock */, a, bv, (const unsigned int*)cp, (const unsigned int*)ri, nbc, nnzb, c_dev);
     } break;
     default: break;
   }

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) meltw_reduce_kernel(const xb_meltw_desc d
           if (kind == 3) v = (v < 0) ? -v : v;
           if ((kind == 2) ? (v <= best) : (v >= best)) { best = v; best_j = j; }
         }
-        if (idx4) ((unsigned int*)a.out_aux)[o] = (unsigned int)best_j; else ((unsigned long long*)a.out_aux)[o] = (unsigned long long)best_j;
+        if (a.out_aux != nullptr) { if (idx4) ((unsigned int*)a.out_aux)[o] = (unsigned int)best_j; else ((unsigned long long*)a.out_aux)[o] = (unsigned long long)best_j; }
       }
       best = __shfl_sync(0xffffffffu, best, 0);
     } else {

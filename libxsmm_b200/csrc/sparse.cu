@@ -359,14 +359,14 @@ extern "C" int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const
   return check_launch("packed_sp");
 }
 
-extern "C" int xb_bcsc_tc_launch(xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
+extern "C" int xb_bcsc_tc_launch(const xb_sparse_desc* d, void** work, const void* a, const void* b_vals, const unsigned int* colptr,
                                  const unsigned int* rowidx, unsigned long long n_blocks, unsigned int nnzb, void* c);
 
-extern "C" int xb_bcsc_launch(const xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
+extern "C" int xb_bcsc_launch(xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
                               const unsigned int* rowidx, unsigned long long n_blocks, unsigned int nnzb, void* c)
 {
   if (d->m > 0 && n_blocks > 0) {   // tensor-core kernel for the bf16 VNNI case; everything else: exact-order kernel below
-    const int rc = xb_bcsc_tc_launch(const_cast<xb_sparse_desc*>(d), a, b_vals, colptr, rowidx, n_blocks, nnzb, c);
+    const int rc = xb_bcsc_tc_launch(d, &d->work, a, b_vals, colptr, rowidx, n_blocks, nnzb, c);
     if (rc >= 0) return rc;
   }
   BcscParams Q;

@@ -64,8 +64,10 @@ typedef struct xb_sparse_desc {
   unsigned int* d_ptr;                /* row_ptr / col_ptr  [nrows+1] */
   unsigned int* d_idx;                /* column / row indices [nnz] */
   void* d_val;                        /* SREG: values as the compute type [nnz] */
-  /* SREG column-major twin (built at create): for every k the rows using it */
   int beta0;
+  /* BCSC: per-(device, stream) scratch owned by the handle (pattern cache, re-packed B); created on first call, never
+   * touched by the descriptor's readers (bcsc_tc.cu: BcscState) */
+  void* work;
 } xb_sparse_desc;
 
 typedef struct xb_slot {
@@ -158,8 +160,11 @@ int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a);
 int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_total);
 int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const void* b, void* c, long long count,
                         long long stride_a, long long stride_b, long long stride_c);
-int xb_bcsc_launch(const xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
+int xb_bcsc_launch(xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr,
                    const unsigned int* rowidx, unsigned long long n_blocks, unsigned int nnzb, void* c);
+/* 0: exact-order CUDA-core kernel, 1: tcgen05 SS-form (round-1 kernel), 2: tcgen05 TS-form (A operand in tensor memory) */
+int xb_bcsc_tc_variant(const xb_sparse_desc* d, unsigned long long n_blocks);
+void xb_bcsc_state_free(void* work);
 
 /* ---- host runtime (host_core.c) ---------------------------------------------------------------- */
 xb_slot* xb_slot_of(const void* fnptr);    /* NULL if not one of our thunks */

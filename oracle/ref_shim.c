@@ -222,3 +222,54 @@ REF_API double ref_bench_bcsc(const int* types, const int* geo, unsigned int fla
   }
   return libxsmm_timer_duration(t0, libxsmm_timer_tick());
 }
+
+/* ---- utilities (libxsmm_utils.h): reference values for tests/test_host_utils.py ------------------------ */
+/* out[0..21] = the 22 doubles of libxsmm_matdiff_info in declaration order, out[22..25] = m, n, i, r, out[26] = epsilon */
+REF_API int ref_matdiff(int dtype, int m, int n, const void* ref, const void* tst, int ldr, int ldt, double* out) {
+  libxsmm_matdiff_info d;
+  const libxsmm_blasint lr = ldr, lt = ldt;
+  const int rc = libxsmm_matdiff(&d, (libxsmm_datatype)dtype, m, n, ref, tst, ldr > 0 ? &lr : NULL, ldt > 0 ? &lt : NULL);
+  memcpy(out, &d, 22 * sizeof(double));
+  out[22] = d.m; out[23] = d.n; out[24] = d.i; out[25] = d.r; out[26] = libxsmm_matdiff_epsilon(&d);
+  return rc;
+}
+/* folds `count` comparisons of column slices with libxsmm_matdiff_reduce; same output image */
+REF_API int ref_matdiff_reduce(int dtype, int m, int n, int count, const void* ref, const void* tst, double* out) {
+  libxsmm_matdiff_info total, d; int i;
+  const size_t ts = (size_t)LIBXSMM_TYPESIZE((libxsmm_datatype)dtype);
+  libxsmm_matdiff_clear(&total);
+  for (i = 0; i < count; ++i) {
+    if (0 != libxsmm_matdiff(&d, (libxsmm_datatype)dtype, m, n, (const char*)ref + ts * m * n * i, (const char*)tst + ts * m * n * i, NULL, NULL)) return 1;
+    libxsmm_matdiff_reduce(&total, &d);
+  }
+  memcpy(out, &total, 22 * sizeof(double));
+  out[22] = total.m; out[23] = total.n; out[24] = total.i; out[25] = total.r; out[26] = libxsmm_matdiff_epsilon(&total);
+  return 0;
+}
+REF_API unsigned long long ref_coprime2(unsigned long long n) { return (unsigned long long)libxsmm_coprime2((size_t)n); }
+REF_API void ref_rng(unsigned int seed, float* f32_seq, int n32, double* f64_seq, int n64, unsigned int* u32_seq, int nu, unsigned int u_range) {
+  int i;
+  libxsmm_rng_set_seed(seed);
+  libxsmm_rng_f32_seq(f32_seq, n32);
+  for (i = 0; i < n64; ++i) f64_seq[i] = libxsmm_rng_f64();
+  for (i = 0; i < nu; ++i) u32_seq[i] = libxsmm_rng_u32(u_range);
+}
+REF_API void ref_lp_convert(int which, const void* in, void* out, unsigned long long n) {
+  switch (which) {
+    case 0: libxsmm_rne_convert_fp32_bf8((const float*)in, (libxsmm_bfloat8*)out, (size_t)n); break;
+    case 1: libxsmm_convert_bf8_f32((const libxsmm_bfloat8*)in, (float*)out, (size_t)n); break;
+    case 2: libxsmm_rne_convert_fp32_hf8((const float*)in, (libxsmm_hfloat8*)out, (size_t)n); break;
+    case 3: libxsmm_convert_hf8_f32((const libxsmm_hfloat8*)in, (float*)out, (size_t)n); break;
+    case 4: libxsmm_rne_convert_fp32_bf16((const float*)in, (libxsmm_bfloat16*)out, (size_t)n); break;
+    case 5: libxsmm_rnaz_convert_fp32_bf16((const float*)in, (libxsmm_bfloat16*)out, (size_t)n); break;
+    case 6: libxsmm_truncate_convert_f32_bf16((const float*)in, (libxsmm_bfloat16*)out, (size_t)n); break;
+    case 7: libxsmm_convert_bf16_f32((const libxsmm_bfloat16*)in, (float*)out, (size_t)n); break;
+    case 8: libxsmm_rne_convert_fp32_f16((const float*)in, (libxsmm_float16*)out, (size_t)n); break;
+    default: libxsmm_convert_f16_f32((const libxsmm_float16*)in, (float*)out, (size_t)n);
+  }
+}
+/* the fill the drivers use (LIBXSMM_MATINIT), f32 and f64 */
+REF_API void ref_matinit(int is_f64, double seed, void* dst, int nrows, int ncols, int ld, double scale) {
+  if (is_f64) { LIBXSMM_MATINIT(double, seed, dst, nrows, ncols, ld, scale); }
+  else { LIBXSMM_MATINIT(float, seed, dst, nrows, ncols, ld, scale); }
+}

@@ -101,14 +101,99 @@ def test_bcsc_bit_exact_vs_oracle(types):
             got = host(d_c, gen.NP_OF[tc])
             want = c0.copy()
             assert _run_bcsc(oracle, types, (mblocks, M, K, N, bk, bn), flags, a, bvals, colptr, rowidx, want) == 0
-            if X.libxsmm_b200_kernel_backend(kernel) == X.BACKEND_STREAM and tc != gen.I32 and False:
-                pass
             if tc == gen.I32:
                 assert np.array_equal(got, want), (types, mblocks, M, K, N)
             else:
                 thr = 5e-3 if tc == gen.BF16 else 1e-4          # spmm_kernel.c:1019-1029
                 assert gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc)) <= thr, (types, mblocks, M, K, N, beta0, trans_a)
             X.libxsmm_release_kernel(kernel)
+
+
+def _bcsc_bf16_run(rng, mblocks, M, K, N, bk, bn, dens, beta0, expect_variant, thr=5e-3):
+    ta = gen.BF16
+    types = (ta, ta, gen.F32, ta)
+    flags = (cases.FLAG_BETA_0 if beta0 else 0) | cases.FLAG_VNNI_A
+    a, bvals, colptr, rowidx, c0 = _bcsc_inputs(rng, ta, ta, ta, mblocks, M, K, N, bk, bn, dens)
+    sh = X.libxsmm_create_gemm_shape(mblocks, 0, K, K, 0, N, ta, ta, ta, gen.F32)
+    kernel = X.libxsmm_create_packed_spgemm_bcsc(sh, flags, 0, X.SpgemmConfig(M, bk, bn))
+    assert kernel
+    assert X.libxsmm_b200_bcsc_variant(kernel, N // bn) == expect_variant, (mblocks, M, K, N, bk, bn, X.libxsmm_b200_bcsc_variant(kernel, N // bn))
+    assert X.libxsmm_b200_kernel_backend(kernel) == (X.BACKEND_TCGEN05 if expect_variant else X.BACKEND_SIMT)
+    d_a, d_b, d_cp, d_ri, d_c = dev(a), dev(bvals), dev(colptr), dev(rowidx), dev(c0)
+    want = c0.copy()
+    assert _run_bcsc(oracle, types, (mblocks, M, K, N, bk, bn), flags, a, bvals, colptr, rowidx, want) == 0
+    for rep in range(2):     # the second call takes the cached-pattern path of the prep kernel
+        d_c.copy_(dev(c0))
+        X.call_gemm(kernel, d_a, d_b, d_c, colptr=d_cp, rowidx=d_ri, nblocks=N // bn); X.check()
+        err = gen.normf_rel(gen.to_f64(want, ta), gen.to_f64(host(d_c, np.uint16), ta))
+        assert err <= thr, ((mblocks, M, K, N, bk, bn, dens, beta0), rep, err)
+    X.libxsmm_release_kernel(kernel)
+
+
+# (m_blocks, M, K, N, bk, bn, density): packed widths 16..128, all three block depths, ragged groups (m_blocks not a multiple of
+# 128/M), K not a multiple of 64, N not a multiple of the 128-column part, empty block-columns (low density), dense B
+_BCSC_TC_GEOMETRIES = ((4, 32, 64, 64, 32, 32, 1.0), (4, 32, 128, 64, 32, 32, 0.5), (5, 32, 512, 512, 32, 32, 0.5), (3, 16, 64, 96, 16, 32, 0.5),
+                       (2, 64, 256, 128, 32, 16, 0.5), (3, 32, 128, 128, 64, 32, 0.5), (9, 32, 96, 320, 32, 32, 0.4), (3, 128, 160, 64, 16, 16, 0.6),
+                       (7, 32, 512, 512, 32, 32, 0.1), (6, 64, 448, 384, 64, 128, 0.7), (11, 16, 192, 48, 16, 48, 0.8))
+
+
+@pytest.mark.parametrize("force_v1", [0, 1])
+def test_bcsc_bf16_tcgen05_kernels(force_v1, monkeypatch):
+    """both tensor-core BCSC kernels (TS-form: A in tensor memory; round-1 SS-form) against the oracle, incl. the BASELINE configs[3]
+    geometry (M=32, N=K=512, 32x32 blocks, 50%) at a small m_blocks; thresholds of samples/xgemm_sparse/spmm_kernel.c:1019-1029"""
+    monkeypatch.setenv("LIBXSMM_B200_BCSC_V1", str(force_v1))
+    rng = np.random.default_rng(77 + force_v1)
+    for geo in _BCSC_TC_GEOMETRIES:
+        for beta0 in (1, 0):
+            _bcsc_bf16_run(rng, *geo, beta0, expect_variant=1 if force_v1 else 2)
+
+
+def test_bcsc_bf16_kernel_selection_by_geometry(monkeypatch):
+    """K > 512 does not fit the TMEM-resident A operand -> round-1 kernel; N > 512 is served by the TS-form kernel only;
+    bn > 128 -> round-1 kernel; K < 64 or an unsupported block shape -> exact-order kernel"""
+    monkeypatch.delenv("LIBXSMM_B200_BCSC_V1", raising=False)
+    rng = np.random.default_rng(5)
+    _bcsc_bf16_run(rng, 5, 32, 640, 256, 32, 32, 0.5, 1, expect_variant=1)
+    _bcsc_bf16_run(rng, 5, 32, 256, 1024, 32, 32, 0.4, 1, expect_variant=2)
+    _bcsc_bf16_run(rng, 3, 32, 128, 512, 32, 256, 0.6, 0, expect_variant=1)
+    _bcsc_bf16_run(rng, 3, 32, 32, 64, 16, 16, 0.6, 0, expect_variant=0)
+    _bcsc_bf16_run(rng, 3, 8, 64, 64, 32, 32, 0.6, 1, expect_variant=0)
+
+
+def test_bcsc_handle_is_reentrant_across_streams():
+    """one handle, two host threads on two streams with different B values and patterns: results must not mix
+    (reference handles are re-entrant; scratch is kept per stream, launches are enqueued under the handle's lock)"""
+    import threading
+    ta = gen.BF16
+    mblocks, M, K, N, bk, bn = 64, 32, 256, 256, 32, 32
+    flags = cases.FLAG_BETA_0 | cases.FLAG_VNNI_A
+    sh = X.libxsmm_create_gemm_shape(mblocks, 0, K, K, 0, N, ta, ta, ta, gen.F32)
+    kernel = X.libxsmm_create_packed_spgemm_bcsc(sh, flags, 0, X.SpgemmConfig(M, bk, bn))
+    assert kernel
+    jobs = []
+    for t in range(2):
+        rng = np.random.default_rng(100 + t)
+        a, bvals, colptr, rowidx, c0 = _bcsc_inputs(rng, ta, ta, ta, mblocks, M, K, N, bk, bn, 0.3 + 0.4 * t)
+        want = c0.copy()
+        assert _run_bcsc(oracle, (ta, ta, gen.F32, ta), (mblocks, M, K, N, bk, bn), flags, a, bvals, colptr, rowidx, want) == 0
+        jobs.append(dict(d=[dev(x) for x in (a, bvals, colptr, rowidx, c0)], want=want, stream=torch.cuda.Stream(), errs=[]))
+    torch.cuda.synchronize()
+
+    def worker(job):
+        X.libxsmm_b200_set_device(0)
+        X.libxsmm_b200_set_stream(job["stream"].cuda_stream)
+        X.libxsmm_b200_set_blocking(0)
+        d_a, d_b, d_cp, d_ri, d_c = job["d"]
+        for _ in range(20):
+            X.call_gemm(kernel, d_a, d_b, d_c, colptr=d_cp, rowidx=d_ri, nblocks=N // bn)
+            job["stream"].synchronize()
+            job["errs"].append(gen.normf_rel(gen.to_f64(job["want"], ta), gen.to_f64(host(d_c, np.uint16), ta)))
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    [th.start() for th in threads]; [th.join() for th in threads]
+    X.check()
+    for j in jobs:
+        assert len(j["errs"]) == 20 and max(j["errs"]) <= 5e-3, j["errs"]
+    X.libxsmm_release_kernel(kernel)
 
 
 @pytest.mark.parametrize("dtype", [gen.F32, gen.F64])

@@ -23,7 +23,7 @@ def probe(mblocks, M, K, N, bk, bn, dens, beta0=1, seed=0):
     got = gen.to_f64(host(d_c, np.uint16), ta).reshape(mblocks, N, M)
     want = c0.copy(); _run_bcsc(oracle, (ta, ta, gen.F32, ta), (mblocks, M, K, N, bk, bn), flags, a, bvals, colptr, rowidx, want)
     want = gen.to_f64(want, ta).reshape(mblocks, N, M)
-    print("cfg", (mblocks, M, K, N, bk, bn, dens, beta0), "sync", rc, X.libxsmm_b200_last_error_string(), "normf_rel %.3e" % gen.normf_rel(want, got), flush=True)
+    print("cfg", (mblocks, M, K, N, bk, bn, dens, beta0), "variant", X.libxsmm_b200_bcsc_variant(k, N // bn), "sync", rc, X.libxsmm_b200_last_error_string(), "normf_rel %.3e" % gen.normf_rel(want, got), flush=True)
     e = np.abs(want - got)
     for mb in range(min(mblocks, 6)):
         print(" mb%d per block-col max err:" % mb, " ".join("%.2f" % e[mb, j * bn:(j + 1) * bn].max() for j in range(N // bn)))
@@ -41,39 +41,12 @@ if __name__ == "__main__" and len(sys.argv) == 1:
     probe(5, 32, 512, 512, 32, 32, 0.5, beta0=0, seed=3)
 
 
-def timing_probe():
-    """per-role wait/total cycles of CTA 0 at the BASELINE size (set LIBXSMM_B200_BCSC_DEBUG=<device ptr>)"""
-    import torch
-    import bench
-    dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
-    os.environ["LIBXSMM_B200_BCSC_DEBUG"] = str(dbg.data_ptr())
-
-    class A: steps = 3; warmup = 2
-    r = bench.also_bcsc(X, torch, bench.peaks(), A)
-    names = ["Aprod.raw_empty ready", "Aprod.total cycles", "Bprod.b_empty ready", "Bprod.total cycles", "mma.t_empty ready (items)", "mma.can_full ready", "mma.b_full ready",
-             "mma.total cycles", "epi.t_full ready (items)", "epi.total cycles", "conv.raw_full ready", "conv.can_empty ready", "conv.total cycles"]
-    print("bcsc ms", r["ms_per_step"])
-    for n, v in zip(names, dbg.cpu().tolist()):
-        print("  %-28s %12d" % (n, v))
-
-
-if len(sys.argv) > 1 and sys.argv[1] == "timing":
-    # remaining args: settings such as "PARTS=1,MMAW=2" (LIBXSMM_B200_BCSC_ prefix implied); one timing run per argument
-    for cfg in (sys.argv[2:] or [""]):
-        for kv in filter(None, cfg.split(",")):
-            k, v = kv.split("="); os.environ["LIBXSMM_B200_BCSC_" + k] = v
-        print("settings", cfg or "(default)")
-        timing_probe()
-        for kv in filter(None, cfg.split(",")):
-            os.environ.pop("LIBXSMM_B200_BCSC_" + kv.split("=")[0], None)
-
-
 if len(sys.argv) > 1 and sys.argv[1] == "bench":
-    # like "timing" but without the instrumented kernel: plain milliseconds per setting
+    # plain milliseconds per setting, e.g. "KPC=1,BST=6" (LIBXSMM_B200_BCSC_ prefix implied)
     import torch
     import bench
 
-    class A: steps = 5; warmup = 3
+    class A: steps = 8; warmup = 3; no_cpu = True
     for cfg in (sys.argv[2:] or [""]):
         for kv in filter(None, cfg.split(",")):
             k, v = kv.split("="); os.environ["LIBXSMM_B200_BCSC_" + k] = v
@@ -88,7 +61,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "scale":
     import torch
     import bench
 
-    class A: steps = 12; warmup = 3
+    class A: steps = 12; warmup = 3; no_cpu = True
     for cfg in (sys.argv[2:] or [""]):
         for kv in filter(None, cfg.split(",")):
             k, v = kv.split("="); os.environ["LIBXSMM_B200_BCSC_" + k] = v
