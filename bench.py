@@ -35,6 +35,7 @@ BR = 8
 BATCH = 65536
 BF16, F32 = 2, 1
 FLAG_BETA_0 = 4
+METRIC = "batched BRGEMM GFLOP/s (bf16, m=n=k=64, br=8, batch=65536/GPU, unique operands)"
 WORKLOAD = ("configs[1]: batched BRGEMM bf16->f32 m=n=k=64 brcount=8 batch=65536 per GPU, stride-BR, beta=0, "
             "mode S (all operands unique)")
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` captures (bytes)
@@ -201,7 +202,7 @@ def run_ours(args):
         kern_ms = sorted(per)[len(per) // 2]
         value = (2.0 * M * N * K * BR * job_tiles) / (ms * 1e-3) / 1e9     # whole job; ms is the max over ranks
         ach = bytes_alg / (kern_ms * 1e-3) / 1e9
-        out = {"metric": "batched BRGEMM GFLOP/s (bf16, m=n=k=64, br=8, batch=65536/GPU, unique operands)", "value": value, "unit": "GFLOP/s",
+        out = {"metric": METRIC, "value": value, "unit": "GFLOP/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": {"workload": WORKLOAD,
@@ -211,8 +212,10 @@ def run_ours(args):
                             "peak_src": pk["src"], "kernel": "gemm_tc_kernel<64>", "kernel_ms": kern_ms,
                             "tensor_frac_of_measured_bf16_peak": (flops / (kern_ms * 1e-3) / 1e12) / pk["bf16_tflops"]},
                "gpu_launches": int(launches), "clocks": clocks.summary()}
-        if rank == 0 and not args.no_e2e:
-            out["e2e"] = brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, c_dev=c)
+        if not args.no_e2e:
+            # every rank drives its own GPU over its own PCIe link at the same time; whole-job value = all tiles / slowest rank
+            bind_to_gpu_numa_node(torch, local)
+            out["e2e"] = brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, c_dev=c, dist=dist, world=world)
         if rank == 0 and not args.no_also:
             out["also"] = {}
             for name, fn in (("fsspmdm", also_fsspmdm), ("bcsc", also_bcsc)):
@@ -235,10 +238,30 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, steps=3, c_dev=None):
+def bind_to_gpu_numa_node(torch, local):
+    """run this rank's host side (pinned allocations are first-touched here) on the CPUs next to its GPU"""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        dev = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % dev) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
+def brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, steps=3, c_dev=None, dist=None, world=1):
     """same call, HOST pinned buffers: the library moves A and B to the device, runs the kernel and brings C back inside the
     step. Two transports are timed: the chunked three-stream copy pipeline (default) and in-place access to the pinned
-    buffers from the kernel (LIBXSMM_B200_ZEROCOPY=1); the better one is the e2e value, both are reported."""
+    buffers from the kernel (LIBXSMM_B200_ZEROCOPY=1); the better one is the e2e value, both are reported. With N ranks every
+    rank runs the call on its own GPU at the same time (barrier before each step); a step costs the slowest rank's time."""
     nb_a, nb_b, nb_c = BATCH * sa, BATCH * sb, BATCH * sc
     ha = torch.empty(nb_a // 2, dtype=torch.bfloat16, pin_memory=True); hb = torch.empty(nb_b // 2, dtype=torch.bfloat16, pin_memory=True)
     hc = torch.empty(nb_c // 4, dtype=torch.float32, pin_memory=True)
@@ -252,10 +275,17 @@ def brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, steps=3, c_dev=None):
             os.environ["LIBXSMM_B200_ZEROCOPY"] = env
         best = None
         for i in range(steps + 1):
-            torch.cuda.synchronize(); t0 = time.perf_counter()
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
             rc = X.libxsmm_b200_gemm_batch_strided(kernel, ha.data_ptr(), hb.data_ptr(), hc.data_ptr(), sa, sb, sc, BR, BATCH)
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
             assert rc == 0, X.libxsmm_b200_last_error_string()
+            if dist is not None:
+                t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
             if i > 0:
                 best = dt if best is None else min(best, dt)
         res[mode] = best
@@ -266,9 +296,11 @@ def brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, steps=3, c_dev=None):
     X.libxsmm_b200_set_blocking(0)
     mode = min(res, key=res.get)
     best = res[mode]
-    return {"value": flops / best / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(nb_a + nb_b), "d2h_bytes_per_step": int(nb_c),
-            "ms_per_step": best * 1e3, "transport": mode, "ms_by_transport": {k: v * 1e3 for k, v in res.items()},
-            "note": "pinned host A,B -> libxsmm_b200_gemm_batch_strided -> pinned host C; wall clock around the blocking call, best of %d" % steps}
+    return {"value": world * flops / best / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(world * (nb_a + nb_b)), "d2h_bytes_per_step": int(world * nb_c),
+            "ms_per_step": best * 1e3, "transport": mode, "ms_by_transport": {k: v * 1e3 for k, v in res.items()}, "ranks": world,
+            "pcie_gbs_per_gpu": (nb_a + nb_b + nb_c) / best / 1e9,
+            "note": "every rank at once: pinned host A,B -> libxsmm_b200_gemm_batch_strided -> pinned host C on its own GPU; wall clock around the "
+                    "blocking call, max over ranks, best of %d; bytes are the whole job's" % steps}
 
 
 def also_fsspmdm(X, torch, pk, args, full=False):
@@ -285,6 +317,8 @@ def also_fsspmdm(X, torch, pk, args, full=False):
 
     def step():
         X.libxsmm_fsspmdm_execute(h, b.data_ptr(), c.data_ptr())
+    step(); X.check()
+    checked = fsspmdm_check(torch, a, b, c, Mf, Kf, Nf)
     steps = max(5, args.steps)
     total_ms, per = time_steps(torch, step, steps, 3)
     X.check()
@@ -296,9 +330,49 @@ def also_fsspmdm(X, torch, pk, args, full=False):
     if full or not getattr(args, "no_cpu", False):
         cpu = cpu_baseline_fsspmdm(a, Mf, Kf, nnz)
     return {"cpu_baseline": cpu, "metric": "fsspmdm GFLOP/s (f32 M=32 K=128 N=1e6, 15% nnz)", "value": 2.0 * nnz * Nf / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (sparse)",
-            "dense_equiv_gflops": 2.0 * Mf * Kf * Nf / (ms * 1e-3) / 1e9, "ms_per_step": ms, "nnz": nnz,
+            "dense_equiv_gflops": 2.0 * Mf * Kf * Nf / (ms * 1e-3) / 1e9, "ms_per_step": ms, "nnz": nnz, "oracle_check": checked,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic("sreg_kernel<float>"), "algorithmic_bytes": bytes_alg, "kernel": "sreg_kernel<float>"},
             "config": {"workload": "configs[2]: fsspmdm f32 M=32 K=128 N=1e6 15% nnz beta=0; B+C = 640 MB per step (> L2)"}}
+
+
+def fsspmdm_check(torch, a_dense, b, c, Mf, Kf, Nf, width=256):
+    """three column strips of the timed output (first, middle, last) against the CPU oracle (checker only)"""
+    import numpy as np
+    from oracle_ffi import oracle
+    import gen
+    one = np.array([1.0], dtype=np.float32); zero = np.array([0.0], dtype=np.float32)
+    worst = 0.0
+    starts = (0, (Nf // 2) // 16 * 16, Nf - width)
+    for n0 in starts:
+        bs = b.view(Kf, Nf)[:, n0:n0 + width].contiguous().cpu().numpy().ravel()
+        want = np.zeros(Mf * width, dtype=np.float32)
+        assert oracle["fsspmdm"](F32, Mf, width, Kf, Kf, width, width, one.ctypes.data, zero.ctypes.data, a_dense.ctypes.data, bs.ctypes.data, want.ctypes.data) == 0
+        got = c.view(Mf, Nf)[:, n0:n0 + width].contiguous().cpu().numpy().ravel()
+        err = gen.normf_rel(want, got)
+        assert err < 1e-4, "fsspmdm bench output differs from the oracle (columns %d.., err %g)" % (n0, err)
+        worst = max(worst, err)
+    return {"strips": len(starts), "width": width, "max_normf_rel": worst}
+
+
+def bcsc_check(torch, a, bv, c, colptr, rowidx, geo, mblocks, picks=None):
+    """a few m_blocks of the timed output against the CPU oracle (driver gold spmm_kernel.c:74-217 restated)"""
+    import numpy as np
+    from oracle_ffi import oracle, iarr
+    import gen
+    Mb, Kb, Nb, bk, bn = geo
+    bvh = bv.view(torch.int16).cpu().numpy().view(np.uint16)
+    worst = 0.0
+    picks = picks or sorted({0, 1, mblocks // 2 + 1, mblocks - 1})
+    for mb in picks:
+        ah = a[mb * Kb * Mb:(mb + 1) * Kb * Mb].view(torch.int16).cpu().numpy().view(np.uint16)
+        want = np.zeros(Nb * Mb, dtype=np.uint16)
+        assert oracle["bcsc"](iarr(BF16, BF16, F32, BF16), iarr(1, Mb, Kb, Nb, bk, bn), FLAG_BETA_0 | 256, ah.ctypes.data, bvh.ctypes.data,
+                              colptr.ctypes.data, rowidx.ctypes.data, want.ctypes.data) == 0
+        got = c[mb * Nb * Mb:(mb + 1) * Nb * Mb].view(torch.int16).cpu().numpy().view(np.uint16)
+        err = gen.normf_rel(gen.to_f64(want, BF16), gen.to_f64(got, BF16))
+        assert err <= 5e-3, "BCSC bench output differs from the oracle (m_block %d, err %g)" % (mb, err)   # bf16 threshold of spmm_kernel.c:1019-1029
+        worst = max(worst, err)
+    return {"m_blocks": len(picks), "max_normf_rel": worst}
 
 
 def also_bcsc(X, torch, pk, args, full=False, mblocks=8192):
@@ -323,6 +397,11 @@ def also_bcsc(X, torch, pk, args, full=False, mblocks=8192):
 
     def step():
         fn(C.byref(p))
+    step(); X.check()
+    checked = bcsc_check(torch, a, bv, c, colptr, rowidx, (Mb, Kb, Nb, bk, bn), mblocks)
+    variant = int(X.libxsmm_b200_bcsc_variant(kernel, nbc))
+    assert variant in (1, 2), "BCSC bench did not take a tcgen05 kernel (variant %d)" % variant
+    kname = "bcsc_ts_kernel<32,2>" if variant == 2 else "bcsc_tc_kernel<32>"
     steps = max(3, args.steps // 4)
     total_ms, per = time_steps(torch, step, steps, 2)
     X.check()
@@ -335,10 +414,31 @@ def also_bcsc(X, torch, pk, args, full=False, mblocks=8192):
         cpu = cpu_baseline_bcsc(colptr, rowidx, nnzb, (Mb, Kb, Nb, bk, bn))
     return {"cpu_baseline": cpu, "metric": "BCSC spmm GFLOP/s dense-equivalent (bf16, M=32 N=K=512, 32x32 blocks, 50%, m_blocks=8192)",
             "value": 2.0 * Mb * mblocks * Nb * Kb / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (dense-equivalent)",
-            "effective_gflops": 2.0 * Mb * mblocks * nnzb * bk * bn / (ms * 1e-3) / 1e9, "ms_per_step": ms,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic("bcsc_tc_kernel<32>"), "algorithmic_bytes": bytes_alg,
-                         "kernel": "bcsc_tc_kernel<32> (+ bcsc_prep_kernel, bcsc_pack_b_kernel: the timed call is all three launches)"},
+            "effective_gflops": 2.0 * Mb * mblocks * nnzb * bk * bn / (ms * 1e-3) / 1e9, "ms_per_step": ms, "oracle_check": checked,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic(kname), "algorithmic_bytes": bytes_alg,
+                         "kernel": kname + " (+ bcsc_prep_kernel, bcsc_pack_b_kernel: the timed call is all three launches)"},
             "config": {"workload": "configs[3] on one GPU: BCSC bf16 M=32 N=K=512 bk=bn=32 50% m_blocks=8192; A+C = 537 MB per step (> L2)"}}
+
+
+def sweep_check(torch, a, b, c, m, types, flags, esz, csz, batch):
+    """first, middle and last tile of a sweep point against the CPU oracle: integers bit-exact, f16 within 1e-3 (normf_rel)"""
+    import numpy as np
+    from oracle_ffi import oracle, run_gemm
+    import gen
+    worst = 0.0
+    a8, b8, c8 = a.view(torch.uint8), b.view(torch.uint8), c.view(torch.uint8)
+    for t in (0, batch // 2, batch - 1):
+        ah = a8[t * m * m * esz:(t + 1) * m * m * esz].cpu().numpy(); bh = b8[t * m * m * esz:(t + 1) * m * m * esz].cpu().numpy()
+        got = c8[t * m * m * csz:(t + 1) * m * m * csz].cpu().numpy()
+        want = np.zeros(m * m * csz, dtype=np.uint8)
+        assert run_gemm(oracle, (m, m, m, m, m, m), types, flags, 0, 0, 0, 1, ah, bh, want) == 0
+        if esz == 1:
+            assert np.array_equal(got, want), "sweep int8 m=%d tile %d differs from the oracle" % (m, t)
+        else:
+            err = gen.normf_rel(want.view(np.float32), got.view(np.float32))
+            assert err < 1e-3, "sweep f16 m=%d tile %d differs from the oracle (err %g)" % (m, t, err)
+            worst = max(worst, err)
+    return {"tiles": 3, "max_normf_rel": worst, "bit_exact": esz == 1}
 
 
 def sweep(X, torch, pk, args, batch=32768):
@@ -362,13 +462,15 @@ def sweep(X, torch, pk, args, batch=32768):
             def step():
                 rc = X.libxsmm_b200_gemm_batch_strided(kernel, a.data_ptr(), b.data_ptr(), c.data_ptr(), sa, sb, sc, 1, batch)
                 assert rc == 0, X.libxsmm_b200_last_error_string()
+            step(); X.check()
+            chk = sweep_check(torch, a, b, c, m, (ta, tb, tcomp, tcc), flags, esz, csz, batch)
             total_ms, per = time_steps(torch, step, max(5, args.steps // 2), 3)
             X.check()
             ms = sorted(per)[len(per) // 2]
             bytes_alg = float(batch) * (sa + sb + sc)
             ach = bytes_alg / (ms * 1e-3) / 1e9
             pts.append({"type": name, "m": m, "gflops": 2.0 * m * m * m * batch / (ms * 1e-3) / 1e9, "ms": ms, "gbs": ach, "hbm_frac": ach / pk["hbm_gbs"],
-                        "backend": int(X.libxsmm_b200_kernel_backend(kernel)), "l2_note": "operands %.0f MB%s" % (bytes_alg / 1e6, "" if bytes_alg > 2.5e8 else " (fits L2: not an HBM number)")})
+                        "backend": int(X.libxsmm_b200_kernel_backend(kernel)), "oracle_check": chk, "l2_note": "operands %.0f MB%s" % (bytes_alg / 1e6, "" if bytes_alg > 2.5e8 else " (fits L2: not an HBM number)")})
     best = max((p for p in pts if "gflops" in p), key=lambda p: p["gflops"])
     return {"metric": "mixed-precision sweep GFLOP/s (configs[4], diagonal m=n=k)", "value": best["gflops"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
             "warmup": 3, "higher_is_better": True, "dtype": "u8/i8->i32, f16->f32", "data": "synthetic",
@@ -377,44 +479,92 @@ def sweep(X, torch, pk, args, batch=32768):
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
-def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core this process may run on.
-    Must run before the OpenMP runtime of oracle/_ref is loaded."""
+def physical_cores():
+    """one logical CPU per physical core among those this process may run on (/proc/cpuinfo: physical id, core id)"""
     try:
-        n = len(os.sched_getaffinity(0))
+        allowed = sorted(os.sched_getaffinity(0))
     except Exception:
-        n = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(n)
-    os.environ.setdefault("OMP_PROC_BIND", "false")
-    return n
+        allowed = list(range(os.cpu_count() or 1))
+    seen, cur = {}, {}
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f.read().split("\n") + [""]:
+                if ":" in line:
+                    k, v = [x.strip() for x in line.split(":", 1)]
+                    cur[k] = v
+                elif cur:
+                    cpu = int(cur.get("processor", -1))
+                    key = (cur.get("physical id", "0"), cur.get("core id", str(cpu)))
+                    if cpu in allowed and key not in seen:
+                        seen[key] = cpu
+                    cur = {}
+    except Exception:
+        pass
+    return sorted(seen.values()) or allowed
 
 
-def cpu_baseline_brgemm(sample_tiles=4096, budget_s=12.0):
-    """the reference's own JIT BRGEMM kernel over a bounded sample of the same batch, all host cores (OpenMP)"""
-    import numpy as np
-    use_all_host_threads()
-    from oracle_ffi import ref_lib, iarr
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every PHYSICAL core this process may run on, one
+    pinned thread per core (hyper-threads share the AMX unit and only add noise). Must run before the OpenMP runtime of
+    oracle/_ref is loaded."""
+    cores = physical_cores()
+    try:
+        os.sched_setaffinity(0, set(cores))
+    except Exception:
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(len(cores))
+    os.environ["OMP_PROC_BIND"] = "close"
+    os.environ["OMP_PLACES"] = "cores"
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    return len(cores)
+
+
+def host_mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 8.0
+
+
+def cpu_brgemm_passes(warm, passes, want_tiles=BATCH):
+    """`passes` timed passes of the reference's JIT over the strided batch, buffers owned and first-touched by the OpenMP
+    threads of oracle/_ref (ref_bench_brgemm_owned). The sample is the full batch when the host can hold it (9.7 GB),
+    else the largest power-of-two fraction that fits a third of the available memory (never below 8192 tiles = 1.2 GB,
+    several times the box's cache)."""
+    ncores = use_all_host_threads()
+    from oracle_ffi import ref_lib
     if ref_lib is None:
-        return {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libxsmm_ref.so missing"}
-    rng = np.random.default_rng(555)
-    na = sample_tiles * BR * M * K
-    a = (rng.integers(-5, 6, size=na).astype(np.float32) / 10).view(np.uint32)
-    a = ((a + 0x7FFF + ((a >> 16) & 1)) >> 16).astype(np.uint16)
-    b = np.roll(a, 12345).copy()
-    c = np.zeros(sample_tiles * M * N, dtype=np.float32)
-    dims, types = iarr(M, N, K, M, K, M), iarr(BF16, BF16, F32, F32)
-    is_ref = C.c_int(0)
-    flags = FLAG_BETA_0 | 256   # VNNI_A: required by the reference's x86 bf16 JIT (AMX/AVX-512 BF16)
-    args = (dims, types, flags, 3, M * K * 2, K * N * 2, BR, a.ctypes.data, b.ctypes.data, c.ctypes.data, BR * M * K * 2, BR * K * N * 2, M * N * 4, sample_tiles)
-    t1 = ref_lib.ref_bench_gemm_batch(*args, 1, C.byref(is_ref))
-    if t1 < 0:
-        return {"value": None, "unit": "GFLOP/s", "cores": int(ref_lib.ref_max_threads()), "kind": "reference", "sample": "JIT dispatch returned NULL on this host"}
-    reps = max(1, min(200, int(budget_s / max(t1, 1e-4))))
-    t = ref_lib.ref_bench_gemm_batch(*args, reps, C.byref(is_ref))
-    fl = 2.0 * M * N * K * BR * sample_tiles * reps
-    return {"value": fl / t / 1e9, "unit": "GFLOP/s", "cores": int(ref_lib.ref_max_threads()), "kind": "reference",
-            "sample": "%d tiles (%.0f MB of A+B, streamed) x %d passes, LIBXSMM JIT target %s%s, VNNI_A layout" % (
-                sample_tiles, (2.0 * na * 2) / 1e6, reps, ref_lib.ref_target_arch().decode(), " [C reference kernel!]" if is_ref.value else "")}
+        return None, {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libxsmm_ref.so missing"}
+    per_tile = (2 * BR * M * K + 2 * BR * K * N + 4 * M * N)
+    tiles = want_tiles
+    while tiles > 8192 and tiles * per_tile / 1e9 > host_mem_available_gb() / 3:
+        tiles //= 2
+    fn = ref_lib.ref_bench_brgemm_owned
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_uint, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    secs = (C.c_double * passes)()
+    is_ref, chk = C.c_int(0), C.c_double(0)
+    flags = FLAG_BETA_0 | 256   # VNNI_A: the layout the reference's x86 bf16 JIT (AMX/AVX-512 BF16) is written for
+    rc = fn(M, N, K, BR, flags, tiles, warm, passes, secs, C.byref(is_ref), C.byref(chk))
+    if rc != 0:
+        return None, {"value": None, "unit": "GFLOP/s", "cores": ncores, "kind": "reference",
+                      "sample": "JIT dispatch returned NULL on this host" if rc == -1 else "host cannot hold the sample"}
+    fl = 2.0 * M * N * K * BR * tiles
+    gf = sorted(fl / t / 1e9 for t in secs)
+    info = {"value": gf[len(gf) // 2], "unit": "GFLOP/s", "cores": ncores, "kind": "reference", "min": gf[0], "max": gf[-1], "passes": passes,
+            "sample": "%d of %d tiles (%.1f GB of A+B+C, every operand unique, first-touched by the thread that streams it) x %d passes after %d warm-up, "
+                      "one pinned OpenMP thread per physical core (OMP_PLACES=cores, close), LIBXSMM JIT target %s%s, VNNI_A layout; value = median pass" % (
+                          tiles, want_tiles, tiles * per_tile / 1e9, passes, warm, ref_lib.ref_target_arch().decode(), " [C reference kernel!]" if is_ref.value else "")}
+    return [float(t) for t in secs], info
+
+
+def cpu_baseline_brgemm(passes=5):
+    """the reference's own JIT BRGEMM kernel over the same batch on the host cores: a bounded number of passes"""
+    return cpu_brgemm_passes(1, passes)[1]
 
 
 def cpu_baseline_fsspmdm(a_dense, Mf, Kf, nnz, n_sample=200000, budget_s=4.0):
@@ -463,28 +613,24 @@ def cpu_baseline_bcsc(colptr, rowidx, nnzb, geo, mblocks=1024, budget_s=4.0):
 
 
 def run_reference(args):
+    """Reference arm: a step is one pass of the reference's JIT kernel over the strided batch on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    vals = []
-    t0 = time.perf_counter()
-    for _ in range(args.warmup + args.steps):
-        vals.append(cpu_baseline_brgemm(sample_tiles=2048, budget_s=1.5))
-    dt = time.perf_counter() - t0
-    good = [v["value"] for v in vals[args.warmup:] if v["value"]]
-    if not good:
-        print(json.dumps({"impl": "reference", "unavailable": vals[-1]["sample"]}))
+    steps = max(1, args.steps)
+    secs, info = cpu_brgemm_passes(max(1, args.warmup), steps)
+    if secs is None:
+        print(json.dumps({"impl": "reference", "unavailable": info["sample"]}))
         return
-    v = sorted(good)[len(good) // 2]
-    base = vals[-1]
-    print(json.dumps({"impl": "reference", "metric": "batched BRGEMM GFLOP/s (bf16, m=n=k=64, br=8, batch=65536/GPU, unique operands)",
-                      "value": v, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                      "ms_per_step": dt / (args.warmup + args.steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    v = info["value"]
+    print(json.dumps({"impl": "reference", "metric": METRIC,
+                      "value": v, "unit": "GFLOP/s", "n_gpus": world, "steps": steps, "warmup": max(1, args.warmup),
+                      "ms_per_step": sum(secs) / len(secs) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "bf16", "data": "synthetic",
                       "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH,
-                                 "reference_arm": "host CPU: each step a bounded sample (2048 tiles) of the batch, LIBXSMM JIT through libxsmm_dispatch_brgemm, OpenMP over tiles"},
-                      "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": base["cores"], "kind": "reference", "sample": base["sample"]},
+                                 "reference_arm": "host CPU (not scaled with --gpus): LIBXSMM JIT through libxsmm_dispatch_brgemm, OpenMP over tiles; " + info["sample"]},
+                      "cpu_baseline": info,
                       "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 

@@ -45,14 +45,10 @@ typedef unsigned char libxsmm_hfloat8;
 #define LIBXSMM_PREFETCH_AUTO 0
 #define LIBXSMM_ALPHA 1
 #define LIBXSMM_BETA 1
-#define LIBXSMM_ALIGNMENT 64
 #define LIBXSMM_DESCRIPTOR_MAXSIZE 96
 #define LIBXSMM_DESCRIPTOR_SIGSIZE 32
 
-#define LIBXSMM_UPDIV(N, MULT) (((N) + ((MULT) - 1)) / (MULT))
-#define LIBXSMM_UP(N, MULT) (LIBXSMM_UPDIV(N, MULT) * (MULT))
-#define LIBXSMM_MIN(A, B) ((A) < (B) ? (A) : (B))
-#define LIBXSMM_MAX(A, B) ((A) < (B) ? (B) : (A))
+#include "libxsmm_macros.h"   /* LIBXSMM_UPDIV, LIBXSMM_UP, LIBXSMM_MIN, LIBXSMM_MAX, LIBXSMM_ALIGNMENT, ... */
 
 /* ---- element types: X(name, bytes) in enumerator order (values 0..26) ------------------------ */
 #define LIBXSMM_B200_DATATYPES(X) \

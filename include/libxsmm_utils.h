@@ -18,37 +18,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include "libxsmm_macros.h"
 #include "libxsmm_typedefs.h"
 
 #if defined(__cplusplus)
 extern "C" {
 #endif
 
-/* ---- helper macros (reference include/libxsmm_macros.h:640-648, 830-832) --------------------------- */
-#if !defined(LIBXSMM_INLINE)
-# define LIBXSMM_INLINE static inline
-#endif
-#if !defined(LIBXSMM_UNUSED)
-# define LIBXSMM_UNUSED(VARIABLE) (void)(VARIABLE)
-#endif
-#define LIBXSMM_FEQ(A, B) ((A) == (B))
-#define LIBXSMM_NEQ(A, B) ((A) != (B))
-#define LIBXSMM_ISNAN(A) LIBXSMM_NEQ(A, A)
-#define LIBXSMM_NOTNAN(A) LIBXSMM_FEQ(A, A)
-#define LIBXSMM_ABS(A) (0 <= (A) ? (A) : -(A))
-#define LIBXSMM_DELTA(T0, T1) ((T0) < (T1) ? ((T1) - (T0)) : ((T0) - (T1)))
-#define LIBXSMM_MOD2(A, NPOT) ((A) & ((NPOT) - 1))
-#define LIBXSMM_CONCATENATE2(A, B) A##B
-#define LIBXSMM_CONCATENATE(A, B) LIBXSMM_CONCATENATE2(A, B)
-#define LIBXSMM_STRINGIFY2(SYMBOL) #SYMBOL
-#define LIBXSMM_STRINGIFY(SYMBOL) LIBXSMM_STRINGIFY2(SYMBOL)
-#define LIBXSMM_PRAGMA(DIRECTIVE) _Pragma(LIBXSMM_STRINGIFY(DIRECTIVE))
-#if defined(_OPENMP)
-# define LIBXSMM_PRAGMA_SIMD LIBXSMM_PRAGMA(omp simd)
-#else
-# define LIBXSMM_PRAGMA_SIMD
-#endif
-/* element type -> datatype enumerator: LIBXSMM_DATATYPE(double) == LIBXSMM_DATATYPE_F64 */
+/* ---- element type -> datatype enumerator: LIBXSMM_DATATYPE(double) == LIBXSMM_DATATYPE_F64 ------------------- */
 #define LIBXSMM_TYPESYMBOL_double F64
 #define LIBXSMM_TYPESYMBOL_float F32
 #define LIBXSMM_TYPESYMBOL_int I32
@@ -57,16 +34,6 @@ extern "C" {
 #define LIBXSMM_TYPESYMBOL_libxsmm_float16 F16
 #define LIBXSMM_TYPESYMBOL(TYPE) LIBXSMM_CONCATENATE(LIBXSMM_TYPESYMBOL_, TYPE)
 #define LIBXSMM_DATATYPE(TYPE) LIBXSMM_CONCATENATE(LIBXSMM_DATATYPE_, LIBXSMM_TYPESYMBOL(TYPE))
-/* identifiers of the reference's x86 targets that callers compare libxsmm_cpuid() against (include/libxsmm_cpuid.h);
- * this backend reports LIBXSMM_B200_SM100A, which orders above every CPU target: feature tests such as
- * "at least Sapphire Rapids (bf16/int8 matrix instructions)" hold */
-#define LIBXSMM_TARGET_ARCH_GENERIC 1
-#define LIBXSMM_X86_AVX512_SKX 1101
-#define LIBXSMM_X86_AVX512_CLX 1102
-#define LIBXSMM_X86_AVX512_CPX 1103
-#define LIBXSMM_X86_AVX512_SPR 1104
-#define LIBXSMM_X86_AVX512_GNR 1105
-#define LIBXSMM_B200_SM100A 100000
 
 /* ---- seeded deterministic fill used by the drivers (reference include/libxsmm_math.h:17-56) ---------------
  * SEED != 0: element (row j, col i) = (SEED*SCALE + SCALE) * (1 + i*NROWS + j), padding rows = SEED;

@@ -492,6 +492,7 @@ struct BcscTsParams {
   const unsigned int* plan;                 // {S, parts per set} from the prep kernel (S = 0: stream B)
   int ring_bytes;                           // shared memory available for the A ring + B (resident set or ring)
   int raw_cap;                              // upper bound on A stages (tuning)
+  int kmajor;                               // resident sets of <= 2 parts: sweep k-major (tuning switch, same result)
   char* c; int beta0;
   uint32_t idesc, b_layout, b_sbo16;
 };
@@ -656,6 +657,50 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
     const uint32_t ops_sa = smem_u32(s_ops), lp_sa = smem_u32(s_lp), wr_sa = smem_u32(s_wr) + 4u * (uint32_t)mw;
     long long item = 0;
     if (resident && n_groups > 0) mbar_wait(b_full, 0);                    // the set's B blocks have landed (once per launch)
+    // all operations of one (part, k-step) list owned by this warp
+    auto issue_list = [&](uint32_t l, uint32_t d_base, uint32_t b_stage_lo, uint32_t e0, int ks) {
+      const uint32_t rng = lds32(wr_sa + 16u * l), ob = rng & 0xFFFFu, on = rng >> 16;
+      const uint32_t b_list_lo = b_stage_lo + (lds32(lp_sa + 4u * l) - e0) * blk16;
+      const uint32_t a_ks = tmem_a + (uint32_t)ks * 32u;
+      uint32_t op_sa = ops_sa + 16u * ob;
+      uint4 op = lds128(op_sa);
+      for (uint32_t o = 0; o < on; ++o) {
+        op_sa += 16u;
+        const uint4 nxt = lds128(op_sa);                          // one past the last operation is allocated
+        const uint32_t d = d_base + (op.x & 0xFFFFu), a_col = a_ks + (op.x >> 20), b_lo = b_list_lo + op.y, idesc = P.idesc | op.z;
+        if (leader) {
+          umma_f16_ts(d, a_col, desc64(b_hi, b_lo), idesc, op.w);
+#pragma unroll
+          for (int kk = 1; kk < KSTEPS; ++kk) umma_f16_ts(d, a_col + (uint32_t)kk * 8u, desc64(b_hi, b_lo + (uint32_t)kk * (32u >> 4)), idesc, 1u);
+        }
+        op = nxt;
+      }
+    };
+    if (resident && P.kmajor && p1 - p0 <= 2) {
+      // k-major sweep: both parts of the set accumulate side by side in the two slots, so the A columns of a k-step are
+      // released as soon as that k-step is consumed and the copy warps refill them for the NEXT group while this group's
+      // later k-steps are still being multiplied (with the part-major order below the refill waits for the last MMA of the
+      // group and the first part of the next group is paced by the copy: measured 10.6K cycles per group against ~5K)
+      const int np = p1 - p0;
+      for (long long i = 0; i < n_groups; ++i) {
+        const uint32_t gpar = (uint32_t)(i & 1);
+        for (int q = 0; q < np; ++q, ++item) mbar_wait(t_empty + 8 * (int)(item & 1), (uint32_t)(((item >> 1) & 1) ^ 1));
+        item -= np;
+        for (int ks = 0; ks < NKS; ++ks) {
+          mbar_wait(a_full + 8 * ks, gpar);
+          tc_fence_after();
+          for (int q = 0; q < np; ++q) {
+            const int slot = (int)((item + q) & 1);
+            issue_list((uint32_t)((p0 + q) * NKS + ks), tmem_base + (uint32_t)(slot * kTsDCols), b_lo0, e_set0, ks);
+          }
+          if (leader) umma_commit(a_empty + 8 * ks);
+          __syncwarp();
+        }
+        if (leader) { for (int q = 0; q < np; ++q) umma_commit(t_full + 8 * (int)((item + q) & 1)); }
+        __syncwarp();
+        item += np;
+      }
+    } else {
     for (long long i = 0; i < n_groups; ++i) {
       const uint32_t gpar = (uint32_t)(i & 1);
       for (int part = p0; part < p1; ++part, ++item) {
@@ -670,25 +715,7 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
           if (!resident) mbar_wait(b_full + 8 * bs, bph);
           tc_fence_after();
           const uint32_t b_stage_lo = b_lo0 + (uint32_t)bs * ((uint32_t)P.b_stage_bytes >> 4);
-          for (int ks = ks0; ks < ks1; ++ks) {
-            const uint32_t l = (uint32_t)(part * NKS + ks);
-            const uint32_t rng = lds32(wr_sa + 16u * l), ob = rng & 0xFFFFu, on = rng >> 16;
-            const uint32_t b_list_lo = b_stage_lo + (lds32(lp_sa + 4u * l) - e0) * blk16;
-            const uint32_t a_ks = tmem_a + (uint32_t)ks * 32u;
-            uint32_t op_sa = ops_sa + 16u * ob;
-            uint4 op = lds128(op_sa);
-            for (uint32_t o = 0; o < on; ++o) {
-              op_sa += 16u;
-              const uint4 nxt = lds128(op_sa);                          // one past the last operation is allocated
-              const uint32_t d = d_base + (op.x & 0xFFFFu), a_col = a_ks + (op.x >> 20), b_lo = b_list_lo + op.y, idesc = P.idesc | op.z;
-              if (leader) {
-                umma_f16_ts(d, a_col, desc64(b_hi, b_lo), idesc, op.w);
-#pragma unroll
-                for (int kk = 1; kk < KSTEPS; ++kk) umma_f16_ts(d, a_col + (uint32_t)kk * 8u, desc64(b_hi, b_lo + (uint32_t)kk * (32u >> 4)), idesc, 1u);
-              }
-              op = nxt;
-            }
-          }
+          for (int ks = ks0; ks < ks1; ++ks) issue_list((uint32_t)(part * NKS + ks), d_base, b_stage_lo, e0, ks);
           if (leader) {
             if (!resident) umma_commit(b_empty + 8 * bs);
             if (part == p1 - 1) { for (int ks = ks0; ks < ks1; ++ks) umma_commit(a_empty + 8 * ks); }   // last reader of these A columns
@@ -699,6 +726,7 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
         if (leader) umma_commit(t_full + 8 * slot);
         __syncwarp();
       }
+    }
     }
   } else if (warp >= 6 && warp < 10) {
     // ========================================= copy: raw VNNI words -> TMEM A ===================
@@ -916,6 +944,7 @@ extern "C" int xb_bcsc_tc_launch(const xb_sparse_desc* d, void** work, const voi
     int raw = (int)(((size_t)P2.ring_bytes - (size_t)P2.b_stages * P2.b_stage_bytes) / A_STAGE); if (raw > 8) raw = 8;
     P2.raw_cap = env_int("LIBXSMM_B200_BCSC_RAW", 2, 8, 8);
     P2.raw_stages = (raw < P2.raw_cap) ? raw : P2.raw_cap;
+    P2.kmajor = env_int("LIBXSMM_B200_BCSC_KMAJOR", 0, 1, 1);
     // resident-B plan: a set of column parts may occupy the ring space minus three A stages (decided by the prep kernel)
     resident_cap_blocks = (env_int("LIBXSMM_B200_BCSC_RESIDENT", 0, 1, 1) == 1) ? (unsigned int)(((size_t)P2.ring_bytes - 3 * (size_t)A_STAGE) / blk_bytes) : 0u;
     smem = total;

@@ -84,6 +84,8 @@ LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csc(const libxsmm_
   if (gemm_shape.ldb == 0 && gemm_shape.lda > 0 && gemm_shape.ldc > 0) kind = XB_KIND_SP_B_CSC;
   else if (gemm_shape.ldc == 0 && gemm_shape.lda > 0 && gemm_shape.ldb > 0) kind = XB_KIND_SP_C_CSC;
   else return NULL;                                                       /* generator_packed_spgemm.c:68-99 */
+  /* C-sparse: f32 and whole 16-lane vectors only (generator_packed_spgemm_csc_csparse_avx_avx2_avx512.c:607-622) */
+  if (kind == XB_KIND_SP_C_CSC && (gemm_shape.a_in_type != LIBXSMM_DATATYPE_F32 || (packed_width % 16) != 0)) return NULL;
   if (!xb_rt_have_gpu()) return NULL;
   nnz = column_ptr[gemm_shape.n];
   slot = xb_host_slot_alloc(kind, 2u * nnz * (unsigned int)(kind == XB_KIND_SP_B_CSC ? gemm_shape.m : gemm_shape.k) * (unsigned int)packed_width);
@@ -202,10 +204,11 @@ void xb_invoke_sparse(const xb_slot* s, const libxsmm_gemm_param* p) {
     } break;
     case XB_KIND_SP_A_CSR: case XB_KIND_SP_B_CSR: case XB_KIND_SP_B_CSC: case XB_KIND_SP_C_CSC: {
       const size_t P = (size_t)d->packed_width;
-      const size_t ab = (d->kind == XB_KIND_SP_A_CSR) ? (size_t)d->nnz * ts : (size_t)d->m * d->lda * P * ts;
+      const size_t ab = (d->kind == XB_KIND_SP_A_CSR) ? (size_t)d->nnz * ts
+                      : (d->kind == XB_KIND_SP_C_CSC) ? (size_t)d->k * d->lda * P * ts   /* A is [K][lda][P] there */ : (size_t)d->m * d->lda * P * ts;
       const size_t bb = (d->kind == XB_KIND_SP_B_CSR || d->kind == XB_KIND_SP_B_CSC) ? (size_t)d->nnz * ts : (size_t)d->k * d->ldb * P * ts;
       const void *a, *b;
-      c_bytes = (d->kind == XB_KIND_SP_C_CSC) ? (size_t)d->nnz * P * ts : (size_t)d->m * d->ldc * P * ts;
+      c_bytes = (d->kind == XB_KIND_SP_C_CSC) ? (size_t)d->nnz * ts /* one scalar per non-zero */ : (size_t)d->m * d->ldc * P * ts;
       a = xb_dev_in(p->a.primary, ab, &staged); b = xb_dev_in(p->b.primary, bb, &staged);
       c_dev = p->c.primary;
       if (xb_rt_ptr_kind(p->c.primary) == 0) { c_host = p->c.primary; c_dev = xb_rt_scratch(c_bytes); if (c_dev) xb_rt_upload(c_dev, c_host, c_bytes); staged = 1; }

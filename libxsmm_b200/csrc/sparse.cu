@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(256) packed_sp_kernel(const PackedParams Q) {
     for (int e = threadIdx.x; e < work; e += blockDim.x) {
       const int p = e % P, j = (e / P) % Q.N, i = e / (P * Q.N);
       if (Q.kind == XB_KIND_SP_A_CSR) {           // C[i][j][p] (+)= sum_z a[z] * B[col[z]][j][p]
+        if (Q.ptr[i] == Q.ptr[i + 1]) continue;    // the reference emits nothing for an empty row, not even the BETA_0 zeroing
         T acc = Q.beta0 ? (T)0 : C[((size_t)i * Q.ldc + j) * P + p];
         for (unsigned int z = Q.ptr[i]; z < Q.ptr[i + 1]; ++z) acc += A[z] * B[((size_t)Q.idx[z] * Q.ldb + j) * P + p];
         C[((size_t)i * Q.ldc + j) * P + p] = acc;
@@ -197,20 +198,28 @@ __global__ void __launch_bounds__(256) packed_sp_kernel(const PackedParams Q) {
 }
 
 // C sparse (CSC pattern): c[z][p] (+)= sum_k A[row[z]][k][p] * B[k][col][p]
+// C sparse (CSC pattern, ldc == 0): ONE scalar per non-zero, the packed dimension is summed away:
+//   C[z] (+)= sum_k sum_p A[k][row(z)][p] * B[k][col(z)][p],   A = [K][lda][P], B = [K][ldb][P]
+// (src/generator_packed_spgemm_csc_csparse_avx_avx2_avx512.c:63-191). One warp per non-zero: lanes stride the packed
+// dimension (coalesced 128-byte rows of A and B), shuffle reduction at the end.
 template <typename T>
 __global__ void __launch_bounds__(256) packed_csparse_kernel(const PackedParams Q) {
-  const int P = Q.P;
-  for (long long item = blockIdx.x; item < Q.count; item += gridDim.x) {
+  const int P = Q.P, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const unsigned int nnz = Q.ptr[Q.N];
+  for (long long item = blockIdx.y; item < Q.count; item += gridDim.y) {
     const T* A = (const T*)(Q.a + item * Q.stride_a); const T* B = (const T*)(Q.b + item * Q.stride_b);
     T* C = (T*)(Q.c + item * Q.stride_c);
-    for (int j = 0; j < Q.N; ++j) {
-      const unsigned int z0 = Q.ptr[j], z1 = Q.ptr[j + 1];
-      for (int e = threadIdx.x; e < (int)(z1 - z0) * P; e += blockDim.x) {
-        const unsigned int z = z0 + e / P; const int p = e % P; const int i = (int)Q.idx[z];
-        T acc = Q.beta0 ? (T)0 : C[(size_t)z * P + p];
-        for (int k = 0; k < Q.K; ++k) acc += A[((size_t)i * Q.lda + k) * P + p] * B[((size_t)k * Q.ldb + j) * P + p];
-        C[(size_t)z * P + p] = acc;
+    for (unsigned int z = blockIdx.x * nwarps + warp; z < nnz; z += gridDim.x * nwarps) {
+      int lo = 0, hi = Q.N;                               // column of z: last j with ptr[j] <= z
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (Q.ptr[mid] <= z) lo = mid; else hi = mid; }
+      const int j = lo, i = (int)Q.idx[z];
+      T acc = 0;
+      for (int k = 0; k < Q.K; ++k) {
+        const T* ar = A + ((size_t)k * Q.lda + i) * P; const T* br = B + ((size_t)k * Q.ldb + j) * P;
+        for (int p = lane; p < P; p += 32) acc += ar[p] * br[p];
       }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) C[z] = Q.beta0 ? acc : acc + C[z];
     }
   }
 }
@@ -352,7 +361,9 @@ extern "C" int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const
   cudaStream_t stream = (cudaStream_t)xb_rt_stream();
   const unsigned int grid = (unsigned int)(count < 65535 ? count : 65535);
   if (d->kind == XB_KIND_SP_C_CSC) {
-    if (Q.is_f64) packed_csparse_kernel<double><<<grid, 256, 0, stream>>>(Q); else packed_csparse_kernel<float><<<grid, 256, 0, stream>>>(Q);
+    const unsigned int gx = (d->nnz + 7) / 8 > 0 ? (d->nnz + 7) / 8 : 1;
+    const dim3 g2(gx < 1024 ? gx : 1024, grid);
+    if (Q.is_f64) packed_csparse_kernel<double><<<g2, 256, 0, stream>>>(Q); else packed_csparse_kernel<float><<<g2, 256, 0, stream>>>(Q);
   } else {
     if (Q.is_f64) packed_sp_kernel<double><<<grid, 256, 0, stream>>>(Q); else packed_sp_kernel<float><<<grid, 256, 0, stream>>>(Q);
   }

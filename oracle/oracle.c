@@ -280,10 +280,11 @@ ORACLE_API int oracle_bcsc(const int* types, const int* geo, unsigned int flags,
 #define PACKED_BODY(T) do { \
   const T* A = (const T*)a; const T* B = (const T*)b; T* C = (T*)c; int i, j, k, p; unsigned int z; \
   if (lda == 0) {                          /* A sparse, CSR over M rows */ \
-    for (i = 0; i < M; ++i) for (j = 0; j < N; ++j) for (p = 0; p < P; ++p) { \
+    for (i = 0; i < M; ++i) { if (ptr[i + 1] == ptr[i]) continue;  /* empty rows are not even zeroed (..._csr_asparse_avx_avx2_avx512.c:347-348) */ \
+     for (j = 0; j < N; ++j) for (p = 0; p < P; ++p) { \
       T acc = beta0 ? (T)0 : C[((size_t)i * ldc + j) * P + p]; \
       for (z = ptr[i]; z < ptr[i + 1]; ++z) acc += A[z] * B[((size_t)idx[z] * ldb + j) * P + p]; \
-      C[((size_t)i * ldc + j) * P + p] = acc; } \
+      C[((size_t)i * ldc + j) * P + p] = acc; } } \
   } else if (ldb == 0 && is_csc) {        /* B sparse, CSC over N columns */ \
     for (i = 0; i < M; ++i) for (j = 0; j < N; ++j) for (p = 0; p < P; ++p) { \
       T acc = beta0 ? (T)0 : C[((size_t)i * ldc + j) * P + p]; \
@@ -294,11 +295,15 @@ ORACLE_API int oracle_bcsc(const int* types, const int* geo, unsigned int flags,
       T acc = beta0 ? (T)0 : C[((size_t)i * ldc + j) * P + p]; \
       for (k = 0; k < K; ++k) for (z = ptr[k]; z < ptr[k + 1]; ++z) if ((int)idx[z] == j) acc += A[((size_t)i * lda + k) * P + p] * B[z]; \
       C[((size_t)i * ldc + j) * P + p] = acc; } \
-  } else if (ldc == 0 && is_csc) {        /* C sparse, CSC pattern */ \
-    for (j = 0; j < N; ++j) for (z = ptr[j]; z < ptr[j + 1]; ++z) for (p = 0; p < P; ++p) { \
-      T acc = beta0 ? (T)0 : C[(size_t)z * P + p]; \
-      for (k = 0; k < K; ++k) acc += A[((size_t)idx[z] * lda + k) * P + p] * B[((size_t)k * ldb + j) * P + p]; \
-      C[(size_t)z * P + p] = acc; } \
+  } else if (ldc == 0 && is_csc) {        /* C sparse, CSC pattern: ONE scalar per non-zero, the packed dimension is summed \
+      away; A is [K][lda][P], B is [K][ldb][P] (..._csc_csparse_avx_avx2_avx512.c:63-79, 123-191) */ \
+    for (j = 0; j < N; ++j) for (z = ptr[j]; z < ptr[j + 1]; ++z) { \
+      T lane[16], acc; int l; for (l = 0; l < 16; ++l) lane[l] = (T)0; \
+      for (k = 0; k < K; ++k) for (p = 0; p < P; ++p) \
+        lane[p % 16] += A[((size_t)k * lda + idx[z]) * P + p] * B[((size_t)k * ldb + j) * P + p]; \
+      for (l = 0; l < 8; ++l) lane[l] += lane[l + 8]; for (l = 0; l < 4; ++l) lane[l] += lane[l + 4]; \
+      acc = (lane[0] + lane[2]) + (lane[1] + lane[3]); \
+      C[z] = beta0 ? acc : acc + C[z]; } \
   } else return 1; } while (0)
 
 ORACLE_API int oracle_packed_sp(int is_csc, int dtype, const int* dims, unsigned int flags, int P,
@@ -307,6 +312,7 @@ ORACLE_API int oracle_packed_sp(int is_csc, int dtype, const int* dims, unsigned
   const int M = dims[0], N = dims[1], K = dims[2], lda = dims[3], ldb = dims[4], ldc = dims[5];
   const int beta0 = (flags & F_BETA_0) != 0;
   (void)values;
+  if (ldc == 0 && (dtype != T_F32 || P % 16 != 0 || P <= 0)) return 1;  /* C-sparse exists for f32, full 16-lane vectors only */
   if (dtype == T_F64) PACKED_BODY(double); else if (dtype == T_F32) PACKED_BODY(float); else return 1;
   return 0;
 }

@@ -162,6 +162,52 @@ REF_API double ref_bench_gemm_batch(const int* dims, const int* types, unsigned 
   return libxsmm_timer_duration(t0, libxsmm_timer_tick());
 }
 
+/* The reference arm of bench.py: the SAME strided batch as the GPU arm (count tiles, all operands unique), owned by this
+ * function so that every page is first touched by the thread that will stream it (NUMA-local like
+ * samples/xgemm/gemm_kernel_parallel.c), filled once, then `passes` timed passes (seconds per pass in out_seconds).
+ * Values: multiples of 0.1 in [-0.5, 0.5] as bf16 (the drivers' fill, spmm_kernel.c:498-527). Returns 0, or -1 when
+ * dispatch fails, -2 when the host cannot hold the buffers. */
+REF_API int ref_bench_brgemm_owned(int m, int n, int k, unsigned long long br, unsigned int flags, long long count, int warm,
+                                   int passes, double* out_seconds, int* is_ref, double* checksum)
+{
+  static const unsigned short tenth_bf16[11] = { 0xBF00, 0xBECD, 0xBE9A, 0xBE4D, 0xBDCD, 0x0000, 0x3DCD, 0x3E4D, 0x3E9A, 0x3ECD, 0x3F00 };
+  const libxsmm_gemm_shape shape = libxsmm_create_gemm_shape(m, n, k, m, k, m, LIBXSMM_DATATYPE_BF16, LIBXSMM_DATATYPE_BF16,
+    LIBXSMM_DATATYPE_F32, LIBXSMM_DATATYPE_F32);
+  const long long ta = (long long)br * m * k, tb = (long long)br * k * n, tc = (long long)m * n;   /* elements per tile */
+  const libxsmm_gemm_batch_reduce_config cfg = ref_brcfg(3, (long long)m * k * 2, (long long)k * n * 2);
+  libxsmm_xmmfunction kern; libxsmm_kernel_info info;
+  unsigned short *a, *b; float* c; long long t; int pass; double sum = 0;
+  libxsmm_init();
+  kern.gemm = libxsmm_dispatch_brgemm(shape, flags, 0, cfg);
+  if (kern.gemm == NULL) return -1;
+  libxsmm_get_kernel_info(kern.ptr_const, &info);
+  if (is_ref != NULL) *is_ref = (int)info.is_reference_kernel;
+  a = (unsigned short*)malloc((size_t)count * ta * 2); b = (unsigned short*)malloc((size_t)count * tb * 2); c = (float*)malloc((size_t)count * tc * 4);
+  if (a == NULL || b == NULL || c == NULL) { free(a); free(b); free(c); return -2; }
+# pragma omp parallel for schedule(static)
+  for (t = 0; t < count; ++t) {
+    unsigned int x = 555u + (unsigned int)t * 2654435761u; long long i;
+    for (i = 0; i < ta; ++i) { x = x * 1664525u + 1013904223u; a[t * ta + i] = tenth_bf16[(x >> 16) % 11u]; }
+    for (i = 0; i < tb; ++i) { x = x * 1664525u + 1013904223u; b[t * tb + i] = tenth_bf16[(x >> 16) % 11u]; }
+    for (i = 0; i < tc; ++i) c[t * tc + i] = 0.f;
+  }
+  for (pass = -warm; pass < passes; ++pass) {
+    const libxsmm_timer_tickint t0 = libxsmm_timer_tick();
+#   pragma omp parallel for schedule(static)
+    for (t = 0; t < count; ++t) {
+      libxsmm_gemm_param p; unsigned long long brv = br;
+      memset(&p, 0, sizeof(p));
+      p.op.tertiary = &brv; p.a.primary = a + t * ta; p.b.primary = b + t * tb; p.c.primary = c + t * tc;
+      kern.gemm(&p);
+    }
+    if (pass >= 0) out_seconds[pass] = libxsmm_timer_duration(t0, libxsmm_timer_tick());
+  }
+  for (t = 0; t < count; t += 997) sum += c[t * tc + (t % tc)];
+  if (checksum != NULL) *checksum = sum;
+  free(a); free(b); free(c);
+  return 0;
+}
+
 /* fsspmdm: N split into one slice per thread like samples/xgemm_sparse_Ainregs/pyfr_driver_asp_reg.c:380-394 */
 REF_API double ref_bench_fsspmdm(int dtype, int M, int N, int K, int lda, const void* alpha, const void* beta,
                                  const void* a_dense, const char* B, char* C, int reps)

@@ -132,3 +132,20 @@ def small_cases(seed=7):
             flags = fl | (FLAG_BETA_0 if beta0 else 0)
             cases.append(GemmCase(m, n, k, *t, flags=flags, br_type=br_type, br=5, pad=pad))
     return cases
+
+
+def packed_sp_case(rng, kind, dtype, M, N, K, P, density=0.3):
+    """kind: 'a_csr' | 'b_csr' | 'b_csc' | 'c_csc' -> (is_csc, dims, ptr, idx, a, b, c0, which operand holds the values)"""
+    rows, cols = {"a_csr": (M, K), "b_csr": (K, N), "b_csc": (K, N), "c_csc": (M, N)}[kind]
+    dense = rng.random((rows, cols)) < density
+    dense[rng.integers(rows), rng.integers(cols)] = True
+    if kind.endswith("csr"):
+        ptr = np.concatenate([[0], np.cumsum(dense.sum(1))]).astype(np.uint32); idx = np.nonzero(dense)[1].astype(np.uint32)
+    else:
+        ptr = np.concatenate([[0], np.cumsum(dense.sum(0))]).astype(np.uint32); idx = np.nonzero(dense.T)[1].astype(np.uint32)
+    nnz = len(idx)
+    a = gen.values(rng, nnz if kind == "a_csr" else K * max(M, K) * P if kind == "c_csc" else M * K * P, dtype)
+    b = gen.values(rng, nnz if kind.startswith("b_") else K * N * P, dtype)
+    c0 = gen.values(rng, nnz if kind == "c_csc" else M * N * P, dtype)     # C-sparse: one scalar per non-zero
+    dims = {"a_csr": (M, N, K, 0, N, N), "b_csr": (M, N, K, K, 0, N), "b_csc": (M, N, K, K, 0, N), "c_csc": (M, N, K, max(M, K), N, 0)}[kind]
+    return int(kind.endswith("csc")), dims, ptr, idx, a, b, c0
