@@ -256,6 +256,25 @@ __device__ __forceinline__ void bcsc_store_chunk(const uint32_t (&v)[32], __nv_b
   }
 }
 
+// all 32 columns present, whole warp valid, beta = 0: one conversion and one 2-byte store per value. The 32 lanes of a
+// store cover 64 contiguous bytes (two full sectors) of C_mb[n][0..31]; nothing depends on anything else, so the stores
+// stream out without the shuffle/select chains of the packed variant (which kept 8 epilogue warps busy 80 % of the time)
+template <int M>
+__device__ __forceinline__ void bcsc_store_chunk_fast(const uint32_t (&v)[32], __nv_bfloat16* dst) {
+#pragma unroll
+  for (int jj = 0; jj < 32; ++jj) dst[jj * M] = __float2bfloat16_rn(__uint_as_float(v[jj]));
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+}
+
 // ---- round-1 kernel: A converted to the canonical shared-memory operand (SS-form MMA) ---------------------------------------
 // Pipeline per CTA (persistent, one per SM, 22 warps): warp 0 A producer (TMA 3-D box of raw VNNI words), warp 2 B producer,
 // warps 12-19 converters (VNNI2 words -> two k-rows of the canonical MN-major SWIZZLE_128B operand, fence.proxy.async),
@@ -471,7 +490,7 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
 }
 
 // ---- main kernel: the A operand lives in tensor memory (TS-form MMA) ---------------------------------------------------------
-constexpr int kTsThreads = 576;      // 18 warps: A producer, B producer, 4 MMA issuers, 4 copy, 8 epilogue
+constexpr int kTsThreads = 832;      // 26 warps: A producer, B producer, 4 MMA issuers, 4 copy, 16 epilogue (one 32-column chunk each)
 constexpr int kTsDCols = 128;        // accumulator columns per column part (two slots: TMEM columns 0..255)
 constexpr int kTsACol0 = 256;        // A operand: TMEM columns 256..511, 32 per k-step of 64
 constexpr int kTsMaxKS = 8;          // => K <= 512
@@ -564,6 +583,9 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
   const uint32_t raw_full = bar0, raw_empty = raw_full + 8 * 8, a_full = raw_empty + 8 * 8, a_empty = a_full + 8 * kTsMaxKS;
   const uint32_t b_full = a_empty + 8 * kTsMaxKS, b_empty = b_full + 8 * 8, t_full = b_empty + 8 * 8, t_empty = t_full + 8 * 2;
   uint32_t* tmem_word = (uint32_t*)(bars + 4 * 8 + 2 * kTsMaxKS + 4);
+  uint32_t* s_fcnt = tmem_word + 1;                                        // [4] records per MMA warp (flat lists)
+  uint4* s_flat = (uint4*)(((uintptr_t)(s_fcnt + 4) + 15) & ~(uintptr_t)15);   // [ops_cap + 4*NKS + 4] flat records
+  const bool flat = resident && P.kmajor && (p1 - p0) == 2;     // one part per CTA: the part-major loop is already k-major
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -579,7 +601,7 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
     for (int i = 0; i < RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
     for (int i = 0; i < NKS; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, (uint32_t)P.mma_warps); }
     for (int i = 0; i < BS; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, (uint32_t)P.mma_warps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, (uint32_t)P.mma_warps); mbar_init(t_empty + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, (uint32_t)P.mma_warps); mbar_init(t_empty + 8 * i, 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -591,6 +613,41 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_word;
   const uint32_t tmem_a = tmem_base + (uint32_t)kTsACol0;
+
+  // ---- flat per-warp operation lists (resident B, k-major sweep) ----------------------------------------------------------
+  // Everything an instruction needs is known once the CTA knows its set: accumulator column (part q lives in slot q),
+  // A columns of the k-step, descriptor of the resident B block. So each MMA warp gets ONE list for a whole group, in issue
+  // order, with absolute operands {D address, A address | accumulate << 31, B descriptor low word, instruction descriptor};
+  // a record with w == 0 ends a k-step (commit a_empty). The issue loop is then one 16-byte shared load per operation.
+  if (flat) {
+    const int np = p1 - p0;
+    const uint32_t blk16f = blk_bytes >> 4, b_lo_base = desc_lo(smem_u32(s_b), 1);
+    if (warp >= 2 && warp < 2 + P.mma_warps && lane == 0) {
+      uint32_t n = 0;
+      for (int ks = 0; ks < NKS; ++ks) { for (int q = 0; q < np; ++q) n += s_wr[4 * ((p0 + q) * NKS + ks) + (warp - 2)] >> 16; }
+      s_fcnt[warp - 2] = n + (uint32_t)NKS;
+    }
+    __syncthreads();
+    if (warp >= 2 && warp < 2 + P.mma_warps && lane == 0) {
+      uint32_t off = 0;
+      for (int w = 0; w < warp - 2; ++w) off += s_fcnt[w];
+      uint4* out = s_flat + off;
+      for (int ks = 0; ks < NKS; ++ks) {
+        for (int q = 0; q < np; ++q) {
+          const uint32_t l = (uint32_t)((p0 + q) * NKS + ks);
+          const uint32_t rng = s_wr[4 * l + (warp - 2)], ob = rng & 0xFFFFu, on = rng >> 16;
+          const uint32_t b_list_lo = b_lo_base + (s_lp[l] - e_set0) * blk16f;
+          for (uint32_t o = 0; o < on; ++o) {
+            const uint4 op = s_ops[ob + o];
+            *out++ = make_uint4(tmem_base + (uint32_t)(q * kTsDCols) + (op.x & 0xFFFFu),
+                                (tmem_a + (uint32_t)ks * 32u + (op.x >> 20)) | (op.w << 31), b_list_lo + op.y, P.idesc | op.z);
+          }
+        }
+        *out++ = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    __syncthreads();
+  }
 
   if (warp == 0) {
     // ========================================= A producer =======================================
@@ -676,29 +733,40 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
         op = nxt;
       }
     };
-    if (resident && P.kmajor && p1 - p0 <= 2) {
+    if (flat) {
       // k-major sweep: both parts of the set accumulate side by side in the two slots, so the A columns of a k-step are
       // released as soon as that k-step is consumed and the copy warps refill them for the NEXT group while this group's
-      // later k-steps are still being multiplied (with the part-major order below the refill waits for the last MMA of the
-      // group and the first part of the next group is paced by the copy: measured 10.6K cycles per group against ~5K)
+      // later k-steps are still being multiplied.
       const int np = p1 - p0;
+      uint32_t foff = 0;
+      for (int w = 0; w < mw; ++w) foff += s_fcnt[w];
+      const uint32_t flat_sa = smem_u32(s_flat) + 16u * foff;
       for (long long i = 0; i < n_groups; ++i) {
         const uint32_t gpar = (uint32_t)(i & 1);
-        for (int q = 0; q < np; ++q, ++item) mbar_wait(t_empty + 8 * (int)(item & 1), (uint32_t)(((item >> 1) & 1) ^ 1));
-        item -= np;
+        uint32_t rec = flat_sa;
+        uint4 op = lds128(rec);
+        for (int q = 0; q < np; ++q) mbar_wait(t_empty + 8 * q, gpar ^ 1);      // part q lives in slot q (np == 2)
         for (int ks = 0; ks < NKS; ++ks) {
           mbar_wait(a_full + 8 * ks, gpar);
           tc_fence_after();
-          for (int q = 0; q < np; ++q) {
-            const int slot = (int)((item + q) & 1);
-            issue_list((uint32_t)((p0 + q) * NKS + ks), tmem_base + (uint32_t)(slot * kTsDCols), b_lo0, e_set0, ks);
+          while (op.w != 0u) {
+            rec += 16u;
+            const uint4 nxt = lds128(rec);
+            if (leader) {
+              const uint32_t a_col = op.y & 0x7FFFFFFFu;
+              umma_f16_ts(op.x, a_col, desc64(b_hi, op.z), op.w, op.y >> 31);
+#pragma unroll
+              for (int kk = 1; kk < KSTEPS; ++kk) umma_f16_ts(op.x, a_col + (uint32_t)kk * 8u, desc64(b_hi, op.z + (uint32_t)kk * (32u >> 4)), op.w, 1u);
+            }
+            op = nxt;
           }
+          rec += 16u;
+          op = lds128(rec);                                                      // first record of the next k-step (one spare record is allocated)
           if (leader) umma_commit(a_empty + 8 * ks);
           __syncwarp();
         }
-        if (leader) { for (int q = 0; q < np; ++q) umma_commit(t_full + 8 * (int)((item + q) & 1)); }
+        if (leader) { for (int q = 0; q < np; ++q) umma_commit(t_full + 8 * q); }
         __syncwarp();
-        item += np;
       }
     } else {
     for (long long i = 0; i < n_groups; ++i) {
@@ -751,8 +819,8 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
       }
     }
   } else if (warp >= 10) {
-    // ========================================= epilogue (8 warps: two per TMEM quadrant, half the columns each) =====
-    const int q = warp & 3, half = (warp - 10) >> 2;
+    // ========================================= epilogue (16 warps: four per TMEM quadrant, one 32-column chunk each) =====
+    const int q = warp & 3, cw = (warp - 10) >> 2;
     const int row = 32 * q + lane;                       // row of the 128-row group
     const int mbl = row / M, m = row % M;
     const bool bn32 = (P.bn % 32) == 0;
@@ -764,21 +832,26 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
         const int slot = (int)(item & 1);
         const int pc0 = part * P.part_cols;                                        // first column of this part
         const int pcols = (P.ncols - pc0 < P.part_cols) ? (P.ncols - pc0) : P.part_cols;
-        const int nchunks = (pcols + 31) / 32, cbeg = half ? (nchunks + 1) / 2 : 0, cend = half ? nchunks : (nchunks + 1) / 2;
+        const int nchunks = (pcols + 31) / 32;                                     // <= 4 (part_cols <= 128)
+        const bool mine = cw < nchunks;
         __nv_bfloat16* cblk = reinterpret_cast<__nv_bfloat16*>(P.c) + ((size_t)mb * P.ncols + pc0) * M + m;
         mbar_wait(t_full + 8 * slot, (uint32_t)((item >> 1) & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(slot * kTsDCols) + ((uint32_t)(q * 32) << 16);
-        if (cbeg == cend) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
-        for (int ch = cbeg; ch < cend; ++ch) {
-          const int c0 = ch * 32;
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)c0, v);
-          if (ch + 1 == cend) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
+        // fetch the chunk, hand the accumulator slot back to the MMA warps at once, then convert and store from registers
+        uint32_t v[32];
+        if (mine) tmem_ld32_nowait(taddr + (uint32_t)(cw * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before(); __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + 8 * slot);
+        if (mine) {
+          const int c0 = cw * 32;
           const int ncol = (pcols - c0 < 32) ? (pcols - c0) : 32;              // 16 or 32 (bn is a multiple of 16)
           const int jb = (pc0 + c0) / P.bn;
           const bool any0 = s_any[jb] != 0, any1 = bn32 ? any0 : (s_any[(pc0 + c0 + 16) / P.bn < P.nbc ? (pc0 + c0 + 16) / P.bn : jb] != 0);
-          bcsc_store_chunk<M>(v, cblk + (size_t)c0 * M, ncol, any0, any1, valid, P.beta0, lane);
+          const bool whole = __all_sync(0xffffffffu, valid) && P.beta0 != 0;
+          if (whole && any0 && any1 && ncol == 32) bcsc_store_chunk_fast<M>(v, cblk + (size_t)c0 * M);
+          else bcsc_store_chunk<M>(v, cblk + (size_t)c0 * M, ncol, any0, any1, valid, P.beta0, lane);
         }
       }
     }
@@ -934,7 +1007,8 @@ extern "C" int xb_bcsc_tc_launch(const xb_sparse_desc* d, void** work, const voi
     kpc = env_int("LIBXSMM_B200_BCSC_KPC", 1, nks, kpc);
     P2.kpc = kpc; P2.nchunks = (nks + kpc - 1) / kpc; P2.b_stage_bytes = ks_bytes * kpc;
     P2.ops_cap = (int)nnzb; P2.mma_warps = mma_warps;
-    const size_t meta = ((size_t)P2.ops_cap + 1) * 16 + ((size_t)5 * nl + 2) * 4 + (size_t)n_blocks + 16 + (4 * 8 + 2 * kTsMaxKS + 4 + 1) * 8;
+    const size_t meta = ((size_t)P2.ops_cap + 1) * 16 + ((size_t)5 * nl + 2) * 4 + (size_t)n_blocks + 16 + (4 * 8 + 2 * kTsMaxKS + 4 + 1) * 8
+                      + 32 + ((size_t)P2.ops_cap + 4 * kTsMaxKS + 4) * 16;       // + flat per-warp lists of the k-major sweep
     const size_t total = 226 * 1024;                       // dynamic shared memory requested: 1 KB alignment slack + rings + metadata
     if (meta + 1024 + 5 * (size_t)A_STAGE > total) return -1;
     P2.ring_bytes = (int)((total - 1024 - meta) & ~(size_t)1023);

@@ -65,6 +65,13 @@ LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csr(const libxsmm_
   s = xb_host_slot(slot);
   xb_fill_sparse_common(&s->u.sp, kind, &gemm_shape, gemm_flags);
   s->u.sp.packed_width = packed_width;
+  s->u.sp.max_n = gemm_shape.n;
+  if (kind == XB_KIND_SP_B_CSR) {   /* only the columns up to the last one that holds a non-zero are computed -- the rest of C is
+                                     * not even zeroed under BETA_0 (generator_packed_spgemm_csr_bsparse_avx_avx2_avx512.c:64-70) */
+    unsigned int z, maxc = 0;
+    for (z = 0; z < nnz; ++z) maxc = (column_idx[z] > maxc) ? column_idx[z] : maxc;
+    s->u.sp.max_n = (nnz > 0 && (int)(maxc + 1) < gemm_shape.n) ? (int)(maxc + 1) : gemm_shape.n;
+  }
   return xb_finish_sparse(slot, xb_upload_pattern(&s->u.sp, row_ptr, nrows, column_idx, nnz));
 }
 

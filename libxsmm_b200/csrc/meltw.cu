@@ -19,7 +19,7 @@
 
 namespace {
 
-enum { FAM_NONE = 0, FAM_MAP, FAM_REDUCE, FAM_SCALAR, FAM_TRANSFORM, FAM_GS, FAM_QUANT };
+enum { FAM_NONE = 0, FAM_MAP, FAM_REDUCE, FAM_SCALAR, FAM_TRANSFORM, FAM_GS, FAM_QUANT, FAM_DROPOUT, FAM_SPLIT };
 
 __host__ __device__ inline bool is_f(int t) { return t == LIBXSMM_DATATYPE_F32 || t == LIBXSMM_DATATYPE_BF16 || t == LIBXSMM_DATATYPE_F16; }
 
@@ -64,6 +64,19 @@ __host__ __device__ inline int family_of(const xb_meltw_desc& d) {
         return (d.t_in0 == LIBXSMM_DATATYPE_F32 && (d.t_out == LIBXSMM_DATATYPE_I8 || d.t_out == LIBXSMM_DATATYPE_I16 || d.t_out == LIBXSMM_DATATYPE_I32)) ? FAM_QUANT : FAM_NONE;
       case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT:
         return (d.t_out == LIBXSMM_DATATYPE_F32 && (d.t_in0 == LIBXSMM_DATATYPE_I8 || d.t_in0 == LIBXSMM_DATATYPE_I16 || d.t_in0 == LIBXSMM_DATATYPE_I32)) ? FAM_QUANT : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8_PAD:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI8_TO_VNNI8T:
+        return (xb_dev_typesize(d.t_in0) <= 2 && xb_dev_typesize(d.t_in0) >= 1) ? FAM_TRANSFORM : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI8T_TO_NORM:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD2:
+        return (xb_dev_typesize(d.t_in0) == 2) ? FAM_TRANSFORM : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD4:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI2:
+        return (xb_dev_typesize(d.t_in0) == 1) ? FAM_TRANSFORM : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_DROPOUT: case LIBXSMM_MELTW_TYPE_UNARY_DROPOUT_INV:
+        return (is_f(d.t_in0) && is_f(d.t_out)) ? FAM_DROPOUT : FAM_NONE;
+      case LIBXSMM_MELTW_TYPE_UNARY_UNZIP: case LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X2: case LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X3:
+        return (d.t_in0 == LIBXSMM_DATATYPE_F32) ? FAM_SPLIT : FAM_NONE;
       default: return FAM_NONE;
     }
   }
@@ -395,6 +408,38 @@ __global__ void __launch_bounds__(256) meltw_transform_kernel(const xb_meltw_des
     case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_NORM:            // out[(i*ldo)+j] = in[((i/4)*ldi*4)+j*4+(i%4)], i<N, j<M (:787-803)
       for (long long e = tid; e < M * N; e += nth) { const long long j = e % M, i = e / M; out[i * ldo + j] = in[(i / 4) * ldi * 4 + j * 4 + (i % 4)]; }
       break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8_PAD: {
+      // :712-786 -- like VNNI2/VNNI4 with groups of 8 columns; columns past N read as zero here (the reference reads past its input)
+      const long long v = 8, Nn = ((N + v - 1) / v) * v;
+      for (long long e = tid; e < ldo * Nn; e += nth) {
+        const long long j = e / (ldo * v), rem = e % (ldo * v), i = rem / v, j2 = rem % v, col = j * v + j2;
+        out[e] = (i < M && col < N) ? in[col * ldi + i] : (E)0;
+      }
+    } break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8T:           // out[(i*ldo*8)+(j*8)+i2] = in[(j*ldi)+(i*8+i2)] (:666-686)
+      for (long long e = tid; e < (M / 8) * N * 8; e += nth) { const long long i2 = e % 8, j = (e / 8) % N, i = e / (8 * N); out[i * ldo * 8 + j * 8 + i2] = in[j * ldi + i * 8 + i2]; }
+      break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI8_TO_VNNI8T:          // out[j*ldo*8+j2+(i*8+i2)*8] = in[i*ldi*8+i2+(j*8+j2)*8] (:489-531)
+      for (long long e = tid; e < (M / 8) * (N / 8) * 64; e += nth) {
+        const long long i2 = e % 8, j2 = (e / 8) % 8, i = (e / 64) % (N / 8), j = e / (64 * (N / 8));
+        out[j * ldo * 8 + j2 + (i * 8 + i2) * 8] = in[i * ldi * 8 + i2 + (j * 8 + j2) * 8];
+      }
+      break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI8T_TO_NORM: {         // roles of m/n swapped (:581-601)
+      const long long Mr = d.n, Nr = d.m;                              // out[(j*ldo)+(i*8)+i2] = in[(i*ldi*8)+(j*8+i2)]
+      for (long long e = tid; e < (Mr / 8) * Nr * 8; e += nth) { const long long i2 = e % 8, j = (e / 8) % Nr, i = e / (8 * Nr); out[j * ldo + i * 8 + i2] = in[i * ldi * 8 + j * 8 + i2]; }
+    } break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI2:            // out[((i/2)*ldo*2)+j*2+(i%2)] = in[((i/4)*ldi*4)+j*4+(i%4)], i<N, j<M (:806-823)
+      for (long long e = tid; e < M * N; e += nth) { const long long j = e % M, i = e / M; out[(i / 2) * ldo * 2 + j * 2 + (i % 2)] = in[(i / 4) * ldi * 4 + j * 4 + (i % 4)]; }
+      break;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD2:
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD4: {
+      // copy into a zero-filled ldo x Nn image; Nn rounds N up for the PADN/PADNM kinds, PADM keeps N (:825-960)
+      const bool mod4 = (d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD4 || d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD4 || d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD4);
+      const bool padm_only = (d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD2 || d.op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD4);
+      const long long v = mod4 ? 4 : 2, Nn = padm_only ? N : ((N + v - 1) / v) * v;
+      for (long long e = tid; e < ldo * Nn; e += nth) { const long long i = e % ldo, j = e / ldo; out[e] = (i < M && j < N) ? in[j * ldi + i] : (E)0; }
+    } break;
     default: break;
   }
 }
@@ -435,6 +480,69 @@ __global__ void __launch_bounds__(256) meltw_quant_kernel(const xb_meltw_desc d,
       else if (d.t_in0 == LIBXSMM_DATATYPE_I16) v = (float)((const short*)a.in0)[ii];
       else v = (float)((const int*)a.in0)[ii];
       ((float*)a.out)[oi] = v * a.alpha;
+    }
+  }
+}
+
+// ---- dropout (:2361-2422). The reference draws 16 uniform numbers per group of 16 rows from a 16-lane xoshiro128+ state
+// (libxsmm_lsfr_Xwide, :43-73) walking the matrix column by column; lane w of group g therefore sees the (g+1)-th number of
+// sequence w. Phase 1 (one warp, lanes 0..15 = the 16 sequences) produces the numbers in that order and leaves the advanced
+// state behind, phase 2 applies them to all elements in parallel. Sequential in the number of groups -- exact by construction.
+__global__ void __launch_bounds__(32) meltw_rng_kernel(unsigned int* __restrict__ state, float* __restrict__ rnd, long long groups) {
+  const int w = threadIdx.x;
+  if (w >= 16) return;
+  unsigned int s0 = state[w], s1 = state[16 + w], s2 = state[32 + w], s3 = state[48 + w];
+  for (long long g = 0; g < groups; ++g) {
+    rnd[g * 16 + w] = __uint_as_float(0x3f800000u | ((s3 + s0) >> 9)) - 1.0f;
+    const unsigned int t = s1 << 9;
+    s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = (s3 << 11) | (s3 >> 21);
+  }
+  state[w] = s0; state[16 + w] = s1; state[32 + w] = s2; state[48 + w] = s3;
+}
+__global__ void __launch_bounds__(256) meltw_dropout_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
+  const int lane = threadIdx.x & 31;
+  const int chunks = (d.m + 31) / 32, gpc = (d.m + 15) / 16;
+  const bool fwd = (d.op == LIBXSMM_MELTW_TYPE_UNARY_DROPOUT);
+  const bool bitm = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0;
+  const float pn = 1.0f - a.alpha, pi = 1.0f / pn;
+  const long long nwork = (long long)chunks * d.n, wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nwork; w += wstride) {
+    const int j = (int)(w / chunks), i0 = (int)(w % chunks) * 32, i = i0 + lane;
+    const bool act = i < d.m;
+    const float x = act ? ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0) : 0.0f;
+    if (fwd) {
+      const bool keep = act && (a.rnd[((long long)j * gpc + i / 16) * 16 + (i % 16)] < pn);
+      if (act) st_f32(a.out, i + (long long)j * d.ldo, d.t_out, keep ? pi * x : 0.0f);
+      if (bitm) mask_store(a.out_aux, i0, j, ((d.ldo + 15) / 16) * 16, d.m, keep, lane);
+    } else if (act) {
+      const long long mld = bitm ? ((d.ldi + 15) / 16) * 16 : d.ldi;
+      st_f32(a.out, i + (long long)j * d.ldo, d.t_out, mask_bit(a.in_aux, i, j, mld) ? x * pi : 0.0f);
+    }
+  }
+}
+
+// ---- f32 -> bf16 planes: UNZIP (low/high halves), DECOMP_FP32_TO_BF16X2/X3 (truncated head + rounded remainders) (:2423-2469)
+__global__ void __launch_bounds__(256) meltw_split_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
+  const float* in = (const float*)a.in0;
+  unsigned short* out = (unsigned short*)a.out;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)d.m * d.n; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % d.m), j = (int)(e / d.m);
+    const float x = in[bidx(d, 0, i, j, d.ldi)];
+    const long long o = i + (long long)j * d.ldo;
+    const unsigned int bits = __float_as_uint(x);
+    if (d.op == LIBXSMM_MELTW_TYPE_UNARY_UNZIP) {
+      out[o] = (unsigned short)(bits & 0xffffu);
+      ((unsigned short*)((char*)a.out + a.off[0]))[o] = (unsigned short)(bits >> 16);
+    } else {
+      const float head = __uint_as_float(bits & 0xffff0000u);
+      const float r1 = __fsub_rn(x, head);
+      out[o] = (unsigned short)(bits >> 16);
+      if (d.op == LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X3) {
+        const unsigned int b1 = __float_as_uint(r1);
+        const float r2 = __fsub_rn(r1, __uint_as_float(b1 & 0xffff0000u));
+        out[o + (long long)(a.off[0] / 2)] = (unsigned short)(b1 >> 16);
+        out[o + (long long)(a.off[1] / 2)] = xb_f32_to_bf16_rne(r2);
+      } else out[o + (long long)(a.off[0] / 2)] = xb_f32_to_bf16_rne(r1);
     }
   }
 }
@@ -493,6 +601,21 @@ extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
       long long grid = ((long long)d->m * d->n + 255) / 256; if (grid > 148 * 16) grid = 148 * 16;
       meltw_quant_kernel<<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
       return launch_done("meltw_quant");
+    }
+    case FAM_DROPOUT: {
+      const long long warps = (long long)((d->m + 31) / 32) * d->n;
+      long long grid = (warps + 7) / 8; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) return 0;
+      if (d->op == LIBXSMM_MELTW_TYPE_UNARY_DROPOUT) {
+        meltw_rng_kernel<<<1, 32, 0, st>>>((unsigned int*)a->rng, a->rnd, (long long)((d->m + 15) / 16) * d->n);
+        if (launch_done("meltw_rng") != 0) return 1;
+      }
+      meltw_dropout_kernel<<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+      return launch_done("meltw_dropout");
+    }
+    case FAM_SPLIT: {
+      long long grid = ((long long)d->m * d->n + 255) / 256; if (grid > 148 * 16) grid = 148 * 16;
+      meltw_split_kernel<<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
+      return launch_done("meltw_split");
     }
     default: return 1;
   }

@@ -354,7 +354,7 @@ extern "C" int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const
                                    long long stride_a, long long stride_b, long long stride_c)
 {
   PackedParams Q;
-  Q.kind = d->kind; Q.M = d->m; Q.N = d->n; Q.K = d->k; Q.P = d->packed_width; Q.lda = d->lda; Q.ldb = d->ldb; Q.ldc = d->ldc;
+  Q.kind = d->kind; Q.M = d->m; Q.N = (d->kind == XB_KIND_SP_B_CSR) ? d->max_n : d->n; Q.K = d->k; Q.P = d->packed_width; Q.lda = d->lda; Q.ldb = d->ldb; Q.ldc = d->ldc;
   Q.beta0 = d->beta0; Q.is_f64 = (d->ta == LIBXSMM_DATATYPE_F64); Q.ptr = d->d_ptr; Q.idx = d->d_idx;
   Q.a = (const char*)a; Q.b = (const char*)b; Q.c = (char*)c; Q.stride_a = stride_a; Q.stride_b = stride_b; Q.stride_c = stride_c; Q.count = count;
   if (count <= 0) return 0;

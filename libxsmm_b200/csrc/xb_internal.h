@@ -154,6 +154,9 @@ typedef struct xb_meltw_args {
   void* out_aux;             /* unary out.secondary: bitmask out / argop indices / scatter index array */
   float alpha;               /* LEAKY_RELU/ELU alpha, QUANT/DEQUANT scale */
   unsigned long long n_rt;   /* REPLICATE_COL_VAR: run-time N; COLS_IDX reductions: number of indices */
+  unsigned long long off[2]; /* UNZIP: byte offset of the high halves; DECOMP_FP32_TO_BF16X2/X3: byte strides of planes 2, 3 */
+  void* rng;                 /* DROPOUT: 4 x 16 words of generator state (device copy, updated by the kernel) */
+  float* rnd;                /* DROPOUT: scratch for the uniform numbers, 16 per group of rows */
 } xb_meltw_args;
 int xb_meltw_supported(const xb_meltw_desc* d);                          /* pure host logic */
 int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a);

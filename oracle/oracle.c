@@ -290,8 +290,10 @@ ORACLE_API int oracle_bcsc(const int* types, const int* geo, unsigned int flags,
       T acc = beta0 ? (T)0 : C[((size_t)i * ldc + j) * P + p]; \
       for (z = ptr[j]; z < ptr[j + 1]; ++z) acc += A[((size_t)i * lda + idx[z]) * P + p] * B[z]; \
       C[((size_t)i * ldc + j) * P + p] = acc; } \
-  } else if (ldb == 0) {                  /* B sparse, CSR over K rows */ \
-    for (i = 0; i < M; ++i) for (j = 0; j < N; ++j) for (p = 0; p < P; ++p) { \
+  } else if (ldb == 0) {                  /* B sparse, CSR over K rows; columns past the last populated one are left alone \
+      (generator_packed_spgemm_csr_bsparse_avx_avx2_avx512.c:64-70) */ \
+    int ncol = 0; for (z = 0; z < ptr[K]; ++z) ncol = ((int)idx[z] + 1 > ncol) ? (int)idx[z] + 1 : ncol; \
+    for (i = 0; i < M; ++i) for (j = 0; j < ncol && j < N; ++j) for (p = 0; p < P; ++p) { \
       T acc = beta0 ? (T)0 : C[((size_t)i * ldc + j) * P + p]; \
       for (k = 0; k < K; ++k) for (z = ptr[k]; z < ptr[k + 1]; ++z) if ((int)idx[z] == j) acc += A[((size_t)i * lda + k) * P + p] * B[z]; \
       C[((size_t)i * ldc + j) * P + p] = acc; } \

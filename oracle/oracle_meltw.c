@@ -222,10 +222,109 @@ static int unary_transform(const mdesc* d, const libxsmm_meltw_unary_param* p) {
     case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_NORM:
       for (i = 0; i < N; ++i) for (j = 0; j < M; ++j) CP(i * ldo + j, (i / 4) * ldi * 4 + j * 4 + (i % 4));
       return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8_PAD: {   /* :712-786 */
+      long long e;                       /* columns past N (only when N % 8 != 0, where the reference reads past its input) count as zero */
+      for (e = 0; e < ldo * (((N + 7) / 8) * 8); ++e) {
+        const long long jj = e / (ldo * 8), rem = e % (ldo * 8), col = jj * 8 + rem % 8;
+        i = rem / 8;
+        if (i < M && col < N) CP(e, col * ldi + i); else memset(out + e * ts, 0, (size_t)ts);
+      }
+      return 0;
+    }
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8T:                                                                   /* :666-686 */
+      for (i = 0; i < M / 8; ++i) for (j = 0; j < N; ++j) for (i2 = 0; i2 < 8; ++i2) CP(i * ldo * 8 + j * 8 + i2, j * ldi + i * 8 + i2);
+      return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI8_TO_VNNI8T:                                                                  /* :489-531 */
+      for (j = 0; j < M / 8; ++j) for (i = 0; i < N / 8; ++i) for (j2 = 0; j2 < 8; ++j2) for (i2 = 0; i2 < 8; ++i2)
+        CP(j * ldo * 8 + j2 + (i * 8 + i2) * 8, i * ldi * 8 + i2 + (j * 8 + j2) * 8);
+      return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI8T_TO_NORM:                                                                   /* :581-601, m/n swapped */
+      for (i = 0; i < N / 8; ++i) for (j = 0; j < M; ++j) for (i2 = 0; i2 < 8; ++i2) CP(j * ldo + i * 8 + i2, i * ldi * 8 + j * 8 + i2);
+      return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI2:                                                                   /* :806-823 */
+      for (i = 0; i < N; ++i) for (j = 0; j < M; ++j) CP((i / 2) * ldo * 2 + j * 2 + (i % 2), (i / 4) * ldi * 4 + j * 4 + (i % 4));
+      return 0;
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD2:
+    case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD4: {
+      const int mod4 = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD4 || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD4 || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD4);
+      const int padm_only = (op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD2 || op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD4);
+      const long long Nn = padm_only ? N : ((N + (mod4 ? 3 : 1)) / (mod4 ? 4 : 2)) * (mod4 ? 4 : 2);                          /* :825-960 */
+      memset(out, 0, (size_t)(ldo * Nn) * ts);
+      for (j = 0; j < N; ++j) for (i = 0; i < M; ++i) CP(j * ldo + i, j * ldi + i);
+      return 0;
+    }
     default: return 2;
   }
 }
 #undef CP
+
+/* dropout forward / backward: reference :2361-2422 with the 16-lane generator step of :43-73 */
+static void lsfr16(unsigned int* st, float* out) {
+  int w;
+  for (w = 0; w < 16; ++w) {
+    unsigned int s0 = st[w], s1 = st[16 + w], s2 = st[32 + w], s3 = st[48 + w], t;
+    union { unsigned int u; float f; } r;
+    r.u = 0x3f800000u | ((s3 + s0) >> 9);
+    out[w] = r.f - 1.0f;
+    t = s1 << 9; s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = (s3 << 11) | (s3 >> 21);
+    st[w] = s0; st[16 + w] = s1; st[32 + w] = s2; st[48 + w] = s3;
+  }
+}
+static void set_bit(unsigned char* m, long long i, long long j, long long ld, int on) {
+  unsigned char* b = m + i / 8 + j * (ld / 8);
+  if (on) *b = (unsigned char)(*b | (1u << (i % 8))); else *b = (unsigned char)(*b & ~(1u << (i % 8)));
+}
+static int unary_dropout(const mdesc* d, const libxsmm_meltw_unary_param* p) {
+  const int bitm = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0;
+  const float prob = *(const float*)p->op.primary, pn = 1.0f - prob, pi = 1.0f / pn;
+  int i, j;
+  if (!(is_f(d->t0) && is_f(d->to))) return 2;
+  if (d->op == LIBXSMM_MELTW_TYPE_UNARY_DROPOUT) {
+    const long long mld = bitm ? ((d->ldo + 15) / 16) * 16 : d->ldo;
+    float r[16];
+    for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+      float x; int keep;
+      if (i % 16 == 0) lsfr16((unsigned int*)p->op.secondary, r);       /* one draw per group of 16 rows, remainder groups included */
+      x = ldf(p->in.primary, bidx(d, 0, i, j, d->ldi), d->t0);
+      keep = r[i % 16] < pn;
+      stf(p->out.primary, i + (long long)j * d->ldo, d->to, keep ? pi * x : 0.0f);
+      if (bitm) set_bit((unsigned char*)p->out.secondary, i, j, mld, keep);
+    }
+  } else {
+    const long long mld = bitm ? ((d->ldi + 15) / 16) * 16 : d->ldi;
+    for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+      const float x = ldf(p->in.primary, bidx(d, 0, i, j, d->ldi), d->t0) * pi;
+      const int bit = (((const unsigned char*)p->in.secondary)[i / 8 + (long long)j * (mld / 8)] >> (i % 8)) & 1;
+      stf(p->out.primary, i + (long long)j * d->ldo, d->to, bit ? x : 0.0f);
+    }
+  }
+  return 0;
+}
+/* f32 -> bf16 planes: reference :2423-2469 */
+static int unary_split(const mdesc* d, const libxsmm_meltw_unary_param* p) {
+  const unsigned long long* offs = (const unsigned long long*)p->out.secondary;
+  uint16_t* out = (uint16_t*)p->out.primary;
+  int i, j;
+  if (d->t0 != LIBXSMM_DATATYPE_F32) return 2;
+  for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
+    union { float f; unsigned int u; } x, h, r1, h1;
+    const long long o = i + (long long)j * d->ldo;
+    x.f = ((const float*)p->in.primary)[bidx(d, 0, i, j, d->ldi)];
+    if (d->op == LIBXSMM_MELTW_TYPE_UNARY_UNZIP) {
+      out[o] = (uint16_t)(x.u & 0xffffu);
+      ((uint16_t*)((char*)p->out.primary + offs[0]))[o] = (uint16_t)(x.u >> 16);
+    } else {
+      h.u = x.u & 0xffff0000u; r1.f = x.f - h.f;
+      out[o] = (uint16_t)(x.u >> 16);
+      if (d->op == LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X3) {
+        h1.u = r1.u & 0xffff0000u;
+        out[o + (long long)(offs[0] / 2)] = (uint16_t)(r1.u >> 16);
+        out[o + (long long)(offs[1] / 2)] = oracle_f32_to_bf16(r1.f - h1.f);
+      } else out[o + (long long)(offs[0] / 2)] = oracle_f32_to_bf16(r1.f);
+    }
+  }
+  return 0;
+}
 
 /* quantise / dequantise: reference :2195-2360 */
 static int unary_quant(const mdesc* d, const libxsmm_meltw_unary_param* p) {
@@ -394,7 +493,16 @@ ORACLE_API int oracle_meltw(const int* desc, void* param, int mode) {
       case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2_TO_VNNI2T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI4T:
       case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI2T_TO_NORM: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4T_TO_NORM:
       case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_NORM:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8_PAD:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI8T: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI8_TO_VNNI8T:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI8T_TO_NORM: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_VNNI4_TO_VNNI2:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD2: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD2:
+      case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADM_MOD4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADN_MOD4: case LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_PADNM_MOD4:
         return unary_transform(&d, (const libxsmm_meltw_unary_param*)param);
+      case LIBXSMM_MELTW_TYPE_UNARY_DROPOUT: case LIBXSMM_MELTW_TYPE_UNARY_DROPOUT_INV:
+        return unary_dropout(&d, (const libxsmm_meltw_unary_param*)param);
+      case LIBXSMM_MELTW_TYPE_UNARY_UNZIP: case LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X2: case LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X3:
+        return unary_split(&d, (const libxsmm_meltw_unary_param*)param);
       case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_TO_SCALAR_OP_ADD:
         return reduce_to_scalar(&d, ((const libxsmm_meltw_unary_param*)param)->in.primary, NULL, ((const libxsmm_meltw_unary_param*)param)->out.primary);
       case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT: case LIBXSMM_MELTW_TYPE_UNARY_QUANT:

@@ -76,3 +76,84 @@ def run_fsspmdm(side, cfg, inp, c):
     M, K, N = cfg["M"], cfg["K"], cfg["N"]
     return side["fsspmdm"](cfg["dtype"], M, N, K, K, N, N, inp["alpha"].ctypes.data, inp["beta"].ctypes.data, inp["a"].ctypes.data,
                            inp["b"].ctypes.data, c.ctypes.data)
+
+
+# ---- real sparsity patterns shipped with the reference's drivers (tests/golden/mtx/*.mtx, copied input DATA of
+# samples/xgemm_sparse_Ainregs/mats (PyFR operators) and samples/xgemm_norm_packed/mats (EDGE/SeisSol operators)) --------
+import os
+
+MTX_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mtx")
+
+
+def read_mtx(name):
+    """MatrixMarket coordinate file -> (rows, cols, dense float64 array); same reading as the drivers' CSR readers"""
+    with open(os.path.join(MTX_DIR, name)) as f:
+        lines = [ln for ln in f if not ln.startswith("%")]
+    rows, cols, nnz = (int(x) for x in lines[0].split())
+    dense = np.zeros((rows, cols))
+    for ln in lines[1:1 + nnz]:
+        r, c, v = ln.split()
+        dense[int(r) - 1, int(c) - 1] = float(v)
+    return rows, cols, dense
+
+
+def pyfr_cases():
+    out = []
+    for i, name in enumerate(("pyfr_p1_tet_m6-sp.mtx", "pyfr_p2_quad_m132-sp.mtx", "pyfr_p3_hex_m6-sp.mtx", "pyfr_p3_hex_m132-sp.mtx")):
+        for dtype in (gen.F64, gen.F32):
+            for beta in (0.0, 1.0):
+                out.append(dict(mtx=name, dtype=dtype, N=96, alpha=1.0, beta=beta, seed=300 + len(out)))
+    return out
+
+
+def pyfr_inputs(cfg):
+    M, K, dense = read_mtx(cfg["mtx"])
+    rng = np.random.default_rng(cfg["seed"])
+    npdt = gen.NP_OF[cfg["dtype"]]
+    return dict(M=M, K=K, a=dense.astype(npdt).ravel().copy(), b=gen.values(rng, K * cfg["N"], cfg["dtype"]), c0=gen.values(rng, M * cfg["N"], cfg["dtype"]),
+                alpha=np.array([cfg["alpha"]], dtype=npdt), beta=np.array([cfg["beta"]], dtype=npdt))
+
+
+def run_pyfr(side, cfg, inp, c):
+    M, K, N = inp["M"], inp["K"], cfg["N"]
+    return side["fsspmdm"](cfg["dtype"], M, N, K, K, N, N, inp["alpha"].ctypes.data, inp["beta"].ctypes.data, inp["a"].ctypes.data,
+                           inp["b"].ctypes.data, c.ctypes.data)
+
+
+def edge_cases():
+    """(kind, file, free dimension, packed width, dtype, beta0): the sparse operand's extents come from the file"""
+    return [dict(kind="a_csr", mtx="tet4_starMatrix_csr.mtx", free=20, P=16, dtype=gen.F32, beta0=0, seed=400),
+            dict(kind="a_csr", mtx="tet4_starMatrix_csr.mtx", free=35, P=8, dtype=gen.F64, beta0=1, seed=401),
+            dict(kind="b_csr", mtx="tet4_2_fluxN_0_csr.mtx", free=9, P=8, dtype=gen.F64, beta0=0, seed=402),
+            dict(kind="b_csc", mtx="tet4_2_fluxN_0_csc.mtx", free=9, P=16, dtype=gen.F32, beta0=0, seed=403),
+            dict(kind="b_csr", mtx="tet4_3_stiffT_0_csr.mtx", free=9, P=16, dtype=gen.F32, beta0=1, seed=404),
+            dict(kind="b_csc", mtx="tet4_3_stiffT_0_csc.mtx", free=9, P=8, dtype=gen.F64, beta0=0, seed=405),
+            dict(kind="b_csr", mtx="tet4_4_fluxT_1_csr.mtx", free=9, P=8, dtype=gen.F64, beta0=0, seed=406),
+            dict(kind="b_csc", mtx="tet4_4_fluxT_1_csc.mtx", free=9, P=16, dtype=gen.F32, beta0=1, seed=407)]
+
+
+def edge_inputs(cfg):
+    rows, cols, dense = read_mtx(cfg["mtx"])
+    rng = np.random.default_rng(cfg["seed"])
+    dtype, P, kind = cfg["dtype"], cfg["P"], cfg["kind"]
+    npdt = gen.NP_OF[dtype]
+    mask = dense != 0
+    if kind.endswith("csr"):
+        ptr = np.concatenate([[0], np.cumsum(mask.sum(1))]).astype(np.uint32); idx = np.nonzero(mask)[1].astype(np.uint32)
+        vals = dense[mask].astype(npdt)
+    else:
+        ptr = np.concatenate([[0], np.cumsum(mask.sum(0))]).astype(np.uint32); idx = np.nonzero(mask.T)[1].astype(np.uint32)
+        vals = dense.T[mask.T].astype(npdt)
+    if kind == "a_csr":
+        M, K, N = rows, cols, cfg["free"]
+        dims = (M, N, K, 0, N, N); a = vals; b = gen.values(rng, K * N * P, dtype)
+    else:
+        K, N, M = rows, cols, cfg["free"]
+        dims = (M, N, K, K, 0, N); a = gen.values(rng, M * K * P, dtype); b = vals
+    return dict(dims=dims, ptr=ptr, idx=idx, vals=vals, a=a, b=b, c0=gen.values(rng, M * N * P, dtype), is_csc=int(kind.endswith("csc")),
+                flags=cases.FLAG_BETA_0 if cfg["beta0"] else 0)
+
+
+def run_edge(side, cfg, inp, c):
+    return side["packed_sp"](inp["is_csc"], cfg["dtype"], iarr(*inp["dims"]), inp["flags"], cfg["P"], inp["ptr"].ctypes.data, inp["idx"].ctypes.data,
+                             inp["vals"].ctypes.data, inp["a"].ctypes.data, inp["b"].ctypes.data, c.ctypes.data)

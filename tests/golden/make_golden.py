@@ -54,6 +54,23 @@ def main():
     np.savez_compressed(os.path.join(HERE, "sparse.npz"), **out)
     print("sparse.npz: %d cases" % (len(out) // 2))
 
+    # the reference's own operator files (tests/golden/mtx): fsspmdm on the PyFR matrices, packed CSR/CSC on the EDGE ones
+    out = {}
+    for i, cfg in enumerate(G.pyfr_cases()):
+        inp = G.pyfr_inputs(cfg)
+        c = inp["c0"].copy()
+        assert G.run_pyfr(ref, cfg, inp, c) == 0, cfg
+        out["pyfr_%02d" % i] = c
+        out["pyfr_%02d_crc" % i] = crc(inp["a"], inp["b"], inp["c0"])
+    for i, cfg in enumerate(G.edge_cases()):
+        inp = G.edge_inputs(cfg)
+        c = inp["c0"].copy()
+        assert G.run_edge(ref, cfg, inp, c) == 0, cfg
+        out["edge_%02d" % i] = c
+        out["edge_%02d_crc" % i] = crc(inp["ptr"], inp["idx"], inp["a"], inp["b"], inp["c0"])
+    np.savez_compressed(os.path.join(HERE, "mtx.npz"), **out)
+    print("mtx.npz: %d cases" % (len(out) // 2))
+
 
 if __name__ == "__main__":
     main()

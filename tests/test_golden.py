@@ -21,6 +21,7 @@ from oracle_ffi import oracle, run_gemm  # noqa: E402
 
 GEMM = np.load(os.path.join(HERE, "golden", "gemm.npz"))
 SPARSE = np.load(os.path.join(HERE, "golden", "sparse.npz"))
+MTX = np.load(os.path.join(HERE, "golden", "mtx.npz"))
 
 
 def crc(*arrs):
@@ -60,6 +61,49 @@ def test_sparse_golden_pins_the_oracle():
         c = inp["c0"].copy()
         assert G.run_fsspmdm(oracle, cfg, inp, c) == 0
         assert gen.normf_rel(SPARSE["fsspmdm_%02d" % i], c) <= sparse_thr(cfg["dtype"], "fsspmdm"), cfg
+
+
+def test_reference_operator_files_pin_the_oracle():
+    """PyFR (samples/xgemm_sparse_Ainregs/mats) and EDGE (samples/xgemm_norm_packed/mats) operators: reference JIT output
+    stored in mtx.npz against the oracle restatement on the same seeded dense operands"""
+    for i, cfg in enumerate(G.pyfr_cases()):
+        inp = G.pyfr_inputs(cfg)
+        assert crc(inp["a"], inp["b"], inp["c0"]) == MTX["pyfr_%02d_crc" % i]
+        c = inp["c0"].copy()
+        assert G.run_pyfr(oracle, cfg, inp, c) == 0
+        assert gen.normf_rel(MTX["pyfr_%02d" % i], c) <= sparse_thr(cfg["dtype"], "fsspmdm"), cfg
+    for i, cfg in enumerate(G.edge_cases()):
+        inp = G.edge_inputs(cfg)
+        assert crc(inp["ptr"], inp["idx"], inp["a"], inp["b"], inp["c0"]) == MTX["edge_%02d_crc" % i]
+        c = inp["c0"].copy()
+        assert G.run_edge(oracle, cfg, inp, c) == 0
+        assert gen.normf_rel(MTX["edge_%02d" % i], c) <= {gen.F32: 2e-6, gen.F64: 1e-14}[cfg["dtype"]], cfg
+
+
+@pytest.mark.gpu
+def test_reference_operator_files_on_gpu():
+    import libxsmm_b200 as X
+    from gpu_util import dev, host
+    for i, cfg in enumerate(G.pyfr_cases()):
+        inp = G.pyfr_inputs(cfg)
+        M, K, N = inp["M"], inp["K"], cfg["N"]
+        h = X.libxsmm_fsspmdm_create(cfg["dtype"], M, N, K, K, N, N, inp["alpha"].ctypes.data, inp["beta"].ctypes.data, inp["a"].ctypes.data, 0, None)
+        assert h, cfg
+        d_b, d_c = dev(inp["b"]), dev(inp["c0"])
+        X.libxsmm_fsspmdm_execute(h, d_b.data_ptr(), d_c.data_ptr()); X.check()
+        assert gen.normf_rel(MTX["pyfr_%02d" % i], host(d_c, gen.NP_OF[cfg["dtype"]])) <= sparse_thr(cfg["dtype"], "fsspmdm"), cfg
+        X.libxsmm_fsspmdm_destroy(h)
+    for i, cfg in enumerate(G.edge_cases()):
+        inp = G.edge_inputs(cfg)
+        dt = cfg["dtype"]
+        create = X.libxsmm_create_packed_spgemm_csc if inp["is_csc"] else X.libxsmm_create_packed_spgemm_csr
+        k = create(X.libxsmm_create_gemm_shape(*inp["dims"], dt, dt, dt, dt), inp["flags"], 0, cfg["P"], inp["ptr"].ctypes.data, inp["idx"].ctypes.data,
+                   inp["vals"].ctypes.data)
+        assert k, cfg
+        d_a, d_b, d_c = dev(inp["a"]), dev(inp["b"]), dev(inp["c0"])
+        X.call_gemm(k, d_a, d_b, d_c); X.check()
+        assert gen.normf_rel(MTX["edge_%02d" % i], host(d_c, gen.NP_OF[dt])) <= {gen.F32: 2e-6, gen.F64: 1e-14}[dt], cfg
+        X.libxsmm_release_kernel(k)
 
 
 @pytest.mark.gpu

@@ -108,7 +108,8 @@ def test_meltw_dispatch_host_logic():
     k = X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_RELU, sh, 0)
     assert k and k == X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_RELU, sh, 0)
     assert k != X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_TANH, sh, 0)
-    assert not X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_DROPOUT, sh, 0)                      # RNG lane order depends on the host vlen: out of scope
+    assert X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_DROPOUT, sh, 0)                          # 16-lane generator like the reference's 512-bit targets
+    assert not X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_STOCHASTIC_ROUND, sh, 0)             # not built
     bs = X.libxsmm_create_meltw_binary_shape(10, 7, 10, 10, 10, gen.F32, gen.F32, gen.F32, gen.F32)
     assert X.libxsmm_dispatch_meltw_binary(X.MELTW_TYPE_BINARY_ADD, bs, 0)
     info = X.KernelInfo(); assert X.libxsmm_get_kernel_info(k, C.byref(info)) == 0

@@ -320,3 +320,95 @@ def test_quant_dequant_and_scalar_reductions():
     X.MELTW_BINARY_FN(k)(C.byref(p)); X.check()
     want = float((a.reshape(n, ld)[:, :m].astype(np.float64) * b.reshape(n, ld)[:, :m]).sum())
     assert abs(float(host(d_o, np.float32)[0]) - want) < 1e-3
+
+
+def test_vnni8_pad_and_vnni4_to_vnni2_transforms_bit_exact():
+    rng = np.random.default_rng(58)
+    cases_ = [("NORM_TO_VNNI8", gen.BF16, "m"), ("NORM_TO_VNNI8", gen.I8, "m"), ("NORM_TO_VNNI8_PAD", gen.BF16, "m"), ("NORM_TO_VNNI8T", gen.BF16, "n"),
+              ("VNNI8_TO_VNNI8T", gen.BF16, "n"), ("VNNI8_TO_VNNI8T", gen.I8, "n"), ("VNNI8T_TO_NORM", gen.BF16, "n"), ("VNNI4_TO_VNNI2", gen.I8, "m"),
+              ("PADM_MOD2", gen.BF16, "m"), ("PADN_MOD2", gen.BF16, "m"), ("PADNM_MOD2", gen.BF16, "m"),
+              ("PADM_MOD4", gen.I8, "m"), ("PADN_MOD4", gen.I8, "m"), ("PADNM_MOD4", gen.I8, "m")]
+    for name, t, ld_of in cases_:
+        op = getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_" + name)
+        shapes = ((32, 16, 0), (64, 8, 8), (8, 64, 0), (40, 24, 8))
+        if name.startswith("PAD"):
+            shapes = shapes + ((33, 7, 3), (5, 9, 1))
+        for (m, n, pad) in shapes:
+            ldi, ldo = m + pad, (n if ld_of == "n" else m) + pad
+            x = rng.integers(0, 256, size=(ldi + 8) * (n + 16) * 8 * gen.TS[t], dtype=np.uint8)
+            o0 = rng.integers(0, 256, size=(ldo + 8) * (max(m, n) + 16) * 8 * gen.TS[t], dtype=np.uint8)
+            k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, t, t, t), 0)
+            assert k, name
+            d_x, d_o = dev(x), dev(o0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_o.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+            _ref_call(_desc(1, op, 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), q)
+            assert np.array_equal(host(d_o, np.uint8), want), (name, t, m, n, pad)
+
+
+@pytest.mark.parametrize("tin,tout", [(gen.F32, gen.F32), (gen.BF16, gen.BF16), (gen.F32, gen.BF16)])
+def test_dropout_same_numbers_as_the_reference_generator(tin, tout):
+    """forward: the 16-lane generator state is consumed column by column like the reference, so outputs, bitmask AND the
+    advanced state must be bit-identical; backward: mask-driven"""
+    rng = np.random.default_rng(59)
+    for (m, n, pad) in ((33, 7, 0), (64, 5, 3), (100, 13, 4), (7, 9, 1)):
+        for bitm in (0, X.MELTW_FLAG_UNARY_BITMASK_2BYTEMULT):
+            ldi, ldo = m + pad, m + 2 * pad
+            x = _rand(rng, ldi * n, tin); y0 = _rand(rng, ldo * n, tout)
+            prob = C.c_float(0.3)
+            mask0 = rng.integers(0, 256, size=((ldo + 15) // 16 * 16) // 8 * n + 8, dtype=np.uint8)
+            st0 = rng.integers(1, 2**32 - 1, size=64, dtype=np.uint64).astype(np.uint32)
+            op = X.MELTW_TYPE_UNARY_DROPOUT
+            k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, tin, tout, gen.F32), bitm)
+            assert k
+            d_x, d_y, d_m, d_s = dev(x), dev(y0), dev(mask0), dev(st0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = d_x.data_ptr(), d_y.data_ptr(), d_m.data_ptr()
+            p.op.primary, p.op.secondary = C.addressof(prob), d_s.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want, wmask, wst = y0.copy(), mask0.copy(), st0.copy()
+            q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary, q.out.secondary = x.ctypes.data, want.ctypes.data, wmask.ctypes.data
+            q.op.primary, q.op.secondary = C.addressof(prob), wst.ctypes.data
+            _ref_call(_desc(1, op, bitm, m, n, ldi, 0, 0, ldo, tin, UNS, UNS, tout, gen.F32), q)
+            assert np.array_equal(host(d_y, want.dtype).view(np.uint8), want.view(np.uint8)), ("dropout", m, n, bitm)
+            assert np.array_equal(host(d_s, np.uint32), wst), "generator state after the call"
+            if bitm:
+                assert np.array_equal(host(d_m, np.uint8), wmask), "dropout mask"
+                # host-resident operands (staging path) must give the same bits and advance the caller's state in place
+                hy, hm, hs = y0.copy(), mask0.copy(), st0.copy()
+                r = X.MeltwUnaryParam(); r.inp.primary, r.out.primary, r.out.secondary = x.ctypes.data, hy.ctypes.data, hm.ctypes.data
+                r.op.primary, r.op.secondary = C.addressof(prob), hs.ctypes.data
+                X.MELTW_UNARY_FN(k)(C.byref(r)); X.check()
+                assert np.array_equal(hy.view(np.uint8), want.view(np.uint8)) and np.array_equal(hm, wmask) and np.array_equal(hs, wst)
+                opi = X.MELTW_TYPE_UNARY_DROPOUT_INV
+                ki = X.libxsmm_dispatch_meltw_unary(opi, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, tin, tout, gen.F32), bitm)
+                assert ki
+                maskb = rng.integers(0, 256, size=((ldi + 15) // 16 * 16) // 8 * n + 8, dtype=np.uint8)
+                d_mb, d_y2 = dev(maskb), dev(y0)
+                pb = X.MeltwUnaryParam(); pb.inp.primary, pb.inp.secondary, pb.out.primary = d_x.data_ptr(), d_mb.data_ptr(), d_y2.data_ptr()
+                pb.op.primary = C.addressof(prob)
+                X.MELTW_UNARY_FN(ki)(C.byref(pb)); X.check()
+                wb = y0.copy(); qb = X.MeltwUnaryParam(); qb.inp.primary, qb.inp.secondary, qb.out.primary = x.ctypes.data, maskb.ctypes.data, wb.ctypes.data
+                qb.op.primary = C.addressof(prob)
+                _ref_call(_desc(1, opi, bitm, m, n, ldi, 0, 0, ldo, tin, UNS, UNS, tout, gen.F32), qb)
+                assert np.array_equal(host(d_y2, wb.dtype).view(np.uint8), wb.view(np.uint8)), ("dropout_inv", m, n)
+
+
+def test_unzip_and_decompose_bit_exact():
+    rng = np.random.default_rng(60)
+    for (m, n, pad) in ((33, 7, 0), (64, 5, 3), (1, 9, 2)):
+        ldi, ldo = m + pad, m + 2 * pad
+        x = (rng.standard_normal(ldi * n) * np.exp(rng.uniform(-8, 8, ldi * n))).astype(np.float32)
+        plane = ldo * n + 5
+        for name, nplanes in (("UNZIP", 2), ("DECOMP_FP32_TO_BF16X2", 2), ("DECOMP_FP32_TO_BF16X3", 3)):
+            op = getattr(X, "MELTW_TYPE_UNARY_" + name)
+            o0 = rng.integers(0, 60000, size=plane * nplanes, dtype=np.uint16)
+            offs = np.array([plane * 2, plane * 4], dtype=np.uint64)
+            k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, gen.F32, gen.BF16, gen.F32), 0)
+            assert k, name
+            d_x, d_o = dev(x), dev(o0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = d_x.data_ptr(), d_o.data_ptr(), offs.ctypes.data
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary, q.out.secondary = x.ctypes.data, want.ctypes.data, offs.ctypes.data
+            _ref_call(_desc(1, op, 0, m, n, ldi, 0, 0, ldo, gen.F32, UNS, UNS, gen.BF16, gen.F32), q)
+            assert np.array_equal(host(d_o, np.uint16), want), (name, m, n)

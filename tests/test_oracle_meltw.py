@@ -239,3 +239,76 @@ def test_reductions_to_scalar(t):
         p = X.MeltwBinaryParam(); p.in0.primary, p.in1.primary, p.out.primary = a.ctypes.data, b.ctypes.data, bufs[0].ctypes.data
         return p
     both((2, X.MELTW_TYPE_BINARY_MUL_AND_REDUCE_TO_SCALAR_OP_ADD, 0, m, n, ld, ld, 0, ld, t, t, UNS, t, tcomp), mkb, [y0])
+
+
+def test_vnni8_pad_and_vnni4_to_vnni2_transforms():
+    """the remaining layout transforms of generator_mateltwise_reference_impl.c:489-531, 581-601, 666-686, 712-786, 806-960;
+    output buffers pre-filled with random bytes so that the zero padding the reference writes is compared too"""
+    rng = np.random.default_rng(68)
+    cases_ = [("NORM_TO_VNNI8", gen.BF16, "m"), ("NORM_TO_VNNI8", gen.I8, "m"), ("NORM_TO_VNNI8_PAD", gen.BF16, "m"), ("NORM_TO_VNNI8T", gen.BF16, "n"),
+              ("VNNI8_TO_VNNI8T", gen.BF16, "n"), ("VNNI8_TO_VNNI8T", gen.I8, "n"), ("VNNI8T_TO_NORM", gen.BF16, "n"), ("VNNI4_TO_VNNI2", gen.I8, "m"),
+              ("PADM_MOD2", gen.BF16, "m"), ("PADN_MOD2", gen.BF16, "m"), ("PADNM_MOD2", gen.BF16, "m"),
+              ("PADM_MOD4", gen.I8, "m"), ("PADN_MOD4", gen.I8, "m"), ("PADNM_MOD4", gen.I8, "m")]
+    for name, t, ld_of in cases_:
+        op = getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_" + name)
+        shapes = ((32, 16, 0), (64, 8, 8), (8, 64, 0), (40, 24, 8))
+        if name.startswith("PAD") or name == "VNNI4_TO_VNNI2":
+            shapes = shapes + ((33, 7, 3), (5, 9, 1)) if name.startswith("PAD") else shapes + ((36, 12, 4),)
+        for (m, n, pad) in shapes:
+            ldi = m + pad
+            ldo = (n if ld_of == "n" else m) + pad
+            x = rng.integers(0, 256, size=(ldi + 8) * (n + 16) * 8 * gen.TS[t], dtype=np.uint8)
+            o0 = rng.integers(0, 256, size=(ldo + 8) * (max(m, n) + 16) * 8 * gen.TS[t], dtype=np.uint8)
+
+            def mkv(bufs, keep):
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
+                return p
+            both((1, op, 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t), mkv, [o0])
+
+
+def rng_state(seed):
+    """64 words like libxsmm_rng_create_extstate would hand out (any non-degenerate state pins the step function)"""
+    return np.random.default_rng(seed).integers(1, 2**32 - 1, size=64, dtype=np.uint64).astype(np.uint32)
+
+
+@pytest.mark.parametrize("tin,tout", [(gen.F32, gen.F32), (gen.BF16, gen.BF16), (gen.F32, gen.BF16), (gen.F16, gen.F16)])
+def test_dropout_forward_and_backward(tin, tout):
+    rng = np.random.default_rng(69)
+    for (m, n, pad) in ((33, 7, 0), (64, 5, 3), (16, 16, 0), (100, 3, 4), (7, 9, 1)):
+        for bitm in (0, X.MELTW_FLAG_UNARY_BITMASK_2BYTEMULT):
+            ldi, ldo = m + pad, m + 2 * pad
+            x = rnd(rng, ldi * n, tin); y0 = rnd(rng, ldo * n, tout)
+            prob = C.c_float(0.3)
+            mask0 = rng.integers(0, 256, size=((ldo + 15) // 16 * 16) // 8 * n + 8, dtype=np.uint8)
+            st0 = rng_state(m * 131 + n)
+
+            def mk(bufs, keep):
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, bufs[0].ctypes.data, bufs[1].ctypes.data
+                p.op.primary, p.op.secondary = C.addressof(prob), bufs[2].ctypes.data
+                return p
+            both((1, X.MELTW_TYPE_UNARY_DROPOUT, bitm, m, n, ldi, 0, 0, ldo, tin, UNS, UNS, tout, gen.F32), mk, [y0, mask0, st0])
+            if bitm:
+                # backward from a mask laid out against ldi
+                maskb = rng.integers(0, 256, size=((ldi + 15) // 16 * 16) // 8 * n + 8, dtype=np.uint8)
+
+                def mkb(bufs, keep):
+                    p = X.MeltwUnaryParam(); p.inp.primary, p.inp.secondary, p.out.primary = x.ctypes.data, maskb.ctypes.data, bufs[0].ctypes.data
+                    p.op.primary = C.addressof(prob)
+                    return p
+                both((1, X.MELTW_TYPE_UNARY_DROPOUT_INV, bitm, m, n, ldi, 0, 0, ldo, tin, UNS, UNS, tout, gen.F32), mkb, [y0])
+
+
+def test_unzip_and_decompose_to_bf16_planes():
+    rng = np.random.default_rng(70)
+    for (m, n, pad) in ((33, 7, 0), (64, 5, 3), (1, 9, 2)):
+        ldi, ldo = m + pad, m + 2 * pad
+        x = (rng.standard_normal(ldi * n) * np.exp(rng.uniform(-8, 8, ldi * n))).astype(np.float32)
+        plane = ldo * n + 5
+        for name, nplanes in (("UNZIP", 2), ("DECOMP_FP32_TO_BF16X2", 2), ("DECOMP_FP32_TO_BF16X3", 3)):
+            o0 = rng.integers(0, 60000, size=plane * nplanes, dtype=np.uint16)
+            offs = np.array([plane * 2, plane * 4], dtype=np.uint64)
+
+            def mk(bufs, keep):
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, bufs[0].ctypes.data, offs.ctypes.data
+                return p
+            both((1, getattr(X, "MELTW_TYPE_UNARY_" + name), 0, m, n, ldi, 0, 0, ldo, gen.F32, UNS, UNS, gen.BF16, gen.F32), mk, [o0])

@@ -1,0 +1,98 @@
+"""The reference's OWN sample drivers, unmodified, compiled against this repository's include/ and linked with -lxsmm
+(libxsmm_b200/lib): the drop-in boundary of SURVEY.md 8b.
+
+  * CPU (`-m "not gpu"`): where /root/reference exists, every driver in DRIVERS must compile and link (build container).
+    The binaries land in tests/c/_drivers/ (git-ignored, travels to the GPU box like the built library).
+  * GPU (`-m gpu`): the prebuilt binaries run on the box and must report success by their own criteria (each driver
+    compares against its own dense/scalar gold and prints/returns the verdict).
+"""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "c", "_drivers")
+LIBDIR = os.path.join(ROOT, "libxsmm_b200", "lib")
+MTX = os.path.join(ROOT, "tests", "golden", "mtx")
+
+# name -> source (relative to the reference tree)
+DRIVERS = {
+    "hello": "samples/hello/hello.c",
+    "pyfr_driver_asp_reg": "samples/xgemm_sparse_Ainregs/pyfr_driver_asp_reg.c",
+    "spmm_kernel": "samples/xgemm_sparse/spmm_kernel.c",
+    "gemm_kernel": "samples/xgemm/gemm_kernel.c",
+    "gemm_kernel_fused": "samples/xgemm/gemm_kernel_fused.c",
+    "eltwise_unary_relu": "samples/eltwise/eltwise_unary_relu.c",
+    "eltwise_unary_transform": "samples/eltwise/eltwise_unary_transform.c",
+}
+
+
+def build_drivers(names=None):
+    """compile the listed reference drivers; returns {name: (rc, stderr tail)}"""
+    os.makedirs(OUT, exist_ok=True)
+    res = {}
+    for name, src in DRIVERS.items():
+        if names and name not in names:
+            continue
+        cmd = ["gcc", "-O2", "-fopenmp", "-I" + os.path.join(ROOT, "include"), os.path.join(REF, src), "-o", os.path.join(OUT, name),
+               "-L" + LIBDIR, "-lxsmm", "-lm", "-Wl,-rpath," + LIBDIR]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        res[name] = (p.returncode, p.stderr[-2000:])
+    return res
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "samples")), reason="the reference tree is not present here")
+def test_reference_drivers_compile_and_link_unmodified():
+    res = build_drivers()
+    bad = {k: v[1] for k, v in res.items() if v[0] != 0}
+    assert not bad, bad
+
+
+def _run(name, *args, timeout=300):
+    exe = os.path.join(OUT, name)
+    if not os.path.exists(exe):
+        pytest.skip("%s was not prebuilt (no reference tree in the build container?)" % name)
+    env = dict(os.environ, LD_LIBRARY_PATH=LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS="4")
+    return subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout, env=env, cwd=OUT)
+
+
+@pytest.mark.gpu
+def test_hello_runs_and_prints_the_sum():
+    """samples/hello/hello.c: 1000 x (C += A_i * B_i), prints the sum of C's entries"""
+    p = _run("hello")
+    assert p.returncode == 0, p.stderr[-800:]
+    # batch of 1000 products 13x5x7 with A[i] = 1/((i+1)%25+1)... the program prints one number; it must be finite and non-zero
+    nums = [float(t) for t in p.stdout.replace("\n", " ").split() if t.replace(".", "", 1).replace("-", "", 1).replace("e", "", 1).replace("+", "", 1).isdigit()]
+    assert nums and all(abs(x) > 0 and x == x for x in nums), p.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mtx", ["pyfr_p1_tet_m6-sp.mtx", "pyfr_p3_hex_m6-sp.mtx"])
+def test_pyfr_driver_on_the_reference_operators(mtx):
+    """samples/xgemm_sparse_Ainregs/pyfr_driver_asp_reg.c <mtx> N reps: validates both beta cases against its own gold loop
+    with libxsmm_matdiff and returns non-zero when the error exceeds its epsilon"""
+    p = _run("pyfr_driver_asp_reg", os.path.join(MTX, mtx), 4800, 3)
+    assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-800:])
+    lines = [ln for ln in p.stdout.splitlines() if "(libxsmm vs. gold)" in ln]
+    assert len(lines) == 2, p.stdout[-1500:]
+    for ln in lines:
+        assert float(ln.split("abs=")[1].split()[0]) < 1e-6, ln
+
+
+@pytest.mark.gpu
+def test_spmm_kernel_driver_bf16_bcsc():
+    """samples/xgemm_sparse/spmm_kernel.c (the BCSC driver) on a reduced configs[3] geometry: bf16, 32x32 blocks, 50 %;
+    the driver checks against its dense gold and returns EXIT_FAILURE above its own bound (0.005 for bf16)"""
+    # A B Comp C  M N K M_BLOCKS  sparsity BK BN  beta trA trB vnniA vnniB vnniC  reps      (spmm_kernel.c:755-786)
+    p = _run("spmm_kernel", "BF16", "BF16", "F32", "BF16", 32, 512, 512, 64, 0.5, 32, 32, 0, 0, 0, 1, 0, 0, 3)
+    assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-800:])
+    assert "Total Max Error" in p.stdout, p.stdout[-1500:]
+
+
+@pytest.mark.gpu
+def test_spmm_kernel_driver_f32_and_int8():
+    for types, vnni in ((("F32", "F32", "F32", "F32"), 0), (("U8", "I8", "I32", "I32"), 1)):
+        p = _run("spmm_kernel", *types, 32, 128, 128, 8, 0.5, 16 if types[0] == "F32" else 32, 16, 1, 0, 0, vnni, 0, 0, 2)
+        assert p.returncode == 0, (types, p.stdout[-1500:], p.stderr[-800:])
