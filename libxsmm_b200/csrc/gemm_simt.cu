@@ -48,6 +48,7 @@ struct TileCtx {
   const long long* a_offs; const long long* b_offs;       // offset mode
   unsigned long long br;
   float scf;
+  const void* colbias; unsigned char* relu_mask;          // fused form (libxsmm_dispatch_brgemm_ext)
 };
 
 __device__ inline void resolve_tile(const xb_gemm_launch& L, long long t, TileCtx& x) {
@@ -57,12 +58,14 @@ __device__ inline void resolve_tile(const xb_gemm_launch& L, long long t, TileCt
   else {
     r.a = (const char*)L.a + t * L.tile_stride_a; r.b = (const char*)L.b + t * L.tile_stride_b;
     r.c = (char*)L.c + t * L.tile_stride_c; r.a_aux = nullptr; r.b_aux = nullptr; r.br = L.br; r.scf = L.one.scf;
+    r.d = L.one.d; r.c_aux = nullptr;                      // a shared bias column; masks only exist per call
     if (L.d.br_type == 2) { r.a_aux = L.one.a_aux; r.b_aux = L.one.b_aux; }
   }
   x.a0 = (const char*)r.a; x.b0 = (const char*)r.b; x.c = (char*)r.c;
   x.a_addr = (const void* const*)r.a; x.b_addr = (const void* const*)r.b;
   x.a_offs = (const long long*)r.a_aux; x.b_offs = (const long long*)r.b_aux;
   x.br = (L.d.br_type == 0) ? 1ull : r.br; x.scf = r.scf;
+  x.colbias = r.d; x.relu_mask = (unsigned char*)r.c_aux;
 }
 
 // base pointers of the r-th batch-reduce operand pair; mirrors libxsmm_calculate_brgemm_offsets
@@ -79,6 +82,128 @@ __device__ inline void br_ptrs(const xb_gemm_desc& d, const TileCtx& x, unsigned
 
 template <typename T> __device__ inline T ldg_as(const char* base, long long idx) {
   return reinterpret_cast<const T*>(base)[idx];
+}
+
+// ---- fused form: column-bias pre-op, ReLU (+bitmask) / sigmoid post-op (reference :255-372) -----------------------------
+// The reference builds an f32 image of C (bias column broadcast, + old C when beta = 1), lets the GEMM accumulate into it
+// with beta = 1 and C type F32, applies the post-op and rounds ONCE into C. Per element that is: seed -> same loop as the
+// F32-output variant of the precision path -> activation -> one conversion. The pre-ops are mateltwise kernels, hence their
+// bf16 load (flushes bf16 subnormals).
+__device__ __forceinline__ float fuse_ld(const void* p, long long i, int t) {
+  if (t == LIBXSMM_DATATYPE_F32) return ((const float*)p)[i];
+  if (t == LIBXSMM_DATATYPE_BF16) { unsigned short h = ((const unsigned short*)p)[i]; if ((h & 0x7f80) == 0) h &= 0x8000; return xb_bf16_to_f32(h); }
+  return xb_f16_to_f32(((const unsigned short*)p)[i]);
+}
+__device__ __forceinline__ void fuse_st(void* p, long long i, int t, float v) {
+  if (t == LIBXSMM_DATATYPE_F32) ((float*)p)[i] = v;
+  else if (t == LIBXSMM_DATATYPE_BF16) ((unsigned short*)p)[i] = xb_f32_to_bf16_rne(v);
+  else ((unsigned short*)p)[i] = xb_f32_to_f16(v);
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_fused_kernel(const xb_gemm_launch L, const int path) {
+  const xb_gemm_desc& d = L.d;
+  const int m = d.m, n = d.n, k = d.k;
+  const long long lda = d.lda, ldb = d.ldb, ldc = d.ldc;
+  const bool trans_a = (d.flags & LIBXSMM_GEMM_FLAG_TRANS_A) != 0, trans_b = (d.flags & LIBXSMM_GEMM_FLAG_TRANS_B) != 0;
+  const bool vnni_a = (d.flags & LIBXSMM_GEMM_FLAG_VNNI_A) != 0, vnni_b = (d.flags & LIBXSMM_GEMM_FLAG_VNNI_B) != 0;
+  const bool ua = (d.ta == LIBXSMM_DATATYPE_U8), ub = (d.tb == LIBXSMM_DATATYPE_U8);
+  const int tsa = xb_dev_typesize(d.ta), tsb = xb_dev_typesize(d.tb);
+  const bool bias = d.fuse_colbias != 0, relu = d.cp_op == LIBXSMM_MELTW_TYPE_UNARY_RELU, sigm = d.cp_op == LIBXSMM_MELTW_TYPE_UNARY_SIGMOID;
+  const bool bitm = relu && (d.cp_flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0;
+  const bool beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) != 0, beta0_eff = beta0 && !bias;
+  const int lane = threadIdx.x & 31, chunks = (m + 31) / 32;
+  const long long mask_ld = ((ldc + 15) / 16) * 16;
+  for (long long t = blockIdx.x; t < L.count; t += gridDim.x) {
+    TileCtx x; resolve_tile(L, t, x);
+    // a warp owns 32 consecutive rows of one column, so that the ReLU bitmask is one ballot per warp
+    for (int w = threadIdx.x >> 5; w < chunks * n; w += blockDim.x >> 5) {
+      const int j = w / chunks, i0 = (w % chunks) * 32, i = i0 + lane;
+      const bool act = i < m;
+      const long long ci = (long long)j * ldc + i;
+      float y = 0.0f, seed = 0.0f;
+      if (act) {
+        if (bias) { const float bv = fuse_ld(x.colbias, i, d.tc); seed = beta0 ? bv : __fadd_rn(bv, fuse_ld(x.c, ci, d.tc)); }
+        else if (!beta0) seed = (d.tc == LIBXSMM_DATATYPE_F32) ? ((const float*)x.c)[ci] : fuse_ld(x.c, ci, d.tc);
+        float acc = 0.0f;
+        switch (path) {
+          case P_F32: {
+            const bool cvt = (d.ta == LIBXSMM_DATATYPE_BF32);
+            acc = beta0_eff ? 0.0f : seed;
+            for (unsigned long long r = 0; r < x.br; ++r) {
+              const char *pa, *pb; br_ptrs(d, x, r, 4, 4, pa, pb);
+              for (int s2 = 0; s2 < k; ++s2) {
+                float av = ldg_as<float>(pa, trans_a ? (i * lda + s2) : (s2 * lda + i));
+                float bv = ldg_as<float>(pb, trans_b ? (s2 * ldb + j) : (j * ldb + s2));
+                if (cvt) { av = xb_bf16_to_f32(xb_f32_to_bf16_rne(av)); bv = xb_bf16_to_f32(xb_f32_to_bf16_rne(bv)); }
+                acc = __fadd_rn(acc, __fmul_rn(av, bv));
+              }
+            }
+          } break;
+          case P_I8_F32: {
+            unsigned int ia = 0u;
+            for (unsigned long long r = 0; r < x.br; ++r) {
+              const char *pa, *pb; br_ptrs(d, x, r, 1, 1, pa, pb);
+              for (int s2 = 0; s2 < k / 4; ++s2) for (int k2 = 0; k2 < 4; ++k2) {
+                const unsigned char ar = ldg_as<unsigned char>(pa, s2 * (lda * 4) + (long long)i * 4 + k2);
+                const unsigned char brw = ldg_as<unsigned char>(pb, j * ldb + (long long)s2 * 4 + k2);
+                ia += (unsigned int)((ua ? (int)ar : (int)(signed char)ar) * (ub ? (int)brw : (int)(signed char)brw));
+              }
+            }
+            acc = __fmul_rn((float)(int)ia, x.scf);
+            if (!beta0_eff) acc = __fadd_rn(acc, seed);
+          } break;
+          case P_F16_F16: case P_F16_F32: {
+            const int kb = vnni_a ? 2 : 1;
+            const bool round_each = (d.tcomp == LIBXSMM_DATATYPE_F16 || d.tcomp == LIBXSMM_DATATYPE_IMPLICIT);
+            for (unsigned long long r = 0; r < x.br; ++r) {
+              const char *pa, *pb; br_ptrs(d, x, r, 2, 2, pa, pb);
+              for (int s2 = 0; s2 < k / kb; ++s2) for (int k2 = 0; k2 < kb; ++k2) {
+                const float av = xb_f16_to_f32(ldg_as<unsigned short>(pa, s2 * (lda * kb) + (long long)i * kb + k2));
+                const long long kk = (long long)s2 * kb + k2;
+                const float bv = xb_f16_to_f32(ldg_as<unsigned short>(pb, trans_b ? (kk * ldb + j) : (j * ldb + kk)));
+                acc = __fadd_rn(acc, __fmul_rn(av, bv));
+                if (round_each) acc = xb_f16_to_f32(xb_f32_to_f16(acc));
+              }
+            }
+            if (!beta0_eff) acc = __fadd_rn(acc, xb_f16_to_f32(xb_f32_to_f16(seed)));   // the F32-C variant rounds the old C through f16 (:2118-2124)
+          } break;
+          default: {   // P_BF16_F32 / P_BF16_BF16
+            const int kb = vnni_a ? 2 : 1;
+            acc = beta0_eff ? 0.0f : seed;
+            for (unsigned long long r = 0; r < x.br; ++r) {
+              const char *pa, *pb; br_ptrs(d, x, r, 2, 2, pa, pb);
+              for (int s2 = 0; s2 < k / kb; ++s2) for (int k2 = kb - 1; k2 >= 0; --k2) {
+                const long long kk = (long long)s2 * kb + k2;
+                unsigned short ar = 0, brw = 0;
+                if (!trans_a) ar = ldg_as<unsigned short>(pa, s2 * (lda * kb) + (long long)i * kb + k2);
+                else if (!vnni_a) ar = ldg_as<unsigned short>(pa, i * lda + kk);
+                if (trans_b && vnni_b) brw = ldg_as<unsigned short>(pb, (long long)j * kb + s2 * (ldb * kb) + k2);
+                else if (trans_b) brw = ldg_as<unsigned short>(pb, kk * ldb + j);
+                else if (!vnni_b) brw = ldg_as<unsigned short>(pb, j * ldb + kk);
+                acc = __fadd_rn(acc, __fmul_rn(xb_bf16_to_f32(ar), xb_bf16_to_f32(brw)));
+              }
+            }
+          } break;
+        }
+        y = relu ? ((acc <= 0.0f) ? 0.0f : acc) : (sigm ? (tanhf(acc / 2.0f) + 1.0f) / 2.0f : acc);
+        fuse_st(x.c, ci, d.tc, y);
+        seed = acc;
+      }
+      if (bitm) {
+        const unsigned int word = __ballot_sync(0xffffffffu, act && !(seed <= 0.0f));
+        if (lane < 4) {
+          const int ib = i0 + lane * 8;
+          if (ib < m) {
+            unsigned char* dst = x.relu_mask + ib / 8 + (long long)j * (mask_ld / 8);
+            const unsigned int valid = (m - ib >= 8) ? 0xffu : ((1u << (m - ib)) - 1u);
+            const unsigned int nb = (word >> (lane * 8)) & 0xffu;
+            *dst = (unsigned char)((valid == 0xffu) ? nb : ((*dst & ~valid) | (nb & valid)));
+          }
+        }
+      }
+    }
+  }
+  (void)tsa; (void)tsb;
 }
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const xb_gemm_launch L, const int path) {
@@ -369,12 +494,27 @@ cudaError_t launch_i8(const xb_gemm_launch& L, int path, int wpt, int words_per_
 }
 }  // namespace
 
-extern "C" int xb_gemm_simt_supported(const xb_gemm_desc* d) { return xb_path_of(*d) != P_NONE; }
+extern "C" int xb_gemm_simt_supported(const xb_gemm_desc* d) {
+  const int path = xb_path_of(*d);
+  if (path == P_NONE) return 0;
+  if (d->fuse_colbias != 0 || d->cp_op != 0) {   // fused form: float C only (the reference's f32 image of C)
+    return path == P_F32 || path == P_I8_F32 || path == P_F16_F16 || path == P_F16_F32 || path == P_BF16_F32 || path == P_BF16_BF16;
+  }
+  return 1;
+}
 
 extern "C" int xb_gemm_simt_launch(const xb_gemm_launch* L) {
   const int path = xb_path_of(L->d);
   if (path == P_NONE) return 1;
   if (L->count <= 0) return 0;
+  if (L->d.fuse_colbias != 0 || L->d.cp_op != 0) {
+    const long long fgrid = L->count < (1 << 20) ? L->count : (1 << 20);
+    gemm_simt_fused_kernel<<<(unsigned int)fgrid, 256, 0, (cudaStream_t)xb_rt_stream()>>>(*L, path);
+    xb_rt_count_launch();
+    const cudaError_t fe = cudaGetLastError();
+    if (fe != cudaSuccess) { xb_rt_note_error((int)fe, "gemm_simt_fused"); return (int)fe; }
+    return 0;
+  }
   if (i8_fast_ok(*L, path) && getenv("LIBXSMM_B200_I8_EXACT_ORDER") == nullptr) {
     const int small = (L->d.m < L->d.n) ? L->d.m : L->d.n;
     const int tm = (small >= 32) ? 4 : ((small >= 16) ? 2 : 1), tn = 2 * tm;           // lane block; a warp covers 8*tm x 4*tn of C

@@ -290,6 +290,7 @@ static int xb_make_gemm_desc(xb_gemm_desc* d, const libxsmm_gemm_shape* shape, u
     if (vnni_a && is16 && (d->k % 2) != 0) return 0;
     if (is8 && d->tc == LIBXSMM_DATATYPE_F32 && (d->k % 4) != 0) return 0;
   }
+  if ((d->flags & LIBXSMM_GEMM_FLAG_VNNI_C) != 0 && ((d->n % 2) != 0 || libxsmm_typesize((libxsmm_datatype)d->tc) != 2)) return 0;   /* 16-bit C in column pairs */
   if (!xb_gemm_simt_supported(d)) return 0;
   d->backend = (!g_force_simt && xb_gemm_tc_supported(d)) ? LIBXSMM_B200_BACKEND_TCGEN05 : LIBXSMM_B200_BACKEND_SIMT;
   return 1;
@@ -329,14 +330,22 @@ LIBXSMM_API libxsmm_gemmfunction_ext libxsmm_dispatch_brgemm_ext(const libxsmm_g
   int slot;
   LIBXSMM_INIT
   if (xb_tilecfg_inconsistent(gemm_flags)) return NULL;
-  /* fused argument/post operations are a later scope row: only the un-fused form of
-   * the extended ABI is served; anything else answers NULL like an unsupported JIT request. */
-  if (unary_argops.ap_unary_type != LIBXSMM_MELTW_TYPE_UNARY_NONE || unary_argops.bp_unary_type != LIBXSMM_MELTW_TYPE_UNARY_NONE
-   || unary_argops.cp_unary_type != LIBXSMM_MELTW_TYPE_UNARY_NONE || binary_postops.d_binary_type != LIBXSMM_MELTW_TYPE_BINARY_NONE)
-  {
-    return NULL;
+  /* the fusions the reference implements (generator_gemm_reference_impl.c:396-427): a column-broadcast bias added before the
+   * product, ReLU (optionally recording a bitmask) or sigmoid applied to C; operand-side argops do not exist there either */
+  if (unary_argops.ap_unary_type != LIBXSMM_MELTW_TYPE_UNARY_NONE || unary_argops.bp_unary_type != LIBXSMM_MELTW_TYPE_UNARY_NONE) return NULL;
+  if (unary_argops.cp_unary_type != LIBXSMM_MELTW_TYPE_UNARY_NONE && unary_argops.cp_unary_type != LIBXSMM_MELTW_TYPE_UNARY_RELU
+   && unary_argops.cp_unary_type != LIBXSMM_MELTW_TYPE_UNARY_SIGMOID) return NULL;
+  if (binary_postops.d_binary_type != LIBXSMM_MELTW_TYPE_BINARY_NONE) {
+    if (binary_postops.d_binary_type != LIBXSMM_MELTW_TYPE_BINARY_ADD) return NULL;
+    if ((binary_postops.d_binary_flags & (LIBXSMM_MELTW_FLAG_BINARY_BCAST_COL_IN_0 | LIBXSMM_MELTW_FLAG_BINARY_BCAST_COL_IN_1)) == 0) return NULL;
   }
   if (!xb_make_gemm_desc(&d, &gemm_shape, gemm_flags, prefetch_flags, &brgemm_config, 1)) return NULL;
+  if (unary_argops.cp_unary_type != LIBXSMM_MELTW_TYPE_UNARY_NONE || binary_postops.d_binary_type != LIBXSMM_MELTW_TYPE_BINARY_NONE) {
+    d.fuse_colbias = (binary_postops.d_binary_type == LIBXSMM_MELTW_TYPE_BINARY_ADD); d.d_type = d.tc; d.ldd = binary_postops.ldd;
+    d.cp_op = (int)unary_argops.cp_unary_type; d.cp_flags = (int)(unary_argops.cp_unary_flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT); d.ldcp = unary_argops.ldcp;
+    if (!xb_gemm_simt_supported(&d)) return NULL;       /* float C only */
+    d.backend = LIBXSMM_B200_BACKEND_SIMT;               /* the fused epilogue lives in the exact-order kernel */
+  }
   slot = xb_registry_get(XB_KIND_GEMM_EXT, &d, sizeof(d), 2u * (unsigned int)d.m * (unsigned int)d.n * (unsigned int)d.k);
   return (slot < 0) ? NULL : (libxsmm_gemmfunction_ext)xb_thunk(slot);
 }
@@ -401,11 +410,12 @@ static void xb_invoke_gemm(const xb_slot* s, const libxsmm_gemm_param* p) {
   const xb_gemm_desc* d = &s->u.gemm;
   const size_t tsa = libxsmm_typesize((libxsmm_datatype)d->ta), tsb = libxsmm_typesize((libxsmm_datatype)d->tb);
   const size_t tsc = libxsmm_typesize((libxsmm_datatype)d->tc);
-  const size_t ext_a = xb_extent_a(d) * tsa, ext_b = xb_extent_b(d) * tsb, ext_c = ((size_t)(d->n - 1) * d->ldc + d->m) * tsc;
+  const int vnni_c = (d->flags & LIBXSMM_GEMM_FLAG_VNNI_C) != 0 && tsc == 2;   /* packs the whole ldc x n image, padding rows included */
+  const size_t ext_a = xb_extent_a(d) * tsa, ext_b = xb_extent_b(d) * tsb, ext_c = (vnni_c ? (size_t)d->n * d->ldc : ((size_t)(d->n - 1) * d->ldc + d->m)) * tsc;
   const unsigned long long br = (d->br_type != 0 && p->op.tertiary != NULL) ? *(const unsigned long long*)p->op.tertiary : 1ull;
   xb_gemm_launch L;
-  xb_copyback cb; int staged = 0, need_cb = 0;
-  memset(&L, 0, sizeof(L)); memset(&cb, 0, sizeof(cb));
+  xb_copyback cb, cb_mask; int staged = 0, need_cb = 0, need_cb_mask = 0;
+  memset(&L, 0, sizeof(L)); memset(&cb, 0, sizeof(cb)); memset(&cb_mask, 0, sizeof(cb_mask));
   L.d = *d; L.count = 1;
   L.one.br = br;
   if (d->br_type != 0 && br == 0) {  /* nothing to reduce: reference still zeroes C for beta=0 */ }
@@ -450,15 +460,45 @@ static void xb_invoke_gemm(const xb_slot* s, const libxsmm_gemm_param* p) {
   if (p->c.primary != NULL && xb_rt_ptr_kind(p->c.primary) == 0) {
     void* dc = xb_rt_scratch(ext_c);
     if (dc == NULL) return;
-    if ((d->flags & LIBXSMM_GEMM_FLAG_BETA_0) == 0 || d->ldc != d->m) xb_rt_upload(dc, p->c.primary, ext_c);
+    if ((d->flags & LIBXSMM_GEMM_FLAG_BETA_0) == 0 || d->ldc != d->m || d->fuse_colbias == 0) xb_rt_upload(dc, p->c.primary, ext_c);
     cb.host = p->c.primary; cb.dev = dc; cb.bytes = ext_c; need_cb = 1; staged = 1;
     L.one.c = dc;
   } else L.one.c = p->c.primary;
   if (d->tc == LIBXSMM_DATATYPE_F32 && (d->ta == LIBXSMM_DATATYPE_I8 || d->ta == LIBXSMM_DATATYPE_U8) && p->c.tertiary != NULL) {
     L.one.scf = *(const float*)p->c.tertiary;
   }
+  if (s->kind == XB_KIND_GEMM_EXT && (d->fuse_colbias != 0 || d->cp_op != 0)) {   /* d.primary: bias column; c.secondary: ReLU bitmask */
+    const libxsmm_gemm_ext_param* pe = (const libxsmm_gemm_ext_param*)p;
+    if (d->fuse_colbias != 0) {
+      L.one.d = xb_stage_in(pe->d.primary, (size_t)d->m * tsc, &staged);
+      if (L.one.d == NULL) { xb_rt_note_error(2, "invoke_gemm_ext: bias column missing"); xb_rt_scratch_reset(); return; }
+    }
+    if ((d->cp_flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0 && pe->c.secondary != NULL) {
+      const size_t mbytes = (size_t)LIBXSMM_UP(d->ldc, 16) / 8 * (size_t)d->n;
+      if (xb_rt_ptr_kind(pe->c.secondary) == 0) {
+        void* dm = xb_rt_scratch(mbytes);
+        if (dm == NULL) return;
+        xb_rt_upload(dm, pe->c.secondary, mbytes);           /* bits of padding rows survive */
+        cb_mask.host = pe->c.secondary; cb_mask.dev = dm; cb_mask.bytes = mbytes; need_cb_mask = 1; staged = 1;
+        L.one.c_aux = dm;
+      } else L.one.c_aux = pe->c.secondary;
+    }
+  }
   if (0 != xb_run_gemm_launch(&L)) { xb_rt_scratch_reset(); return; }
+  if (vnni_c) {   /* C re-packed norm -> VNNI2 through a copy (reference :2803-2815) */
+    void* copy = xb_rt_scratch(ext_c);
+    xb_meltw_desc md; xb_meltw_args ma;
+    if (copy == NULL) { xb_rt_scratch_reset(); return; }
+    xb_rt_memcpy_async(copy, L.one.c, ext_c);
+    memset(&md, 0, sizeof(md)); memset(&ma, 0, sizeof(ma));
+    md.op_class = LIBXSMM_MELTW_OPERATION_UNARY; md.op = LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2; md.m = d->m; md.n = d->n;
+    md.ldi = d->ldc; md.ldo = d->ldc; md.t_in0 = md.t_out = md.t_comp = d->tc; md.t_in1 = md.t_in2 = LIBXSMM_DATATYPE_UNSUPPORTED;
+    ma.in0 = copy; ma.out = L.one.c; ma.alpha = 1.0f;
+    if (0 != xb_meltw_launch(&md, &ma)) { xb_rt_scratch_reset(); return; }
+    staged = 1;
+  }
   if (need_cb) xb_rt_memcpy_async(cb.host, cb.dev, cb.bytes);
+  if (need_cb_mask) xb_rt_memcpy_async(cb_mask.host, cb_mask.dev, cb_mask.bytes);
   if (staged || xb_rt_blocking()) { xb_rt_sync(); xb_rt_scratch_reset(); }
 }
 

@@ -193,6 +193,70 @@ ORACLE_API int oracle_gemm(const int* dims, const int* types, unsigned int flags
   return gemm_run(&g);
 }
 
+/* ---- fused form (libxsmm_dispatch_brgemm_ext): reference :255-372, 2803-2842 ------------------------------------------
+ * fuse = {colbias (0/1), cp_op (0 none, 5 RELU, 9 SIGMOID), relu bitmask (0/1), vnni_c (0/1)}. With any of the first three and a
+ * C type other than F32 the product is accumulated in an f32 image of C (bias column broadcast, plus the old C when beta=1),
+ * the post-op reads that image and rounds ONCE into C. For F32 C everything happens in place. */
+static float ld_c(const void* p, long long i, int t) {
+  if (t == T_F32) return ((const float*)p)[i];
+  if (t == T_BF16) return oracle_bf16_to_f32(((const uint16_t*)p)[i]);   /* the pre-ops are mateltwise kernels: their bf16 load */
+  return oracle_f16_to_f32(((const uint16_t*)p)[i]);
+}
+static void st_c(void* p, long long i, int t, float v) {
+  if (t == T_F32) ((float*)p)[i] = v;
+  else if (t == T_BF16) ((uint16_t*)p)[i] = oracle_f32_to_bf16(v);
+  else ((uint16_t*)p)[i] = oracle_f32_to_f16(v);
+}
+ORACLE_API int oracle_gemm_ext(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a, long long stride_b,
+                               unsigned long long br, void* a, void* b, void* c, long long* offs_a, long long* offs_b, float scf,
+                               const int* fuse, const void* colbias, unsigned char* relu_mask)
+{
+  const int m = dims[0], n = dims[1], ldc = dims[5], tc = types[3];
+  const int f_bias = fuse[0], cp = fuse[1], f_mask = fuse[2], f_vnni = fuse[3];
+  const int fused = f_bias || cp != 0, via = fused && tc != T_F32;
+  float* img = via ? (float*)malloc((size_t)ldc * n * 4) : (float*)c;
+  int tt[4], i, j, rc; unsigned int fl = flags;
+  if (tc != T_F32 && tc != T_BF16 && tc != T_F16) return 1;
+  if (fused) {
+    if (f_bias) {                                          /* :296-317 */
+      for (j = 0; j < n; ++j) for (i = 0; i < m; ++i) {
+        const float bias = ld_c(colbias, i, tc);
+        img[(size_t)j * ldc + i] = (flags & F_BETA_0) ? bias : bias + ld_c(c, (long long)j * ldc + i, tc);
+      }
+      fl &= ~(unsigned int)F_BETA_0;
+    } else if (via && !(flags & F_BETA_0)) {               /* :319-328 */
+      for (j = 0; j < n; ++j) for (i = 0; i < m; ++i) img[(size_t)j * ldc + i] = ld_c(c, (long long)j * ldc + i, tc);
+    }
+  }
+  tt[0] = types[0]; tt[1] = types[1]; tt[2] = types[2]; tt[3] = via ? T_F32 : tc;
+  rc = oracle_gemm(dims, tt, fl, br_type, stride_a, stride_b, br, a, b, via ? (void*)img : c, offs_a, offs_b, scf, 0);
+  if (rc == 0 && fused) {                                  /* :336-371 */
+    const long long mld = ((ldc + 15) / 16) * 16;
+    for (j = 0; j < n; ++j) for (i = 0; i < m; ++i) {
+      const float x = img[(size_t)j * ldc + i];
+      float y = x;
+      if (cp == 5) { y = (x <= 0.0f) ? 0.0f : x;
+        if (f_mask) { unsigned char* bp = relu_mask + i / 8 + (long long)j * (mld / 8);
+          if (x <= 0.0f) *bp = (unsigned char)(*bp & ~(1u << (i % 8))); else *bp = (unsigned char)(*bp | (1u << (i % 8))); } }
+      else if (cp == 9) y = (tanhf(x / 2.0f) + 1.0f) / 2.0f;
+      if (via || cp != 0) st_c(c, (long long)j * ldc + i, tc, y);
+    }
+  }
+  if (via) free(img);
+  if (rc == 0 && f_vnni) {                                 /* :2803-2815: C (16-bit) re-packed norm -> VNNI2 through a copy */
+    const int ts = tsize(tc); const long long Nn = ((n + 1) / 2) * 2;
+    char* copy = (char*)malloc((size_t)ldc * Nn * ts); long long e;
+    if (ts != 2) { free(copy); return 1; }
+    memset(copy, 0, (size_t)ldc * Nn * ts); memcpy(copy, c, (size_t)ldc * n * ts);
+    for (e = 0; e < (long long)ldc * Nn; ++e) {
+      const long long jj = e / (ldc * 2), rem = e % (ldc * 2), col = jj * 2 + rem % 2; i = (int)(rem / 2);
+      ((uint16_t*)c)[e] = (i < m && col < n) ? ((const uint16_t*)copy)[col * ldc + i] : 0;
+    }
+    free(copy);
+  }
+  return rc;
+}
+
 /* strided batch of tiles = the caller's loop of the reference (samples/xgemm/gemm_kernel.c:3179-3259), OpenMP over tiles */
 ORACLE_API int oracle_gemm_batch(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a, long long stride_b,
                                  unsigned long long br, char* a, char* b, char* c, long long ta, long long tb, long long tc, long long count)

@@ -60,6 +60,39 @@ REF_API int ref_gemm(const int* dims, const int* types, unsigned int flags, int 
   }
 }
 
+/* fused form: fuse = {colbias, cp_op (0 / RELU / SIGMOID), relu bitmask, vnni_c}; same calling convention as oracle_gemm_ext */
+REF_API int ref_gemm_ext(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a, long long stride_b,
+                         unsigned long long br, void* a, void* b, void* c, long long* offs_a, long long* offs_b, float scf,
+                         const int* fuse, void* colbias, unsigned char* relu_mask, int mode)
+{
+  const libxsmm_gemm_shape shape = libxsmm_create_gemm_shape(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5],
+    (libxsmm_datatype)types[0], (libxsmm_datatype)types[1], (libxsmm_datatype)types[3], (libxsmm_datatype)types[2]);
+  const libxsmm_gemm_batch_reduce_config cfg = ref_brcfg(br_type, stride_a, stride_b);
+  const libxsmm_gemm_ext_unary_argops argops = libxsmm_create_gemm_ext_unary_argops(0, LIBXSMM_MELTW_TYPE_UNARY_NONE, LIBXSMM_MELTW_FLAG_UNARY_NONE, 0,
+    0, LIBXSMM_MELTW_TYPE_UNARY_NONE, LIBXSMM_MELTW_FLAG_UNARY_NONE, 0,
+    dims[5], (libxsmm_meltw_unary_type)fuse[1], fuse[2] ? LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT : LIBXSMM_MELTW_FLAG_UNARY_NONE, 0);
+  const libxsmm_gemm_ext_binary_postops postops = libxsmm_create_gemm_ext_binary_postops(dims[5], (libxsmm_datatype)types[3],
+    fuse[0] ? LIBXSMM_MELTW_TYPE_BINARY_ADD : LIBXSMM_MELTW_TYPE_BINARY_NONE, fuse[0] ? LIBXSMM_MELTW_FLAG_BINARY_BCAST_COL_IN_0 : LIBXSMM_MELTW_FLAG_BINARY_NONE);
+  libxsmm_gemm_ext_param p; unsigned long long brv = br;
+  const unsigned int fl = flags | (fuse[3] ? LIBXSMM_GEMM_FLAG_VNNI_C : 0);
+  libxsmm_init();
+  memset(&p, 0, sizeof(p));
+  p.op.tertiary = &brv; p.a.primary = a; p.b.primary = b; p.c.primary = c; p.a.secondary = offs_a; p.b.secondary = offs_b; p.c.tertiary = &scf;
+  p.d.primary = colbias; p.c.secondary = relu_mask;
+  if (mode == 0) {
+    libxsmm_descriptor_blob blob;
+    const libxsmm_gemm_descriptor* desc = libxsmm_gemm_descriptor_init_brgemm_ext(&blob, shape, fl, 0, cfg, argops, postops);
+    if (desc == NULL) return 1;
+    libxsmm_reference_gemm(&p, desc);
+    return 0;
+  } else {
+    libxsmm_gemmfunction_ext k = libxsmm_dispatch_brgemm_ext(shape, fl, 0, cfg, argops, postops);
+    if (k == NULL) return 1;
+    k(&p);
+    return 0;
+  }
+}
+
 /* desc = {op_class, op, flags, m, n, ldi, ldi2, ldi3, ldo, t_in0, t_in1, t_in2, t_out, t_comp};
  * param points to a libxsmm_meltw_{unary,binary,ternary}_param image. mode as above. */
 REF_API int ref_meltw(const int* desc, void* param, int mode) {

@@ -6,7 +6,7 @@ import numpy as np
 
 import gen
 
-FLAG_TRANS_A, FLAG_TRANS_B, FLAG_BETA_0, FLAG_VNNI_A, FLAG_VNNI_B = 1, 2, 4, 256, 512
+FLAG_TRANS_A, FLAG_TRANS_B, FLAG_BETA_0, FLAG_VNNI_A, FLAG_VNNI_B, FLAG_VNNI_C = 1, 2, 4, 256, 512, 1024
 
 
 class GemmCase:
@@ -149,3 +149,19 @@ def packed_sp_case(rng, kind, dtype, M, N, K, P, density=0.3):
     c0 = gen.values(rng, nnz if kind == "c_csc" else M * N * P, dtype)     # C-sparse: one scalar per non-zero
     dims = {"a_csr": (M, N, K, 0, N, N), "b_csr": (M, N, K, K, 0, N), "b_csc": (M, N, K, K, 0, N), "c_csc": (M, N, K, max(M, K), N, 0)}[kind]
     return int(kind.endswith("csc")), dims, ptr, idx, a, b, c0
+
+
+RELU, SIGMOID = 5, 9       # libxsmm_meltw_unary_type values the fused GEMM accepts as post-op
+
+
+def fused_variants():
+    """(colbias, cp_op, relu bitmask, vnni_c) like samples/xgemm/kernel_test/gemm_kernel_fused.tpl (BINARY_POSTOP x UNARY_POSTOP x CVNNI)"""
+    return [(1, 0, 0, 0), (0, RELU, 0, 0), (0, RELU, 1, 0), (1, RELU, 1, 0), (0, SIGMOID, 0, 0), (1, SIGMOID, 0, 0), (1, RELU, 0, 1), (0, 0, 0, 1)]
+
+
+def run_gemm_ext(side, case, ops, fuse, colbias, mask, c):
+    """one fused call on tile 0 of `ops` (stride / plain modes); c in/out"""
+    from oracle_ffi import iarr
+    return side["gemm_ext"](iarr(*case.dims), iarr(*case.types), case.flags, case.br_type, ops.stride_a, ops.stride_b, case.br,
+                            ops.a.ctypes.data, ops.b.ctypes.data, c.ctypes.data, None, None, 0.0, iarr(*fuse),
+                            colbias.ctypes.data if colbias is not None else None, mask.ctypes.data if mask is not None else None)

@@ -51,6 +51,9 @@ for _n, _r, _a in (("f32_to_bf16", C.c_ushort, [_F]), ("f32_to_f16", C.c_ushort,
     oracle[_n] = _fn
 oracle_lib.oracle_meltw.restype, oracle_lib.oracle_meltw.argtypes = _I, [_P, _P, _I]
 oracle["meltw"] = oracle_lib.oracle_meltw          # 0 = computed, 2 = op not restated (the reference stays the only checker)
+oracle_lib.oracle_gemm_ext.restype = _I
+oracle_lib.oracle_gemm_ext.argtypes = [_P, _P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _P, _P, _F, _P, _P, _P]
+oracle["gemm_ext"] = oracle_lib.oracle_gemm_ext
 _fn = oracle_lib.oracle_gemm_batch
 _fn.restype, _fn.argtypes = _I, [_P, _P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _LL, _LL, _LL, _LL]
 oracle["gemm_batch"] = _fn
@@ -67,6 +70,9 @@ if os.path.exists(REF_SO):
         ref[_n] = _fn
     ref_lib.ref_meltw.restype, ref_lib.ref_meltw.argtypes = _I, [_P, _P, _I]
     ref["meltw"] = ref_lib.ref_meltw
+    ref_lib.ref_gemm_ext.restype = _I
+    ref_lib.ref_gemm_ext.argtypes = [_P, _P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I]
+    ref["gemm_ext"] = lambda *a: ref_lib.ref_gemm_ext(*a, 0)
     ref_lib.ref_target_arch.restype = C.c_char_p
     ref_lib.ref_max_threads.restype = _I
     ref_lib.ref_bench_gemm_batch.restype = C.c_double

@@ -13,6 +13,7 @@ import torch
 import cases
 import gen
 import libxsmm_b200 as X
+import gpu_util
 from gpu_util import dev, dispatch, host, run_single_calls
 from oracle_ffi import oracle, ref, run_gemm
 
@@ -162,3 +163,59 @@ def test_host_resident_batch_goes_through_the_copy_pipeline(pinned, monkeypatch)
             assert np.array_equal(got, want)
         else:
             assert gen.normf_rel(gen.to_f64(want, case.tc), gen.to_f64(got, case.tc)) <= (1.2e-5 if case.tc == gen.F32 else 5e-3)
+
+
+@pytest.mark.parametrize("types", [(gen.F32, gen.F32, gen.F32, gen.F32), (gen.BF16, gen.BF16, gen.F32, gen.BF16), (gen.BF16, gen.BF16, gen.F32, gen.F32),
+                                   (gen.F16, gen.F16, gen.F32, gen.F16)])
+def test_fused_brgemm_ext_matches_oracle(types):
+    """libxsmm_dispatch_brgemm_ext: column-bias pre-op, ReLU (+bitmask) / sigmoid post-op, VNNI-packed C, over the matrix of
+    samples/xgemm/kernel_test/gemm_kernel_fused.tpl (beta x batch-reduce mode x fusion). ReLU / bias / packing are bit-exact
+    (same operation order and rounding points as the reference); sigmoid within 1 ulp of the output type (device tanhf)."""
+    import ctypes as C
+    from oracle_ffi import oracle
+    rng = np.random.default_rng(89)
+    ta, tb, tcomp, tc = types
+    for (m, n, k, pad) in ((32, 16, 32, 0), (13, 6, 8, 3), (64, 64, 64, 0)):
+        for beta0 in (1, 0):
+            for br_type, br in ((0, 1), (3, 3)):
+                for fuse in cases.fused_variants():
+                    if fuse[3] and (tc == gen.F32 or n % 2):
+                        continue
+                    flags = (cases.FLAG_BETA_0 if beta0 else 0) | (cases.FLAG_VNNI_A if ta != gen.F32 and k % 2 == 0 and m % 2 == 0 else 0)
+                    case = cases.GemmCase(m, n, k, ta, tb, tcomp, tc, flags=flags, br_type=br_type, br=br, pad=pad)
+                    ops = cases.Operands(case, seed=int(rng.integers(1 << 30)))
+                    bias = gen.values(rng, m, tc)
+                    mask0 = rng.integers(0, 256, size=((case.ldc + 15) // 16 * 16) // 8 * n + 8, dtype=np.uint8)
+                    want, wmask = ops.c0.copy(), mask0.copy()
+                    assert cases.run_gemm_ext(oracle, case, ops, fuse, bias if fuse[0] else None, wmask if fuse[2] else None, want) == 0
+                    argops = X.libxsmm_create_gemm_ext_unary_argops(0, 0, 0, 0, 0, 0, 0, 0, case.ldc, fuse[1], X.MELTW_FLAG_UNARY_BITMASK_2BYTEMULT if fuse[2] else 0, 0)
+                    postops = X.libxsmm_create_gemm_ext_binary_postops(case.ldc, tc, X.MELTW_TYPE_BINARY_ADD if fuse[0] else 0,
+                                                                       X.MELTW_FLAG_BINARY_BCAST_COL_IN_0 if fuse[0] else 0)
+                    brt = {0: X.GEMM_BATCH_REDUCE_NONE, 3: X.GEMM_BATCH_REDUCE_STRIDE}[br_type]
+                    cfg = X.libxsmm_create_gemm_batch_reduce_config(brt, ops.stride_a, ops.stride_b, 0)
+                    k_ext = X.libxsmm_dispatch_brgemm_ext(gpu_util.shape_of(case), case.flags | (cases.FLAG_VNNI_C if fuse[3] else 0), 0, cfg, argops, postops)
+                    assert k_ext, (case, fuse)
+                    for resident in (1, 0):      # device buffers, then host buffers through the staging path
+                        if resident:
+                            d_a, d_b, d_c, d_bias, d_m = dev(ops.a), dev(ops.b), dev(ops.c0), dev(bias), dev(mask0)
+                            pa, pb, pc, pd, pm = d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(), d_bias.data_ptr(), d_m.data_ptr()
+                        else:
+                            hc, hm = ops.c0.copy(), mask0.copy()
+                            pa, pb, pc, pd, pm = ops.a.ctypes.data, ops.b.ctypes.data, hc.ctypes.data, bias.ctypes.data, hm.ctypes.data
+                        p = X.GemmExtParam(); brv = C.c_ulonglong(case.br)
+                        p.op.tertiary = C.addressof(brv); p.a.primary, p.b.primary, p.c.primary = pa, pb, pc
+                        if fuse[0]:
+                            p.d.primary = pd
+                        if fuse[2]:
+                            p.c.secondary = pm
+                        X.GEMMFUNCTION_EXT(k_ext)(C.byref(p)); X.check()
+                        got = host(d_c, gen.NP_OF[tc]) if resident else hc
+                        gm = host(d_m, np.uint8) if resident else hm
+                        if fuse[1] == cases.SIGMOID:
+                            g64, w64 = gen.to_f64(got, tc), gen.to_f64(want, tc)
+                            tol = {gen.F32: 3e-7, gen.BF16: 8e-3, gen.F16: 1e-3}[tc]
+                            assert np.allclose(g64, w64, rtol=tol, atol=tol), (case, fuse, resident)
+                        else:
+                            assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (case, fuse, resident)
+                        if fuse[2]:
+                            assert np.array_equal(gm, wmask), (case, fuse, resident, "relu mask")

@@ -153,3 +153,31 @@ def test_packed_sparse_oracle_matches_reference_jit(kind):
                 ran += 1
                 assert gen.normf_rel(c_r, c_o) <= eps, (kind, dtype, (M, N, K, P), beta0)
     assert ran > 0, "the reference JIT built none of the cases"
+
+
+@needs_ref
+@pytest.mark.parametrize("types", [(gen.F32, gen.F32, gen.F32, gen.F32), (gen.BF16, gen.BF16, gen.F32, gen.BF16), (gen.BF16, gen.BF16, gen.F32, gen.F32),
+                                   (gen.F16, gen.F16, gen.F32, gen.F16)])
+def test_fused_gemm_restatement_matches_reference(types):
+    """oracle_gemm_ext against libxsmm_reference_gemm on the extended ABI: column-bias pre-op, ReLU (+bitmask) / sigmoid post-op,
+    VNNI-packed C (generator_gemm_reference_impl.c:255-372, 2803-2842) -- bit for bit (same libm on the same host)"""
+    rng = np.random.default_rng(88)
+    ta, tb, tcomp, tc = types
+    for (m, n, k, pad) in ((32, 16, 32, 0), (13, 6, 8, 3), (64, 64, 64, 0)):
+        for beta0 in (1, 0):
+            for br_type, br in ((0, 1), (3, 3)):
+                for fuse in cases.fused_variants():
+                    if fuse[3] and (tc == gen.F32 or n % 2):
+                        continue
+                    flags = (cases.FLAG_BETA_0 if beta0 else 0) | (cases.FLAG_VNNI_A if ta != gen.F32 and k % 2 == 0 and m % 2 == 0 else 0)
+                    case = cases.GemmCase(m, n, k, ta, tb, tcomp, tc, flags=flags, br_type=br_type, br=br, pad=pad)
+                    ops = cases.Operands(case, seed=int(rng.integers(1 << 30)))
+                    bias = gen.values(rng, m, tc)
+                    mask0 = rng.integers(0, 256, size=((case.ldc + 15) // 16 * 16) // 8 * n + 8, dtype=np.uint8)
+                    outs = []
+                    for side in (ref, oracle):
+                        c = ops.c0.copy(); mk = mask0.copy()
+                        assert cases.run_gemm_ext(side, case, ops, fuse, bias if fuse[0] else None, mk if fuse[2] else None, c) == 0, (case, fuse)
+                        outs.append((c, mk))
+                    assert np.array_equal(outs[0][0].view(np.uint8), outs[1][0].view(np.uint8)), (case, fuse)
+                    assert np.array_equal(outs[0][1], outs[1][1]), (case, fuse, "mask")
