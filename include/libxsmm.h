@@ -110,6 +110,17 @@ LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csr(const libxsmm_
 LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csc(const libxsmm_gemm_shape gemm_shape,
   const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width,
   const unsigned int* column_ptr, const unsigned int* row_idx, const void* values);
+/* packed DENSE GEMM (EDGE/SeisSol): every matrix element is a vector of `packed_width` independent problems (innermost);
+ * F32 / F64; caller-owned handles (libxsmm_release_kernel). Layouts [row][col][packed] with the leading dimensions counted in vectors:
+ *   libxsmm_create_packed_gemm        C[n][m][p] (+)= A[k][m][p] * B[n][k][p]
+ *   libxsmm_create_packed_gemm_ac_rm  C[m][n][p] (+)= A[m][k][p] * B[k][n]        (B is a plain row-major matrix)
+ *   libxsmm_create_packed_gemm_bc_rm  C[m][n][p] (+)= A[m][k]    * B[k][n][p]     (A is a plain row-major matrix) */
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_gemm(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width);
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_gemm_ac_rm(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width);
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_gemm_bc_rm(const libxsmm_gemm_shape gemm_shape,
+  const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width);
 LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_bcsc(const libxsmm_gemm_shape gemm_shape,
   const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_spgemm_config spgemm_config);
 LIBXSMM_API libxsmm_tilecfgfunction libxsmm_create_tilecfg_packed_spgemm_bcsc(const libxsmm_gemm_shape gemm_shape,

@@ -216,6 +216,9 @@ libxsmm_dispatch_tilecfg_gemm = _sig("libxsmm_dispatch_tilecfg_gemm", _P, [GemmS
 libxsmm_dispatch_meltw_unary = _sig("libxsmm_dispatch_meltw_unary", _P, [_I, MeltwUnaryShape, _U])
 libxsmm_dispatch_meltw_binary = _sig("libxsmm_dispatch_meltw_binary", _P, [_I, MeltwBinaryShape, _U])
 libxsmm_dispatch_meltw_ternary = _sig("libxsmm_dispatch_meltw_ternary", _P, [_I, MeltwTernaryShape, _U])
+libxsmm_create_packed_gemm = _sig("libxsmm_create_packed_gemm", _P, [GemmShape, _U, _U, _I])
+libxsmm_create_packed_gemm_ac_rm = _sig("libxsmm_create_packed_gemm_ac_rm", _P, [GemmShape, _U, _U, _I])
+libxsmm_create_packed_gemm_bc_rm = _sig("libxsmm_create_packed_gemm_bc_rm", _P, [GemmShape, _U, _U, _I])
 libxsmm_create_packed_spgemm_csr = _sig("libxsmm_create_packed_spgemm_csr", _P, [GemmShape, _U, _U, _I, _P, _P, _P])
 libxsmm_create_packed_spgemm_csc = _sig("libxsmm_create_packed_spgemm_csc", _P, [GemmShape, _U, _U, _I, _P, _P, _P])
 libxsmm_create_packed_spgemm_bcsc = _sig("libxsmm_create_packed_spgemm_bcsc", _P, [GemmShape, _U, _U, SpgemmConfig])

@@ -73,6 +73,11 @@ struct BcscIdxLayout {
 };
 
 
+// programmatic dependent launch: the three kernels of a call are chained without host-visible gaps -- a kernel lets its
+// successor start launching at once and the successor waits (for completion and visibility of its predecessors) right
+// before it first reads what they wrote
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
@@ -114,6 +119,7 @@ __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((
 __global__ void __launch_bounds__(256) bcsc_prep_kernel(const unsigned int* __restrict__ colptr, const unsigned int* __restrict__ rowidx,
                                                         int nbc, int nkb, int bn, int bk, int nparts, int bpp, int cpw, unsigned int cap,
                                                         unsigned int resident_cap_blocks, unsigned int* buf) {
+  pdl_launch_dependents();
   const int KBS = 64 / bk, nks = (nkb + KBS - 1) / KBS, nl = nparts * nks;
   const BcscIdxLayout L((unsigned int)nbc, (unsigned int)nl, cap);
   __shared__ unsigned int s_cp[257];
@@ -212,6 +218,8 @@ __global__ void __launch_bounds__(256) bcsc_prep_kernel(const unsigned int* __re
 // 2D tensor map costs the TMA unit ~5 cycles per 64-byte row: measured 287K of 357K cycles per CTA.)
 __global__ void __launch_bounds__(256) bcsc_pack_b_kernel(const uint4* __restrict__ b_vals, const unsigned int* __restrict__ entries,
                                                           const unsigned int* __restrict__ list_ptr, int nl, uint4* __restrict__ out, int bn, int bk) {
+  pdl_launch_dependents();
+  pdl_wait();                                                        // the visiting order comes from the prep kernel
   const unsigned int nnzb = list_ptr[nl];
   const unsigned int cpr = (unsigned int)bk >> 3;                    // 16-byte chunks per row (2, 4 or 8)
   const unsigned int cpb = (unsigned int)bn * cpr;                   // chunks per block
@@ -287,6 +295,7 @@ constexpr int A_STAGE = 128 * 64 * 2;               // bytes of one k-step of A 
 template <int M>
 __global__ void __launch_bounds__(kThreads, 1)
 bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) {
+  pdl_wait();
   constexpr int G = 128 / M;                       // m_blocks per group
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -490,7 +499,7 @@ bcsc_tc_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTcParams P) 
 }
 
 // ---- main kernel: the A operand lives in tensor memory (TS-form MMA) ---------------------------------------------------------
-constexpr int kTsThreads = 832;      // 26 warps: A producer, B producer, 4 MMA issuers, 4 copy, 16 epilogue (one 32-column chunk each)
+constexpr int kTsThreads = 960;      // 30 warps: A producer, B producer, 4 MMA issuers, 4 copy, 16 epilogue (one 32-column chunk each), 4 more MMA issuers (k-major sweep)
 constexpr int kTsDCols = 128;        // accumulator columns per column part (two slots: TMEM columns 0..255)
 constexpr int kTsACol0 = 256;        // A operand: TMEM columns 256..511, 32 per k-step of 64
 constexpr int kTsMaxKS = 8;          // => K <= 512
@@ -556,6 +565,8 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
   const uint32_t blk_bytes = (uint32_t)P.bn * P.bk * 2;
   const long long Gd = gridDim.x, bid = blockIdx.x;
 
+  if (threadIdx.x == 0) asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
+  pdl_wait();                                          // plan, operation lists and packed B come from the two kernels in front
   // ---- mode and work assignment (uniform per CTA) ----
   const int S = (int)P.plan[0];
   const bool resident = S > 0;
@@ -583,8 +594,8 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
   const uint32_t raw_full = bar0, raw_empty = raw_full + 8 * 8, a_full = raw_empty + 8 * 8, a_empty = a_full + 8 * kTsMaxKS;
   const uint32_t b_full = a_empty + 8 * kTsMaxKS, b_empty = b_full + 8 * 8, t_full = b_empty + 8 * 8, t_empty = t_full + 8 * 2;
   uint32_t* tmem_word = (uint32_t*)(bars + 4 * 8 + 2 * kTsMaxKS + 4);
-  uint32_t* s_fcnt = tmem_word + 1;                                        // [4] records per MMA warp (flat lists)
-  uint4* s_flat = (uint4*)(((uintptr_t)(s_fcnt + 4) + 15) & ~(uintptr_t)15);   // [ops_cap + 4*NKS + 4] flat records
+  uint32_t* s_fcnt = tmem_word + 1;                                        // [8] records per MMA warp (flat lists)
+  uint4* s_flat = (uint4*)(((uintptr_t)(s_fcnt + 8) + 15) & ~(uintptr_t)15);   // [ops_cap + 8*NKS + 8] flat records
   const bool flat = resident && P.kmajor && (p1 - p0) == 2;     // one part per CTA: the part-major loop is already k-major
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -599,7 +610,7 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
     for (int i = 0; i < RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
-    for (int i = 0; i < NKS; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, (uint32_t)P.mma_warps); }
+    for (int i = 0; i < NKS; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, (uint32_t)(flat ? 2 * P.mma_warps : P.mma_warps)); }
     for (int i = 0; i < BS; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, (uint32_t)P.mma_warps); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, (uint32_t)P.mma_warps); mbar_init(t_empty + 8 * i, 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -619,29 +630,33 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
   // A columns of the k-step, descriptor of the resident B block. So each MMA warp gets ONE list for a whole group, in issue
   // order, with absolute operands {D address, A address | accumulate << 31, B descriptor low word, instruction descriptor};
   // a record with w == 0 ends a k-step (commit a_empty). The issue loop is then one 16-byte shared load per operation.
+  // In this mode EIGHT warps issue: warps 2..5 own part p0 (slot 0), warps 26..29 part p0+1 (slot 1), each one block-column
+  // range of its part -- the issue loop of one thread (~30 instructions per operation), not the tensor pipe, bounds the
+  // sweep (measured: tensor pipe 25 % active with four issuers), and accumulator columns stay owned by one thread.
+  const int MW = P.mma_warps;
+  const bool issuer = (warp >= 2 && warp < 2 + MW) || (flat && warp >= 26 && warp < 26 + MW);
+  const int mw = (warp >= 26) ? MW + (warp - 26) : warp - 2;            // issuer index; flat: part = mw / MW, column range = mw % MW
   if (flat) {
-    const int np = p1 - p0;
     const uint32_t blk16f = blk_bytes >> 4, b_lo_base = desc_lo(smem_u32(s_b), 1);
-    if (warp >= 2 && warp < 2 + P.mma_warps && lane == 0) {
+    const int q = mw / MW, ww = mw % MW;
+    if (issuer && lane == 0) {
       uint32_t n = 0;
-      for (int ks = 0; ks < NKS; ++ks) { for (int q = 0; q < np; ++q) n += s_wr[4 * ((p0 + q) * NKS + ks) + (warp - 2)] >> 16; }
-      s_fcnt[warp - 2] = n + (uint32_t)NKS;
+      for (int ks = 0; ks < NKS; ++ks) n += s_wr[4 * ((p0 + q) * NKS + ks) + ww] >> 16;
+      s_fcnt[mw] = n + (uint32_t)NKS;
     }
     __syncthreads();
-    if (warp >= 2 && warp < 2 + P.mma_warps && lane == 0) {
+    if (issuer && lane == 0) {
       uint32_t off = 0;
-      for (int w = 0; w < warp - 2; ++w) off += s_fcnt[w];
+      for (int w = 0; w < mw; ++w) off += s_fcnt[w];
       uint4* out = s_flat + off;
       for (int ks = 0; ks < NKS; ++ks) {
-        for (int q = 0; q < np; ++q) {
-          const uint32_t l = (uint32_t)((p0 + q) * NKS + ks);
-          const uint32_t rng = s_wr[4 * l + (warp - 2)], ob = rng & 0xFFFFu, on = rng >> 16;
-          const uint32_t b_list_lo = b_lo_base + (s_lp[l] - e_set0) * blk16f;
-          for (uint32_t o = 0; o < on; ++o) {
-            const uint4 op = s_ops[ob + o];
-            *out++ = make_uint4(tmem_base + (uint32_t)(q * kTsDCols) + (op.x & 0xFFFFu),
-                                (tmem_a + (uint32_t)ks * 32u + (op.x >> 20)) | (op.w << 31), b_list_lo + op.y, P.idesc | op.z);
-          }
+        const uint32_t l = (uint32_t)((p0 + q) * NKS + ks);
+        const uint32_t rng = s_wr[4 * l + ww], ob = rng & 0xFFFFu, on = rng >> 16;
+        const uint32_t b_list_lo = b_lo_base + (s_lp[l] - e_set0) * blk16f;
+        for (uint32_t o = 0; o < on; ++o) {
+          const uint4 op = s_ops[ob + o];
+          *out++ = make_uint4(tmem_base + (uint32_t)(q * kTsDCols) + (op.x & 0xFFFFu),
+                              (tmem_a + (uint32_t)ks * 32u + (op.x >> 20)) | (op.w << 31), b_list_lo + op.y, P.idesc | op.z);
         }
         *out++ = make_uint4(0u, 0u, 0u, 0u);
       }
@@ -697,7 +712,7 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
         }
       }
     }
-  } else if (warp >= 2 && warp < 2 + P.mma_warps) {
+  } else if (issuer) {
     // ========================================= MMA issuers ======================================
     // Each warp OWNS a range of block-columns of every part (lists are stored owner-major by the prep kernel), so every
     // accumulator column is written by one thread in k order. The whole warp runs the loop (warp-uniform control flow);
@@ -706,7 +721,6 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
     // cycles per group against ~100 cycles per operation in the first version).
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-    const int mw = warp - 2;
     int bs = 0; uint32_t bph = 0;
     const uint32_t b_hi = desc_hi(P.b_sbo16, P.b_layout);
     const uint32_t b_lo0 = desc_lo(smem_u32(s_b), 1);
@@ -737,7 +751,7 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
       // k-major sweep: both parts of the set accumulate side by side in the two slots, so the A columns of a k-step are
       // released as soon as that k-step is consumed and the copy warps refill them for the NEXT group while this group's
       // later k-steps are still being multiplied.
-      const int np = p1 - p0;
+      const int q = mw / MW;                                                    // this warp's part lives in slot q
       uint32_t foff = 0;
       for (int w = 0; w < mw; ++w) foff += s_fcnt[w];
       const uint32_t flat_sa = smem_u32(s_flat) + 16u * foff;
@@ -745,7 +759,8 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
         const uint32_t gpar = (uint32_t)(i & 1);
         uint32_t rec = flat_sa;
         uint4 op = lds128(rec);
-        for (int q = 0; q < np; ++q) mbar_wait(t_empty + 8 * q, gpar ^ 1);      // part q lives in slot q (np == 2)
+        mbar_wait(t_empty + 8 * q, gpar ^ 1);
+        tc_fence_after();
         for (int ks = 0; ks < NKS; ++ks) {
           mbar_wait(a_full + 8 * ks, gpar);
           tc_fence_after();
@@ -761,11 +776,11 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
             op = nxt;
           }
           rec += 16u;
-          op = lds128(rec);                                                      // first record of the next k-step (one spare record is allocated)
+          op = lds128(rec);                                                      // first record of the next k-step (spare records are allocated)
           if (leader) umma_commit(a_empty + 8 * ks);
           __syncwarp();
         }
-        if (leader) { for (int q = 0; q < np; ++q) umma_commit(t_full + 8 * q); }
+        if (leader) umma_commit(t_full + 8 * q);
         __syncwarp();
       }
     } else {
@@ -895,16 +910,24 @@ template <int M>
 cudaError_t launch_v1(long long grid, size_t smem, cudaStream_t stream, const CUtensorMap& ma, const BcscTcParams& P) {
   static unsigned long long done = 0;
   ensure_smem_attr(bcsc_tc_kernel<M>, 227 * 1024, &done);
-  bcsc_tc_kernel<M><<<(unsigned int)grid, kThreads, smem, stream>>>(ma, P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned int)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, bcsc_tc_kernel<M>, ma, P);
 }
 
 template <int M, int KSTEPS>
 cudaError_t launch_ts2(long long grid, size_t smem, cudaStream_t stream, const CUtensorMap& ma, const BcscTsParams& P) {
   static unsigned long long done = 0;
   ensure_smem_attr(bcsc_ts_kernel<M, KSTEPS>, 227 * 1024, &done);
-  bcsc_ts_kernel<M, KSTEPS><<<(unsigned int)grid, kTsThreads, smem, stream>>>(ma, P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned int)grid); cfg.blockDim = dim3(kTsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, bcsc_ts_kernel<M, KSTEPS>, ma, P);
 }
 template <int M>
 cudaError_t launch_ts(long long grid, size_t smem, cudaStream_t stream, const CUtensorMap& ma, const BcscTsParams& P) {
@@ -1008,7 +1031,7 @@ extern "C" int xb_bcsc_tc_launch(const xb_sparse_desc* d, void** work, const voi
     P2.kpc = kpc; P2.nchunks = (nks + kpc - 1) / kpc; P2.b_stage_bytes = ks_bytes * kpc;
     P2.ops_cap = (int)nnzb; P2.mma_warps = mma_warps;
     const size_t meta = ((size_t)P2.ops_cap + 1) * 16 + ((size_t)5 * nl + 2) * 4 + (size_t)n_blocks + 16 + (4 * 8 + 2 * kTsMaxKS + 4 + 1) * 8
-                      + 32 + ((size_t)P2.ops_cap + 4 * kTsMaxKS + 4) * 16;       // + flat per-warp lists of the k-major sweep
+                      + 48 + ((size_t)P2.ops_cap + 8 * kTsMaxKS + 8) * 16;       // + flat per-warp lists of the k-major sweep
     const size_t total = 226 * 1024;                       // dynamic shared memory requested: 1 KB alignment slack + rings + metadata
     if (meta + 1024 + 5 * (size_t)A_STAGE > total) return -1;
     P2.ring_bytes = (int)((total - 1024 - meta) & ~(size_t)1023);
@@ -1072,7 +1095,12 @@ extern "C" int xb_bcsc_tc_launch(const xb_sparse_desc* d, void** work, const voi
   {
     const unsigned long long chunks = (unsigned long long)bneed / 16;
     const unsigned int pgrid = (unsigned int)((chunks + 255) / 256 < 1024 ? (chunks + 255) / 256 : 1024);
-    bcsc_pack_b_kernel<<<pgrid ? pgrid : 1, 256, 0, stream>>>((const uint4*)b_vals, buf + L.entries, buf + L.list_ptr, nl, (uint4*)bufs->val, bn, bk);
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(pgrid ? pgrid : 1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, bcsc_pack_b_kernel, (const uint4*)b_vals, (const unsigned int*)(buf + L.entries), (const unsigned int*)(buf + L.list_ptr), nl, (uint4*)bufs->val, bn, bk);
     xb_rt_count_launch();
   }
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(128 >> 4) << 24);   // N is filled in per (merged) operation

@@ -22,12 +22,24 @@
 
 namespace {
 
-enum { P_F64 = 0, P_F32, P_I16, P_I8_I32, P_I8_F32, P_F16_F16, P_F16_F32, P_BF16_F32, P_BF16_BF16, P_NONE };
+enum { P_F64 = 0, P_F32, P_I16, P_I8_I32, P_I8_F32, P_F16_F16, P_F16_F32, P_BF16_F32, P_BF16_BF16, P_I4_I32, P_BITMAP, P_NONE };
 
 __host__ __device__ inline int xb_path_of(const xb_gemm_desc& d) {
   const int a = d.ta, b = d.tb, c = d.tc, comp = d.tcomp;
   const bool a8 = (a == LIBXSMM_DATATYPE_I8 || a == LIBXSMM_DATATYPE_U8);
   const bool b8 = (b == LIBXSMM_DATATYPE_I8 || b == LIBXSMM_DATATYPE_U8);
+  if ((d.flags & LIBXSMM_GEMM_FLAG_DECOMPRESS_A_VIA_BITMASK) != 0) {   // bitmap-compressed A (reference :857-948): float operands, no batch reduce
+    const bool fa = (a == LIBXSMM_DATATYPE_F32 || a == LIBXSMM_DATATYPE_BF16 || a == LIBXSMM_DATATYPE_F16);
+    const bool fb = (b == LIBXSMM_DATATYPE_F32 || b == LIBXSMM_DATATYPE_BF16 || b == LIBXSMM_DATATYPE_F16);
+    const bool fc = (c == LIBXSMM_DATATYPE_F32 || c == LIBXSMM_DATATYPE_BF16 || c == LIBXSMM_DATATYPE_F16);
+    const int kb = (a == LIBXSMM_DATATYPE_F32) ? 1 : ((b == LIBXSMM_DATATYPE_F32) ? 1 : 2);
+    return (fa && fb && fc && d.br_type == 0 && (d.k % kb) == 0 && d.fuse_colbias == 0 && d.cp_op == 0) ? P_BITMAP : P_NONE;
+  }
+  if (a == LIBXSMM_DATATYPE_I4X2 || a == LIBXSMM_DATATYPE_U4X2) {       // 4-bit A with zero points x 8-bit B -> I32 (reference :1273-1321)
+    const unsigned int need = LIBXSMM_GEMM_FLAG_VNNI_A | LIBXSMM_GEMM_FLAG_INTLV_A_FORMAT;
+    return ((d.flags & need) == need && b8 && c == LIBXSMM_DATATYPE_I32 && comp == LIBXSMM_DATATYPE_I32 && (d.k % 8) == 0
+            && (d.br_type == 0 || d.br_type == 3)) ? P_I4_I32 : P_NONE;
+  }
   if (a == LIBXSMM_DATATYPE_F64 && b == a && c == a && comp == a) return P_F64;
   if ((a == LIBXSMM_DATATYPE_F32 || a == LIBXSMM_DATATYPE_BF32) && (b == LIBXSMM_DATATYPE_F32 || b == LIBXSMM_DATATYPE_BF32)
       && c == LIBXSMM_DATATYPE_F32 && comp == LIBXSMM_DATATYPE_F32) return P_F32;
@@ -49,6 +61,7 @@ struct TileCtx {
   unsigned long long br;
   float scf;
   const void* colbias; unsigned char* relu_mask;          // fused form (libxsmm_dispatch_brgemm_ext)
+  const unsigned char* a_q;                                // int4: zero points; bitmap-compressed A: the bitmap
 };
 
 __device__ inline void resolve_tile(const xb_gemm_launch& L, long long t, TileCtx& x) {
@@ -59,13 +72,14 @@ __device__ inline void resolve_tile(const xb_gemm_launch& L, long long t, TileCt
     r.a = (const char*)L.a + t * L.tile_stride_a; r.b = (const char*)L.b + t * L.tile_stride_b;
     r.c = (char*)L.c + t * L.tile_stride_c; r.a_aux = nullptr; r.b_aux = nullptr; r.br = L.br; r.scf = L.one.scf;
     r.d = L.one.d; r.c_aux = nullptr;                      // a shared bias column; masks only exist per call
+    r.a_q = L.one.a_q;
     if (L.d.br_type == 2) { r.a_aux = L.one.a_aux; r.b_aux = L.one.b_aux; }
   }
   x.a0 = (const char*)r.a; x.b0 = (const char*)r.b; x.c = (char*)r.c;
   x.a_addr = (const void* const*)r.a; x.b_addr = (const void* const*)r.b;
   x.a_offs = (const long long*)r.a_aux; x.b_offs = (const long long*)r.b_aux;
   x.br = (L.d.br_type == 0) ? 1ull : r.br; x.scf = r.scf;
-  x.colbias = r.d; x.relu_mask = (unsigned char*)r.c_aux;
+  x.colbias = r.d; x.relu_mask = (unsigned char*)r.c_aux; x.a_q = (const unsigned char*)r.a_q;
 }
 
 // base pointers of the r-th batch-reduce operand pair; mirrors libxsmm_calculate_brgemm_offsets
@@ -327,9 +341,79 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const xb_gemm_launch L, 
           if (path == P_BF16_F32) reinterpret_cast<float*>(x.c)[ci] = acc;
           else reinterpret_cast<unsigned short*>(x.c)[ci] = xb_f32_to_bf16_rne(acc);
         } break;
+        case P_I4_I32: {   // reference :1273-1321; zero point subtracted in 8-bit arithmetic, B read as unsigned bytes
+          unsigned int acc = beta0 ? 0u : (unsigned int)ldg_as<int>(x.c, ci);
+          for (unsigned long long r = 0; r < x.br; ++r) {
+            const char *pa, *pb; br_ptrs(d, x, r, 1, 1, pa, pb);
+            const unsigned char z = (d.br_type == 3) ? x.a_q[((d.br_stride_a * 2) / k) * (long long)r + i] : x.a_q[i];
+            for (int s = 0; s < k / 8; ++s) for (int q = 0; q < 4; ++q) {
+              const unsigned char pk = ldg_as<unsigned char>(pa, s * lda * 4 + 4 * (long long)i + q);
+              const int ev = (int)(signed char)((pk & 0x0f) - z), od = (int)(signed char)(((pk >> 4) & 0x0f) - z);
+              acc += (unsigned int)(ev * (int)ldg_as<unsigned char>(pb, j * ldb + (long long)s * 8 + q));
+              acc += (unsigned int)(od * (int)ldg_as<unsigned char>(pb, j * ldb + (long long)s * 8 + 4 + q));
+            }
+          }
+          reinterpret_cast<int*>(x.c)[ci] = (int)acc;
+        } break;
         default: break;
       }
     }
+  }
+}
+
+// ---- bitmap-compressed A (DECOMPRESS_A_VIA_BITMASK, reference :857-948) ---------------------------------------------------
+// A stores only the elements whose bit is set, in bit order; bit (s, i, k2) sits at position s*(m*kb) + i*kb + k2. The index
+// of an element in the compressed array is the number of set bits in front of it: phase 1 scans the bitmap once (per-word
+// population counts -> exclusive prefix in `prefix`), phase 2 is the exact-order element loop of the reference with
+// idx = prefix[word] + popc(bits below). One CTA per call (the flag excludes batch reduce; single-tile launches only).
+__device__ __forceinline__ unsigned int bitmap_word(const unsigned char* bm, long long w, long long nbytes) {
+  unsigned int v = 0;
+  for (int q = 0; q < 4; ++q) { const long long bi = w * 4 + q; if (bi < nbytes) v |= (unsigned int)bm[bi] << (8 * q); }
+  return v;
+}
+__global__ void __launch_bounds__(1024) gemm_bitmap_kernel(const xb_gemm_launch L, unsigned int* __restrict__ prefix) {
+  const xb_gemm_desc& d = L.d;
+  const int m = d.m, n = d.n, k = d.k;
+  const long long ldb = d.ldb, ldc = d.ldc;
+  const bool beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) != 0;
+  const int kb = (d.ta == LIBXSMM_DATATYPE_F32) ? 1 : ((d.tb == LIBXSMM_DATATYPE_F32) ? 1 : 2);
+  const long long nbits = (long long)m * k, nbytes = (nbits + 7) / 8, nwords = (nbits + 31) / 32;
+  const unsigned char* bm = (const unsigned char*)L.one.a_q;
+  const char* a = (const char*)L.one.a; const char* b = (const char*)L.one.b; char* c = (char*)L.one.c;
+  __shared__ unsigned int seg_total[1024];
+  // phase 1: thread t owns a contiguous range of words
+  const long long per = (nwords + blockDim.x - 1) / blockDim.x, w0 = (long long)threadIdx.x * per, w1 = (w0 + per < nwords) ? w0 + per : nwords;
+  unsigned int run = 0;
+  for (long long w = w0; w < w1; ++w) { prefix[w] = run; run += __popc(bitmap_word(bm, w, nbytes)); }
+  seg_total[threadIdx.x] = run;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned int acc = 0; for (unsigned int t = 0; t < blockDim.x; ++t) { const unsigned int v = seg_total[t]; seg_total[t] = acc; acc += v; } }
+  __syncthreads();
+  { const unsigned int base = seg_total[threadIdx.x]; for (long long w = w0; w < w1; ++w) prefix[w] += base; }
+  __syncthreads();
+  // phase 2
+  for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
+    const int i = e % m, j = e / m;
+    const long long ci = (long long)j * ldc + i;
+    float acc;
+    if (d.tc == LIBXSMM_DATATYPE_F32) acc = beta0 ? 0.0f : ((const float*)c)[ci];
+    else acc = beta0 ? 0.0f : ((d.tc == LIBXSMM_DATATYPE_BF16) ? xb_bf16_to_f32(((const unsigned short*)c)[ci]) : xb_f16_to_f32(((const unsigned short*)c)[ci]));
+    for (int s = 0; s < k / kb; ++s) for (int k2 = 0; k2 < kb; ++k2) {
+      const long long bit = (long long)s * m * kb + (long long)i * kb + k2, w = bit >> 5;
+      const unsigned int word = bitmap_word(bm, w, nbytes), sh = (unsigned int)(bit & 31);
+      if ((word >> sh) & 1u) {
+        const long long idx = (long long)prefix[w] + __popc(word & ((1u << sh) - 1u));
+        const float av = (d.ta == LIBXSMM_DATATYPE_F32) ? ((const float*)a)[idx]
+                       : ((d.ta == LIBXSMM_DATATYPE_BF16) ? xb_bf16_to_f32(((const unsigned short*)a)[idx]) : xb_f16_to_f32(((const unsigned short*)a)[idx]));
+        const long long bi = j * ldb + (long long)s * kb + k2;
+        const float bv = (d.tb == LIBXSMM_DATATYPE_F32) ? ((const float*)b)[bi]
+                       : ((d.tb == LIBXSMM_DATATYPE_BF16) ? xb_bf16_to_f32(((const unsigned short*)b)[bi]) : xb_f16_to_f32(((const unsigned short*)b)[bi]));
+        acc = __fadd_rn(acc, __fmul_rn(av, bv));
+      }
+    }
+    if (d.tc == LIBXSMM_DATATYPE_F32) ((float*)c)[ci] = acc;
+    else if (d.tc == LIBXSMM_DATATYPE_BF16) ((unsigned short*)c)[ci] = xb_f32_to_bf16_rne(acc);
+    else ((unsigned short*)c)[ci] = xb_f32_to_f16(acc);
   }
 }
 
@@ -507,6 +591,17 @@ extern "C" int xb_gemm_simt_launch(const xb_gemm_launch* L) {
   const int path = xb_path_of(L->d);
   if (path == P_NONE) return 1;
   if (L->count <= 0) return 0;
+  if (path == P_BITMAP) {
+    if (L->count != 1 || L->recs != nullptr || L->one.a_q == nullptr) { xb_rt_note_error(1, "bitmap-compressed A: single calls only"); return 1; }
+    unsigned int* prefix = (unsigned int*)xb_rt_scratch((size_t)(((long long)L->d.m * L->d.k + 31) / 32) * 4 + 16);
+    if (prefix == nullptr) return 2;
+    gemm_bitmap_kernel<<<1, 1024, 0, (cudaStream_t)xb_rt_stream()>>>(*L, prefix);
+    xb_rt_count_launch();
+    const cudaError_t be = cudaGetLastError();
+    if (be != cudaSuccess) { xb_rt_note_error((int)be, "gemm_bitmap"); return (int)be; }
+    return 0;
+  }
+  if (path == P_I4_I32 && L->one.a_q == nullptr && L->recs == nullptr) { xb_rt_note_error(1, "int4 A: zero points missing (a.quaternary)"); return 1; }
   if (L->d.fuse_colbias != 0 || L->d.cp_op != 0) {
     const long long fgrid = L->count < (1 << 20) ? L->count : (1 << 20);
     gemm_simt_fused_kernel<<<(unsigned int)fgrid, 256, 0, (cudaStream_t)xb_rt_stream()>>>(*L, path);

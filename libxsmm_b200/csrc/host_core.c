@@ -369,6 +369,7 @@ LIBXSMM_API libxsmm_tilecfgfunction libxsmm_dispatch_tilecfg_gemm(const libxsmm_
 typedef struct xb_copyback { void* host; const void* dev; size_t bytes; } xb_copyback;
 
 static size_t xb_extent_a(const xb_gemm_desc* d) {   /* elements touched in one A operand */
+  if (d->ta == LIBXSMM_DATATYPE_I4X2 || d->ta == LIBXSMM_DATATYPE_U4X2) return (size_t)(d->k / 8 - 1) * d->lda * 4 + (size_t)d->m * 4;   /* bytes: 8 k per 4 bytes */
   const int trans_a = (d->flags & LIBXSMM_GEMM_FLAG_TRANS_A) != 0, vnni_a = (d->flags & LIBXSMM_GEMM_FLAG_VNNI_A) != 0;
   const int is8 = (d->ta == LIBXSMM_DATATYPE_I8 || d->ta == LIBXSMM_DATATYPE_U8);
   const int v = (is8 ? 4 : 2);
@@ -453,8 +454,23 @@ static void xb_invoke_gemm(const xb_slot* s, const libxsmm_gemm_param* p) {
       L.one.a_aux = dev; L.one.b_aux = (const char*)dev + (size_t)br * sizeof(long long);
       staged = 1;
     }
-    L.one.a = xb_stage_in(p->a.primary, span_a, &staged);
+    if ((d->flags & LIBXSMM_GEMM_FLAG_DECOMPRESS_A_VIA_BITMASK) != 0) {   /* a.secondary: bitmap; A holds one element per set bit */
+      const size_t bbytes = ((size_t)d->m * d->k + 7) / 8;
+      if (p->a.secondary == NULL) { xb_rt_note_error(2, "invoke_gemm: bitmap missing (a.secondary)"); xb_rt_scratch_reset(); return; }
+      if (xb_rt_ptr_kind(p->a.secondary) != 1) {   /* host-readable bitmap: count the stored elements */
+        const unsigned char* bm = (const unsigned char*)p->a.secondary; size_t nz = 0, q;
+        for (q = 0; q < bbytes; ++q) nz += (size_t)__builtin_popcount(bm[q]);
+        span_a = nz * tsa;
+      } else if (xb_rt_ptr_kind(p->a.primary) == 0) { xb_rt_note_error(2, "invoke_gemm: device bitmap with host A"); xb_rt_scratch_reset(); return; }
+      L.one.a_q = xb_stage_in(p->a.secondary, bbytes, &staged);
+    }
+    L.one.a = xb_stage_in(p->a.primary, span_a ? span_a : 1, &staged);
     L.one.b = xb_stage_in(p->b.primary, span_b, &staged);
+  }
+  if (d->ta == LIBXSMM_DATATYPE_I4X2 || d->ta == LIBXSMM_DATATYPE_U4X2) {   /* a.quaternary: one zero-point byte per row (and per reduce step) */
+    const size_t zb = (size_t)d->m + ((d->br_type == 3 && br > 0) ? (size_t)(br - 1) * (size_t)((d->br_stride_a * 2) / d->k) : 0);
+    L.one.a_q = xb_stage_in(p->a.quaternary, zb, &staged);
+    if (L.one.a_q == NULL) { xb_rt_note_error(2, "invoke_gemm: int4 A needs zero points in a.quaternary"); xb_rt_scratch_reset(); return; }
   }
   /* C: staged copy is seeded from the host whenever old contents can survive (beta=1 or ldc>m) */
   if (p->c.primary != NULL && xb_rt_ptr_kind(p->c.primary) == 0) {
@@ -692,7 +708,8 @@ void xb_invoke(int slot, const void* param) {
     case XB_KIND_TILECFG: break;
     case XB_KIND_MELTW: xb_invoke_meltw(s, param); break;
     case XB_KIND_SP_A_CSR: case XB_KIND_SP_B_CSR: case XB_KIND_SP_B_CSC: case XB_KIND_SP_C_CSC:
-    case XB_KIND_BCSC: case XB_KIND_SREG: xb_invoke_sparse(s, (const libxsmm_gemm_param*)param); break;
+    case XB_KIND_BCSC: case XB_KIND_SREG: case XB_KIND_PK_GEMM: case XB_KIND_PK_AC_RM: case XB_KIND_PK_BC_RM:
+      xb_invoke_sparse(s, (const libxsmm_gemm_param*)param); break;
     default:
       if (libxsmm_verbosity != 0) fprintf(stderr, "LIBXSMM-B200 ERROR: call through a released kernel handle\n");
   }

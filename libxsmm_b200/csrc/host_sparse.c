@@ -103,6 +103,34 @@ LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csc(const libxsmm_
   return xb_finish_sparse(slot, xb_upload_pattern(&s->u.sp, column_ptr, (unsigned int)gemm_shape.n, row_idx, nnz));
 }
 
+/* ---- packed dense GEMM (include/libxsmm.h:195-214; src/libxsmm_main.c:3733-3840): F32/F64, caller-owned handles ------------ */
+static libxsmm_gemmfunction xb_create_packed_dense(int kind, const libxsmm_gemm_shape* sh, unsigned int flags, libxsmm_blasint packed_width) {
+  int slot; xb_slot* s;
+  LIBXSMM_INIT
+  if (packed_width <= 0 || sh->m <= 0 || sh->n <= 0 || sh->k <= 0) return NULL;
+  if (sh->a_in_type != sh->b_in_type || !xb_is_fp((int)sh->a_in_type) || sh->out_type != sh->a_in_type) return NULL;
+  if ((flags & (LIBXSMM_GEMM_FLAG_TRANS_A | LIBXSMM_GEMM_FLAG_TRANS_B)) != 0) return NULL;
+  /* leading dimensions in units of packed vectors, as the golds index them */
+  if (kind == XB_KIND_PK_GEMM) { if (sh->lda < sh->m || sh->ldb < sh->k || sh->ldc < sh->m) return NULL; }
+  else if (sh->lda < sh->k || sh->ldb < sh->n || sh->ldc < sh->n) return NULL;
+  if (!xb_rt_have_gpu()) return NULL;
+  slot = xb_host_slot_alloc(kind, 2u * (unsigned int)sh->m * (unsigned int)sh->n * (unsigned int)sh->k * (unsigned int)packed_width);
+  if (slot < 0) return NULL;
+  s = xb_host_slot(slot);
+  xb_fill_sparse_common(&s->u.sp, kind, sh, flags);
+  s->u.sp.packed_width = packed_width;
+  return (libxsmm_gemmfunction)xb_thunk(slot);
+}
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_gemm(const libxsmm_gemm_shape gemm_shape, const libxsmm_bitfield gemm_flags,
+  const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width)
+{ (void)prefetch_flags; return xb_create_packed_dense(XB_KIND_PK_GEMM, &gemm_shape, gemm_flags, packed_width); }
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_gemm_ac_rm(const libxsmm_gemm_shape gemm_shape, const libxsmm_bitfield gemm_flags,
+  const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width)
+{ (void)prefetch_flags; return xb_create_packed_dense(XB_KIND_PK_AC_RM, &gemm_shape, gemm_flags, packed_width); }
+LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_gemm_bc_rm(const libxsmm_gemm_shape gemm_shape, const libxsmm_bitfield gemm_flags,
+  const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width)
+{ (void)prefetch_flags; return xb_create_packed_dense(XB_KIND_PK_BC_RM, &gemm_shape, gemm_flags, packed_width); }
+
 /* ---- BCSC block-sparse B ------------------------------------------------------------------------------ */
 static int xb_bcsc_types_ok(const libxsmm_gemm_shape* s) {
   const int a = (int)s->a_in_type, b = (int)s->b_in_type, c = (int)s->out_type, comp = (int)s->comp_type;
@@ -216,6 +244,18 @@ void xb_invoke_sparse(const xb_slot* s, const libxsmm_gemm_param* p) {
       const size_t bb = (d->kind == XB_KIND_SP_B_CSR || d->kind == XB_KIND_SP_B_CSC) ? (size_t)d->nnz * ts : (size_t)d->k * d->ldb * P * ts;
       const void *a, *b;
       c_bytes = (d->kind == XB_KIND_SP_C_CSC) ? (size_t)d->nnz * ts /* one scalar per non-zero */ : (size_t)d->m * d->ldc * P * ts;
+      a = xb_dev_in(p->a.primary, ab, &staged); b = xb_dev_in(p->b.primary, bb, &staged);
+      c_dev = p->c.primary;
+      if (xb_rt_ptr_kind(p->c.primary) == 0) { c_host = p->c.primary; c_dev = xb_rt_scratch(c_bytes); if (c_dev) xb_rt_upload(c_dev, c_host, c_bytes); staged = 1; }
+      if (a == NULL || b == NULL || c_dev == NULL) { rc = 2; break; }
+      rc = xb_packed_sp_launch(d, a, b, c_dev, 1, 0, 0, 0);
+    } break;
+    case XB_KIND_PK_GEMM: case XB_KIND_PK_AC_RM: case XB_KIND_PK_BC_RM: {
+      const size_t P = (size_t)d->packed_width;
+      const size_t ab = (d->kind == XB_KIND_PK_GEMM) ? (size_t)d->k * d->lda * P * ts : ((d->kind == XB_KIND_PK_AC_RM) ? (size_t)d->m * d->lda * P * ts : (size_t)d->m * d->lda * ts);
+      const size_t bb = (d->kind == XB_KIND_PK_GEMM) ? (size_t)d->n * d->ldb * P * ts : ((d->kind == XB_KIND_PK_AC_RM) ? (size_t)d->k * d->ldb * ts : (size_t)d->k * d->ldb * P * ts);
+      const void *a, *b;
+      c_bytes = ((d->kind == XB_KIND_PK_GEMM) ? (size_t)d->n : (size_t)d->m) * d->ldc * P * ts;
       a = xb_dev_in(p->a.primary, ab, &staged); b = xb_dev_in(p->b.primary, bb, &staged);
       c_dev = p->c.primary;
       if (xb_rt_ptr_kind(p->c.primary) == 0) { c_host = p->c.primary; c_dev = xb_rt_scratch(c_bytes); if (c_dev) xb_rt_upload(c_dev, c_host, c_bytes); staged = 1; }

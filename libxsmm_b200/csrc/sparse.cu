@@ -225,6 +225,37 @@ __global__ void __launch_bounds__(256) packed_csparse_kernel(const PackedParams 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// packed DENSE GEMM (EDGE/SeisSol, src/generator_packed_gemm*.c): the packed dimension P (a vector of independent problems)
+// is innermost in every packed operand, so consecutive lanes take consecutive p: every access is a coalesced row.
+//   PK_GEMM   C[n][m][p] (+)= sum_k A[k][m][p] * B[n][k][p]          (gold: samples/xgemm_packed/gemm_packed_kernel.c:36-66)
+//   PK_AC_RM  C[m][n][p] (+)= sum_k A[m][k][p] * B[k][n]             (gold: samples/xgemm_norm_packed/dense_packedacrm.c:37-49)
+//   PK_BC_RM  C[m][n][p] (+)= sum_k A[m][k]    * B[k][n][p]          (gold: samples/xgemm_norm_packed/dense_packedbcrm.c)
+// k ascending with fused multiply-add like the reference's FMA kernels; one thread per C element.
+template <typename T>
+__global__ void __launch_bounds__(256) packed_dense_kernel(const PackedParams Q) {
+  const long long P = Q.P, total = (long long)Q.M * Q.N * P;
+  for (long long item = blockIdx.y; item < Q.count; item += gridDim.y) {
+    const T* A = (const T*)(Q.a + item * Q.stride_a); const T* B = (const T*)(Q.b + item * Q.stride_b);
+    T* C = (T*)(Q.c + item * Q.stride_c);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const long long p = e % P, rest = e / P;
+      long long ci; T acc;
+      if (Q.kind == XB_KIND_PK_GEMM) {
+        const long long mm = rest % Q.M, nn = rest / Q.M;
+        ci = (nn * Q.ldc + mm) * P + p; acc = Q.beta0 ? (T)0 : C[ci];
+        for (int k = 0; k < Q.K; ++k) acc = fma(A[((long long)k * Q.lda + mm) * P + p], B[(nn * Q.ldb + k) * P + p], acc);
+      } else {
+        const long long nn = rest % Q.N, mm = rest / Q.N;
+        ci = (mm * Q.ldc + nn) * P + p; acc = Q.beta0 ? (T)0 : C[ci];
+        if (Q.kind == XB_KIND_PK_AC_RM) { for (int k = 0; k < Q.K; ++k) acc = fma(A[(mm * Q.lda + k) * P + p], B[(long long)k * Q.ldb + nn], acc); }
+        else { for (int k = 0; k < Q.K; ++k) acc = fma(A[mm * Q.lda + k], B[((long long)k * Q.ldb + nn) * P + p], acc); }
+      }
+      C[ci] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // BCSC exact-order kernel. One CTA per (m_block, block-column); thread per (m, n_local) element.
 struct BcscParams {
   int M, K, bk, bn, ta, tb, tc, beta0, trans_a, vnni_a, vnni_b_t;
@@ -360,6 +391,13 @@ extern "C" int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const
   if (count <= 0) return 0;
   cudaStream_t stream = (cudaStream_t)xb_rt_stream();
   const unsigned int grid = (unsigned int)(count < 65535 ? count : 65535);
+  if (d->kind == XB_KIND_PK_GEMM || d->kind == XB_KIND_PK_AC_RM || d->kind == XB_KIND_PK_BC_RM) {
+    const long long total = (long long)Q.M * Q.N * Q.P;
+    long long gx = (total + 255) / 256; if (gx > 148 * 8) gx = 148 * 8; if (gx < 1) gx = 1;
+    const dim3 g2((unsigned int)gx, grid);
+    if (Q.is_f64) packed_dense_kernel<double><<<g2, 256, 0, stream>>>(Q); else packed_dense_kernel<float><<<g2, 256, 0, stream>>>(Q);
+    return check_launch("packed_dense");
+  }
   if (d->kind == XB_KIND_SP_C_CSC) {
     const unsigned int gx = (d->nnz + 7) / 8 > 0 ? (d->nnz + 7) / 8 : 1;
     const dim3 g2(gx < 1024 ? gx : 1024, grid);

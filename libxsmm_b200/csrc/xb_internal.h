@@ -24,7 +24,10 @@ enum {
   XB_KIND_SP_B_CSC,      /* packed: C[M][N][P] += A[M][K][P] * B_csc */
   XB_KIND_SP_C_CSC,      /* packed: C_csc pattern only */
   XB_KIND_BCSC,          /* packed block-sparse B */
-  XB_KIND_SREG           /* fsspmdm kernel: sparse A fixed at create time, row-major B/C */
+  XB_KIND_SREG,          /* fsspmdm kernel: sparse A fixed at create time, row-major B/C */
+  XB_KIND_PK_GEMM,       /* packed dense: C[N][M][P] += A[K][M][P] * B[N][K][P] */
+  XB_KIND_PK_AC_RM,      /* packed dense: C[M][N][P] += A[M][K][P] * B[K][N] */
+  XB_KIND_PK_BC_RM       /* packed dense: C[M][N][P] += A[M][K] * B[K][N][P] */
 };
 
 /* normalised dense-GEMM descriptor == registry key for GEMM kinds (memcmp'd, so zero-filled) */
@@ -86,6 +89,7 @@ typedef struct xb_gemm_rec {
   const void* b_aux;
   const void* d;        /* ext: colbias */
   void* c_aux;          /* ext: relu bitmask out */
+  const void* a_q;      /* int4 A: zero points (a.quaternary); bitmap-compressed A: the bitmap (a.secondary) */
   unsigned long long br;
   float scf;            /* I8 x I8 -> F32 scalar scale */
   int pad_;

@@ -193,6 +193,95 @@ ORACLE_API int oracle_gemm(const int* dims, const int* types, unsigned int flags
   return gemm_run(&g);
 }
 
+/* ---- packed DENSE GEMM: golds of samples/xgemm_packed/gemm_packed_kernel.c:36-66 (kind 0), samples/xgemm_norm_packed/
+ * dense_packedacrm.c:37-49 (kind 1) and dense_packedbcrm.c (kind 2); k outermost, plain multiply-add --------------------------- */
+#define PKD_BODY(T) do { \
+  const T* A = (const T*)a; const T* B = (const T*)b; T* C = (T*)c; long long mm, nn, kk, p; \
+  if (kind == 0) { \
+    if (beta0) for (nn = 0; nn < N; ++nn) for (mm = 0; mm < M; ++mm) for (p = 0; p < P; ++p) C[(nn * ldc + mm) * P + p] = 0; \
+    for (kk = 0; kk < K; ++kk) for (mm = 0; mm < M; ++mm) for (nn = 0; nn < N; ++nn) for (p = 0; p < P; ++p) \
+      C[(nn * ldc + mm) * P + p] += A[(kk * lda + mm) * P + p] * B[(nn * ldb + kk) * P + p]; \
+  } else { \
+    if (beta0) for (mm = 0; mm < M; ++mm) for (nn = 0; nn < N; ++nn) for (p = 0; p < P; ++p) C[(mm * ldc + nn) * P + p] = 0; \
+    for (kk = 0; kk < K; ++kk) for (mm = 0; mm < M; ++mm) for (nn = 0; nn < N; ++nn) for (p = 0; p < P; ++p) \
+      C[(mm * ldc + nn) * P + p] += (kind == 1) ? A[(mm * lda + kk) * P + p] * B[kk * ldb + nn] : A[mm * lda + kk] * B[(kk * ldb + nn) * P + p]; \
+  } } while (0)
+ORACLE_API int oracle_packed_dense(int kind, int dtype, const int* dims, unsigned int flags, int P, const void* a, const void* b, void* c)
+{
+  const long long M = dims[0], N = dims[1], K = dims[2], lda = dims[3], ldb = dims[4], ldc = dims[5];
+  const int beta0 = (flags & F_BETA_0) != 0;
+  if (kind < 0 || kind > 2) return 1;
+  if (dtype == T_F64) PKD_BODY(double); else if (dtype == T_F32) PKD_BODY(float); else return 1;
+  return 0;
+}
+
+/* ---- 4-bit A x 8-bit B -> I32 with zero points (U4_U8_I32_I32 of the reference's test matrix), reference :1273-1321.
+ * A: VNNI_A | INTLV_A_FORMAT: byte [(k/8)*lda*4 + 4*m + q] holds k = 8*(k/8)+q in the low and k = 8*(k/8)+4+q in the high nibble;
+ * the zero point of row m (one byte) is subtracted in 8-bit arithmetic (`char even_use = even - zpt`, :833-834, 1290-1291),
+ * B is read as unsigned bytes. zpt: br_type 0: column vector [m]; stride mode: vector r at +(stride_a*2/k)*r (:240-252). */
+ORACLE_API int oracle_gemm_i4(const int* dims, unsigned int flags, int br_type, long long stride_a, long long stride_b, unsigned long long br,
+                              const unsigned char* a, const unsigned char* b, int* c, const unsigned char* zpt)
+{
+  const int m = dims[0], n = dims[1], k = dims[2]; const long long lda = dims[3], ldb = dims[4], ldc = dims[5];
+  int i, j, s, q; unsigned long long r;
+  if (br_type != 0 && br_type != 3) return 1;
+  if (br_type == 0) br = 1;
+  for (j = 0; j < n; ++j) for (i = 0; i < m; ++i) {
+    int acc = (flags & F_BETA_0) ? 0 : c[j * ldc + i];
+    for (r = 0; r < br; ++r) {
+      const unsigned char* pa = a + (br_type == 3 ? (long long)r * stride_a : 0);
+      const unsigned char* pb = b + (br_type == 3 ? (long long)r * stride_b : 0);
+      const unsigned char z = (br_type == 3) ? zpt[((stride_a * 2) / k) * (long long)r + i] : zpt[i];
+      for (s = 0; s < k / 8; ++s) for (q = 0; q < 4; ++q) {
+        const unsigned char pk = pa[s * lda * 4 + 4 * i + q];
+        const signed char ev = (signed char)((pk & 0x0f) - z), od = (signed char)(((pk >> 4) & 0x0f) - z);
+        acc = (int)((unsigned int)acc + (unsigned int)(ev * (int)pb[j * ldb + s * 8 + q]));
+        acc = (int)((unsigned int)acc + (unsigned int)(od * (int)pb[j * ldb + s * 8 + 4 + q]));
+      }
+    }
+    c[j * ldc + i] = acc;
+  }
+  return 0;
+}
+
+/* ---- bitmap-compressed A ("spmm", DECOMPRESS_A_VIA_BITMASK), reference :857-948. A holds only the elements whose bit is set, in
+ * bit order; bit (s, i, k2) = position s*(m*kb) + i*kb + k2 with kb = 1 for F32 A, else the pack factor of B's type (2). No batch
+ * reduce. Non-F32 C accumulates in an f32 image (seeded from C when beta = 1) and is rounded once at the end. */
+ORACLE_API int oracle_gemm_bitmap(const int* dims, const int* types, unsigned int flags, const void* a, const void* b, void* c, const unsigned char* bitmap)
+{
+  const int m = dims[0], n = dims[1], k = dims[2]; const long long ldb = dims[4], ldc = dims[5];
+  const int ta = types[0], tb = types[1], tc = types[3];
+  const int kb = (ta == T_F32) ? 1 : ((tsize(tb) == 2) ? 2 : (tsize(tb) == 1 ? 4 : 1));
+  float* img = (tc == T_F32) ? NULL : (float*)malloc((size_t)m * n * 4);
+  unsigned long long ci = 0; int s, i, j, k2;
+  if ((ta != T_F32 && ta != T_BF16 && ta != T_F16) || (tb != T_F32 && tb != T_BF16 && tb != T_F16) || (tc != T_F32 && tc != T_BF16 && tc != T_F16)) { free(img); return 1; }
+  for (s = 0; s < k / kb; ++s) for (i = 0; i < m; ++i) {
+    if (s == 0) for (j = 0; j < n; ++j) {
+      if (tc == T_F32) { if (flags & F_BETA_0) ((float*)c)[j * ldc + i] = 0.0f; }
+      else img[(size_t)j * m + i] = (flags & F_BETA_0) ? 0.0f : (tc == T_BF16 ? oracle_bf16_widen(((uint16_t*)c)[j * ldc + i]) : oracle_f16_to_f32(((uint16_t*)c)[j * ldc + i]));
+    }
+    for (k2 = 0; k2 < kb; ++k2) {
+      const long long bit = (long long)s * m * kb + (long long)i * kb + k2;
+      if ((bitmap[bit / 8] >> (bit % 8)) & 1) {
+        const float av = (ta == T_F32) ? ((const float*)a)[ci] : (ta == T_BF16 ? oracle_bf16_widen(((const uint16_t*)a)[ci]) : oracle_f16_to_f32(((const uint16_t*)a)[ci]));
+        for (j = 0; j < n; ++j) {
+          const long long bi = j * ldb + (long long)s * kb + k2;
+          const float bv = (tb == T_F32) ? ((const float*)b)[bi] : (tb == T_BF16 ? oracle_bf16_widen(((const uint16_t*)b)[bi]) : oracle_f16_to_f32(((const uint16_t*)b)[bi]));
+          if (tc == T_F32) ((float*)c)[j * ldc + i] += av * bv; else img[(size_t)j * m + i] += av * bv;
+        }
+        ++ci;
+      }
+    }
+  }
+  if (tc != T_F32) {
+    for (i = 0; i < m; ++i) for (j = 0; j < n; ++j) {
+      if (tc == T_BF16) ((uint16_t*)c)[j * ldc + i] = oracle_f32_to_bf16(img[(size_t)j * m + i]); else ((uint16_t*)c)[j * ldc + i] = oracle_f32_to_f16(img[(size_t)j * m + i]);
+    }
+    free(img);
+  }
+  return 0;
+}
+
 /* ---- fused form (libxsmm_dispatch_brgemm_ext): reference :255-372, 2803-2842 ------------------------------------------
  * fuse = {colbias (0/1), cp_op (0 none, 5 RELU, 9 SIGMOID), relu bitmask (0/1), vnni_c (0/1)}. With any of the first three and a
  * C type other than F32 the product is accumulated in an f32 image of C (bias column broadcast, plus the old C when beta=1),

@@ -60,6 +60,42 @@ REF_API int ref_gemm(const int* dims, const int* types, unsigned int flags, int 
   }
 }
 
+/* packed dense GEMM through the reference's JIT; kind 0: libxsmm_create_packed_gemm, 1: _ac_rm, 2: _bc_rm */
+REF_API int ref_packed_dense(int kind, int dtype, const int* dims, unsigned int flags, int packed_width, void* a, void* b, void* c)
+{
+  const libxsmm_gemm_shape shape = libxsmm_create_gemm_shape(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5],
+    (libxsmm_datatype)dtype, (libxsmm_datatype)dtype, (libxsmm_datatype)dtype, (libxsmm_datatype)dtype);
+  libxsmm_gemm_param p; libxsmm_gemmfunction k;
+  libxsmm_init();
+  k = (kind == 0) ? libxsmm_create_packed_gemm(shape, flags, 0, packed_width)
+    : ((kind == 1) ? libxsmm_create_packed_gemm_ac_rm(shape, flags, 0, packed_width) : libxsmm_create_packed_gemm_bc_rm(shape, flags, 0, packed_width));
+  if (k == NULL) return 1;
+  memset(&p, 0, sizeof(p));
+  p.a.primary = a; p.b.primary = b; p.c.primary = c;
+  k(&p);
+  libxsmm_release_kernel((const void*)k);
+  return 0;
+}
+
+/* aux_kind 1: int4 A with zero points (aux -> a.quaternary, flags completed like samples/xgemm/gemm_kernel.c:2892-2900);
+ * aux_kind 2: bitmap-compressed A (aux -> a.secondary). C reference kernel only. */
+REF_API int ref_gemm_aux(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a, long long stride_b,
+                         unsigned long long br, void* a, void* b, void* c, int aux_kind, void* aux)
+{
+  const libxsmm_gemm_shape shape = libxsmm_create_gemm_shape(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5],
+    (libxsmm_datatype)types[0], (libxsmm_datatype)types[1], (libxsmm_datatype)types[3], (libxsmm_datatype)types[2]);
+  const libxsmm_gemm_batch_reduce_config cfg = ref_brcfg(br_type, stride_a, stride_b);
+  libxsmm_gemm_param p; unsigned long long brv = br; libxsmm_descriptor_blob blob; const libxsmm_gemm_descriptor* desc;
+  libxsmm_init();
+  memset(&p, 0, sizeof(p));
+  p.op.tertiary = &brv; p.a.primary = a; p.b.primary = b; p.c.primary = c;
+  if (aux_kind == 1) p.a.quaternary = aux; else p.a.secondary = aux;
+  desc = libxsmm_gemm_descriptor_init_brgemm(&blob, shape, flags, 0, cfg);
+  if (desc == NULL) return 1;
+  libxsmm_reference_gemm(&p, desc);
+  return 0;
+}
+
 /* fused form: fuse = {colbias, cp_op (0 / RELU / SIGMOID), relu bitmask, vnni_c}; same calling convention as oracle_gemm_ext */
 REF_API int ref_gemm_ext(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a, long long stride_b,
                          unsigned long long br, void* a, void* b, void* c, long long* offs_a, long long* offs_b, float scf,

@@ -165,3 +165,15 @@ def run_gemm_ext(side, case, ops, fuse, colbias, mask, c):
     return side["gemm_ext"](iarr(*case.dims), iarr(*case.types), case.flags, case.br_type, ops.stride_a, ops.stride_b, case.br,
                             ops.a.ctypes.data, ops.b.ctypes.data, c.ctypes.data, None, None, 0.0, iarr(*fuse),
                             colbias.ctypes.data if colbias is not None else None, mask.ctypes.data if mask is not None else None)
+
+
+def packed_dense_case(rng, kind, dtype, M, N, K, P, pad=0):
+    """kind 0: C[n][m][p] += A[k][m][p] B[n][k][p]; 1 (ac_rm): C[m][n][p] += A[m][k][p] B[k][n]; 2 (bc_rm): C[m][n][p] += A[m][k] B[k][n][p]"""
+    if kind == 0:
+        lda, ldb, ldc = M + pad, K + pad, M + pad
+        a = gen.values(rng, K * lda * P, dtype); b = gen.values(rng, N * ldb * P, dtype); c0 = gen.values(rng, N * ldc * P, dtype)
+    else:
+        lda, ldb, ldc = K + pad, N + pad, N + pad
+        a = gen.values(rng, M * lda * (P if kind == 1 else 1), dtype); b = gen.values(rng, K * ldb * (1 if kind == 1 else P), dtype)
+        c0 = gen.values(rng, M * ldc * P, dtype)
+    return (M, N, K, lda, ldb, ldc), a, b, c0

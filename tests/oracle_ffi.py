@@ -38,6 +38,7 @@ def _bind(lib, prefix):
     sig("fsspmdm", _I, [_I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P])
     sig("bcsc", _I, [_P, _P, _U, _P, _P, _P, _P, _P])
     sig("packed_sp", _I, [_I, _I, _P, _U, _I, _P, _P, _P, _P, _P, _P])
+    sig("packed_dense", _I, [_I, _I, _P, _U, _I, _P, _P, _P])
     return ns
 
 
@@ -51,6 +52,12 @@ for _n, _r, _a in (("f32_to_bf16", C.c_ushort, [_F]), ("f32_to_f16", C.c_ushort,
     oracle[_n] = _fn
 oracle_lib.oracle_meltw.restype, oracle_lib.oracle_meltw.argtypes = _I, [_P, _P, _I]
 oracle["meltw"] = oracle_lib.oracle_meltw          # 0 = computed, 2 = op not restated (the reference stays the only checker)
+oracle_lib.oracle_gemm_i4.restype = _I
+oracle_lib.oracle_gemm_i4.argtypes = [_P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _P]
+oracle["gemm_i4"] = oracle_lib.oracle_gemm_i4
+oracle_lib.oracle_gemm_bitmap.restype = _I
+oracle_lib.oracle_gemm_bitmap.argtypes = [_P, _P, _U, _P, _P, _P, _P]
+oracle["gemm_bitmap"] = oracle_lib.oracle_gemm_bitmap
 oracle_lib.oracle_gemm_ext.restype = _I
 oracle_lib.oracle_gemm_ext.argtypes = [_P, _P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _P, _P, _F, _P, _P, _P]
 oracle["gemm_ext"] = oracle_lib.oracle_gemm_ext
@@ -70,6 +77,9 @@ if os.path.exists(REF_SO):
         ref[_n] = _fn
     ref_lib.ref_meltw.restype, ref_lib.ref_meltw.argtypes = _I, [_P, _P, _I]
     ref["meltw"] = ref_lib.ref_meltw
+    ref_lib.ref_gemm_aux.restype = _I
+    ref_lib.ref_gemm_aux.argtypes = [_P, _P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _I, _P]
+    ref["gemm_aux"] = ref_lib.ref_gemm_aux
     ref_lib.ref_gemm_ext.restype = _I
     ref_lib.ref_gemm_ext.argtypes = [_P, _P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I]
     ref["gemm_ext"] = lambda *a: ref_lib.ref_gemm_ext(*a, 0)

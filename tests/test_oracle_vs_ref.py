@@ -181,3 +181,81 @@ def test_fused_gemm_restatement_matches_reference(types):
                         outs.append((c, mk))
                     assert np.array_equal(outs[0][0].view(np.uint8), outs[1][0].view(np.uint8)), (case, fuse)
                     assert np.array_equal(outs[0][1], outs[1][1]), (case, fuse, "mask")
+
+
+I4X2 = 18
+FLAG_COL_VEC_ZPT, FLAG_INTLV_A, FLAG_BITMASK_A, FLAG_MXK_ZPT = 131072, 262144, 524288, 1048576
+
+
+def int4_case(rng, m, n, k, br, pad=0):
+    lda, ldb, ldc = m + pad, k + pad, m + pad
+    blk_a, blk_b = (k // 8) * lda * 4, n * ldb
+    a = rng.integers(0, 256, size=blk_a * br, dtype=np.uint8)
+    b = rng.integers(0, 256, size=blk_b * br, dtype=np.uint8)
+    zpt = rng.integers(0, 16, size=max(m, (blk_a * 2 // k) * br + m), dtype=np.uint8)
+    c0 = rng.integers(-1000, 1000, size=n * ldc).astype(np.int32)
+    return (m, n, k, lda, ldb, ldc), a, b, zpt, c0, blk_a, blk_b
+
+
+@needs_ref
+def test_int4_gemm_restatement_is_bit_exact():
+    """U4 x U8 -> I32 with zero points (reference :1273-1321): plain and stride batch-reduce, beta 0/1"""
+    rng = np.random.default_rng(90)
+    for (m, n, k, pad) in ((32, 16, 32, 0), (13, 6, 8, 3), (64, 64, 64, 0), (5, 3, 16, 1)):
+        for br_type, br in ((0, 1), (3, 4)):
+            for beta0 in (0, 1):
+                dims, a, b, zpt, c0, blk_a, blk_b = int4_case(rng, m, n, k, br, pad)
+                flags = (cases.FLAG_BETA_0 if beta0 else 0) | cases.FLAG_VNNI_A | FLAG_INTLV_A | (FLAG_MXK_ZPT if br_type else FLAG_COL_VEC_ZPT)
+                c_o, c_r = c0.copy(), c0.copy()
+                assert oracle["gemm_i4"](iarr(*dims), flags, br_type, blk_a, blk_b, br, a.ctypes.data, b.ctypes.data, c_o.ctypes.data, zpt.ctypes.data) == 0
+                assert ref["gemm_aux"](iarr(*dims), iarr(I4X2, gen.U8, gen.I32, gen.I32), flags, br_type, blk_a, blk_b, br, a.ctypes.data, b.ctypes.data,
+                                       c_r.ctypes.data, 1, zpt.ctypes.data) == 0
+                assert np.array_equal(c_o, c_r), (dims, br_type, beta0)
+
+
+def bitmap_case(rng, m, n, k, ta, tb, tc, density=0.4, pad=0):
+    kb = 1 if ta == gen.F32 else 2
+    ldb, ldc = k + pad, m + pad
+    bits = rng.random((k // kb) * m * kb) < density
+    bitmap = np.packbits(bits, bitorder="little")
+    bitmap = np.concatenate([bitmap, np.zeros(8, dtype=np.uint8)])
+    a = gen.values(rng, int(bits.sum()) + 4, ta)
+    b = gen.values(rng, n * ldb, tb); c0 = gen.values(rng, n * ldc, tc)
+    return (m, n, k, m, ldb, ldc), a, b, bitmap, c0
+
+
+@needs_ref
+def test_bitmap_sparse_a_restatement_is_bit_exact():
+    """bitmap-compressed A (DECOMPRESS_A_VIA_BITMASK, reference :857-948): F32 and 16-bit operands, beta 0/1"""
+    rng = np.random.default_rng(91)
+    for ta, tb, tc in ((gen.F32, gen.F32, gen.F32), (gen.BF16, gen.BF16, gen.F32), (gen.BF16, gen.BF16, gen.BF16), (gen.F16, gen.F16, gen.F16)):
+        for (m, n, k, pad) in ((32, 16, 32, 0), (16, 6, 8, 3), (64, 64, 64, 0)):
+            for beta0 in (0, 1):
+                dims, a, b, bitmap, c0 = bitmap_case(rng, m, n, k, ta, tb, tc, pad=pad)
+                flags = (cases.FLAG_BETA_0 if beta0 else 0) | FLAG_BITMASK_A | (cases.FLAG_VNNI_A if ta != gen.F32 else 0)
+                c_o, c_r = c0.copy(), c0.copy()
+                assert oracle["gemm_bitmap"](iarr(*dims), iarr(ta, tb, gen.F32, tc), flags, a.ctypes.data, b.ctypes.data, c_o.ctypes.data, bitmap.ctypes.data) == 0
+                assert ref["gemm_aux"](iarr(*dims), iarr(ta, tb, gen.F32, tc), flags, 0, 0, 0, 1, a.ctypes.data, b.ctypes.data, c_r.ctypes.data, 2, bitmap.ctypes.data) == 0
+                assert np.array_equal(c_o.view(np.uint8), c_r.view(np.uint8)), (dims, (ta, tb, tc), beta0)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_packed_dense_oracle_matches_reference_jit(kind):
+    """libxsmm_create_packed_gemm / _ac_rm / _bc_rm (include/libxsmm.h:195-214): restated driver golds against the reference JIT"""
+    rng = np.random.default_rng(94)
+    ran = 0
+    for dtype, eps in ((gen.F32, 3e-6), (gen.F64, 1e-14)):
+        for (M, N, K, P, pad) in ((9, 9, 9, 8, 0), (20, 9, 35, 16, 0), (56, 9, 56, 16, 0), (4, 3, 5, 8, 0), (16, 16, 16, 8, 0)):
+            if dtype == gen.F32 and P == 8:
+                P = 16
+            for beta0 in (0, 1):
+                dims, a, b, c0 = cases.packed_dense_case(rng, kind, dtype, M, N, K, P, pad)
+                flags = cases.FLAG_BETA_0 if beta0 else 0
+                c_o, c_r = c0.copy(), c0.copy()
+                assert oracle["packed_dense"](kind, dtype, iarr(*dims), flags, P, a.ctypes.data, b.ctypes.data, c_o.ctypes.data) == 0
+                if ref["packed_dense"](kind, dtype, iarr(*dims), flags, P, a.ctypes.data, b.ctypes.data, c_r.ctypes.data) != 0:
+                    continue
+                ran += 1
+                assert gen.normf_rel(c_r, c_o) <= eps, (kind, dtype, dims, P, beta0)
+    assert ran > 0, "the reference JIT built none of the cases"

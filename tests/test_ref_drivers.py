@@ -59,13 +59,13 @@ def _run(name, *args, timeout=300):
 
 
 @pytest.mark.gpu
-def test_hello_runs_and_prints_the_sum():
-    """samples/hello/hello.c: 1000 x (C += A_i * B_i), prints the sum of C's entries"""
+def test_hello_runs():
+    """samples/hello/hello.c: dispatches one F64 13x5x7 kernel and calls it 1000 times on malloc'ed (host) matrices, C += A_i * B_i;
+    the program prints nothing and returns 0 -- what is checked here is that an unmodified caller runs to completion on this
+    library (host operands staged per call) without the library reporting an error (LIBXSMM_VERBOSE=1 would print it)"""
     p = _run("hello")
-    assert p.returncode == 0, p.stderr[-800:]
-    # batch of 1000 products 13x5x7 with A[i] = 1/((i+1)%25+1)... the program prints one number; it must be finite and non-zero
-    nums = [float(t) for t in p.stdout.replace("\n", " ").split() if t.replace(".", "", 1).replace("-", "", 1).replace("e", "", 1).replace("+", "", 1).isdigit()]
-    assert nums and all(abs(x) > 0 and x == x for x in nums), p.stdout
+    assert p.returncode == 0, (p.stdout[-400:], p.stderr[-800:])
+    assert "error" not in p.stderr.lower(), p.stderr[-800:]
 
 
 @pytest.mark.gpu

@@ -230,3 +230,27 @@ def test_packed_csr_csc_all_four_kinds(kind, dtype):
             X.call_gemm(k, a.ctypes.data, b.ctypes.data, c_h.ctypes.data); X.check()
             assert np.array_equal(c_h, got), (kind, "host pointers")
             X.libxsmm_release_kernel(k)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("dtype", [gen.F32, gen.F64])
+def test_packed_dense_gemm_matches_oracle(kind, dtype):
+    """packed dense GEMM, the three layouts of include/libxsmm.h:195-214; FMA vs separate multiply-add => tolerance"""
+    rng = np.random.default_rng(95)
+    create = (X.libxsmm_create_packed_gemm, X.libxsmm_create_packed_gemm_ac_rm, X.libxsmm_create_packed_gemm_bc_rm)[kind]
+    for (M, N, K, P, pad) in ((9, 9, 9, 8, 0), (20, 9, 35, 16, 2), (56, 9, 56, 64, 0), (4, 3, 5, 1, 1)):
+        for beta0 in (0, 1):
+            dims, a, b, c0 = cases.packed_dense_case(rng, kind, dtype, M, N, K, P, pad)
+            flags = cases.FLAG_BETA_0 if beta0 else 0
+            k = create(X.libxsmm_create_gemm_shape(*dims, dtype, dtype, dtype, dtype), flags, 0, P)
+            assert k, (kind, dims)
+            want = c0.copy()
+            assert oracle["packed_dense"](kind, dtype, iarr(*dims), flags, P, a.ctypes.data, b.ctypes.data, want.ctypes.data) == 0
+            d_a, d_b, d_c = dev(a), dev(b), dev(c0)
+            X.call_gemm(k, d_a, d_b, d_c); X.check()
+            got = host(d_c, gen.NP_OF[dtype])
+            assert gen.normf_rel(want, got) <= (3e-6 if dtype == gen.F32 else 1e-14), (kind, dims, P, beta0)
+            hc = c0.copy()
+            X.call_gemm(k, a.ctypes.data, b.ctypes.data, hc.ctypes.data); X.check()
+            assert np.array_equal(hc, got), "host operands through the staging path"
+            X.libxsmm_release_kernel(k)
