@@ -110,6 +110,27 @@ LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csr(const libxsmm_
 LIBXSMM_API libxsmm_gemmfunction libxsmm_create_packed_spgemm_csc(const libxsmm_gemm_shape gemm_shape,
   const libxsmm_bitfield gemm_flags, const libxsmm_bitfield prefetch_flags, const libxsmm_blasint packed_width,
   const unsigned int* column_ptr, const unsigned int* row_idx, const void* values);
+/* ---- matrix equations: a tree of element-wise / reduction nodes built in pre-order, evaluated by one call (reference
+ * include/libxsmm.h:149-162). GEMM nodes are not available in this backend (dispatch returns NULL for such trees). ---- */
+LIBXSMM_API libxsmm_blasint libxsmm_meqn_create(void);
+LIBXSMM_API libxsmm_meqn_arg_shape libxsmm_create_meqn_arg_shape(const libxsmm_blasint m, const libxsmm_blasint n, const libxsmm_blasint ld, const libxsmm_datatype type);
+LIBXSMM_API libxsmm_matrix_arg_attributes libxsmm_create_matrix_arg_attributes(const libxsmm_matrix_arg_type type, const libxsmm_matrix_arg_set_type set_type,
+  const libxsmm_blasint set_cardinality_hint, const libxsmm_blasint set_stride_hint);
+LIBXSMM_API libxsmm_meqn_arg_metadata libxsmm_create_meqn_arg_metadata(const libxsmm_blasint eqn_idx, const libxsmm_blasint in_arg_pos);
+LIBXSMM_API libxsmm_meqn_op_metadata libxsmm_create_meqn_op_metadata(const libxsmm_blasint eqn_idx, const libxsmm_blasint op_arg_pos);
+LIBXSMM_API int libxsmm_meqn_push_back_arg(const libxsmm_meqn_arg_metadata arg_metadata, const libxsmm_meqn_arg_shape arg_shape, libxsmm_matrix_arg_attributes arg_attr);
+LIBXSMM_API int libxsmm_meqn_push_back_unary_op(const libxsmm_meqn_op_metadata op_metadata, const libxsmm_meltw_unary_type type, const libxsmm_datatype dtype, const libxsmm_bitfield flags);
+LIBXSMM_API int libxsmm_meqn_push_back_binary_op(const libxsmm_meqn_op_metadata op_metadata, const libxsmm_meltw_binary_type type, const libxsmm_datatype dtype, const libxsmm_bitfield flags);
+LIBXSMM_API int libxsmm_meqn_push_back_ternary_op(const libxsmm_meqn_op_metadata op_metadata, const libxsmm_meltw_ternary_type type, const libxsmm_datatype dtype, const libxsmm_bitfield flags);
+LIBXSMM_API void libxsmm_meqn_tree_print(const libxsmm_blasint idx);
+LIBXSMM_API void libxsmm_meqn_rpn_print(const libxsmm_blasint idx);
+LIBXSMM_API libxsmm_meqn_function libxsmm_dispatch_meqn(const libxsmm_blasint idx, const libxsmm_meqn_arg_shape out_shape);
+
+/* ---- user key/value registry (reference include/libxsmm.h:106-125): binary keys up to LIBXSMM_DESCRIPTOR_MAXSIZE bytes ---- */
+LIBXSMM_API void* libxsmm_xregister(const void* key, size_t key_size, size_t value_size, const void* value_init);
+LIBXSMM_API void* libxsmm_xdispatch(const void* key, size_t key_size);
+LIBXSMM_API void libxsmm_xrelease(const void* key, size_t key_size);
+
 /* packed DENSE GEMM (EDGE/SeisSol): every matrix element is a vector of `packed_width` independent problems (innermost);
  * F32 / F64; caller-owned handles (libxsmm_release_kernel). Layouts [row][col][packed] with the leading dimensions counted in vectors:
  *   libxsmm_create_packed_gemm        C[n][m][p] (+)= A[k][m][p] * B[n][k][p]

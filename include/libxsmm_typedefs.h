@@ -227,6 +227,26 @@ typedef struct libxsmm_matrix_op_arg {
   void *primary, *secondary, *tertiary, *quaternary;
 } libxsmm_matrix_op_arg;
 
+/* ---- matrix equations (include/libxsmm_typedefs.h:586-694 of the reference): argument description and call structs ---- */
+typedef enum libxsmm_matrix_arg_type { LIBXSMM_MATRIX_ARG_TYPE_SINGULAR = 0, LIBXSMM_MATRIX_ARG_TYPE_SET = 1 } libxsmm_matrix_arg_type;
+typedef enum libxsmm_matrix_arg_set_type {
+  LIBXSMM_MATRIX_ARG_SET_TYPE_NONE = 0, LIBXSMM_MATRIX_ARG_SET_TYPE_ABS_ADDRESS = 1, LIBXSMM_MATRIX_ARG_SET_TYPE_OFFSET_BASE = 2,
+  LIBXSMM_MATRIX_ARG_SET_TYPE_STRIDE_BASE = 3
+} libxsmm_matrix_arg_set_type;
+typedef struct libxsmm_meqn_arg_shape { libxsmm_blasint m, n, ld; libxsmm_datatype type; } libxsmm_meqn_arg_shape;
+typedef struct libxsmm_matrix_arg_attributes {
+  libxsmm_matrix_arg_type type; libxsmm_matrix_arg_set_type set_type; libxsmm_blasint set_cardinality_hint, set_stride_hint;
+} libxsmm_matrix_arg_attributes;
+typedef struct libxsmm_meqn_op_metadata { libxsmm_blasint eqn_idx, op_arg_pos; } libxsmm_meqn_op_metadata;
+typedef struct libxsmm_meqn_arg_metadata { libxsmm_blasint eqn_idx, in_arg_pos; } libxsmm_meqn_arg_metadata;
+typedef struct libxsmm_meqn_param {
+  const libxsmm_matrix_op_arg* ops_args;    /* per-operation parameters, indexed by op_arg_pos */
+  const libxsmm_matrix_arg* inputs;         /* input matrices, indexed by in_arg_pos */
+  libxsmm_matrix_arg output;
+} libxsmm_meqn_param;
+typedef void (*libxsmm_meqn_function)(const libxsmm_meqn_param* in_struct);
+
+
 typedef struct libxsmm_meltw_unary_shape {
   libxsmm_blasint m, n, ldi, ldo;
   libxsmm_datatype in0_type, out_type, comp_type;

@@ -122,6 +122,22 @@ class MeltwTernaryParam(C.Structure):
     _fields_ = [("op", MatrixOpArg), ("in0", MatrixArg), ("in1", MatrixArg), ("in2", MatrixArg), ("out", MatrixArg)]
 
 
+class MeqnArgShape(C.Structure):
+    _fields_ = [("m", C.c_int), ("n", C.c_int), ("ld", C.c_int), ("type", C.c_int)]
+
+
+class MatrixArgAttributes(C.Structure):
+    _fields_ = [("type", C.c_int), ("set_type", C.c_int), ("set_cardinality_hint", C.c_int), ("set_stride_hint", C.c_int)]
+
+
+class MeqnMetadata(C.Structure):
+    _fields_ = [("eqn_idx", C.c_int), ("pos", C.c_int)]
+
+
+class MeqnParam(C.Structure):
+    _fields_ = [("ops_args", C.c_void_p), ("inputs", C.c_void_p), ("output", MatrixArg)]
+
+
 class GemmShape(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("m", "n", "k", "lda", "ldb", "ldc", "a_in_type", "b_in_type", "out_type", "comp_type")]
 
@@ -216,6 +232,20 @@ libxsmm_dispatch_tilecfg_gemm = _sig("libxsmm_dispatch_tilecfg_gemm", _P, [GemmS
 libxsmm_dispatch_meltw_unary = _sig("libxsmm_dispatch_meltw_unary", _P, [_I, MeltwUnaryShape, _U])
 libxsmm_dispatch_meltw_binary = _sig("libxsmm_dispatch_meltw_binary", _P, [_I, MeltwBinaryShape, _U])
 libxsmm_dispatch_meltw_ternary = _sig("libxsmm_dispatch_meltw_ternary", _P, [_I, MeltwTernaryShape, _U])
+libxsmm_meqn_create = _sig("libxsmm_meqn_create", _I, [])
+libxsmm_create_meqn_arg_shape = _sig("libxsmm_create_meqn_arg_shape", MeqnArgShape, [_I, _I, _I, _I])
+libxsmm_create_matrix_arg_attributes = _sig("libxsmm_create_matrix_arg_attributes", MatrixArgAttributes, [_I, _I, _I, _I])
+libxsmm_create_meqn_arg_metadata = _sig("libxsmm_create_meqn_arg_metadata", MeqnMetadata, [_I, _I])
+libxsmm_create_meqn_op_metadata = _sig("libxsmm_create_meqn_op_metadata", MeqnMetadata, [_I, _I])
+libxsmm_meqn_push_back_arg = _sig("libxsmm_meqn_push_back_arg", _I, [MeqnMetadata, MeqnArgShape, MatrixArgAttributes])
+libxsmm_meqn_push_back_unary_op = _sig("libxsmm_meqn_push_back_unary_op", _I, [MeqnMetadata, _I, _I, _U])
+libxsmm_meqn_push_back_binary_op = _sig("libxsmm_meqn_push_back_binary_op", _I, [MeqnMetadata, _I, _I, _U])
+libxsmm_meqn_push_back_ternary_op = _sig("libxsmm_meqn_push_back_ternary_op", _I, [MeqnMetadata, _I, _I, _U])
+libxsmm_dispatch_meqn = _sig("libxsmm_dispatch_meqn", _P, [_I, MeqnArgShape])
+MEQN_FN = C.CFUNCTYPE(None, C.POINTER(MeqnParam))
+libxsmm_xregister = _sig("libxsmm_xregister", _P, [_P, C.c_size_t, C.c_size_t, _P])
+libxsmm_xdispatch = _sig("libxsmm_xdispatch", _P, [_P, C.c_size_t])
+libxsmm_xrelease = _sig("libxsmm_xrelease", None, [_P, C.c_size_t])
 libxsmm_create_packed_gemm = _sig("libxsmm_create_packed_gemm", _P, [GemmShape, _U, _U, _I])
 libxsmm_create_packed_gemm_ac_rm = _sig("libxsmm_create_packed_gemm_ac_rm", _P, [GemmShape, _U, _U, _I])
 libxsmm_create_packed_gemm_bc_rm = _sig("libxsmm_create_packed_gemm_bc_rm", _P, [GemmShape, _U, _U, _I])

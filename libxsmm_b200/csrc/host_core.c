@@ -710,6 +710,7 @@ void xb_invoke(int slot, const void* param) {
     case XB_KIND_SP_A_CSR: case XB_KIND_SP_B_CSR: case XB_KIND_SP_B_CSC: case XB_KIND_SP_C_CSC:
     case XB_KIND_BCSC: case XB_KIND_SREG: case XB_KIND_PK_GEMM: case XB_KIND_PK_AC_RM: case XB_KIND_PK_BC_RM:
       xb_invoke_sparse(s, (const libxsmm_gemm_param*)param); break;
+    case XB_KIND_MEQN: xb_invoke_meqn(s, param); break;
     default:
       if (libxsmm_verbosity != 0) fprintf(stderr, "LIBXSMM-B200 ERROR: call through a released kernel handle\n");
   }
@@ -796,7 +797,8 @@ LIBXSMM_API void libxsmm_release_kernel(const void* kernel) {
     return;
   }
   pthread_mutex_lock(&g_lock);
-  if (s->kind >= XB_KIND_SP_A_CSR) xb_sparse_release(&s->u.sp);
+  if (s->kind == XB_KIND_MEQN) xb_meqn_release(s->u.sp.work);
+  else if (s->kind >= XB_KIND_SP_A_CSR) xb_sparse_release(&s->u.sp);
   memset(s, 0, sizeof(*s));
   pthread_mutex_unlock(&g_lock);
 }

@@ -27,7 +27,8 @@ enum {
   XB_KIND_SREG,          /* fsspmdm kernel: sparse A fixed at create time, row-major B/C */
   XB_KIND_PK_GEMM,       /* packed dense: C[N][M][P] += A[K][M][P] * B[N][K][P] */
   XB_KIND_PK_AC_RM,      /* packed dense: C[M][N][P] += A[M][K][P] * B[K][N] */
-  XB_KIND_PK_BC_RM       /* packed dense: C[M][N][P] += A[M][K] * B[K][N][P] */
+  XB_KIND_PK_BC_RM,      /* packed dense: C[M][N][P] += A[M][K] * B[K][N][P] */
+  XB_KIND_MEQN           /* matrix equation: tree of mateltwise nodes (host_meqn.c), plan in u.sp.work */
 };
 
 /* normalised dense-GEMM descriptor == registry key for GEMM kinds (memcmp'd, so zero-filled) */
@@ -162,6 +163,8 @@ typedef struct xb_meltw_args {
   void* rng;                 /* DROPOUT: 4 x 16 words of generator state (device copy, updated by the kernel) */
   float* rnd;                /* DROPOUT: scratch for the uniform numbers, 16 per group of rows */
 } xb_meltw_args;
+void xb_invoke_meqn(const struct xb_slot* s, const void* param);
+void xb_meqn_release(void* work);
 int xb_meltw_supported(const xb_meltw_desc* d);                          /* pure host logic */
 int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a);
 int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_total);

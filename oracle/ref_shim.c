@@ -60,6 +60,30 @@ REF_API int ref_gemm(const int* dims, const int* types, unsigned int flags, int 
   }
 }
 
+/* matrix equation through the reference (JIT): nodes in pre-order, 8 ints each {type 1 arg / 2 unary / 3 binary / 4 ternary, op, dtype,
+ * flags, pos, m, n, ld}; out = {m, n, ld, type}; inputs[] = the argument matrices */
+REF_API int ref_meqn(const int* nodes, int nnodes, const int* out, void** inputs, int ninputs, void* output)
+{
+  libxsmm_blasint eq; int i; libxsmm_meqn_function f; libxsmm_meqn_param p; libxsmm_matrix_arg args[16];
+  libxsmm_init();
+  eq = libxsmm_meqn_create();
+  for (i = 0; i < nnodes; ++i) {
+    const int* nd = nodes + 8 * i;
+    if (nd[0] == 1) libxsmm_meqn_push_back_arg(libxsmm_create_meqn_arg_metadata(eq, nd[4]), libxsmm_create_meqn_arg_shape(nd[5], nd[6], nd[7], (libxsmm_datatype)nd[2]),
+                                               libxsmm_create_matrix_arg_attributes(LIBXSMM_MATRIX_ARG_TYPE_SINGULAR, LIBXSMM_MATRIX_ARG_SET_TYPE_NONE, 0, 0));
+    else if (nd[0] == 2) libxsmm_meqn_push_back_unary_op(libxsmm_create_meqn_op_metadata(eq, nd[4]), (libxsmm_meltw_unary_type)nd[1], (libxsmm_datatype)nd[2], (libxsmm_bitfield)nd[3]);
+    else if (nd[0] == 3) libxsmm_meqn_push_back_binary_op(libxsmm_create_meqn_op_metadata(eq, nd[4]), (libxsmm_meltw_binary_type)nd[1], (libxsmm_datatype)nd[2], (libxsmm_bitfield)nd[3]);
+    else libxsmm_meqn_push_back_ternary_op(libxsmm_create_meqn_op_metadata(eq, nd[4]), (libxsmm_meltw_ternary_type)nd[1], (libxsmm_datatype)nd[2], (libxsmm_bitfield)nd[3]);
+  }
+  f = libxsmm_dispatch_meqn(eq, libxsmm_create_meqn_arg_shape(out[0], out[1], out[2], (libxsmm_datatype)out[3]));
+  if (f == NULL || ninputs > 16) return 1;
+  memset(&p, 0, sizeof(p)); memset(args, 0, sizeof(args));
+  for (i = 0; i < ninputs; ++i) args[i].primary = inputs[i];
+  p.inputs = args; p.output.primary = output;
+  f(&p);
+  return 0;
+}
+
 /* packed dense GEMM through the reference's JIT; kind 0: libxsmm_create_packed_gemm, 1: _ac_rm, 2: _bc_rm */
 REF_API int ref_packed_dense(int kind, int dtype, const int* dims, unsigned int flags, int packed_width, void* a, void* b, void* c)
 {

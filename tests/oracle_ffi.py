@@ -77,6 +77,9 @@ if os.path.exists(REF_SO):
         ref[_n] = _fn
     ref_lib.ref_meltw.restype, ref_lib.ref_meltw.argtypes = _I, [_P, _P, _I]
     ref["meltw"] = ref_lib.ref_meltw
+    ref_lib.ref_meqn.restype = _I
+    ref_lib.ref_meqn.argtypes = [_P, _I, _P, _P, _I, _P]
+    ref["meqn"] = ref_lib.ref_meqn
     ref_lib.ref_gemm_aux.restype = _I
     ref_lib.ref_gemm_aux.argtypes = [_P, _P, _U, _I, _LL, _LL, _ULL, _P, _P, _P, _I, _P]
     ref["gemm_aux"] = ref_lib.ref_gemm_aux
