@@ -216,9 +216,11 @@ def run_ours(args):
             # every rank drives its own GPU over its own PCIe link at the same time; whole-job value = all tiles / slowest rank
             bind_to_gpu_numa_node(torch, local)
             out["e2e"] = brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, c_dev=c, dist=dist, world=world)
+        if world > 1 and not args.no_also:
+            out["strong"] = strong_scaling(X, torch, pk, args, dist, world, rank)
         if rank == 0 and not args.no_also:
             out["also"] = {}
-            for name, fn in (("fsspmdm", also_fsspmdm), ("bcsc", also_bcsc)):
+            for name, fn in (("fsspmdm", also_fsspmdm), ("bcsc", also_bcsc), ("sweep", sweep), ("meltw", also_meltw)):
                 try:
                     out["also"][name] = fn(X, torch, pk, args)
                 except Exception as e:  # secondary numbers must not take the headline down
@@ -303,9 +305,9 @@ def brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, steps=3, c_dev=None, d
                     "blocking call, max over ranks, best of %d; bytes are the whole job's" % steps}
 
 
-def also_fsspmdm(X, torch, pk, args, full=False):
+def also_fsspmdm(X, torch, pk, args, full=False, n_cols=1000000, dist=None):
     import numpy as np
-    Mf, Kf, Nf = 32, 128, 1000000
+    Mf, Kf, Nf = 32, 128, n_cols
     rng = np.random.default_rng(555)
     a = ((rng.integers(-5, 6, size=Mf * Kf) / 10.0) * (rng.random(Mf * Kf) < 0.15)).astype(np.float32)
     nnz = int(np.count_nonzero(a))
@@ -320,14 +322,14 @@ def also_fsspmdm(X, torch, pk, args, full=False):
     step(); X.check()
     checked = fsspmdm_check(torch, a, b, c, Mf, Kf, Nf)
     steps = max(5, args.steps)
-    total_ms, per = time_steps(torch, step, steps, 3)
+    total_ms, per = time_steps(torch, step, steps, 3, dist)
     X.check()
-    ms = sorted(per)[len(per) // 2]
+    ms = sorted(per)[len(per) // 2] if dist is None else total_ms / steps
     bytes_alg = 4.0 * (Kf * Nf + Mf * Nf)
     ach = bytes_alg / (ms * 1e-3) / 1e9
     X.libxsmm_fsspmdm_destroy(h)
     cpu = None
-    if full or not getattr(args, "no_cpu", False):
+    if dist is None and (full or not getattr(args, "no_cpu", False)):
         cpu = cpu_baseline_fsspmdm(a, Mf, Kf, nnz)
     return {"cpu_baseline": cpu, "metric": "fsspmdm GFLOP/s (f32 M=32 K=128 N=1e6, 15% nnz)", "value": 2.0 * nnz * Nf / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (sparse)",
             "dense_equiv_gflops": 2.0 * Mf * Kf * Nf / (ms * 1e-3) / 1e9, "ms_per_step": ms, "nnz": nnz, "oracle_check": checked,
@@ -375,7 +377,7 @@ def bcsc_check(torch, a, bv, c, colptr, rowidx, geo, mblocks, picks=None):
     return {"m_blocks": len(picks), "max_normf_rel": worst}
 
 
-def also_bcsc(X, torch, pk, args, full=False, mblocks=8192):
+def also_bcsc(X, torch, pk, args, full=False, mblocks=8192, dist=None):
     import numpy as np
     Mb, Kb, Nb, bk, bn = 32, 512, 512, 32, 32
     rng = np.random.default_rng(555)
@@ -403,14 +405,14 @@ def also_bcsc(X, torch, pk, args, full=False, mblocks=8192):
     assert variant in (1, 2), "BCSC bench did not take a tcgen05 kernel (variant %d)" % variant
     kname = "bcsc_ts_kernel<32,2>" if variant == 2 else "bcsc_tc_kernel<32>"
     steps = max(3, args.steps // 4)
-    total_ms, per = time_steps(torch, step, steps, 2)
+    total_ms, per = time_steps(torch, step, steps, 3, dist)
     X.check()
-    ms = sorted(per)[len(per) // 2]
+    ms = sorted(per)[len(per) // 2] if dist is None else total_ms / steps
     bytes_alg = 2.0 * (mblocks * Kb * Mb + mblocks * Nb * Mb) + 2.0 * nnzb * bk * bn
     ach = bytes_alg / (ms * 1e-3) / 1e9
     X.libxsmm_release_kernel(kernel)
     cpu = None
-    if mblocks == 8192 and (full or not getattr(args, "no_cpu", False)):
+    if dist is None and mblocks == 8192 and (full or not getattr(args, "no_cpu", False)):
         cpu = cpu_baseline_bcsc(colptr, rowidx, nnzb, (Mb, Kb, Nb, bk, bn))
     return {"cpu_baseline": cpu, "metric": "BCSC spmm GFLOP/s dense-equivalent (bf16, M=32 N=K=512, 32x32 blocks, 50%, m_blocks=8192)",
             "value": 2.0 * Mb * mblocks * Nb * Kb / (ms * 1e-3) / 1e9, "unit": "GFLOP/s (dense-equivalent)",
@@ -476,6 +478,76 @@ def sweep(X, torch, pk, args, batch=32768):
             "warmup": 3, "higher_is_better": True, "dtype": "u8/i8->i32, f16->f32", "data": "synthetic",
             "config": {"workload": "configs[4]: int8 and f16 GEMM m=n=k in {8,16,32,64,128}, batch=32768, br=1, beta=0, unique operands"},
             "points": pts, "roofline": {"bound": "hbm", "achieved": best["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": best["hbm_frac"], "traffic": None}}
+
+
+def strong_scaling(X, torch, pk, args, dist, world, rank):
+    """configs[3]/[2] as BASELINE.json words them: the FIXED job (BCSC m_blocks = 8192, fsspmdm N = 1e6) cut over the ranks with
+    shard_range -- contiguous ranges, nothing exchanged on the data path. Every rank runs its range at the same time; the job time is
+    the slowest rank's (barrier + max). The one optional collective -- gathering the C ranges into one buffer on every rank with NCCL
+    over NVLink -- is timed separately."""
+    from libxsmm_b200.shard import shard_range
+    res = {"scaling": "strong", "ranks": world}
+    b0, b1 = shard_range(8192, world, rank, granule=4)              # 4 m_blocks of 32 rows form one 128-row MMA group
+    r = also_bcsc(X, torch, pk, args, mblocks=b1 - b0, dist=dist)
+    job_flops = 2.0 * 32 * 8192 * 512 * 512
+    res["bcsc"] = {"m_blocks_total": 8192, "m_blocks_this_rank": b1 - b0, "ms_per_step": r["ms_per_step"], "value": job_flops / (r["ms_per_step"] * 1e-3) / 1e9,
+                   "unit": "GFLOP/s (dense-equivalent, whole job)", "hbm_frac_per_gpu": r["roofline"]["frac"], "oracle_check": r.get("oracle_check")}
+    n0, n1 = shard_range(1000000, world, rank, granule=16)
+    f = also_fsspmdm(X, torch, pk, args, n_cols=n1 - n0, dist=dist)
+    res["fsspmdm"] = {"n_total": 1000000, "n_this_rank": n1 - n0, "ms_per_step": f["ms_per_step"], "value": 2.0 * f["nnz"] * 1000000 / (f["ms_per_step"] * 1e-3) / 1e9,
+                      "unit": "GFLOP/s (sparse, whole job)", "hbm_frac_per_gpu": f["roofline"]["frac"], "oracle_check": f.get("oracle_check")}
+    # the optional gather: every rank contributes its C range of the BCSC job (8192/world m_blocks x 32 x 512 bf16)
+    shard = torch.empty((b1 - b0) * 32 * 512, dtype=torch.bfloat16, device="cuda")
+    full = torch.empty(world * shard.numel(), dtype=torch.bfloat16, device="cuda")
+    for _ in range(3):
+        dist.all_gather_into_tensor(full, shard)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        dist.all_gather_into_tensor(full, shard)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gms = float(t.item())
+    res["gather"] = {"collective": "ncclAllGather of the C ranges (torch.distributed all_gather_into_tensor)", "bytes_received_per_rank": int((world - 1) * shard.numel() * 2),
+                     "ms": gms, "GBps_in_per_gpu": (world - 1) * shard.numel() * 2 / (gms * 1e-3) / 1e9}
+    return res
+
+
+def also_meltw(X, torch, pk, args, n=4096):
+    """three mateltwise kernels at 4096 x 4096 (> L2): f32 transpose, bf16 NORM->VNNI2 pack, f32 column-sum; roofline = operand + result bytes"""
+    import numpy as np
+    F32_, BF16_ = 1, 2
+    out = []
+    x32 = torch.randn(n * n, device="cuda"); y32 = torch.empty(n * n, device="cuda")
+    x16 = torch.randn(n * n, device="cuda").bfloat16(); y16 = torch.empty(n * n, dtype=torch.bfloat16, device="cuda")
+    r32 = torch.empty(n, device="cuda")
+    cases_ = [("transpose f32", X.MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT, 0, F32_, F32_, x32, y32, 8.0 * n * n),
+              ("norm->vnni2 bf16", X.MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2, 0, BF16_, BF16_, x16, y16, 4.0 * n * n),
+              ("reduce cols x_op_add f32", X.MELTW_TYPE_UNARY_REDUCE_X_OP_ADD, X.MELTW_FLAG_UNARY_REDUCE_COLS, F32_, F32_, x32, r32, 4.0 * n * n + 4.0 * n)]
+    for name, op, flags, tin, tout, src, dst, nbytes in cases_:
+        k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(n, n, n, n, tin, tout, F32_), flags)
+        if not k:
+            out.append({"op": name, "error": "dispatch returned NULL"}); continue
+        p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = src.data_ptr(), dst.data_ptr()
+        fn = X.MELTW_UNARY_FN(k)
+
+        def step():
+            fn(C.byref(p))
+        step(); X.check()
+        if name.startswith("transpose"):
+            assert torch.equal(dst.view(n, n)[:64, :64], src.view(n, n).t()[:64, :64]), "transpose check"
+        elif name.startswith("reduce"):
+            want = src.view(n, n).sum(0)
+            assert torch.allclose(dst, want, rtol=1e-3, atol=1e-2), "column-sum check"
+        total_ms, per = time_steps(torch, step, max(5, args.steps // 2), 3)
+        X.check()
+        ms = sorted(per)[len(per) // 2]
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"op": name, "ms": ms, "GBps": gbs, "hbm_frac": gbs / pk["hbm_gbs"], "algorithmic_bytes": nbytes})
+    return {"metric": "mateltwise GB/s at 4096x4096", "points": out}
 
 
 # ------------------------------------------------------------------------------------------------ CPU side

@@ -61,6 +61,11 @@ LIBXSMM_API int libxsmm_b200_memcpy(void* dst, const void* src, size_t size); /*
 LIBXSMM_API int libxsmm_b200_gemm_batch_strided(libxsmm_gemmfunction kernel,
   const void* a, const void* b, void* c, long long stride_a, long long stride_b, long long stride_c,
   unsigned long long br_count, long long count);
+/* the same batch spread over the first `ndevices` GPUs of this process (contiguous ranges, one worker thread and one PCIe link per
+ * device, no exchange between devices); operands must be host memory (pageable or pinned). Returns 0 or the first error. */
+LIBXSMM_API int libxsmm_b200_gemm_batch_strided_multi(libxsmm_gemmfunction kernel,
+  const void* a, const void* b, void* c, long long stride_a, long long stride_b, long long stride_c,
+  unsigned long long br_count, long long count, int ndevices);
 /* general form: one reference argument struct per tile (address/offset batch-reduce modes, scale
  * factors...). All matrix pointers must be device-accessible. */
 LIBXSMM_API int libxsmm_b200_gemm_batch(libxsmm_gemmfunction kernel, const libxsmm_gemm_param* params, long long count);

@@ -833,7 +833,7 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
         if (++rs == RS) { rs = 0; rph ^= 1; }
       }
     }
-  } else if (warp >= 10) {
+  } else if (warp >= 10 && warp < 26) {
     // ========================================= epilogue (16 warps: four per TMEM quadrant, one 32-column chunk each) =====
     const int q = warp & 3, cw = (warp - 10) >> 2;
     const int row = 32 * q + lane;                       // row of the 128-row group

@@ -569,8 +569,8 @@ cudaError_t launch_i8(const xb_gemm_launch& L, int path, int wpt, int words_per_
   const bool ua = (L.d.ta == LIBXSMM_DATATYPE_U8), ub = (L.d.tb == LIBXSMM_DATATYPE_U8);
   const int to_f32 = (path == P_I8_F32);
 #define XB_I8_CASE(A, B) do { \
-    static int attr_set = 0; \
-    if (!attr_set) { cudaFuncSetAttribute(gemm_i8_kernel<TM, TN, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = 1; } \
+    static unsigned long long attr_set = 0ull; \
+    if (xb_rt_first_use_on_device(&attr_set)) cudaFuncSetAttribute(gemm_i8_kernel<TM, TN, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
     gemm_i8_kernel<TM, TN, A, B><<<grid, I8_WARPS * 32, smem, st>>>(L, to_f32, wpt, words_per_group); } while (0)
   if (ua && ub) XB_I8_CASE(true, true); else if (ua) XB_I8_CASE(true, false); else if (ub) XB_I8_CASE(false, true); else XB_I8_CASE(false, false);
 #undef XB_I8_CASE

@@ -267,7 +267,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
-int g_attr_set[2] = {0, 0};
+unsigned long long g_attr_set[2] = {0ull, 0ull};   // MaxDynamicSharedMemorySize is a per-device attribute: one bit per device
 
 int tc_init_once() {
   if (g_encode == nullptr) {
@@ -381,10 +381,10 @@ extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
   cudaStream_t stream = (cudaStream_t)xb_rt_stream();
   cudaError_t e;
   if (UM == 64) {
-    if (!g_attr_set[0]) { cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_attr_set[0] = 1; }
+    if (xb_rt_first_use_on_device(&g_attr_set[0])) cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     gemm_tc_kernel<64><<<(unsigned int)grid, 192, smem, stream>>>(map_a, map_b, P);
   } else {
-    if (!g_attr_set[1]) { cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_attr_set[1] = 1; }
+    if (xb_rt_first_use_on_device(&g_attr_set[1])) cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     gemm_tc_kernel<128><<<(unsigned int)grid, 192, smem, stream>>>(map_a, map_b, P);
   }
   xb_rt_count_launch();

@@ -558,6 +558,51 @@ LIBXSMM_API int libxsmm_b200_gemm_batch_strided(libxsmm_gemmfunction kernel, con
   return rc;
 }
 
+/* ---- one process, several GPUs: the batch is the only shard axis. Host-resident operands are cut into
+ * `ndevices` contiguous ranges; one worker thread per device moves its range over its own PCIe link through the chunked copy
+ * pipeline and runs the kernel there. Nothing is exchanged between devices; the results land in the caller's C. ---------- */
+typedef struct xb_multi_job {
+  libxsmm_gemmfunction kernel; const char* a; const char* b; char* c; long long sa, sb, sc, first, count; unsigned long long br; int device, rc;
+} xb_multi_job;
+
+static void* xb_multi_worker(void* arg) {
+  xb_multi_job* j = (xb_multi_job*)arg;
+  j->rc = xb_rt_set_device(j->device);
+  if (j->rc == 0) {
+    xb_rt_set_stream(NULL); xb_rt_set_blocking(1);
+    j->rc = libxsmm_b200_gemm_batch_strided(j->kernel, j->a + j->first * j->sa, j->b + j->first * j->sb, j->c + j->first * j->sc,
+                                            j->sa, j->sb, j->sc, j->br, j->count);
+    xb_rt_scratch_reset();
+  }
+  return NULL;
+}
+
+LIBXSMM_API int libxsmm_b200_gemm_batch_strided_multi(libxsmm_gemmfunction kernel, const void* a, const void* b, void* c,
+  long long stride_a, long long stride_b, long long stride_c, unsigned long long br_count, long long count, int ndevices)
+{
+  xb_multi_job jobs[64]; pthread_t th[64];
+  int d, rc = 0, started = 0, prev_dev;
+  const int avail = xb_rt_device_count();
+  if (xb_gemm_slot((const void*)kernel) == NULL || count < 0 || ndevices <= 0) return -1;
+  if (ndevices > avail) ndevices = avail;
+  if (ndevices > 64) ndevices = 64;
+  if (ndevices <= 0) return -1;
+  if (xb_rt_ptr_kind(a) == 1 || xb_rt_ptr_kind(b) == 1 || xb_rt_ptr_kind(c) == 1) return -4;   /* device memory belongs to one GPU: use the per-device call */
+  prev_dev = xb_rt_current_device();
+  for (d = 0; d < ndevices; ++d) {
+    const long long base = count / ndevices, extra = count % ndevices;
+    xb_multi_job* j = &jobs[d];
+    j->kernel = kernel; j->a = (const char*)a; j->b = (const char*)b; j->c = (char*)c; j->sa = stride_a; j->sb = stride_b; j->sc = stride_c; j->br = br_count;
+    j->first = d * base + (d < extra ? d : extra); j->count = base + (d < extra ? 1 : 0); j->device = d; j->rc = 0;
+    if (j->count == 0) { th[d] = 0; continue; }
+    if (0 != pthread_create(&th[d], NULL, xb_multi_worker, j)) { j->rc = -5; th[d] = 0; } else ++started;
+  }
+  for (d = 0; d < ndevices; ++d) { if (th[d] != 0) pthread_join(th[d], NULL); if (jobs[d].rc != 0 && rc == 0) rc = jobs[d].rc; }
+  (void)started;
+  xb_rt_set_device(prev_dev);
+  return rc;
+}
+
 typedef struct xb_hostbatch {
   const xb_gemm_desc* d; const char* a; const char* b; char* c;
   long long sa, sb, sc, chunk, count; unsigned long long br;

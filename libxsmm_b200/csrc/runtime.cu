@@ -13,6 +13,7 @@ struct ThreadState {
   cudaStream_t stream = nullptr;
   int blocking = 1;
   char* scratch = nullptr; size_t scratch_cap = 0, scratch_used = 0;
+  int scratch_device = -1;                  // the arena belongs to one device: a thread that switches device gets a new one
   // overflow blocks (kept until reset) when a request does not fit the arena
   void* spill[64]; int nspill = 0;
 };
@@ -201,8 +202,27 @@ int xb_rt_pipeline(long long nchunks, size_t max_a, size_t max_b, size_t max_c, 
   return rc;
 }
 
+int xb_rt_current_device(void) { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; } return dev; }
+
+/* per-(kernel, device) one-time work such as cudaFuncSetAttribute: `mask` holds one bit per device ordinal */
+int xb_rt_first_use_on_device(unsigned long long* mask) {
+  const int dev = xb_rt_current_device();
+  if (dev < 0 || dev >= 64) return 1;
+  const unsigned long long bit = 1ull << dev;
+  const unsigned long long old = __atomic_fetch_or(mask, bit, __ATOMIC_ACQ_REL);
+  return (old & bit) == 0;
+}
+
 void* xb_rt_scratch(size_t bytes) {
   bytes = (bytes + 255) & ~(size_t)255;
+  {
+    const int dev = xb_rt_current_device();
+    if (tls.scratch != nullptr && tls.scratch_device != dev && tls.scratch_used == 0) {   // device switched: drop the old arena
+      const int cur = dev; cudaSetDevice(tls.scratch_device); cudaFree(tls.scratch); cudaSetDevice(cur);
+      tls.scratch = nullptr; tls.scratch_cap = 0;
+    }
+    tls.scratch_device = dev;
+  }
   if (tls.scratch_used + bytes <= tls.scratch_cap) {
     void* p = tls.scratch + tls.scratch_used; tls.scratch_used += bytes; return p;
   }

@@ -325,7 +325,7 @@ int check_launch(const char* where) {
   if (e != cudaSuccess) { xb_rt_note_error((int)e, where); return (int)e; }
   return 0;
 }
-int g_sreg_attr[2] = {0, 0};
+unsigned long long g_sreg_attr[2] = {0ull, 0ull};   // one bit per device ordinal
 
 }  // namespace
 
@@ -372,10 +372,10 @@ extern "C" int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, l
     }
   }
   if (f64) {
-    if (!g_sreg_attr[1]) { cudaFuncSetAttribute(sreg_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_sreg_attr[1] = 1; }
+    if (xb_rt_first_use_on_device(&g_sreg_attr[1])) cudaFuncSetAttribute(sreg_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     sreg_kernel<double><<<(unsigned int)grid, threads, smem, stream>>>(map_b, P);
   } else {
-    if (!g_sreg_attr[0]) { cudaFuncSetAttribute(sreg_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); g_sreg_attr[0] = 1; }
+    if (xb_rt_first_use_on_device(&g_sreg_attr[0])) cudaFuncSetAttribute(sreg_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     sreg_kernel<float><<<(unsigned int)grid, threads, smem, stream>>>(map_b, P);
   }
   return check_launch("sreg");

@@ -147,6 +147,8 @@ int xb_rt_ptr_kind(const void* p);
 int xb_rt_have_gpu(void);
 /* scratch arena on the device, grown on demand, reset by the caller after sync */
 void* xb_rt_scratch(size_t bytes);
+int xb_rt_current_device(void);
+int xb_rt_first_use_on_device(unsigned long long* mask);   /* 1 once per device ordinal */
 void xb_rt_scratch_reset(void);
 
 /* ---- kernel launchers (one per .cu file) ------------------------------------------------------- */

@@ -2,7 +2,7 @@
 # executed on the GPU box through gpurun; everything interesting lands in gpurun_out/. Every step has its own short timeout.
 mkdir -p gpurun_out
 echo "=== smoke"; timeout -s KILL 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
-for f in test_sparse_gpu test_meltw_gpu test_golden test_ref_drivers test_gemm_gpu; do
+for f in test_sparse_gpu test_meltw_gpu test_golden test_ref_drivers test_meqn test_gemm_gpu; do
   echo "=== $f"; timeout -s KILL 300 python -m pytest tests/$f.py -m gpu -q -x > gpurun_out/$f.log 2>&1; echo "$f rc=$?"; tail -8 gpurun_out/$f.log
 done
 if [ "$1" != "nobench" ]; then
