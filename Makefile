@@ -12,7 +12,7 @@ CSRC      := libxsmm_b200/csrc
 OBJDIR    := build/obj
 LIB       := libxsmm_b200/lib/libxsmm_b200.so
 HOST_C    := host_core.c host_thunks.c host_sparse.c host_meltw.c host_utils.c host_meqn.c
-DEVICE_CU := runtime.cu gemm_simt.cu gemm_tc.cu sparse.cu bcsc_tc.cu meltw.cu
+DEVICE_CU := runtime.cu gemm_simt.cu gemm_tc.cu gemm_ts.cu sparse.cu bcsc_tc.cu meltw.cu
 OBJS      := $(addprefix $(OBJDIR)/,$(HOST_C:.c=.o) $(DEVICE_CU:.cu=.o))
 REFDIR    ?= /root/reference
 

@@ -214,8 +214,14 @@ def run_ours(args):
                "gpu_launches": int(launches), "clocks": clocks.summary()}
         if not args.no_e2e:
             # every rank drives its own GPU over its own PCIe link at the same time; whole-job value = all tiles / slowest rank
+            try:
+                old_aff = os.sched_getaffinity(0)
+            except Exception:
+                old_aff = None
             bind_to_gpu_numa_node(torch, local)
             out["e2e"] = brgemm_e2e(X, torch, kernel, a, b, sa, sb, sc, flops, c_dev=c, dist=dist, world=world)
+            if old_aff:
+                os.sched_setaffinity(0, old_aff)        # the CPU baselines below use every core again
         if world > 1 and not args.no_also:
             out["strong"] = strong_scaling(X, torch, pk, args, dist, world, rank)
         if rank == 0 and not args.no_also:

@@ -886,6 +886,7 @@ bcsc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const BcscTsParams P) 
 // while concurrent callers on different streams get different buffers. The three launches of a call are enqueued under the
 // handle's mutex, so two host threads sharing a stream cannot interleave them. Nothing in the handle's descriptor is mutated
 // by a call (the reference's handles are re-entrant).
+int env_int(const char* name, int lo, int hi, int dflt);
 struct BcscBuffers { int device; cudaStream_t stream; unsigned int* idx; size_t idx_bytes; void* val; size_t val_bytes; };
 struct BcscState { std::mutex mu; std::vector<BcscBuffers> sets; };
 std::mutex g_state_mu;
@@ -913,7 +914,7 @@ cudaError_t launch_v1(long long grid, size_t smem, cudaStream_t stream, const CU
   cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned int)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = env_int("LIBXSMM_B200_BCSC_PDL", 0, 1, 0);
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, bcsc_tc_kernel<M>, ma, P);
 }
@@ -925,7 +926,7 @@ cudaError_t launch_ts2(long long grid, size_t smem, cudaStream_t stream, const C
   cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned int)grid); cfg.blockDim = dim3(kTsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = env_int("LIBXSMM_B200_BCSC_PDL", 0, 1, 0);
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, bcsc_ts_kernel<M, KSTEPS>, ma, P);
 }
@@ -1098,7 +1099,7 @@ extern "C" int xb_bcsc_tc_launch(const xb_sparse_desc* d, void** work, const voi
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(pgrid ? pgrid : 1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = env_int("LIBXSMM_B200_BCSC_PDL", 0, 1, 0);
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, bcsc_pack_b_kernel, (const uint4*)b_vals, (const unsigned int*)(buf + L.entries), (const unsigned int*)(buf + L.list_ptr), nl, (uint4*)bufs->val, bn, bk);
     xb_rt_count_launch();

@@ -292,7 +292,7 @@ static int xb_make_gemm_desc(xb_gemm_desc* d, const libxsmm_gemm_shape* shape, u
   }
   if ((d->flags & LIBXSMM_GEMM_FLAG_VNNI_C) != 0 && ((d->n % 2) != 0 || libxsmm_typesize((libxsmm_datatype)d->tc) != 2)) return 0;   /* 16-bit C in column pairs */
   if (!xb_gemm_simt_supported(d)) return 0;
-  d->backend = (!g_force_simt && xb_gemm_tc_supported(d)) ? LIBXSMM_B200_BACKEND_TCGEN05 : LIBXSMM_B200_BACKEND_SIMT;
+  d->backend = (!g_force_simt && (xb_gemm_tc_supported(d) || xb_gemm_ts_supported(d))) ? LIBXSMM_B200_BACKEND_TCGEN05 : LIBXSMM_B200_BACKEND_SIMT;
   return 1;
 }
 
@@ -404,7 +404,8 @@ static const void* xb_stage_in(const void* p, size_t bytes, int* staged) {
 }
 
 static int xb_run_gemm_launch(const xb_gemm_launch* L) {
-  return (L->d.backend == LIBXSMM_B200_BACKEND_TCGEN05) ? xb_gemm_tc_launch(L) : xb_gemm_simt_launch(L);
+  if (L->d.backend != LIBXSMM_B200_BACKEND_TCGEN05) return xb_gemm_simt_launch(L);
+  return xb_gemm_ts_supported(&L->d) ? xb_gemm_ts_launch(L) : xb_gemm_tc_launch(L);
 }
 
 static void xb_invoke_gemm(const xb_slot* s, const libxsmm_gemm_param* p) {

@@ -444,6 +444,67 @@ __global__ void __launch_bounds__(256) meltw_transform_kernel(const xb_meltw_des
   }
 }
 
+// ---- bandwidth versions of the three layout/reduction kernels that matter at size (K7 of SURVEY.md 2.3) ------------------------
+// transpose: 32 x 32 tiles through shared memory, both the read (rows of the input) and the write (rows of the output) coalesced
+template <typename E>
+__global__ void __launch_bounds__(256) meltw_transpose_tiled_kernel(const E* __restrict__ in, E* __restrict__ out, long long M, long long N, long long ldi, long long ldo) {
+  __shared__ E tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                 // 32 x 8 threads
+  const long long tiles_j = (M + 31) / 32, tiles_i = (N + 31) / 32;
+  for (long long t = blockIdx.x; t < tiles_j * tiles_i; t += gridDim.x) {
+    const long long j0 = (t % tiles_j) * 32, i0 = (t / tiles_j) * 32;     // in[i*ldi + j], j contiguous, j < M, i < N
+    for (int ii = ty; ii < 32; ii += 8) if (i0 + ii < N && j0 + tx < M) tile[ii][tx] = in[(i0 + ii) * ldi + j0 + tx];
+    __syncthreads();
+    for (int jj = ty; jj < 32; jj += 8) if (j0 + jj < M && i0 + tx < N) out[(j0 + jj) * ldo + i0 + tx] = tile[tx][jj];
+    __syncthreads();
+  }
+}
+// NORM -> VNNI-v pack: a thread takes 4 consecutive rows of one group of v columns: v loads of 4 elements, 4 stores of one
+// v-element word each (16 contiguous bytes); zero padding of the last group and of rows [m, ldo) like the generic kernel
+template <typename E, int V>
+__global__ void __launch_bounds__(256) meltw_vnni_pack_kernel(const E* __restrict__ in, E* __restrict__ out, long long M, long long N, long long ldi, long long ldo) {
+  const long long groups = (N + V - 1) / V, quads = (ldo + 3) / 4;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < groups * quads; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e / quads, i0 = (e % quads) * 4;
+    E v[V][4];
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+      const long long col = g * V + c;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[c][r] = (col < N && i0 + r < M) ? in[col * ldi + i0 + r] : (E)0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (i0 + r < ldo) {
+#pragma unroll
+      for (int c = 0; c < V; ++c) out[(g * ldo + i0 + r) * V + c] = v[c][r];
+    }
+  }
+}
+// column reduction (one result per ROW i, the input's contiguous index): lanes take consecutive rows, so every load of a
+// warp is one 128-byte line; the columns are cut into gridDim.y slices whose partial sums go to `part` and are added up, in
+// slice order, by a second small kernel
+__global__ void __launch_bounds__(256) meltw_reduce_cols_partial_kernel(const xb_meltw_desc d, const xb_meltw_args a, float* __restrict__ part, int want_x2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = (d.n + gridDim.y - 1) / gridDim.y, j0 = blockIdx.y * per, j1 = (j0 + per < d.n) ? j0 + per : d.n;
+  if (i >= d.m) return;
+  float sx = 0.0f, sx2 = 0.0f;
+  for (int j = j0; j < j1; ++j) { const float v = ld_f32(a.in0, i + (long long)j * d.ldi, d.t_in0); sx += v; sx2 += v * v; }
+  part[(size_t)blockIdx.y * d.m + i] = sx;
+  if (want_x2) part[(size_t)(gridDim.y + blockIdx.y) * d.m + i] = sx2;
+}
+__global__ void __launch_bounds__(256) meltw_reduce_cols_final_kernel(const xb_meltw_desc d, const xb_meltw_args a, const float* __restrict__ part, int slices) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.m) return;
+  const bool init_acc = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_INIT_ACC) != 0;
+  const bool want_x = (d.op != LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD);
+  const bool want_x2 = (d.op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD || d.op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD);
+  float sx = 0.0f, sx2 = 0.0f;
+  for (int s2 = 0; s2 < slices; ++s2) { sx += part[(size_t)s2 * d.m + i]; if (want_x2) sx2 += part[(size_t)(slices + s2) * d.m + i]; }
+  char* base2 = (char*)a.out + (want_x ? (size_t)d.ldo * xb_dev_typesize(d.t_out) : 0);
+  if (want_x) { if (init_acc) sx += ld_f32(a.out, i, d.t_out); st_f32(a.out, i, d.t_out, sx); }
+  if (want_x2) { if (init_acc) sx2 += ld_f32(base2, i, d.t_out); st_f32(base2, i, d.t_out, sx2); }
+}
+
 // ---- gather / scatter (:1444-1794) ------------------------------------------------------------------------------------
 template <typename E>
 __global__ void __launch_bounds__(256) meltw_gs_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
@@ -571,6 +632,20 @@ extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
       return launch_done("meltw_map");
     }
     case FAM_REDUCE: {
+      const bool sum_op = (d->op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ADD || d->op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD || d->op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD);
+      if (sum_op && (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_ROWS) == 0 && d->t_in0 != LIBXSMM_DATATYPE_F64 && (long long)d->m * d->n >= (1 << 18) && d->m >= 256) {
+        // big column reduction: coalesced two-phase version (partial sums per column slice, then the slices in order)
+        int slices = (int)(((long long)148 * 8 * 256 + d->m - 1) / d->m); if (slices > d->n / 16) slices = d->n / 16; if (slices < 1) slices = 1; if (slices > 256) slices = 256;
+        const int want_x2 = (d->op != LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ADD);
+        float* part = (float*)xb_rt_scratch((size_t)2 * slices * d->m * sizeof(float));
+        if (part != nullptr) {
+          const dim3 g((d->m + 255) / 256, slices);
+          meltw_reduce_cols_partial_kernel<<<g, 256, 0, st>>>(*d, *a, part, want_x2);
+          if (launch_done("meltw_reduce_partial") != 0) return 1;
+          meltw_reduce_cols_final_kernel<<<(d->m + 255) / 256, 256, 0, st>>>(*d, *a, part, slices);
+          return launch_done("meltw_reduce_final");
+        }
+      }
       const int nres = (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_ROWS) ? d->n : d->m;
       int grid = (nres + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
       if (d->t_in0 == LIBXSMM_DATATYPE_F64) meltw_reduce_kernel<double><<<grid, 256, 0, st>>>(*d, *a);
@@ -585,6 +660,24 @@ extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
       const long long work = (long long)(d->ldo > d->m ? d->ldo : d->m) * ((d->n + 3) / 4 * 4);
       long long grid = (work + 255) / 256; if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
       const int ts = xb_dev_typesize(d->t_in0);
+      if (fam == FAM_TRANSFORM && d->op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT && (long long)d->m * d->n >= 4096) {
+        const long long tiles = (long long)((d->m + 31) / 32) * ((d->n + 31) / 32);
+        const unsigned int tg = (unsigned int)(tiles < 148 * 16 ? tiles : 148 * 16);
+        if (ts == 8) meltw_transpose_tiled_kernel<unsigned long long><<<tg, 256, 0, st>>>((const unsigned long long*)a->in0, (unsigned long long*)a->out, d->m, d->n, d->ldi, d->ldo);
+        else if (ts == 4) meltw_transpose_tiled_kernel<unsigned int><<<tg, 256, 0, st>>>((const unsigned int*)a->in0, (unsigned int*)a->out, d->m, d->n, d->ldi, d->ldo);
+        else if (ts == 2) meltw_transpose_tiled_kernel<unsigned short><<<tg, 256, 0, st>>>((const unsigned short*)a->in0, (unsigned short*)a->out, d->m, d->n, d->ldi, d->ldo);
+        else meltw_transpose_tiled_kernel<unsigned char><<<tg, 256, 0, st>>>((const unsigned char*)a->in0, (unsigned char*)a->out, d->m, d->n, d->ldi, d->ldo);
+        return launch_done("meltw_transpose");
+      }
+      if (fam == FAM_TRANSFORM && (long long)d->ldo * d->n >= 4096 && ((ts == 2 && (d->op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2 || d->op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI2_PAD))
+                                  || (ts == 1 && (d->op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4 || d->op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_VNNI4_PAD)))) {
+        const int V = (ts == 2) ? 2 : 4;
+        const long long workp = (long long)((d->n + V - 1) / V) * ((d->ldo + 3) / 4);
+        long long pg = (workp + 255) / 256; if (pg > 148 * 16) pg = 148 * 16;
+        if (ts == 2) meltw_vnni_pack_kernel<unsigned short, 2><<<(unsigned int)pg, 256, 0, st>>>((const unsigned short*)a->in0, (unsigned short*)a->out, d->m, d->n, d->ldi, d->ldo);
+        else meltw_vnni_pack_kernel<unsigned char, 4><<<(unsigned int)pg, 256, 0, st>>>((const unsigned char*)a->in0, (unsigned char*)a->out, d->m, d->n, d->ldi, d->ldo);
+        return launch_done("meltw_vnni_pack");
+      }
       if (fam == FAM_TRANSFORM) {
         if (ts == 8) meltw_transform_kernel<unsigned long long><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
         else if (ts == 4) meltw_transform_kernel<unsigned int><<<(unsigned int)grid, 256, 0, st>>>(*d, *a);

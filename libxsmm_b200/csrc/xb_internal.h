@@ -155,6 +155,8 @@ void xb_rt_scratch_reset(void);
 int xb_gemm_simt_launch(const xb_gemm_launch* L);
 int xb_gemm_tc_supported(const xb_gemm_desc* d);          /* pure host logic, no CUDA call */
 int xb_gemm_tc_launch(const xb_gemm_launch* L);
+int xb_gemm_ts_supported(const xb_gemm_desc* d);          /* VNNI-packed A through tensor memory (gemm_ts.cu); pure host logic */
+int xb_gemm_ts_launch(const xb_gemm_launch* L);
 typedef struct xb_meltw_args {
   const void* in0; const void* in1; const void* in2; void* out;
   const void* in_aux;        /* unary in.secondary: bitmask in / index array / fwd output (ELU_INV) */

@@ -280,3 +280,39 @@ def test_bitmap_compressed_a_bit_exact():
                     X.GEMMFUNCTION(kern)(C.byref(p)); X.check()
                     got = host(d_c, gen.NP_OF[tc]) if resident else hc
                     assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (dims, (ta, tb, tc), beta0, resident)
+
+
+@pytest.mark.parametrize("types", [(gen.U8, gen.I8, gen.I32, gen.I32), (gen.I8, gen.U8, gen.I32, gen.I32), (gen.I8, gen.I8, gen.I32, gen.I32), (gen.U8, gen.U8, gen.I32, gen.I32),
+                                   (gen.U8, gen.I8, gen.I32, gen.F32), (gen.BF16, gen.BF16, gen.F32, gen.F32), (gen.BF16, gen.BF16, gen.F32, gen.BF16),
+                                   (gen.F16, gen.F16, gen.F32, gen.F16)])
+def test_vnni_a_on_tensor_cores(types):
+    """VNNI-packed A (the reference's canonical low-precision layout) through tensor memory (gemm_ts.cu): tcgen05.mma kind::i8 /
+    kind::f16 in TS form. Integer tuples bit-exact against the oracle (integer sums are order-free), I8->F32 exact as well (one
+    int->float conversion and one multiply), 16-bit tuples within the reference drivers' norms. Batches through the strided API."""
+    rng = np.random.default_rng(97)
+    ta, tb, tcomp, tc = types
+    is8 = ta in (gen.I8, gen.U8)
+    shapes = [(64, 64, 64, 3, 8, 0), (128, 128, 128, 0, 1, 0), (16, 16, 16, 0, 1, 0), (32, 48, 96, 3, 2, 16), (12, 20, 48 if is8 else 40, 0, 1, 0),
+              (128, 64, 256 + 32, 3, 2, 0), (64, 128, 32, 0, 1, 0)]
+    for (m, n, k, br_type, br, pad) in shapes:
+        for beta0 in (1, 0):
+            flags = (cases.FLAG_BETA_0 if beta0 else 0) | cases.FLAG_VNNI_A
+            case = cases.GemmCase(m, n, k, ta, tb, tcomp, tc, flags=flags, br_type=br_type, br=br, pad=pad)
+            count = 37
+            ops = cases.Operands(case, seed=int(rng.integers(1 << 30)), count=count)
+            kernel = dispatch(case, ops)
+            assert kernel, case
+            assert X.libxsmm_b200_kernel_backend(kernel) == X.BACKEND_TCGEN05, case
+            d_a, d_b, d_c = dev(ops.a), dev(ops.b), dev(ops.c0)
+            if tc == gen.F32 and is8:      # the scalar scale travels with the call: per-call path
+                run_single_calls(kernel, case, ops, d_a, d_b, d_c)
+            else:
+                assert X.libxsmm_b200_gemm_batch_strided(kernel, d_a.data_ptr(), d_b.data_ptr(), d_c.data_ptr(), ops.tile_a, ops.tile_b, ops.tile_c, case.br, count) == 0
+                X.check()
+            want = cases.ref_result(oracle, case, ops, run_gemm)
+            got = host(d_c, gen.NP_OF[tc])
+            if is8:
+                assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (case, beta0)
+            else:
+                thr = 1.2e-5 if tc == gen.F32 else 5e-3
+                assert gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc)) <= thr, (case, beta0)

@@ -412,3 +412,52 @@ def test_unzip_and_decompose_bit_exact():
             want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary, q.out.secondary = x.ctypes.data, want.ctypes.data, offs.ctypes.data
             _ref_call(_desc(1, op, 0, m, n, ldi, 0, 0, ldo, gen.F32, UNS, UNS, gen.BF16, gen.F32), q)
             assert np.array_equal(host(d_o, np.uint16), want), (name, m, n)
+
+
+def test_large_shapes_take_the_bandwidth_kernels_and_stay_exact():
+    """sizes at which the tiled transpose, the vectorised VNNI packers and the two-phase column reduction are selected; data movement
+    bit-exact against the oracle restatement, the reduction within the summation-order tolerance"""
+    rng = np.random.default_rng(61)
+    # transposes with ragged edges and padded leading dimensions
+    for t in (gen.F64, gen.F32, gen.BF16, gen.I8):
+        for (m, n, pi, po) in ((1000, 777, 0, 0), (257, 129, 3, 5)):
+            ldi, ldo = m + pi, n + po
+            x = rng.integers(0, 256, size=ldi * n * gen.TS[t], dtype=np.uint8); o0 = rng.integers(0, 256, size=ldo * m * gen.TS[t], dtype=np.uint8)
+            op = X.MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT
+            k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, t, t, t), 0)
+            d_x, d_o = dev(x), dev(o0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_o.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+            assert oracle["meltw"](iarr(*_desc(1, op, 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t)), C.addressof(q), 0) == 0
+            assert np.array_equal(host(d_o, np.uint8), want), ("normt", t, m, n)
+    # VNNI packers
+    for name, t in (("NORM_TO_VNNI2", gen.BF16), ("NORM_TO_VNNI2_PAD", gen.BF16), ("NORM_TO_VNNI4", gen.I8), ("NORM_TO_VNNI4_PAD", gen.I8)):
+        op = getattr(X, "MELTW_TYPE_UNARY_TRANSFORM_" + name)
+        for (m, n, pad) in ((512, 300, 0), (130, 64, 6)):
+            ldi, ldo = m + pad, m + pad
+            x = rng.integers(0, 256, size=(ldi + 8) * (n + 8) * gen.TS[t], dtype=np.uint8)
+            o0 = rng.integers(0, 256, size=(ldo + 8) * (n + 8) * gen.TS[t], dtype=np.uint8)
+            k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, t, t, t), 0)
+            d_x, d_o = dev(x), dev(o0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_o.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            want = o0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+            assert oracle["meltw"](iarr(*_desc(1, op, 0, m, n, ldi, 0, 0, ldo, t, UNS, UNS, t, t)), C.addressof(q), 0) == 0
+            assert np.array_equal(host(d_o, np.uint8), want), (name, m, n, pad)
+    # column reductions (one result per row): sums and sums of squares
+    for t in (gen.F32, gen.BF16):
+        for opname in ("REDUCE_X_OP_ADD", "REDUCE_X2_OP_ADD", "REDUCE_X_X2_OP_ADD"):
+            for init_acc in (0, X.MELTW_FLAG_UNARY_REDUCE_INIT_ACC):
+                m, n, ld = 2048, 600, 2050
+                op = getattr(X, "MELTW_TYPE_UNARY_" + opname)
+                flags = X.MELTW_FLAG_UNARY_REDUCE_COLS | init_acc
+                x = _rand(rng, ld * n, t); y0 = _rand(rng, 2 * ld, t)
+                k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, t, t, gen.F32), flags)
+                assert k
+                d_x, d_y = dev(x), dev(y0)
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_y.data_ptr()
+                X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+                want = y0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+                assert oracle["meltw"](iarr(*_desc(1, op, flags, m, n, ld, 0, 0, ld, t, UNS, UNS, t, gen.F32)), C.addressof(q), 0) == 0
+                _cmp(host(d_y, want.dtype), want, t, False, 2e-2 if t == gen.BF16 else 2e-4)
