@@ -74,6 +74,8 @@ typedef struct libxsmm_b200_gemm_plan libxsmm_b200_gemm_plan;
 LIBXSMM_API libxsmm_b200_gemm_plan* libxsmm_b200_gemm_plan_create(libxsmm_gemmfunction kernel,
   const libxsmm_gemm_param* params, long long count);
 LIBXSMM_API int libxsmm_b200_gemm_plan_run(const libxsmm_b200_gemm_plan* plan);
+/* 1 if the plan walks a regular pool of block-sets on the tensor-core kernel (address batch-reduce), else 0 */
+LIBXSMM_API int libxsmm_b200_gemm_plan_is_pooled(const libxsmm_b200_gemm_plan* plan);
 LIBXSMM_API void libxsmm_b200_gemm_plan_destroy(libxsmm_b200_gemm_plan* plan);
 
 #if defined(__cplusplus)

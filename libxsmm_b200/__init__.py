@@ -294,6 +294,7 @@ libxsmm_b200_gemm_batch = _sig("libxsmm_b200_gemm_batch", _I, [_P, C.POINTER(Gem
 libxsmm_b200_gemm_plan_create = _sig("libxsmm_b200_gemm_plan_create", _P, [_P, C.POINTER(GemmParam), _LL])
 libxsmm_b200_gemm_plan_run = _sig("libxsmm_b200_gemm_plan_run", _I, [_P])
 libxsmm_b200_gemm_plan_destroy = _sig("libxsmm_b200_gemm_plan_destroy", None, [_P])
+libxsmm_b200_gemm_plan_is_pooled = _sig("libxsmm_b200_gemm_plan_is_pooled", _I, [_P])
 
 EXPORTED = [n for n in dir() if n.startswith("libxsmm_") and callable(globals()[n])]
 

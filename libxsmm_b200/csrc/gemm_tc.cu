@@ -44,6 +44,10 @@ struct TcParams {
   int c_type, a_type, beta0;
   uint32_t idesc;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // in 16-byte units
+  // pooled address mode (libxsmm_b200_gemm_plan over ADDRESS batch-reduce): tile p reads block-set sets[p].x of A and
+  // sets[p].y of B (4th tensor-map coordinate) and writes cptrs[p]; positions are sorted by set pair, a CTA owns a
+  // contiguous range and keeps the operands of a run of equal pairs resident in its stage ring
+  const int2* sets; char* const* cptrs;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,7 +124,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long G = gridDim.x, b = blockIdx.x;
-  const long long n_local = (b < P.count) ? (P.count - b + G - 1) / G : 0;
+  const bool pooled = P.sets != nullptr;
+  const long long chunk = (P.count + G - 1) / G;                       // pooled: contiguous range per CTA
+  const long long n_local = pooled ? ((b * chunk < P.count) ? ((P.count - b * chunk < chunk) ? P.count - b * chunk : chunk) : 0)
+                                   : ((b < P.count) ? (P.count - b + G - 1) / G : 0);
+  const int loads_per_tile = (int)P.br * P.kchunks;
+  const bool can_hold = pooled && loads_per_tile <= P.stages;          // a tile's operands fit the ring: equal neighbours re-use them
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
@@ -144,8 +153,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       uint64_t policy = 0;
       if (P.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      int2 prev = make_int2(-1, -1);
       for (long long i = 0; i < n_local; ++i) {
-        const long long t = b + i * G;
+        const long long t = pooled ? b * chunk + i : b + i * G;
+        int ta = (int)t, tb = (int)t;
+        if (pooled) {
+          const int2 st = P.sets[t];
+          const bool same = can_hold && i > 0 && st.x == prev.x && st.y == prev.y;
+          prev = st; ta = st.x; tb = st.y;
+          if (same) continue;                                          // operands of the previous tile are still in the ring
+        }
         for (unsigned long long r = 0; r < P.br; ++r) {
           for (int kc = 0; kc < P.kchunks; ++kc) {
             mbar_wait(bar_base + 8 * (S + stage), phase ^ 1);
@@ -153,13 +170,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
             mbar_expect_tx(full, (uint32_t)P.stage_bytes);
             if (P.evict_first) {
-              tma_load_4d_hint(sa, &map_a, full, 0, kc * 64, (int)r, (int)t, policy);
-              if (UM == 128) tma_load_4d_hint(sa + 8192, &map_a, full, 64, kc * 64, (int)r, (int)t, policy);
-              tma_load_4d_hint(sb, &map_b, full, kc * 64, 0, (int)r, (int)t, policy);
+              tma_load_4d_hint(sa, &map_a, full, 0, kc * 64, (int)r, ta, policy);
+              if (UM == 128) tma_load_4d_hint(sa + 8192, &map_a, full, 64, kc * 64, (int)r, ta, policy);
+              tma_load_4d_hint(sb, &map_b, full, kc * 64, 0, (int)r, tb, policy);
             } else {
-              tma_load_4d(sa, &map_a, full, 0, kc * 64, (int)r, (int)t);
-              if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, 64, kc * 64, (int)r, (int)t);
-              tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, (int)t);
+              tma_load_4d(sa, &map_a, full, 0, kc * 64, (int)r, ta);
+              if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, 64, kc * 64, (int)r, ta);
+              tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, tb);
             }
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
@@ -169,8 +186,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0; uint32_t phase = 0;                  // cursor of the next freshly loaded stage
+      int run_stage = 0; uint32_t run_phase = 0;          // first stage of the run of equal set pairs this tile belongs to
       for (long long i = 0; i < n_local; ++i) {
+        bool reuse = false, last_of_run = true;
+        if (can_hold) {
+          const long long pp = b * chunk + i;
+          const int2 st = P.sets[pp];
+          if (i > 0) { const int2 pv = P.sets[pp - 1]; reuse = (pv.x == st.x && pv.y == st.y); }
+          if (i + 1 < n_local) { const int2 nx = P.sets[pp + 1]; last_of_run = !(nx.x == st.x && nx.y == st.y); }
+        }
+        if (!reuse) { run_stage = stage; run_phase = phase; }
+        int cs = run_stage; uint32_t cph = run_phase;
         const long long slot_seq = i / TPS; const int half = (int)(i % TPS);
         const int slot = (int)(slot_seq % NS);
         if (half == 0) {
@@ -181,9 +208,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t accumulate = 0;
         for (unsigned long long r = 0; r < P.br; ++r) {
           for (int kc = 0; kc < P.kchunks; ++kc) {
-            mbar_wait(bar_base + 8 * stage, phase);
+            if (!reuse) mbar_wait(bar_base + 8 * cs, cph);
             tc_fence_after();
-            const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
+            const uint32_t sa = smem_base + cs * P.stage_bytes, sb = sa + P.a_bytes;
             const int krem = P.k - kc * 64;
             const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -192,10 +219,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               umma_f16(d_tmem, adesc, bdesc, P.idesc, accumulate);
               accumulate = 1;
             }
-            umma_commit(bar_base + 8 * (S + stage));     // stage reusable once these MMAs retired
-            if (++stage == S) { stage = 0; phase ^= 1; }
+            if (last_of_run) umma_commit(bar_base + 8 * (S + cs));     // stage reusable once the MMAs of the whole run retired
+            if (++cs == S) { cs = 0; cph ^= 1; }
           }
         }
+        if (!reuse) { stage = cs; phase = cph; }
         if (half == TPS - 1 || i == n_local - 1) umma_commit(bar_base + 8 * (2 * S + slot));
       }
     }
@@ -211,8 +239,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const long long i = slot_seq * TPS + half;
       const bool valid = (i < n_local) && (row < P.m);
-      const long long t = b + i * G;
-      char* ctile = P.c + t * P.tile_stride_c;
+      const long long t = pooled ? b * chunk + i : b + i * G;
+      char* ctile = pooled ? ((i < n_local) ? P.cptrs[t] : nullptr) : P.c + t * P.tile_stride_c;
       const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < P.np; c0 += 32) {
         uint32_t v[32];
@@ -292,6 +320,13 @@ int env_int(const char* name, int fallback) {
 
 }  // namespace
 
+extern "C" int xb_gemm_tc_supported(const xb_gemm_desc* d);
+extern "C" int xb_gemm_tc_shape_ok(const xb_gemm_desc* d) {
+  xb_gemm_desc t = *d;
+  t.br_type = 0;
+  return xb_gemm_tc_supported(&t);
+}
+
 extern "C" int xb_gemm_tc_supported(const xb_gemm_desc* d) {
   const unsigned int bad = LIBXSMM_GEMM_FLAG_TRANS_A | LIBXSMM_GEMM_FLAG_TRANS_B | LIBXSMM_GEMM_FLAG_VNNI_A
                          | LIBXSMM_GEMM_FLAG_VNNI_B | LIBXSMM_GEMM_FLAG_VNNI_C | LIBXSMM_GEMM_FLAG_DECOMPRESS_A_VIA_BITMASK;
@@ -307,7 +342,16 @@ extern "C" int xb_gemm_tc_supported(const xb_gemm_desc* d) {
   return 1;
 }
 
-extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
+static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool);
+extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) { return tc_launch_common(L, nullptr); }
+extern "C" int xb_gemm_tc_launch_pooled(const xb_gemm_desc* d, const xb_tc_pool* pool, unsigned long long br, long long count) {
+  xb_gemm_launch L; memset(&L, 0, sizeof(L));
+  L.d = *d; L.count = count; L.br = br;
+  L.a = pool->base_a; L.b = pool->base_b; L.c = (void*)pool->cptrs;        // non-null markers; the pool carries the real addressing
+  L.tile_stride_a = pool->set_a; L.tile_stride_b = pool->set_b; L.tile_stride_c = 16;
+  return tc_launch_common(&L, pool);
+}
+static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   const xb_gemm_desc& d = L->d;
   // resolve the uniform strided form (count==1 by-value record included)
   const char* a = (const char*)L->a; const char* b = (const char*)L->b; char* c = (char*)L->c;
@@ -315,12 +359,12 @@ extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
   unsigned long long br = L->br;
   if (L->recs != nullptr) return xb_gemm_simt_launch(L);
   if (a == nullptr && c == nullptr) { a = (const char*)L->one.a; b = (const char*)L->one.b; c = (char*)L->one.c; br = L->one.br; sa = sb = sc = 0; }
-  if (d.br_type == 0) br = 1;
+  if (d.br_type == 0 && pool == nullptr) br = 1;
   const int es = 2;
   const bool aligned = (((uintptr_t)a | (uintptr_t)b) & 15) == 0 && (sa % 16) == 0 && (sb % 16) == 0
                     && (L->count == 1 || (sa > 0 && sb > 0));
   if (br == 0 || !aligned || L->count <= 0 || br > 0x7fffffffull || L->count > 0x7fffffffll || tc_init_once() != 0) {
-    return xb_gemm_simt_launch(L);
+    return (pool != nullptr) ? 1 : xb_gemm_simt_launch(L);
   }
 
   const int UM = (d.m <= 64) ? 64 : 128;
@@ -337,15 +381,19 @@ extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
   P.slot_cols = (P.np + 31) & ~31;
   // six CTAs leave 64 TMEM columns each: worth it only while that still holds two accumulator slots (f16 64^3: 4 CTAs 83%, 6 CTAs 77%)
   int ctas = env_int("LIBXSMM_B200_TC_CTAS", loads_per_tile <= 2 ? ((2 * P.slot_cols <= 64) ? 6 : 4) : (loads_per_tile <= 4 ? 4 : 2));
+  if (pool != nullptr && loads_per_tile * (long long)P.stage_bytes + 2048 <= 224 * 1024) {   // pooled: the ring must hold a whole tile so that equal neighbours share it
+    ctas = 1; while (ctas < 4 && loads_per_tile * (long long)P.stage_bytes + 2048 <= (224 * 1024) / (ctas * 2)) ctas *= 2;
+  }
   if (ctas < 1) ctas = 1; if (ctas > 6) ctas = 6;
   auto tmem_for = [](int c) { return c == 1 ? 512 : (c == 2 ? 256 : (c <= 4 ? 128 : 64)); };   // power-of-two allocations that sum to <= 512
   while (ctas > 1 && (2 * P.stage_bytes + 2048 > (224 * 1024) / ctas || P.slot_cols > tmem_for(ctas))) --ctas;
   P.stages = ((224 * 1024) / ctas - 2048) / P.stage_bytes; if (P.stages > 12) P.stages = 12; if (P.stages < 2) P.stages = 2;
-  { const int st = env_int("LIBXSMM_B200_TC_STAGES", ctas > 1 ? 4 : P.stages); if (st >= 2 && st <= P.stages) P.stages = st; }
+  { const int st = env_int("LIBXSMM_B200_TC_STAGES", (ctas > 1 && pool == nullptr) ? 4 : P.stages); if (st >= 2 && st <= P.stages) P.stages = st; }
   P.tmem_cols = tmem_for(ctas);
   P.nslot = P.tmem_cols / P.slot_cols; if (P.nslot > 4) P.nslot = 4;
   P.evict_first = env_int("LIBXSMM_B200_TC_EVICT_FIRST", 0);
   P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
+  if (pool != nullptr) { P.sets = (const int2*)pool->sets; P.cptrs = (char* const*)pool->cptrs; }
   P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0;
   // instruction descriptor: D=f32, A/B format, A MN-major, B K-major, N>>3, M>>4
   const uint32_t fmt = (d.ta == LIBXSMM_DATATYPE_BF16) ? 1u : 0u;
@@ -359,20 +407,22 @@ extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) {
   const cuuint64_t pad_a = (ext_a + 15) & ~(size_t)15, pad_b = (ext_b + 15) & ~(size_t)15;
   CUtensorMap map_a, map_b;
   {
-    const cuuint64_t dims[4] = {(cuuint64_t)d.m, (cuuint64_t)d.k, (cuuint64_t)br, (cuuint64_t)L->count};
-    const cuuint64_t strides[3] = {(cuuint64_t)d.lda * es, (d.br_type == 3) ? (cuuint64_t)d.br_stride_a : pad_a, (L->count > 1) ? (cuuint64_t)sa : pad_a};
+    const cuuint64_t dims[4] = {(cuuint64_t)d.m, (cuuint64_t)d.k, (cuuint64_t)br, (cuuint64_t)(pool ? pool->nsets_a : L->count)};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.lda * es, pool ? (cuuint64_t)pool->blk_a : ((d.br_type == 3) ? (cuuint64_t)d.br_stride_a : pad_a),
+                                   pool ? (cuuint64_t)pool->set_a : ((L->count > 1) ? (cuuint64_t)sa : pad_a)};
     const cuuint32_t box[4] = {64, 64, 1, 1};
     const CUresult r = g_encode(&map_a, dt, 4, (void*)a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return xb_gemm_simt_launch(L);
+    if (r != CUDA_SUCCESS) return (pool != nullptr) ? 1 : xb_gemm_simt_launch(L);
   }
   {
-    const cuuint64_t dims[4] = {(cuuint64_t)d.k, (cuuint64_t)d.n, (cuuint64_t)br, (cuuint64_t)L->count};
-    const cuuint64_t strides[3] = {(cuuint64_t)d.ldb * es, (d.br_type == 3) ? (cuuint64_t)d.br_stride_b : pad_b, (L->count > 1) ? (cuuint64_t)sb : pad_b};
+    const cuuint64_t dims[4] = {(cuuint64_t)d.k, (cuuint64_t)d.n, (cuuint64_t)br, (cuuint64_t)(pool ? pool->nsets_b : L->count)};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.ldb * es, pool ? (cuuint64_t)pool->blk_b : ((d.br_type == 3) ? (cuuint64_t)d.br_stride_b : pad_b),
+                                   pool ? (cuuint64_t)pool->set_b : ((L->count > 1) ? (cuuint64_t)sb : pad_b)};
     const cuuint32_t box[4] = {64, (cuuint32_t)P.np, 1, 1};
     const CUresult r = g_encode(&map_b, dt, 4, (void*)b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return xb_gemm_simt_launch(L);
+    if (r != CUDA_SUCCESS) return (pool != nullptr) ? 1 : xb_gemm_simt_launch(L);
   }
 
   const size_t smem = (size_t)P.stages * P.stage_bytes + 1024 /*align slack*/ + (2 * 16 + 2 * 8) * 8 + 64;

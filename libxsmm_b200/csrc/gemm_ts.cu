@@ -278,7 +278,9 @@ extern "C" int xb_gemm_ts_supported(const xb_gemm_desc* d) {
   const unsigned int bad = LIBXSMM_GEMM_FLAG_TRANS_A | LIBXSMM_GEMM_FLAG_TRANS_B | LIBXSMM_GEMM_FLAG_VNNI_B | LIBXSMM_GEMM_FLAG_VNNI_C
                          | LIBXSMM_GEMM_FLAG_DECOMPRESS_A_VIA_BITMASK | LIBXSMM_GEMM_FLAG_INTLV_A_FORMAT;
   const int a8 = (d->ta == LIBXSMM_DATATYPE_I8 || d->ta == LIBXSMM_DATATYPE_U8), b8 = (d->tb == LIBXSMM_DATATYPE_I8 || d->tb == LIBXSMM_DATATYPE_U8);
-  if ((d->flags & bad) != 0 || d->fuse_colbias != 0 || d->cp_op != 0) return 0;
+  static int enabled = -1;
+  if (enabled < 0) enabled = ts_env_int("LIBXSMM_B200_TS", 1) != 0 ? 1 : 0;
+  if (!enabled || (d->flags & bad) != 0 || d->fuse_colbias != 0 || d->cp_op != 0) return 0;
   if (a8 && b8) {
     if (d->tcomp != LIBXSMM_DATATYPE_I32 || !(d->tc == LIBXSMM_DATATYPE_I32 || d->tc == LIBXSMM_DATATYPE_F32)) return 0;
     if ((d->flags & LIBXSMM_GEMM_FLAG_VNNI_A) == 0 && d->tc != LIBXSMM_DATATYPE_F32) return 0;   // flat int8 A: exact-order kernel (the F32-out path is always VNNI4)

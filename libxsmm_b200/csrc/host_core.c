@@ -664,7 +664,78 @@ struct libxsmm_b200_gemm_plan {
   xb_gemm_rec* d_recs;       /* device */
   void* d_arrays;            /* device: per-tile pointer/offset arrays */
   long long count;
+  /* address batch-reduce whose blocks form regular block-sets in a pool (base + set*set_stride + r*block_stride): served by the
+   * tcgen05 kernel with the set index as tensor-map coordinate; tiles are visited sorted by set pair so that a CTA re-uses
+   * the operands of equal neighbours from its stage ring (the reference calls the kernel once per tile, the order is free) */
+  int pooled; xb_tc_pool pool; unsigned long long br; void* d_sets; void* d_cptrs;
 };
+
+typedef struct xb_pool_key { long long sa, sb; long long t; } xb_pool_key;
+static int xb_pool_key_cmp(const void* x, const void* y) {
+  const xb_pool_key* a = (const xb_pool_key*)x; const xb_pool_key* b = (const xb_pool_key*)y;
+  if (a->sa != b->sa) return (a->sa < b->sa) ? -1 : 1;
+  if (a->sb != b->sb) return (a->sb < b->sb) ? -1 : 1;
+  return (a->t < b->t) ? -1 : (a->t > b->t);
+}
+static long long xb_gcd_ll(long long a, long long b) { while (b != 0) { const long long c = a % b; a = b; b = c; } return a; }
+
+/* returns 1 and fills the plan if the address-mode batch is a regular pool the tensor-core kernel can walk */
+static int xb_plan_try_pool(libxsmm_b200_gemm_plan* plan, const xb_slot* s, const libxsmm_gemm_param* params, long long count) {
+  const xb_gemm_desc* d = &s->u.gemm;
+  unsigned long long br; long long t, blk_a = 0, blk_b = 0, set_a = 0, set_b = 0; unsigned long long r;
+  uintptr_t base_a = (uintptr_t)-1, base_b = (uintptr_t)-1;
+  xb_pool_key* keys; int* sets; void** cptrs; int ok = 1;
+  if (d->br_type != 1 || g_force_simt || !xb_gemm_tc_shape_ok(d) || count > 0x7fffffffll) return 0;
+  if (params[0].op.tertiary == NULL) return 0;
+  br = *(const unsigned long long*)params[0].op.tertiary;
+  if (br == 0 || br > 4096) return 0;
+  for (t = 0; t < count && ok; ++t) {          /* pass 1: common block stride, lowest address */
+    const libxsmm_gemm_param* p = &params[t];
+    const void* const* pa = (const void* const*)p->a.primary; const void* const* pb = (const void* const*)p->b.primary;
+    if (p->op.tertiary == NULL || *(const unsigned long long*)p->op.tertiary != br || pa == NULL || pb == NULL
+     || xb_rt_ptr_kind(pa) == 1 || xb_rt_ptr_kind(pb) == 1 || xb_rt_ptr_kind(p->c.primary) == 0) { ok = 0; break; }
+    for (r = 1; r < br; ++r) {
+      const long long da = (long long)((uintptr_t)pa[r] - (uintptr_t)pa[r - 1]), db = (long long)((uintptr_t)pb[r] - (uintptr_t)pb[r - 1]);
+      if (blk_a == 0) { blk_a = da; blk_b = db; }
+      if (da != blk_a || db != blk_b || da <= 0 || db <= 0 || (da % 16) != 0 || (db % 16) != 0) { ok = 0; break; }
+    }
+    if ((uintptr_t)pa[0] < base_a) base_a = (uintptr_t)pa[0];
+    if ((uintptr_t)pb[0] < base_b) base_b = (uintptr_t)pb[0];
+  }
+  if (!ok || (base_a & 15) != 0 || (base_b & 15) != 0) return 0;
+  if (br == 1) { blk_a = 16; blk_b = 16; }
+  for (t = 0; t < count; ++t) {                /* pass 2: set stride = gcd of the set offsets */
+    set_a = xb_gcd_ll(set_a, (long long)((uintptr_t)((const void* const*)params[t].a.primary)[0] - base_a));
+    set_b = xb_gcd_ll(set_b, (long long)((uintptr_t)((const void* const*)params[t].b.primary)[0] - base_b));
+  }
+  if (set_a == 0) set_a = 16;
+  if (set_b == 0) set_b = 16;
+  if ((set_a % 16) != 0 || (set_b % 16) != 0) return 0;
+  keys = (xb_pool_key*)malloc((size_t)count * sizeof(*keys)); sets = (int*)malloc((size_t)count * 2 * sizeof(int)); cptrs = (void**)malloc((size_t)count * sizeof(void*));
+  if (keys == NULL || sets == NULL || cptrs == NULL) { free(keys); free(sets); free(cptrs); return 0; }
+  plan->pool.nsets_a = plan->pool.nsets_b = 1;
+  for (t = 0; t < count; ++t) {
+    keys[t].sa = (long long)((uintptr_t)((const void* const*)params[t].a.primary)[0] - base_a) / set_a;
+    keys[t].sb = (long long)((uintptr_t)((const void* const*)params[t].b.primary)[0] - base_b) / set_b;
+    keys[t].t = t;
+    if (keys[t].sa >= 0x7fffffffll || keys[t].sb >= 0x7fffffffll) ok = 0;
+    if (keys[t].sa + 1 > plan->pool.nsets_a) plan->pool.nsets_a = keys[t].sa + 1;
+    if (keys[t].sb + 1 > plan->pool.nsets_b) plan->pool.nsets_b = keys[t].sb + 1;
+  }
+  if (ok) {
+    qsort(keys, (size_t)count, sizeof(*keys), xb_pool_key_cmp);
+    for (t = 0; t < count; ++t) { sets[2 * t] = (int)keys[t].sa; sets[2 * t + 1] = (int)keys[t].sb; cptrs[t] = params[keys[t].t].c.primary; }
+    plan->d_sets = xb_rt_device_malloc((size_t)count * 2 * sizeof(int)); plan->d_cptrs = xb_rt_device_malloc((size_t)count * sizeof(void*));
+    if (plan->d_sets == NULL || plan->d_cptrs == NULL || 0 != xb_rt_memcpy(plan->d_sets, sets, (size_t)count * 2 * sizeof(int))
+     || 0 != xb_rt_memcpy(plan->d_cptrs, cptrs, (size_t)count * sizeof(void*))) { xb_rt_device_free(plan->d_sets); xb_rt_device_free(plan->d_cptrs); plan->d_sets = plan->d_cptrs = NULL; ok = 0; }
+  }
+  free(keys); free(sets); free(cptrs);
+  if (!ok) return 0;
+  plan->pool.base_a = (const void*)base_a; plan->pool.base_b = (const void*)base_b; plan->pool.blk_a = blk_a; plan->pool.blk_b = blk_b;
+  plan->pool.set_a = set_a; plan->pool.set_b = set_b; plan->pool.sets = plan->d_sets; plan->pool.cptrs = plan->d_cptrs;
+  plan->pooled = 1; plan->br = br; plan->slot = s; plan->count = count;
+  return 1;
+}
 
 LIBXSMM_API libxsmm_b200_gemm_plan* libxsmm_b200_gemm_plan_create(libxsmm_gemmfunction kernel,
   const libxsmm_gemm_param* params, long long count)
@@ -676,6 +747,7 @@ LIBXSMM_API libxsmm_b200_gemm_plan* libxsmm_b200_gemm_plan_create(libxsmm_gemmfu
   long long t;
   if (s == NULL || params == NULL || count <= 0) return NULL;
   plan = (libxsmm_b200_gemm_plan*)calloc(1, sizeof(*plan));
+  if (plan != NULL && xb_plan_try_pool(plan, s, params, count)) return plan;
   recs = (xb_gemm_rec*)calloc((size_t)count, sizeof(xb_gemm_rec));
   if (plan == NULL || recs == NULL) { free(plan); free(recs); return NULL; }
   /* pass 1: size of the per-tile index arrays (address: 2*br pointers, offset: 2*br offsets) */
@@ -718,6 +790,11 @@ LIBXSMM_API int libxsmm_b200_gemm_plan_run(const libxsmm_b200_gemm_plan* plan) {
   xb_gemm_launch L;
   int rc;
   if (plan == NULL) return -1;
+  if (plan->pooled) {
+    rc = xb_gemm_tc_launch_pooled(&plan->slot->u.gemm, &plan->pool, plan->br, plan->count);
+    if (rc == 0 && xb_rt_blocking()) rc = xb_rt_sync();
+    return rc;
+  }
   memset(&L, 0, sizeof(L));
   L.d = plan->slot->u.gemm; L.count = plan->count; L.recs = plan->d_recs;
   rc = xb_run_gemm_launch(&L);
@@ -725,9 +802,11 @@ LIBXSMM_API int libxsmm_b200_gemm_plan_run(const libxsmm_b200_gemm_plan* plan) {
   return rc;
 }
 
+LIBXSMM_API int libxsmm_b200_gemm_plan_is_pooled(const libxsmm_b200_gemm_plan* plan) { return (plan != NULL && plan->pooled) ? 1 : 0; }
+
 LIBXSMM_API void libxsmm_b200_gemm_plan_destroy(libxsmm_b200_gemm_plan* plan) {
   if (plan == NULL) return;
-  xb_rt_device_free(plan->d_recs); xb_rt_device_free(plan->d_arrays);
+  xb_rt_device_free(plan->d_recs); xb_rt_device_free(plan->d_arrays); xb_rt_device_free(plan->d_sets); xb_rt_device_free(plan->d_cptrs);
   free(plan);
 }
 

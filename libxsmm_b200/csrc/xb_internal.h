@@ -155,6 +155,14 @@ void xb_rt_scratch_reset(void);
 int xb_gemm_simt_launch(const xb_gemm_launch* L);
 int xb_gemm_tc_supported(const xb_gemm_desc* d);          /* pure host logic, no CUDA call */
 int xb_gemm_tc_launch(const xb_gemm_launch* L);
+/* pooled address mode (gemm plan): block r of tile p is base + set[p]*set_stride + r*blk_stride; see gemm_tc.cu */
+typedef struct xb_tc_pool {
+  const void* base_a; const void* base_b; long long blk_a, blk_b, set_a, set_b, nsets_a, nsets_b;
+  const void* sets;          /* device int2[count], sorted by (set of A, set of B) */
+  const void* cptrs;         /* device char*[count], C tile of every position */
+} xb_tc_pool;
+int xb_gemm_tc_shape_ok(const xb_gemm_desc* d);           /* everything xb_gemm_tc_supported checks except the batch-reduce mode */
+int xb_gemm_tc_launch_pooled(const xb_gemm_desc* d, const xb_tc_pool* pool, unsigned long long br, long long count);
 int xb_gemm_ts_supported(const xb_gemm_desc* d);          /* VNNI-packed A through tensor memory (gemm_ts.cu); pure host logic */
 int xb_gemm_ts_launch(const xb_gemm_launch* L);
 typedef struct xb_meltw_args {

@@ -25,7 +25,7 @@ def dispatch(case, ops):
     if case.br_type == 0:
         return X.libxsmm_dispatch_gemm(sh, case.flags, 0)
     brt = {1: X.GEMM_BATCH_REDUCE_ADDRESS, 2: X.GEMM_BATCH_REDUCE_OFFSET, 3: X.GEMM_BATCH_REDUCE_STRIDE}[case.br_type]
-    cfg = X.libxsmm_create_gemm_batch_reduce_config(brt, ops.stride_a, ops.stride_b, 0)
+    cfg = X.libxsmm_create_gemm_batch_reduce_config(brt, ops.stride_a if ops is not None else 0, ops.stride_b if ops is not None else 0, 0)
     return X.libxsmm_dispatch_brgemm(sh, case.flags, 0, cfg)
 
 

@@ -316,3 +316,44 @@ def test_vnni_a_on_tensor_cores(types):
             else:
                 thr = 1.2e-5 if tc == gen.F32 else 5e-3
                 assert gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc)) <= thr, (case, beta0)
+
+
+@pytest.mark.parametrize("tc", [gen.F32, gen.BF16])
+def test_address_mode_pool_on_tensor_cores(tc):
+    """ADDRESS batch-reduce whose pointers walk a pool of block-sets (mode R of the benchmark): the plan recognises the pool and
+    runs the tcgen05 kernel (set index = tensor-map coordinate, tiles visited sorted by set pair, operands of equal neighbours
+    shared through the stage ring). Every tile against the oracle called exactly like the reference (pointer arrays)."""
+    rng = np.random.default_rng(98)
+    for (m, n, k, br, nsets, count) in ((64, 64, 64, 8, 5, 300), (32, 48, 64, 2, 3, 41), (128, 64, 128, 3, 4, 57), (64, 64, 64, 1, 2, 9)):
+        case = cases.GemmCase(m, n, k, gen.BF16, gen.BF16, gen.F32, tc, flags=cases.FLAG_BETA_0, br_type=1, br=br)
+        blk_a, blk_b = m * k * 2, k * n * 2
+        pool_a = gen.values(rng, nsets * br * m * k, gen.BF16); pool_b = gen.values(rng, nsets * br * k * n, gen.BF16)
+        c0 = gen.values(rng, count * m * n, tc)
+        sa = rng.integers(0, nsets, size=count); sb = rng.integers(0, nsets, size=count)
+        kernel = dispatch(case, None)
+        assert kernel
+        d_a, d_b, d_c = dev(pool_a), dev(pool_b), dev(c0)
+        params = (X.GemmParam * count)(); keep = []
+        tsc = gen.TS[tc]
+        for t in range(count):
+            aa = (C.c_void_p * br)(*[d_a.data_ptr() + (int(sa[t]) * br + r) * blk_a for r in range(br)])
+            ab = (C.c_void_p * br)(*[d_b.data_ptr() + (int(sb[t]) * br + r) * blk_b for r in range(br)])
+            brv = C.c_ulonglong(br); keep += [aa, ab, brv]
+            params[t].op.tertiary = C.addressof(brv)
+            params[t].a.primary, params[t].b.primary = C.addressof(aa), C.addressof(ab)
+            params[t].c.primary = d_c.data_ptr() + t * m * n * tsc
+        plan = X.libxsmm_b200_gemm_plan_create(kernel, params, count)
+        assert plan and X.libxsmm_b200_gemm_plan_is_pooled(plan) == 1, (m, n, k, br)
+        for rep in range(2):
+            assert X.libxsmm_b200_gemm_plan_run(plan) == 0
+            X.check()
+        got = host(d_c, gen.NP_OF[tc])
+        want = c0.copy()
+        for t in range(count):
+            ha = (C.c_void_p * br)(*[pool_a.ctypes.data + (int(sa[t]) * br + r) * blk_a for r in range(br)])
+            hb = (C.c_void_p * br)(*[pool_b.ctypes.data + (int(sb[t]) * br + r) * blk_b for r in range(br)])
+            cv = want[t * m * n:(t + 1) * m * n]
+            assert run_gemm(oracle, case.dims, case.types, case.flags, 1, 0, 0, br, ha, hb, cv) == 0
+        thr = 1.2e-5 if tc == gen.F32 else 5e-3
+        assert gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc)) <= thr, (m, n, k, br, tc)
+        X.libxsmm_b200_gemm_plan_destroy(plan)
