@@ -29,6 +29,7 @@
 #include <string.h>
 #include "xb_internal.h"
 #include "xb_device.cuh"
+#include "xb_epilogue.cuh"
 
 namespace {
 
@@ -42,6 +43,8 @@ struct TcParams {
   long long count;
   char* c; long long tile_stride_c; long long ldc;
   int c_type, a_type, beta0;
+  int ep_mode, c_esz;                 // xb_epilogue.cuh
+  int sets_in_smem;                   // pooled: the CTA's slice of `sets` is copied behind the barriers at start
   uint32_t idesc;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // in 16-byte units
   // pooled address mode (libxsmm_b200_gemm_plan over ADDRESS batch-reduce): tile p reads block-set sets[p].x of A and
@@ -128,6 +131,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const long long chunk = (P.count + G - 1) / G;                       // pooled: contiguous range per CTA
   const long long n_local = pooled ? ((b * chunk < P.count) ? ((P.count - b * chunk < chunk) ? P.count - b * chunk : chunk) : 0)
                                    : ((b < P.count) ? (P.count - b + G - 1) / G : 0);
+  const int2* s_sets = reinterpret_cast<const int2*>(bars + 2 * MAX_STAGES + 2 * MAX_SLOTS + 2);     // pooled: this CTA's slice of the set pairs
+  const int2* my_sets = P.sets_in_smem ? s_sets : (pooled ? P.sets + b * chunk : nullptr);
+  if (P.sets_in_smem) { int2* w = const_cast<int2*>(s_sets); for (long long i = threadIdx.x; i < n_local; i += blockDim.x) w[i] = P.sets[b * chunk + i]; }
   const int loads_per_tile = (int)P.br * P.kchunks;
   const bool can_hold = pooled && loads_per_tile <= P.stages;          // a tile's operands fit the ring: equal neighbours re-use them
 
@@ -158,7 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const long long t = pooled ? b * chunk + i : b + i * G;
         int ta = (int)t, tb = (int)t;
         if (pooled) {
-          const int2 st = P.sets[t];
+          const int2 st = my_sets[i];
           const bool same = can_hold && i > 0 && st.x == prev.x && st.y == prev.y;
           prev = st; ta = st.x; tb = st.y;
           if (same) continue;                                          // operands of the previous tile are still in the ring
@@ -191,10 +197,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (long long i = 0; i < n_local; ++i) {
         bool reuse = false, last_of_run = true;
         if (can_hold) {
-          const long long pp = b * chunk + i;
-          const int2 st = P.sets[pp];
-          if (i > 0) { const int2 pv = P.sets[pp - 1]; reuse = (pv.x == st.x && pv.y == st.y); }
-          if (i + 1 < n_local) { const int2 nx = P.sets[pp + 1]; last_of_run = !(nx.x == st.x && nx.y == st.y); }
+          const int2 st = my_sets[i];
+          if (i > 0) { const int2 pv = my_sets[i - 1]; reuse = (pv.x == st.x && pv.y == st.y); }
+          if (i + 1 < n_local) { const int2 nx = my_sets[i + 1]; last_of_run = !(nx.x == st.x && nx.y == st.y); }
         }
         if (!reuse) { run_stage = stage; run_phase = phase; }
         int cs = run_stage; uint32_t cph = run_phase;
@@ -242,6 +247,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long t = pooled ? b * chunk + i : b + i * G;
       char* ctile = pooled ? ((i < n_local) ? P.cptrs[t] : nullptr) : P.c + t * P.tile_stride_c;
       const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
+      const long long ldcb = P.ldc * P.c_esz;
+      char* crow = valid ? ctile + (long long)row * P.c_esz : nullptr;
       for (int c0 = 0; c0 < P.np; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
@@ -250,33 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_base + 8 * (2 * S + NS + slot));
         }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c0 + j;
-            if (col < P.n) {
-              const long long idx = (long long)col * P.ldc + row;
-              float acc = __uint_as_float(v[j]);
-              if (P.c_type == LIBXSMM_DATATYPE_F32) {
-                float* dst = reinterpret_cast<float*>(ctile) + idx;
-                if (!P.beta0) {
-                  float old = *dst;
-                  if (P.a_type == LIBXSMM_DATATYPE_F16) old = xb_f16_to_f32(xb_f32_to_f16(old));  // reference :2118-2123
-                  acc += old;
-                }
-                *dst = acc;
-              } else if (P.c_type == LIBXSMM_DATATYPE_BF16) {
-                unsigned short* dst = reinterpret_cast<unsigned short*>(ctile) + idx;
-                if (!P.beta0) acc += xb_bf16_to_f32(*dst);
-                *dst = xb_f32_to_bf16_rne(acc);
-              } else {
-                unsigned short* dst = reinterpret_cast<unsigned short*>(ctile) + idx;
-                if (!P.beta0) acc += xb_f16_to_f32(*dst);
-                *dst = xb_f32_to_f16(acc);
-              }
-            }
-          }
-        }
+        if (valid && c0 < P.n) xb_ep_store_chunk(P.ep_mode, P.beta0, v, crow + c0 * ldcb, ldcb, P.n - c0, 0.0f);
       }
     }
   }
@@ -395,6 +376,7 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
   if (pool != nullptr) { P.sets = (const int2*)pool->sets; P.cptrs = (char* const*)pool->cptrs; }
   P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0;
+  P.ep_mode = xb_ep_mode(d.ta, d.tc, &P.c_esz);
   // instruction descriptor: D=f32, A/B format, A MN-major, B K-major, N>>3, M>>4
   const uint32_t fmt = (d.ta == LIBXSMM_DATATYPE_BF16) ? 1u : 0u;
   P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(P.np >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
@@ -425,9 +407,13 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
     if (r != CUDA_SUCCESS) return (pool != nullptr) ? 1 : xb_gemm_simt_launch(L);
   }
 
-  const size_t smem = (size_t)P.stages * P.stage_bytes + 1024 /*align slack*/ + (2 * 16 + 2 * 8) * 8 + 64;
+  size_t smem = (size_t)P.stages * P.stage_bytes + 1024 /*align slack*/ + (2 * 16 + 2 * 8) * 8 + 64;
   const long long tiles_per_cta_unit = (UM == 64) ? 2 : 1;
   long long grid = (L->count + tiles_per_cta_unit - 1) / tiles_per_cta_unit; if (grid > (long long)g_num_sms * ctas) grid = (long long)g_num_sms * ctas; if (grid < 1) grid = 1;
+  if (pool != nullptr) {
+    const size_t sets_bytes = (size_t)((L->count + grid - 1) / grid) * sizeof(int2);
+    if (sets_bytes <= 16 * 1024 && smem + sets_bytes <= (size_t)(227 * 1024) / ctas) { P.sets_in_smem = 1; smem += sets_bytes; }
+  }
   cudaStream_t stream = (cudaStream_t)xb_rt_stream();
   cudaError_t e;
   if (UM == 64) {

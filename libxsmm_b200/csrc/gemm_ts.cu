@@ -28,6 +28,7 @@
 #include "xb_internal.h"
 #include "xb_device.cuh"
 #include "xb_tma.cuh"
+#include "xb_epilogue.cuh"
 
 namespace {
 
@@ -41,8 +42,10 @@ struct TsParams {
   long long count;
   char* c; long long tile_stride_c, ldc;
   int c_type, a_type, beta0, is_i8;
+  int ep_mode, c_esz;           // xb_epilogue.cuh
   float scf;
   uint32_t idesc;
+  int skip;                     // diagnostic (LIBXSMM_B200_TS_SKIP): 1 no C stores, 2 no MMAs, 4 no TMEM copy, 8 no TMA loads, 16 no A load, 32 no B load
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,6 +145,14 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int kc = 0; kc < P.kchunks; ++kc) {
             mbar_wait(empty + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
+            if (P.skip & 8) { mbar_arrive(full + 8 * stage); if (++stage == S) { stage = 0; phase ^= 1; } continue; }
+            if (P.skip & 48) {
+              mbar_expect_tx(full + 8 * stage, (uint32_t)((P.skip & 16) ? P.np * 128 : P.m * 128));
+              if (!(P.skip & 16)) tma_load_4d(sa, &map_a, full + 8 * stage, 0, kc * 32, (int)r, (int)t);
+              if (!(P.skip & 32)) tma_load_4d(sb, &map_b, full + 8 * stage, kc * P.kc_elems, 0, (int)r, (int)t);
+              if (++stage == S) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_expect_tx(full + 8 * stage, (uint32_t)P.tx_bytes);         // rows / words beyond the matrix are zero-filled and counted
             tma_load_4d(sa, &map_a, full + 8 * stage, 0, kc * 32, (int)r, (int)t);               // m words x 32 word-rows
             tma_load_4d(sb, &map_b, full + 8 * stage, kc * P.kc_elems, 0, (int)r, (int)t);       // 128 bytes of k x np rows
@@ -169,7 +180,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int krem = P.k - kc * P.kc_elems;
             const int ksteps = (krem >= P.kc_elems) ? 4 : (krem + P.kinst - 1) / P.kinst;
             const uint32_t a_slot = tmem_a + (uint32_t)stage * 32u;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = 0; ks < ((P.skip & 2) ? 0 : ksteps); ++ks) {
               const uint64_t bdesc = make_desc_b(sb + ks * 32);                 // 32 bytes of k inside the swizzled 128-byte row
               if (P.is_i8) umma_i8_ts(d_tmem, a_slot + (uint32_t)ks * 8u, bdesc, P.idesc, accumulate);
               else umma_f16_ts(d_tmem, a_slot + (uint32_t)ks * 8u, bdesc, P.idesc, accumulate);
@@ -190,48 +201,15 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int slot = (int)(i % NS);
       mbar_wait(t_full + 8 * slot, (uint32_t)((i / NS) & 1));
       tc_fence_after();
-      const bool valid = row < P.m;
-      char* ctile = P.c + (b + i * G) * P.tile_stride_c;
+      const bool valid = row < P.m && !(P.skip & 1);
+      const long long ldcb = P.ldc * P.c_esz;
+      char* crow = P.c + (b + i * G) * P.tile_stride_c + (long long)row * P.c_esz;
       const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < P.np; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         if (c0 + 32 >= P.np) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c0 + j;
-            if (col < P.n) {
-              const long long idx = (long long)col * P.ldc + row;
-              if (P.is_i8) {
-                if (P.c_type == LIBXSMM_DATATYPE_I32) {
-                  int* dst = reinterpret_cast<int*>(ctile) + idx;
-                  *dst = (int)(v[j] + (P.beta0 ? 0u : (unsigned int)*dst));           // wrap-around like the reference's int accumulator
-                } else {                                                                 // I8 x I8 -> F32 with the scalar scale (:1556-1683)
-                  float* dst = reinterpret_cast<float*>(ctile) + idx;
-                  float f = __fmul_rn((float)(int)v[j], P.scf);
-                  if (!P.beta0) f = __fadd_rn(f, *dst);
-                  *dst = f;
-                }
-              } else {
-                float acc = __uint_as_float(v[j]);
-                if (P.c_type == LIBXSMM_DATATYPE_F32) {
-                  float* dst = reinterpret_cast<float*>(ctile) + idx;
-                  if (!P.beta0) { float old = *dst; if (P.a_type == LIBXSMM_DATATYPE_F16) old = xb_f16_to_f32(xb_f32_to_f16(old)); acc += old; }
-                  *dst = acc;
-                } else if (P.c_type == LIBXSMM_DATATYPE_BF16) {
-                  unsigned short* dst = reinterpret_cast<unsigned short*>(ctile) + idx;
-                  if (!P.beta0) acc += xb_bf16_to_f32(*dst);
-                  *dst = xb_f32_to_bf16_rne(acc);
-                } else {
-                  unsigned short* dst = reinterpret_cast<unsigned short*>(ctile) + idx;
-                  if (!P.beta0) acc += xb_f16_to_f32(*dst);
-                  *dst = xb_f32_to_f16(acc);
-                }
-              }
-            }
-          }
-        }
+        if (valid && c0 < P.n) xb_ep_store_chunk(P.ep_mode, P.beta0, v, crow + c0 * ldcb, ldcb, P.n - c0, P.scf);
       }
     }
   } else {
@@ -247,10 +225,12 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kc = 0; kc < P.kchunks; ++kc) {
           mbar_wait(full + 8 * stage, phase);
           const unsigned int* src = reinterpret_cast<const unsigned int*>(smem + (size_t)stage * P.stage_bytes) + rr;
+          if (!(P.skip & 4)) {
           uint32_t w[32];
 #pragma unroll
           for (int kv = 0; kv < 32; ++kv) w[kv] = src[(size_t)kv * P.m];
           tmem_st32(tmem_a + (uint32_t)stage * 32u + ((uint32_t)(q * 32) << 16), w);
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full + 8 * stage);
@@ -333,6 +313,8 @@ extern "C" int xb_gemm_ts_launch(const xb_gemm_launch* L) {
   if (P.stages < 2) return xb_gemm_simt_launch(L);
   P.a_col0 = P.nslot * P.slot_cols;
   P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
+  P.skip = ts_env_int("LIBXSMM_B200_TS_SKIP", 0);
+  P.ep_mode = xb_ep_mode(d.ta, d.tc, &P.c_esz);
   P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0; P.is_i8 = is_i8; P.scf = L->one.scf;
   if (is_i8) {
     const uint32_t fa = (d.ta == LIBXSMM_DATATYPE_I8) ? 1u : 0u, fb = (d.tb == LIBXSMM_DATATYPE_I8) ? 1u : 0u;

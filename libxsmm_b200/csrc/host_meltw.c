@@ -189,15 +189,23 @@ void xb_invoke_meltw(const xb_slot* s, const void* param) {
     const libxsmm_meltw_unary_param* p = (const libxsmm_meltw_unary_param*)param;
     const int op = d->op;
     long long n = d->n;
-    size_t ext_in, ext_out = ((size_t)(d->n - 1) * d->ldo + d->m) * ts_out;
+    size_t ext_in, ext_out = ((size_t)(d->n - 1) * d->ldo + d->m) * ts_out, mx_scales = 0;
     if (op == LIBXSMM_MELTW_TYPE_UNARY_REPLICATE_COL_VAR) { n = (long long)*(const unsigned long long*)p->op.primary; a.n_rt = (unsigned long long)n; ext_out = ((size_t)(n - 1) * d->ldo + d->m) * ts_out; }
     ext_in = in_extent(d, d->flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_ROW, (d->flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_COL) | (op == LIBXSMM_MELTW_TYPE_UNARY_REPLICATE_COL_VAR),
                        d->flags & LIBXSMM_MELTW_FLAG_UNARY_BCAST_SCALAR, d->ldi, n) * ts_in;
     switch (op) {
       case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU: case LIBXSMM_MELTW_TYPE_UNARY_ELU: case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU_INV:
       case LIBXSMM_MELTW_TYPE_UNARY_ELU_INV: a.alpha = *(const float*)p->op.primary; break;
-      case LIBXSMM_MELTW_TYPE_UNARY_QUANT: case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT:
-        a.alpha = ((d->flags & LIBXSMM_MELTW_FLAG_UNARY_NO_SCF_QUANT) != 0) ? 1.0f : *(const float*)p->in.secondary; break;
+      case LIBXSMM_MELTW_TYPE_UNARY_QUANT: case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT: {
+        const int mx = (d->t_out == LIBXSMM_DATATYPE_MXFP4X2 || d->t_out == LIBXSMM_DATATYPE_NVFP4X2 || d->t_out == LIBXSMM_DATATYPE_MXBF8);
+        a.alpha = (mx || (d->flags & LIBXSMM_MELTW_FLAG_UNARY_NO_SCF_QUANT) != 0 || p->in.secondary == NULL) ? 1.0f : *(const float*)p->in.secondary;
+        if (mx) {   /* block formats: 4-bit data at ldo/2 bytes per column, one scale byte per block in out.secondary (reference :2247-2326) */
+          const int blk = (d->t_out == LIBXSMM_DATATYPE_NVFP4X2) ? 16 : 32;
+          const size_t per = (d->t_out == LIBXSMM_DATATYPE_MXBF8) ? 1 : 2;
+          ext_out = ((size_t)(d->n - 1) * (d->ldo / per) + (size_t)(d->m / blk) * blk / per);
+          mx_scales = ((size_t)(d->n - 1) * (d->ldo / blk) + (size_t)(d->m / blk));
+        }
+      } break;
       case LIBXSMM_MELTW_TYPE_UNARY_DROPOUT: case LIBXSMM_MELTW_TYPE_UNARY_DROPOUT_INV: {   /* op.primary -> drop probability p */
         if (xb_rt_ptr_kind(p->op.primary) == 1) xb_rt_memcpy(&a.alpha, p->op.primary, sizeof(float)); else a.alpha = *(const float*)p->op.primary;
       } break;
@@ -251,6 +259,7 @@ void xb_invoke_meltw(const xb_slot* s, const void* param) {
         else { a.off[0] = offs[0]; if (op == LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X3) a.off[1] = offs[1]; }
         a.out = p->out.primary;
       } else a.out = stage_inout(&st, p->out.primary, ext_out);
+      if (mx_scales != 0) { a.out_aux = stage_inout(&st, p->out.secondary, mx_scales); if (a.out_aux == NULL) st.failed = 1; }
       if (op == LIBXSMM_MELTW_TYPE_UNARY_DROPOUT) {      /* op.secondary: generator state, read AND advanced (:2091, :43-73) */
         a.rng = stage_inout(&st, p->op.secondary, 64 * sizeof(unsigned int));
         a.rnd = (float*)xb_rt_scratch((size_t)LIBXSMM_UPDIV(d->m, 16) * d->n * 16 * sizeof(float));

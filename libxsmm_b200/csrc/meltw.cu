@@ -19,9 +19,11 @@
 
 namespace {
 
-enum { FAM_NONE = 0, FAM_MAP, FAM_REDUCE, FAM_SCALAR, FAM_TRANSFORM, FAM_GS, FAM_QUANT, FAM_DROPOUT, FAM_SPLIT };
+enum { FAM_NONE = 0, FAM_MAP, FAM_REDUCE, FAM_SCALAR, FAM_TRANSFORM, FAM_GS, FAM_QUANT, FAM_DROPOUT, FAM_SPLIT, FAM_MXQUANT };
 
-__host__ __device__ inline bool is_f(int t) { return t == LIBXSMM_DATATYPE_F32 || t == LIBXSMM_DATATYPE_BF16 || t == LIBXSMM_DATATYPE_F16; }
+__host__ __device__ inline bool is_f(int t) {
+  return t == LIBXSMM_DATATYPE_F32 || t == LIBXSMM_DATATYPE_BF16 || t == LIBXSMM_DATATYPE_F16 || t == LIBXSMM_DATATYPE_BF8 || t == LIBXSMM_DATATYPE_HF8;
+}
 
 __host__ __device__ inline int family_of(const xb_meltw_desc& d) {
   if (d.op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
@@ -61,6 +63,7 @@ __host__ __device__ inline int family_of(const xb_meltw_desc& d) {
       case LIBXSMM_MELTW_TYPE_UNARY_GATHER: case LIBXSMM_MELTW_TYPE_UNARY_SCATTER:
         return (xb_dev_typesize(d.t_in0) <= 4 && xb_dev_typesize(d.t_in0) >= 1) ? FAM_GS : FAM_NONE;
       case LIBXSMM_MELTW_TYPE_UNARY_QUANT:
+        if (d.t_in0 == LIBXSMM_DATATYPE_BF16 && (d.t_out == LIBXSMM_DATATYPE_MXFP4X2 || d.t_out == LIBXSMM_DATATYPE_NVFP4X2 || d.t_out == LIBXSMM_DATATYPE_MXBF8)) return FAM_MXQUANT;
         return (d.t_in0 == LIBXSMM_DATATYPE_F32 && (d.t_out == LIBXSMM_DATATYPE_I8 || d.t_out == LIBXSMM_DATATYPE_I16 || d.t_out == LIBXSMM_DATATYPE_I32)) ? FAM_QUANT : FAM_NONE;
       case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT:
         return (d.t_out == LIBXSMM_DATATYPE_F32 && (d.t_in0 == LIBXSMM_DATATYPE_I8 || d.t_in0 == LIBXSMM_DATATYPE_I16 || d.t_in0 == LIBXSMM_DATATYPE_I32)) ? FAM_QUANT : FAM_NONE;
@@ -114,11 +117,15 @@ __host__ __device__ inline int family_of(const xb_meltw_desc& d) {
 __device__ __forceinline__ float ld_f32(const void* p, long long idx, int t) {
   if (t == LIBXSMM_DATATYPE_F32) return ((const float*)p)[idx];
   if (t == LIBXSMM_DATATYPE_BF16) { unsigned short h = ((const unsigned short*)p)[idx]; if ((h & 0x7f80) == 0) h &= 0x8000; return xb_bf16_to_f32(h); }
+  if (t == LIBXSMM_DATATYPE_BF8) return xb_bf8_to_f32(((const unsigned char*)p)[idx]);
+  if (t == LIBXSMM_DATATYPE_HF8) return xb_hf8_to_f32(((const unsigned char*)p)[idx]);
   return xb_f16_to_f32(((const unsigned short*)p)[idx]);
 }
 __device__ __forceinline__ void st_f32(void* p, long long idx, int t, float v) {
   if (t == LIBXSMM_DATATYPE_F32) ((float*)p)[idx] = v;
   else if (t == LIBXSMM_DATATYPE_BF16) ((unsigned short*)p)[idx] = xb_f32_to_bf16_rne(v);
+  else if (t == LIBXSMM_DATATYPE_BF8) ((unsigned char*)p)[idx] = xb_f32_to_bf8(v);
+  else if (t == LIBXSMM_DATATYPE_HF8) ((unsigned char*)p)[idx] = xb_f32_to_hf8(v);
   else ((unsigned short*)p)[idx] = xb_f32_to_f16(v);
 }
 // operand index with broadcast flags; which: 0,1,2 = in0,in1,in2
@@ -445,18 +452,30 @@ __global__ void __launch_bounds__(256) meltw_transform_kernel(const xb_meltw_des
 }
 
 // ---- bandwidth versions of the three layout/reduction kernels that matter at size (K7 of SURVEY.md 2.3) ------------------------
-// transpose: 32 x 32 tiles through shared memory, both the read (rows of the input) and the write (rows of the output) coalesced
+// transpose: 64 x 64 tiles through shared memory, one tile per CTA; both the read (rows of the input) and the write (rows of
+// the output) are coalesced and every thread has its 16 loads in flight before the first store
 template <typename E>
 __global__ void __launch_bounds__(256) meltw_transpose_tiled_kernel(const E* __restrict__ in, E* __restrict__ out, long long M, long long N, long long ldi, long long ldo) {
-  __shared__ E tile[32][33];
+  __shared__ E tile[64][65];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                 // 32 x 8 threads
-  const long long tiles_j = (M + 31) / 32, tiles_i = (N + 31) / 32;
-  for (long long t = blockIdx.x; t < tiles_j * tiles_i; t += gridDim.x) {
-    const long long j0 = (t % tiles_j) * 32, i0 = (t / tiles_j) * 32;     // in[i*ldi + j], j contiguous, j < M, i < N
-    for (int ii = ty; ii < 32; ii += 8) if (i0 + ii < N && j0 + tx < M) tile[ii][tx] = in[(i0 + ii) * ldi + j0 + tx];
-    __syncthreads();
-    for (int jj = ty; jj < 32; jj += 8) if (j0 + jj < M && i0 + tx < N) out[(j0 + jj) * ldo + i0 + tx] = tile[tx][jj];
-    __syncthreads();
+  const long long tiles_j = (M + 63) / 64;
+  const long long t = blockIdx.x;
+  const long long j0 = (t % tiles_j) * 64, i0 = (t / tiles_j) * 64;       // in[i*ldi + j], j contiguous, j < M, i < N
+  E v[16];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const long long i = i0 + ty + 8 * r;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) v[2 * r + h] = (i < N && j0 + tx + 32 * h < M) ? in[i * ldi + j0 + tx + 32 * h] : (E)0;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) { tile[ty + 8 * r][tx] = v[2 * r]; tile[ty + 8 * r][tx + 32] = v[2 * r + 1]; }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const long long j = j0 + ty + 8 * r;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) if (j < M && i0 + tx + 32 * h < N) out[j * ldo + i0 + tx + 32 * h] = tile[tx + 32 * h][ty + 8 * r];
   }
 }
 // NORM -> VNNI-v pack: a thread takes 4 consecutive rows of one group of v columns: v loads of 4 elements, 4 stores of one
@@ -478,6 +497,70 @@ __global__ void __launch_bounds__(256) meltw_vnni_pack_kernel(const E* __restric
 #pragma unroll
       for (int c = 0; c < V; ++c) out[(g * ldo + i0 + r) * V + c] = v[c][r];
     }
+  }
+}
+// the same pack with 16-byte accesses: a thread takes R = 16/sizeof(E) consecutive rows of one group of v columns (v loads of
+// 16 bytes, v stores of 16 contiguous bytes); needs M, ldi, ldo multiples of R and 16-byte aligned bases
+template <typename E, int V>
+__global__ void __launch_bounds__(256) meltw_vnni_pack_vec_kernel(const E* __restrict__ in, E* __restrict__ out, long long M, long long N, long long ldi, long long ldo) {
+  constexpr int R = 16 / (int)sizeof(E);
+  const long long groups = (N + V - 1) / V, chunks = ldo / R;
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= groups * chunks) return;
+  const long long g = e / chunks, i0 = (e % chunks) * R;
+  union { uint4 q; E e[R]; } src[V];
+  union { uint4 q[V]; E e[R * V]; } dst;
+#pragma unroll
+  for (int c = 0; c < V; ++c) {
+    const long long col = g * V + c;
+    src[c].q = (col < N && i0 < M) ? *reinterpret_cast<const uint4*>(in + col * ldi + i0) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int c = 0; c < V; ++c) dst.e[r * V + c] = src[c].e[r];
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + (g * ldo + i0) * V);
+#pragma unroll
+  for (int c = 0; c < V; ++c) o[c] = dst.q[c];
+}
+// column sums of an f32 matrix with 16-byte loads: a warp covers 128 consecutive rows (one float4 per lane), the 8 warps of a
+// CTA take the columns of the CTA's slice round-robin, four columns in flight per warp; the CTA's eight partial sums are added
+// in warp order through shared memory
+__global__ void __launch_bounds__(256) meltw_reduce_cols_partial_vec_kernel(const float* __restrict__ in, long long M, long long N, long long ldi, float* __restrict__ part, int want_x2) {
+  __shared__ float4 sh[2][8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long i = ((long long)blockIdx.x * 32 + lane) * 4;
+  const long long per = (N + gridDim.y - 1) / gridDim.y, j0 = blockIdx.y * per, j1 = (j0 + per < N) ? j0 + per : N;
+  float4 sx = make_float4(0.f, 0.f, 0.f, 0.f), sq = sx;
+  if (i < M) {
+    long long j = j0 + w;
+    for (; j + 24 < j1; j += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(in + (j + 8 * u) * ldi + i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sx.x += v[u].x; sx.y += v[u].y; sx.z += v[u].z; sx.w += v[u].w;
+        sq.x += v[u].x * v[u].x; sq.y += v[u].y * v[u].y; sq.z += v[u].z * v[u].z; sq.w += v[u].w * v[u].w;
+      }
+    }
+    for (; j < j1; j += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(in + j * ldi + i);
+      sx.x += v.x; sx.y += v.y; sx.z += v.z; sx.w += v.w;
+      sq.x += v.x * v.x; sq.y += v.y * v.y; sq.z += v.z * v.z; sq.w += v.w * v.w;
+    }
+  }
+  sh[0][w][lane] = sx; sh[1][w][lane] = sq;
+  __syncthreads();
+  if (w == 0 && i < M) {
+    float4 a = sh[0][0][lane], b = sh[1][0][lane];
+    for (int k = 1; k < 8; ++k) {
+      const float4 x = sh[0][k][lane], y = sh[1][k][lane];
+      a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w; b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+    }
+    *reinterpret_cast<float4*>(part + (size_t)blockIdx.y * M + i) = a;
+    if (want_x2) *reinterpret_cast<float4*>(part + (size_t)(gridDim.y + blockIdx.y) * M + i) = b;
   }
 }
 // column reduction (one result per ROW i, the input's contiguous index): lanes take consecutive rows, so every load of a
@@ -520,6 +603,79 @@ __global__ void __launch_bounds__(256) meltw_gs_kernel(const xb_meltw_desc d, co
     const long long x = idx8 ? (long long)((const unsigned long long*)idxp)[sel] : (long long)((const unsigned int*)idxp)[sel];
     if (gather) out[i + j * ldo] = cols ? in[i + x * ldi] : (rows ? in[x + j * ldi] : in[x]);
     else { if (cols) out[i + x * ldo] = in[i + j * ldi]; else if (rows) out[x + j * ldo] = in[i + j * ldi]; else out[x] = in[i + j * ldi]; }
+  }
+}
+
+// ---- block-scaled quantisers: bf16 -> MXFP4 (32 rows, E8M0 scale), NVFP4 (16 rows, E4M3 scale), MXBF8 (32 rows, E8M0) -------------
+// reference :1796-2073 (block converters) and :2247-2326 (layout: data ld = ldo/2 bytes for the 4-bit formats, scales ld = ldo/block).
+// One thread owns one block: the block's values stay in registers between the amax pass and the encode pass.
+__device__ __forceinline__ unsigned int mx_e2m1(float a) {             // |x| -> code of {0, .5, 1, 1.5, 2, 3, 4, 6}; ties to the even code
+  if (a != a) return 7u;
+  unsigned int c = (a > 0.25f) + (a >= 0.75f) + (a > 1.25f) + (a >= 1.75f) + (a > 2.5f) + (a >= 3.5f) + (a > 5.0f);
+  return c;
+}
+__device__ __forceinline__ unsigned int mx_e4m3_scale(float v) {       // RNE, clamp to 448, flush below 2^-10 (:1812-1893)
+  const unsigned int u = __float_as_uint(v), sign = (u >> 31) << 7, ef = (u >> 23) & 0xffu, mf = u & 0x7fffffu;
+  int e = (int)ef - 127;
+  if (ef == 0xffu && mf != 0u) return sign | 0x7fu;
+  if (ef == 0xffu || fabsf(v) > 448.0f || e > 8) return sign | 0x78u;
+  if (ef == 0u || e < -9) return sign;
+  if (e >= -6) {
+    unsigned int m = mf >> 20;
+    if (((mf >> 19) & 1u) && ((mf & 0x7ffffu) || (m & 1u))) ++m;
+    if (m == 8u) { m = 0u; ++e; }
+    return (e + 7 >= 15) ? (sign | 0x78u) : (sign | ((unsigned int)(e + 7) << 3) | m);
+  }
+  const int sh = -6 - e;
+  const unsigned int full = 8u | (mf >> 20);
+  const bool sticky = ((full & ((1u << (sh - 1)) - 1u)) != 0u) || ((mf & 0xfffffu) != 0u);
+  unsigned int m = full >> sh;
+  if (((full >> (sh - 1)) & 1u) && (sticky || (m & 1u))) ++m;
+  return (m >= 8u) ? (sign | 0x08u) : (sign | (m & 7u));
+}
+__device__ __forceinline__ float mx_bf16_round(float f) { return __uint_as_float((unsigned int)xb_f32_to_bf16_rne(f) << 16); }
+template <int BLK, int KIND>     // KIND 0: MXFP4, 1: NVFP4, 2: MXBF8
+__global__ void __launch_bounds__(128) meltw_mxquant_kernel(const unsigned short* __restrict__ in, unsigned char* __restrict__ out, unsigned char* __restrict__ scl,
+                                                            int m, int n, long long ldi, long long ldo) {
+  const long long blocks_m = m / BLK, ld_data = (KIND == 2) ? ldo : ldo / 2, ld_scl = ldo / BLK;
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= blocks_m * n) return;
+  const long long b = e % blocks_m, j = e / blocks_m;
+  const unsigned short* src = in + j * ldi + b * BLK;
+  float x[BLK];
+  float amax = 0.0f;
+#pragma unroll
+  for (int k = 0; k < BLK; ++k) { x[k] = __uint_as_float((unsigned int)src[k] << 16); const float a = fabsf(x[k]); if (a > amax || a != a) amax = a; }
+  unsigned char* o = out + j * ld_data + b * ((KIND == 2) ? BLK : BLK / 2);
+  if (KIND == 1) {
+    unsigned int sc = 0u; float sv = 0.0f;
+    if (amax != 0.0f) { sc = mx_e4m3_scale(mx_bf16_round(__fmul_rn(mx_bf16_round(amax), __uint_as_float(0x3e2a0000u)))); sv = xb_hf8_to_f32((uint8_t)sc); }
+    scl[j * ld_scl + b] = (unsigned char)sc;
+    const float rcp = (sv == 0.0f) ? 0.0f : mx_bf16_round(__fdiv_rn(1.0f, mx_bf16_round(sv)));
+#pragma unroll
+    for (int k = 0; k < BLK / 2; ++k) {
+      const unsigned int lo = ((__float_as_uint(x[2 * k]) >> 31) << 3) | mx_e2m1(fabsf(mx_bf16_round(__fmul_rn(x[2 * k], rcp))));
+      const unsigned int hi = ((__float_as_uint(x[2 * k + 1]) >> 31) << 3) | mx_e2m1(fabsf(mx_bf16_round(__fmul_rn(x[2 * k + 1], rcp))));
+      o[k] = (sv == 0.0f) ? (unsigned char)0 : (unsigned char)((hi << 4) | lo);
+    }
+  } else {
+    int se = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+    const bool special = (se == 0xff);
+    const int emax = (KIND == 0) ? 2 : 15;
+    se = special ? 0xff : (se - emax < 0 ? 0 : se - emax);
+    scl[j * ld_scl + b] = (unsigned char)se;
+    const float scale = __uint_as_float(((unsigned int)se << 23) | ((se == 0 || special) ? 0x400000u : 0u));
+    if (KIND == 0) {
+#pragma unroll
+      for (int k = 0; k < BLK / 2; ++k) {
+        const unsigned int lo = ((__float_as_uint(x[2 * k]) >> 31) << 3) | mx_e2m1(fabsf(__fdiv_rn(x[2 * k], scale)));
+        const unsigned int hi = ((__float_as_uint(x[2 * k + 1]) >> 31) << 3) | mx_e2m1(fabsf(__fdiv_rn(x[2 * k + 1], scale)));
+        o[k] = special ? (unsigned char)0x77 : (unsigned char)((hi << 4) | lo);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < BLK; ++k) o[k] = special ? (unsigned char)0x7b : (unsigned char)xb_f32_to_bf8(__fdiv_rn(x[k], scale));
+    }
   }
 }
 
@@ -635,11 +791,15 @@ extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
       const bool sum_op = (d->op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ADD || d->op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X2_OP_ADD || d->op == LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_X2_OP_ADD);
       if (sum_op && (d->flags & LIBXSMM_MELTW_FLAG_UNARY_REDUCE_ROWS) == 0 && d->t_in0 != LIBXSMM_DATATYPE_F64 && (long long)d->m * d->n >= (1 << 18) && d->m >= 256) {
         // big column reduction: coalesced two-phase version (partial sums per column slice, then the slices in order)
-        int slices = (int)(((long long)148 * 8 * 256 + d->m - 1) / d->m); if (slices > d->n / 16) slices = d->n / 16; if (slices < 1) slices = 1; if (slices > 256) slices = 256;
+        int slices = (int)(((long long)148 * 4 * 128 + d->m - 1) / d->m); if (slices > d->n / 16) slices = d->n / 16; if (slices < 1) slices = 1; if (slices > 256) slices = 256;
         const int want_x2 = (d->op != LIBXSMM_MELTW_TYPE_UNARY_REDUCE_X_OP_ADD);
         float* part = (float*)xb_rt_scratch((size_t)2 * slices * d->m * sizeof(float));
         if (part != nullptr) {
           const dim3 g((d->m + 255) / 256, slices);
+          if (d->t_in0 == LIBXSMM_DATATYPE_F32 && (d->m % 4) == 0 && (d->ldi % 4) == 0 && ((uintptr_t)a->in0 & 15) == 0) {
+            const dim3 gv((d->m + 127) / 128, slices);
+            meltw_reduce_cols_partial_vec_kernel<<<gv, 256, 0, st>>>((const float*)a->in0, d->m, d->n, d->ldi, part, want_x2);
+          } else
           meltw_reduce_cols_partial_kernel<<<g, 256, 0, st>>>(*d, *a, part, want_x2);
           if (launch_done("meltw_reduce_partial") != 0) return 1;
           meltw_reduce_cols_final_kernel<<<(d->m + 255) / 256, 256, 0, st>>>(*d, *a, part, slices);
@@ -661,8 +821,9 @@ extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
       long long grid = (work + 255) / 256; if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
       const int ts = xb_dev_typesize(d->t_in0);
       if (fam == FAM_TRANSFORM && d->op == LIBXSMM_MELTW_TYPE_UNARY_TRANSFORM_NORM_TO_NORMT && (long long)d->m * d->n >= 4096) {
-        const long long tiles = (long long)((d->m + 31) / 32) * ((d->n + 31) / 32);
-        const unsigned int tg = (unsigned int)(tiles < 148 * 16 ? tiles : 148 * 16);
+        const long long tiles = (long long)((d->m + 63) / 64) * ((d->n + 63) / 64);
+        if (tiles > 0x7fffffffll) return 1;
+        const unsigned int tg = (unsigned int)tiles;
         if (ts == 8) meltw_transpose_tiled_kernel<unsigned long long><<<tg, 256, 0, st>>>((const unsigned long long*)a->in0, (unsigned long long*)a->out, d->m, d->n, d->ldi, d->ldo);
         else if (ts == 4) meltw_transpose_tiled_kernel<unsigned int><<<tg, 256, 0, st>>>((const unsigned int*)a->in0, (unsigned int*)a->out, d->m, d->n, d->ldi, d->ldo);
         else if (ts == 2) meltw_transpose_tiled_kernel<unsigned short><<<tg, 256, 0, st>>>((const unsigned short*)a->in0, (unsigned short*)a->out, d->m, d->n, d->ldi, d->ldo);
@@ -674,6 +835,16 @@ extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
         const int V = (ts == 2) ? 2 : 4;
         const long long workp = (long long)((d->n + V - 1) / V) * ((d->ldo + 3) / 4);
         long long pg = (workp + 255) / 256; if (pg > 148 * 16) pg = 148 * 16;
+        const int R = 16 / ts;
+        if ((d->m % R) == 0 && (d->ldi % R) == 0 && (d->ldo % R) == 0 && (((uintptr_t)a->in0 | (uintptr_t)a->out) & 15) == 0) {
+          const long long items = (long long)((d->n + V - 1) / V) * (d->ldo / R);
+          const long long vg = (items + 255) / 256;
+          if (vg <= 0x7fffffffll) {
+            if (ts == 2) meltw_vnni_pack_vec_kernel<unsigned short, 2><<<(unsigned int)vg, 256, 0, st>>>((const unsigned short*)a->in0, (unsigned short*)a->out, d->m, d->n, d->ldi, d->ldo);
+            else meltw_vnni_pack_vec_kernel<unsigned char, 4><<<(unsigned int)vg, 256, 0, st>>>((const unsigned char*)a->in0, (unsigned char*)a->out, d->m, d->n, d->ldi, d->ldo);
+            return launch_done("meltw_vnni_pack_vec");
+          }
+        }
         if (ts == 2) meltw_vnni_pack_kernel<unsigned short, 2><<<(unsigned int)pg, 256, 0, st>>>((const unsigned short*)a->in0, (unsigned short*)a->out, d->m, d->n, d->ldi, d->ldo);
         else meltw_vnni_pack_kernel<unsigned char, 4><<<(unsigned int)pg, 256, 0, st>>>((const unsigned char*)a->in0, (unsigned char*)a->out, d->m, d->n, d->ldi, d->ldo);
         return launch_done("meltw_vnni_pack");
@@ -694,6 +865,17 @@ extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
       long long grid = ((long long)d->m * d->n + 255) / 256; if (grid > 148 * 16) grid = 148 * 16;
       meltw_quant_kernel<<<(unsigned int)grid, 256, 0, st>>>(*d, *a);
       return launch_done("meltw_quant");
+    }
+    case FAM_MXQUANT: {
+      const int blk = (d->t_out == LIBXSMM_DATATYPE_NVFP4X2) ? 16 : 32;
+      const long long items = (long long)(d->m / blk) * d->n;
+      if (items <= 0) return 0;
+      const unsigned int g = (unsigned int)((items + 127) / 128);
+      const unsigned short* in = (const unsigned short*)a->in0; unsigned char* out = (unsigned char*)a->out; unsigned char* sc = (unsigned char*)a->out_aux;
+      if (d->t_out == LIBXSMM_DATATYPE_MXFP4X2) meltw_mxquant_kernel<32, 0><<<g, 128, 0, st>>>(in, out, sc, d->m, d->n, d->ldi, d->ldo);
+      else if (d->t_out == LIBXSMM_DATATYPE_NVFP4X2) meltw_mxquant_kernel<16, 1><<<g, 128, 0, st>>>(in, out, sc, d->m, d->n, d->ldi, d->ldo);
+      else meltw_mxquant_kernel<32, 2><<<g, 128, 0, st>>>(in, out, sc, d->m, d->n, d->ldi, d->ldo);
+      return launch_done("meltw_mxquant");
     }
     case FAM_DROPOUT: {
       const long long warps = (long long)((d->m + 31) / 32) * d->n;

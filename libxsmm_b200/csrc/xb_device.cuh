@@ -104,4 +104,45 @@ XB_HD uint16_t xb_f32_to_f16(float f) {
   return (uint16_t)(sign | (e << 10) | m);
 }
 
+// bf8 (E5M2) is the upper byte of an IEEE half: convert to half, round the lower byte away to nearest even, keep
+// Inf, quiet NaN (reference src/libxsmm_math.c:731-746)
+XB_HD uint8_t xb_f32_to_bf8(float f) {
+  unsigned short h = xb_f32_to_f16(f);
+  if ((h & 0x7c00) == 0x7c00) { if ((h & 0x03ff) != 0) h |= 0x0200; }
+  else h = (unsigned short)(h + 0x007f + ((h >> 8) & 1));
+  return (uint8_t)(h >> 8);
+}
+// hf8 (E4M3, bias 7, no infinities: 0x7f is NaN, max normal 448): via half with nearest-even on the dropped 7 mantissa
+// bits, subnormals for exponents below the bias, overflow -> NaN (reference src/libxsmm_math.c:749-822)
+XB_HD uint8_t xb_f32_to_hf8(float f) {
+  unsigned short h = xb_f32_to_f16(f);
+  const unsigned short sign = (unsigned short)((h & 0x8000) >> 8);
+  const unsigned int e16 = (h & 0x7c00u) >> 10, m16 = h & 0x03ffu;
+  unsigned int e, m;
+  if (e16 == 0x1f) { e = 0xf; m = 0x7; }
+  else if (e16 > 23 || (e16 == 23 && m16 > 0x0340)) { e = 0xf; m = 0x7; }      // beyond 448 (+ half an ulp)
+  else if (e16 < 5) { e = 0; m = 0; }                                              // below half the smallest subnormal
+  else if (e16 <= 8) {                                                             // subnormal result
+    m = (m16 | 0x0400u) >> (9 - e16);
+    m |= ((m16 & 0x007fu) + 0x007fu) >> 7;                                         // sticky bit of what the shift dropped
+    m = (m + 0x003fu + ((m >> 7) & 1u)) >> 7;
+    e = 0;
+  } else {
+    h = (unsigned short)(h + 0x003f + ((m16 >> 7) & 1u));
+    e = ((h & 0x7c00u) >> 10) - 8; m = (h & 0x03ffu) >> 7;
+  }
+  return (uint8_t)(sign | (e << 3) | m);
+}
+XB_HD float xb_hf8_to_f32(uint8_t in) {
+  const unsigned int sign = ((unsigned int)in & 0x80u) << 24, e = ((unsigned int)in & 0x78u) >> 3;
+  unsigned int m = (unsigned int)in & 0x07u, e32 = e + 120;
+  if (e == 0 && m != 0) {                          // subnormal: renormalise
+    const unsigned int lz = (m > 3) ? 0 : ((m > 1) ? 1 : 2);
+    e32 -= lz; m = (m << (lz + 1)) & 0x07u;
+  } else if (e == 0) e32 = 0;
+  else if (e == 0xf && m == 0x7) { e32 = 0xff; m = 0x4; }
+  return xb_bits_f32(sign | (e32 << 23) | (m << 20));
+}
+XB_HD float xb_bf8_to_f32(uint8_t in) { return xb_f16_to_f32((uint16_t)((uint16_t)in << 8)); }   // libxsmm_convert_bf8_to_f32 (:546-551)
+
 #endif  // XB_DEVICE_CUH

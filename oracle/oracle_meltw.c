@@ -27,7 +27,9 @@ uint16_t oracle_f32_to_f16(float f);
 
 typedef struct mdesc { int op_class, op; unsigned int flags; int m, n; long long ldi, ldi2, ldi3, ldo; int t0, t1, t2, to, tc; } mdesc;
 
-static int is_f(int t) { return t == LIBXSMM_DATATYPE_F32 || t == LIBXSMM_DATATYPE_BF16 || t == LIBXSMM_DATATYPE_F16; }
+static int is_f(int t) { return t == LIBXSMM_DATATYPE_F32 || t == LIBXSMM_DATATYPE_BF16 || t == LIBXSMM_DATATYPE_F16 || t == LIBXSMM_DATATYPE_BF8 || t == LIBXSMM_DATATYPE_HF8; }
+static float bf8_value(unsigned b);  static unsigned bf8_rne(float f);      /* 8-bit floats: defined with the block quantisers below */
+static float e4m3_value(unsigned b); static unsigned e4m3_rne(float f);
 static int tsz(int t) {
   switch (t) { case LIBXSMM_DATATYPE_F64: case LIBXSMM_DATATYPE_I64: case LIBXSMM_DATATYPE_U64: return 8;
                case LIBXSMM_DATATYPE_F32: case LIBXSMM_DATATYPE_I32: case LIBXSMM_DATATYPE_U32: return 4;
@@ -38,11 +40,15 @@ static int tsz(int t) {
 static float ldf(const void* p, long long i, int t) {
   if (t == LIBXSMM_DATATYPE_F32) return ((const float*)p)[i];
   if (t == LIBXSMM_DATATYPE_BF16) return oracle_bf16_to_f32(((const uint16_t*)p)[i]);
+  if (t == LIBXSMM_DATATYPE_BF8) return bf8_value(((const uint8_t*)p)[i]);
+  if (t == LIBXSMM_DATATYPE_HF8) return e4m3_value(((const uint8_t*)p)[i]);
   return oracle_f16_to_f32(((const uint16_t*)p)[i]);
 }
 static void stf(void* p, long long i, int t, float v) {
   if (t == LIBXSMM_DATATYPE_F32) ((float*)p)[i] = v;
   else if (t == LIBXSMM_DATATYPE_BF16) ((uint16_t*)p)[i] = oracle_f32_to_bf16(v);
+  else if (t == LIBXSMM_DATATYPE_BF8) ((uint8_t*)p)[i] = (uint8_t)bf8_rne(v);
+  else if (t == LIBXSMM_DATATYPE_HF8) ((uint8_t*)p)[i] = (uint8_t)e4m3_rne(v);
   else ((uint16_t*)p)[i] = oracle_f32_to_f16(v);
 }
 /* operand index under the broadcast flags: reference :241-272 (row-bcast -> j*ld, col-bcast -> i, scalar -> 0) */
@@ -326,9 +332,122 @@ static int unary_split(const mdesc* d, const libxsmm_meltw_unary_param* p) {
   return 0;
 }
 
+/* ---- block-scaled quantisers (bf16 -> MXFP4 / NVFP4 / MXBF8): reference :1796-2073, :2247-2326 ------------------------------
+ * one scale byte per block of consecutive rows of a column; data and scales have their own leading dimensions derived from ldo */
+static float bits_f32(uint32_t u) { union { uint32_t u; float f; } x; x.u = u; return x.f; }
+static uint32_t f32_bits(float f) { union { uint32_t u; float f; } x; x.f = f; return x.u; }
+static float bf16_round(float f) { return bits_f32((uint32_t)oracle_f32_to_bf16(f) << 16); }    /* f32 -> bf16 (RNE) -> f32 */
+/* |x| -> 3-bit E2M1 code {0, .5, 1, 1.5, 2, 3, 4, 6}: round to nearest, ties to the even code, NaN and overflow saturate (:1796-1808) */
+static unsigned e2m1_code(float a) {
+  static const float edge[7] = { 0.25f, 0.75f, 1.25f, 1.75f, 2.5f, 3.5f, 5.0f };   /* midpoints between neighbouring codes */
+  unsigned c = 0;
+  if (a != a) return 7;
+  while (c < 7 && (a > edge[c] || (a == edge[c] && (c & 1u)))) ++c;                /* a tie goes up only out of an odd code */
+  return c;
+}
+/* f32 -> E4M3 byte for the NVFP4 scale (:1812-1893): RNE, clamps to 448 (0x78) instead of NaN, flushes below 2^-10 */
+static unsigned e4m3_scale_code(float v) {
+  const uint32_t u = f32_bits(v), sign = (u >> 31) << 7, ef = (u >> 23) & 0xffu, mf = u & 0x7fffffu;
+  int e = (int)ef - 127;
+  uint32_t m;
+  if (ef == 0xff && mf != 0) return sign | 0x7f;
+  if (ef == 0xff || fabsf(v) > 448.0f || e > 8) return sign | 0x78;
+  if (ef == 0 || e < -9) return sign;
+  if (e >= -6) {                                          /* normal: keep 3 mantissa bits */
+    m = mf >> 20;
+    if (((mf >> 19) & 1u) && ((mf & 0x7ffffu) || (m & 1u))) ++m;
+    if (m == 8) { m = 0; ++e; }
+    return (e + 7 >= 15) ? (sign | 0x78) : (sign | ((uint32_t)(e + 7) << 3) | m);
+  } else {                                                /* subnormal: 1.mmm shifted right by (-6 - e) in 1..3 */
+    const int sh = -6 - e;
+    const uint32_t full = 8u | (mf >> 20);
+    uint32_t sticky = ((full & ((1u << (sh - 1)) - 1u)) != 0) || ((mf & 0xfffffu) != 0);
+    m = full >> sh;
+    if (((full >> (sh - 1)) & 1u) && (sticky || (m & 1u))) ++m;
+    return (m >= 8) ? (sign | 0x08) : (sign | (m & 7u));
+  }
+}
+static float e4m3_value(unsigned b) {                     /* libxsmm_convert_hf8_to_f32 (src/libxsmm_math.c): 0x7f/0xff are NaN */
+  const unsigned e = (b >> 3) & 0xf, m = b & 7;
+  float v;
+  if (e == 0xf && m == 7) return bits_f32(((uint32_t)(b & 0x80) << 24) | 0x7fc00000u);
+  v = (e == 0) ? ldexpf((float)m, -9) : ldexpf((float)(8 + m), (int)e - 10);
+  return (b & 0x80) ? -v : v;
+}
+static unsigned bf8_rne(float f) {                        /* libxsmm_convert_f32_to_bf8_rne (src/libxsmm_math.c:731-746): via f16, RNE on the low byte */
+  unsigned h = oracle_f32_to_f16(f);
+  if ((h & 0x7c00u) == 0x7c00u) { if (h & 0x03ffu) h |= 0x0200u; }
+  else h = (h + 0x7fu + ((h >> 8) & 1u)) & 0xffffu;
+  return h >> 8;
+}
+static float bf8_value(unsigned b) { return oracle_f16_to_f32((uint16_t)(b << 8)); }        /* libxsmm_convert_bf8_to_f32 (:546-551) */
+/* libxsmm_convert_f32_to_hf8_rne (src/libxsmm_math.c:749-822): through f16; RNE on the 7 dropped mantissa bits; results below 2^-6 are
+ * sub-normal (sticky bit kept across the alignment shift); beyond 448 (+ half an ulp) and Inf/NaN all give the NaN code */
+static unsigned e4m3_rne(float f) {
+  const unsigned h = oracle_f32_to_f16(f), sign = (h & 0x8000u) >> 8, e16 = (h >> 10) & 0x1fu, m16 = h & 0x3ffu;
+  unsigned e, m, r;
+  if (e16 == 0x1f || e16 > 23 || (e16 == 23 && m16 > 0x340u)) return sign | 0x7fu;
+  if (e16 < 5) return sign;
+  if (e16 > 8) { r = (h & 0x7fffu) + 0x3fu + ((m16 >> 7) & 1u); e = ((r >> 10) & 0x1fu) - 8u; m = (r & 0x3ffu) >> 7; return sign | (e << 3) | m; }
+  m = ((m16 | 0x400u) >> (9 - e16)) | (((m16 & 0x7fu) + 0x7fu) >> 7);
+  m = (m + 0x3fu + ((m >> 7) & 1u)) >> 7;
+  return sign | m;
+}
+/* E8M0 shared exponent of a block: biased exponent of the largest |x| (NaN sticks) minus the element format's emax (:1911-1921) */
+static int mx_shared_exp(const float* x, int n, int emax, float* scale, int* special) {
+  float amax = 0.0f; int i, e;
+  for (i = 0; i < n; ++i) { const float a = fabsf(x[i]); if (a > amax || a != a) amax = a; }
+  e = (int)((f32_bits(amax) >> 23) & 0xffu);
+  *special = (e == 0xff);
+  e = *special ? 0xff : (e - emax < 0 ? 0 : e - emax);
+  *scale = bits_f32(((uint32_t)e << 23) | ((e == 0 || *special) ? 0x400000u : 0u));     /* 2^(e-127); e = 0 stands for 2^-127 */
+  return e;
+}
+static int unary_mxquant(const mdesc* d, const libxsmm_meltw_unary_param* p) {
+  const uint16_t* in = (const uint16_t*)p->in.primary;
+  unsigned char* out = (unsigned char*)p->out.primary; unsigned char* scl = (unsigned char*)p->out.secondary;
+  const int blk = (d->to == LIBXSMM_DATATYPE_NVFP4X2) ? 16 : 32;
+  const long long ld_data = (d->to == LIBXSMM_DATATYPE_MXBF8) ? d->ldo : d->ldo / 2, ld_scl = d->ldo / blk;
+  int j, b, k;
+  if (d->t0 != LIBXSMM_DATATYPE_BF16 || scl == NULL) return 2;
+  for (j = 0; j < d->n; ++j) for (b = 0; b < d->m / blk; ++b) {
+    float x[32], scale; int special;
+    unsigned char* o = out + (size_t)j * ld_data + (size_t)b * ((d->to == LIBXSMM_DATATYPE_MXBF8) ? blk : blk / 2);
+    for (k = 0; k < blk; ++k) x[k] = bits_f32((uint32_t)in[(size_t)j * d->ldi + (size_t)b * blk + k] << 16);   /* no denormal flush here */
+    if (d->to == LIBXSMM_DATATYPE_NVFP4X2) {              /* :1948-2025: E4M3 scale = amax/6 and the scaling itself in bf16 precision */
+      float amax = 0.0f, sv = 0.0f, rcp; unsigned sc = 0;
+      for (k = 0; k < blk; ++k) { const float a = fabsf(x[k]); if (a > amax || a != a) amax = a; }
+      if (amax != 0.0f) { sc = e4m3_scale_code(bf16_round(bf16_round(amax) * bits_f32(0x3e2a0000u))); sv = e4m3_value(sc); }
+      scl[(size_t)j * ld_scl + b] = (unsigned char)sc;
+      if (sv == 0.0f) { memset(o, 0, 8); continue; }
+      rcp = bf16_round(1.0f / bf16_round(sv));
+      for (k = 0; k < 8; ++k) {
+        const unsigned lo = ((f32_bits(x[2 * k]) >> 31) << 3) | e2m1_code(fabsf(bf16_round(x[2 * k] * rcp)));
+        const unsigned hi = ((f32_bits(x[2 * k + 1]) >> 31) << 3) | e2m1_code(fabsf(bf16_round(x[2 * k + 1] * rcp)));
+        o[k] = (unsigned char)((hi << 4) | lo);
+      }
+    } else if (d->to == LIBXSMM_DATATYPE_MXFP4X2) {       /* :1898-1945 */
+      scl[(size_t)j * ld_scl + b] = (unsigned char)mx_shared_exp(x, 32, 2, &scale, &special);
+      if (special) { memset(o, 0x77, 16); continue; }
+      for (k = 0; k < 16; ++k) {
+        const unsigned lo = ((f32_bits(x[2 * k]) >> 31) << 3) | e2m1_code(fabsf(x[2 * k] / scale));
+        const unsigned hi = ((f32_bits(x[2 * k + 1]) >> 31) << 3) | e2m1_code(fabsf(x[2 * k + 1] / scale));
+        o[k] = (unsigned char)((hi << 4) | lo);
+      }
+    } else {                                              /* MXBF8, :2030-2071 */
+      scl[(size_t)j * ld_scl + b] = (unsigned char)mx_shared_exp(x, 32, 15, &scale, &special);
+      if (special) { memset(o, 0x7b, 32); continue; }
+      for (k = 0; k < 32; ++k) o[k] = (unsigned char)bf8_rne(x[k] / scale);
+    }
+  }
+  return 0;
+}
+
 /* quantise / dequantise: reference :2195-2360 */
 static int unary_quant(const mdesc* d, const libxsmm_meltw_unary_param* p) {
   int i, j;
+  if (d->op == LIBXSMM_MELTW_TYPE_UNARY_QUANT && (d->to == LIBXSMM_DATATYPE_MXFP4X2 || d->to == LIBXSMM_DATATYPE_NVFP4X2 || d->to == LIBXSMM_DATATYPE_MXBF8))
+    return unary_mxquant(d, p);
   if (d->op == LIBXSMM_MELTW_TYPE_UNARY_DEQUANT) {
     const float scf = *(const float*)p->in.secondary;
     if (d->to != LIBXSMM_DATATYPE_F32) return 2;
@@ -357,7 +476,7 @@ static int unary_quant(const mdesc* d, const libxsmm_meltw_unary_param* p) {
     }
     return 0;
   }
-  return 2;   /* MX / NV block formats stay with the reference */
+  return 2;
 }
 
 /* gather / scatter, pure data movement: reference :1444-1794. Index array in in.secondary (gather) or out.secondary

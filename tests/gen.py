@@ -5,6 +5,7 @@ Value distributions follow the reference drivers: multiples of 0.1 in [-0.5, 0.5
 import numpy as np
 
 F64, F32, BF16, F16, I32, I16, I8, U8 = 0, 1, 2, 3, 8, 10, 12, 13
+BF8, HF8, MXBF8, MXFP4X2, NVFP4X2 = 4, 5, 14, 20, 21
 NP_OF = {F64: np.float64, F32: np.float32, BF16: np.uint16, F16: np.uint16, I32: np.int32, I16: np.int16, I8: np.int8, U8: np.uint8}
 TS = {F64: 8, F32: 4, BF16: 2, F16: 2, I32: 4, I16: 2, I8: 1, U8: 1}
 

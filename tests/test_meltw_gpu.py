@@ -461,3 +461,28 @@ def test_large_shapes_take_the_bandwidth_kernels_and_stay_exact():
                 want = y0.copy(); q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
                 assert oracle["meltw"](iarr(*_desc(1, op, flags, m, n, ld, 0, 0, ld, t, UNS, UNS, t, gen.F32)), C.addressof(q), 0) == 0
                 _cmp(host(d_y, want.dtype), want, t, False, 2e-2 if t == gen.BF16 else 2e-4)
+
+
+def test_block_scaled_quantisers_bit_exact():
+    """bf16 -> MXFP4 / NVFP4 / MXBF8 (reference :1896-2073, :2247-2326): data bytes and scale bytes, device buffers and host buffers"""
+    from test_oracle_meltw import mx_inputs
+    rng = np.random.default_rng(71)
+    for tout, blk in ((gen.MXFP4X2, 32), (gen.NVFP4X2, 16), (gen.MXBF8, 32)):
+        for (m, n, ldi, ldo) in ((64, 9, 64, 64), (96, 8, 100, 128), (32, 7, 32, 32), (512, 300, 512, 512)):
+            x = mx_inputs(rng, m, n, ldi)
+            y0 = rng.integers(0, 255, size=ldo * n, dtype=np.uint8); s0 = rng.integers(0, 255, size=(ldo // blk) * n + 8, dtype=np.uint8)
+            k = X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_QUANT, X.libxsmm_create_meltw_unary_shape(m, n, ldi, ldo, gen.BF16, tout, gen.F32), 0)
+            assert k, (tout, m, n)
+            want, wscl = y0.copy(), s0.copy()
+            q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary, q.out.secondary = x.ctypes.data, want.ctypes.data, wscl.ctypes.data
+            _ref_call(_desc(1, X.MELTW_TYPE_UNARY_QUANT, 0, m, n, ldi, 0, 0, ldo, gen.BF16, UNS, UNS, tout, gen.F32), q)
+            d_x, d_y, d_s = dev(x), dev(y0), dev(s0)
+            p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = d_x.data_ptr(), d_y.data_ptr(), d_s.data_ptr()
+            X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+            assert np.array_equal(host(d_y, np.uint8), want), (tout, m, n, "data")
+            assert np.array_equal(host(d_s, np.uint8), wscl), (tout, m, n, "scales")
+            if m == 96:      # plain host buffers: staged through the device arena with the exact byte extents
+                hy, hs = y0.copy(), s0.copy()
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, hy.ctypes.data, hs.ctypes.data
+                X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+                assert np.array_equal(hy, want) and np.array_equal(hs, wscl), (tout, "host buffers")

@@ -222,6 +222,62 @@ def test_gather_scatter_and_quant():
             both((1, X.MELTW_TYPE_UNARY_QUANT, sat, m, n, ld, 0, 0, ld, gen.F32, UNS, UNS, tout, gen.F32), mkq, [y0])
 
 
+def test_eight_bit_float_element_types():
+    """BF8 (E5M2) and HF8 (E4M3) as input / output element types of the map kernels: every byte pattern as input, f32 values over the
+    whole exponent range (incl. halfway cases, overflow, sub-normal results) as output"""
+    rng = np.random.default_rng(69)
+    m, n, ld = 64, 16, 66
+    wide = (rng.standard_normal(ld * n) * np.exp2(rng.integers(-22, 18, size=ld * n))).astype(np.float32)
+    wide[::5] = np.ldexp(rng.integers(8, 32, size=wide[::5].size) / 16.0 + 1.0 / 32.0, rng.integers(-12, 10, size=wide[::5].size)).astype(np.float32)   # exact ties
+    wide[3] = np.inf; wide[4] = -np.inf; wide[7] = np.nan; wide[9] = 448.0; wide[10] = 464.0; wide[11] = 480.0; wide[12] = 57344.0; wide[13] = 61440.0
+    allbytes = np.resize(np.arange(256, dtype=np.uint8), ld * n)
+    for t8 in (gen.BF8, gen.HF8):
+        for name in ("IDENTITY", "X2", "NEGATE", "RELU"):
+            op = getattr(X, "MELTW_TYPE_UNARY_" + name)
+            for tin, tout, x in ((gen.F32, t8, wide), (t8, gen.F32, allbytes), (t8, t8, allbytes), (gen.BF16, t8, gen.f32_to_bf16_bits(wide)), (t8, gen.F16, allbytes)):
+                y0 = np.zeros(ld * n * (4 if tout == gen.F32 else (2 if tout in (gen.F16, gen.BF16) else 1)), dtype=np.uint8)
+
+                def mk(bufs, keep):
+                    p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = x.ctypes.data, bufs[0].ctypes.data
+                    return p
+                both((1, op, 0, m, n, ld, 0, 0, ld, tin, UNS, UNS, tout, gen.F32), mk, [y0])
+    # binary add with mixed 8-bit inputs
+    a8, b8 = rng.integers(0, 256, size=ld * n, dtype=np.uint8), rng.integers(0, 256, size=ld * n, dtype=np.uint8)
+    y0 = np.zeros(ld * n, dtype=np.uint8)
+
+    def mkb(bufs, keep):
+        p = X.MeltwBinaryParam(); p.in0.primary, p.in1.primary, p.out.primary = a8.ctypes.data, b8.ctypes.data, bufs[0].ctypes.data
+        return p
+    both((2, X.MELTW_TYPE_BINARY_ADD, 0, m, n, ld, ld, 0, ld, gen.BF8, gen.HF8, UNS, gen.HF8, gen.F32), mkb, [y0])
+
+
+def mx_inputs(rng, m, n, ld):
+    """bf16 blocks that reach every branch of the block quantisers: wide exponent range, exact ties of the 4-bit code grid, all-zero
+    blocks, blocks with Inf / NaN, sub-normal magnitudes"""
+    x = (rng.standard_normal(ld * n) * np.exp2(rng.integers(-20, 20, size=ld * n))).astype(np.float32)
+    x[::7] = rng.choice(np.array([0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0, 6.0, -0.75, -2.5], dtype=np.float32), size=x[::7].size) * 4.0
+    xb = gen.f32_to_bf16_bits(x).reshape(n, ld)
+    xb[0, :32] = 0; xb[1, :32] = 0x8000                       # +0 and -0 blocks
+    xb[2, 5] = 0x7f80; xb[3, 20] = 0x7fc1; xb[4, 3] = 0xff80   # +Inf, NaN, -Inf inside a block
+    xb[5, :32] = rng.integers(1, 0x7f, size=32)               # bf16 sub-normals
+    xb[6, :32] = gen.f32_to_bf16_bits(np.full(32, 3.0e38, dtype=np.float32))
+    return xb.reshape(-1).copy()
+
+
+def test_block_scaled_quantisers():
+    """bf16 -> MXFP4 (32-blocks, E8M0 scale), NVFP4 (16-blocks, E4M3 scale), MXBF8 (32-blocks): data and scale bytes"""
+    rng = np.random.default_rng(70)
+    for tout, blk in ((gen.MXFP4X2, 32), (gen.NVFP4X2, 16), (gen.MXBF8, 32)):
+        for (m, n, ldi, ldo) in ((64, 9, 64, 64), (96, 8, 100, 128), (32, 7, 32, 32)):
+            x = mx_inputs(rng, m, n, ldi)
+            y0 = rng.integers(0, 255, size=ldo * n, dtype=np.uint8); s0 = rng.integers(0, 255, size=(ldo // blk) * n + 8, dtype=np.uint8)
+
+            def mk(bufs, keep):
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, bufs[0].ctypes.data, bufs[1].ctypes.data
+                return p
+            both((1, X.MELTW_TYPE_UNARY_QUANT, 0, m, n, ldi, 0, 0, ldo, gen.BF16, UNS, UNS, tout, gen.F32), mk, [y0, s0])
+
+
 @pytest.mark.parametrize("t", [gen.F32, gen.BF16, gen.F64])
 def test_reductions_to_scalar(t):
     rng = np.random.default_rng(67)

@@ -41,7 +41,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         print(run_points([int(sys.argv[2])], kinds=(sys.argv[3] if len(sys.argv) > 3 else "i8",)))
     elif len(sys.argv) > 1 and sys.argv[1] == "child":
-        print(" | ".join(run_points([16, 32, 64, 128])), flush=True)
+        print(" | ".join(run_points([int(x) for x in os.environ.get("TS_PROBE_M", "16,32,64,128").split(",")])), flush=True)
     else:
         for cfg in (sys.argv[1:] or [""]):
             env = dict(os.environ)
