@@ -80,16 +80,19 @@ MELTW_FLAG_UNARY_GS_COLS = 32
 MELTW_FLAG_UNARY_GS_OFFS = 8192
 MELTW_FLAG_UNARY_NO_SCF_QUANT = 1024
 MELTW_FLAG_UNARY_SIGN_SAT_QUANT = 16
+MELTW_FLAG_UNARY_STOCHASTIC_ROUND = 4096
 MELTW_FLAG_BINARY_NONE = 0
 MELTW_FLAG_BINARY_BCAST_ROW_IN_0, MELTW_FLAG_BINARY_BCAST_ROW_IN_1 = 1, 2
 MELTW_FLAG_BINARY_BCAST_COL_IN_0, MELTW_FLAG_BINARY_BCAST_COL_IN_1 = 4, 8
 MELTW_FLAG_BINARY_BCAST_SCALAR_IN_0, MELTW_FLAG_BINARY_BCAST_SCALAR_IN_1 = 16, 32
 MELTW_FLAG_BINARY_BITMASK_2BYTEMULT = 128
+MELTW_FLAG_BINARY_STOCHASTIC_ROUND = 64
 MELTW_FLAG_TERNARY_NONE = 0
 MELTW_FLAG_TERNARY_BCAST_ROW_IN_0, MELTW_FLAG_TERNARY_BCAST_ROW_IN_1, MELTW_FLAG_TERNARY_BCAST_ROW_IN_2 = 1, 2, 4
 MELTW_FLAG_TERNARY_BCAST_COL_IN_0, MELTW_FLAG_TERNARY_BCAST_COL_IN_1, MELTW_FLAG_TERNARY_BCAST_COL_IN_2 = 8, 16, 32
 MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_0, MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_1, MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_2 = 64, 128, 256
 MELTW_FLAG_TERNARY_BITMASK_2BYTEMULT = 1024
+MELTW_FLAG_TERNARY_STOCHASTIC_ROUND = 2048
 
 
 # ---- structs (layouts of include/libxsmm_typedefs.h) --------------------------------------------------

@@ -178,6 +178,27 @@ static size_t in_extent(const xb_meltw_desc* d, unsigned int row, unsigned int c
   return (size_t)((n - 1) * ld + d->m);
 }
 
+/* the element-wise ops that go through the reference's generic load -> f32 -> op -> store loop (:2470-2498): the only unary
+ * ops that honour STOCHASTIC_ROUND */
+static int unary_is_generic_map(int op) {
+  switch (op) {
+    case LIBXSMM_MELTW_TYPE_UNARY_IDENTITY: case LIBXSMM_MELTW_TYPE_UNARY_XOR: case LIBXSMM_MELTW_TYPE_UNARY_X2: case LIBXSMM_MELTW_TYPE_UNARY_SQRT:
+    case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: case LIBXSMM_MELTW_TYPE_UNARY_INC: case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT:
+    case LIBXSMM_MELTW_TYPE_UNARY_TANH: case LIBXSMM_MELTW_TYPE_UNARY_TANH_INV: case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID: case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID_INV:
+    case LIBXSMM_MELTW_TYPE_UNARY_GELU: case LIBXSMM_MELTW_TYPE_UNARY_GELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_EXP: case LIBXSMM_MELTW_TYPE_UNARY_DUMP:
+    case LIBXSMM_MELTW_TYPE_UNARY_REPLICATE_COL_VAR: return 1;
+    default: return 0;
+  }
+}
+/* STOCHASTIC_ROUND to BF8 (libxsmm_elementwise_store_value, :310-316): the 4 x 16-word generator state in op.secondary is read and
+ * advanced; one random byte per element goes through device scratch */
+static void stage_stochastic(xb_stager* st, xb_meltw_args* a, const void* state, long long elements) {
+  if (state == NULL || elements <= 0) { st->failed = 1; return; }
+  a->rng = stage_inout(st, (void*)(uintptr_t)state, 64 * sizeof(unsigned int));
+  a->rnd8 = (unsigned char*)xb_rt_scratch((size_t)elements);
+  if (a->rng == NULL || a->rnd8 == NULL) st->failed = 1;
+}
+
 void xb_invoke_meltw(const xb_slot* s, const void* param) {
   const xb_meltw_desc* d = &s->u.meltw;
   xb_meltw_args a; xb_stager st;
@@ -260,6 +281,9 @@ void xb_invoke_meltw(const xb_slot* s, const void* param) {
         a.out = p->out.primary;
       } else a.out = stage_inout(&st, p->out.primary, ext_out);
       if (mx_scales != 0) { a.out_aux = stage_inout(&st, p->out.secondary, mx_scales); if (a.out_aux == NULL) st.failed = 1; }
+      if (op == LIBXSMM_MELTW_TYPE_UNARY_DUMP) { a.out_aux = stage_inout(&st, p->out.secondary, ext_out); if (a.out_aux == NULL) st.failed = 1; }
+      if ((d->flags & LIBXSMM_MELTW_FLAG_UNARY_STOCHASTIC_ROUND) != 0 && d->t_out == LIBXSMM_DATATYPE_BF8 && unary_is_generic_map(op)
+          && !(d->t_in0 == LIBXSMM_DATATYPE_F64)) stage_stochastic(&st, &a, p->op.secondary, (long long)d->m * n);
       if (op == LIBXSMM_MELTW_TYPE_UNARY_DROPOUT) {      /* op.secondary: generator state, read AND advanced (:2091, :43-73) */
         a.rng = stage_inout(&st, p->op.secondary, 64 * sizeof(unsigned int));
         a.rnd = (float*)xb_rt_scratch((size_t)LIBXSMM_UPDIV(d->m, 16) * d->n * 16 * sizeof(float));
@@ -296,6 +320,8 @@ void xb_invoke_meltw(const xb_slot* s, const void* param) {
     a.in1 = stage_in(&st, p->in1.primary, in_extent(d, d->flags & LIBXSMM_MELTW_FLAG_BINARY_BCAST_ROW_IN_1, d->flags & LIBXSMM_MELTW_FLAG_BINARY_BCAST_COL_IN_1,
                                                      d->flags & LIBXSMM_MELTW_FLAG_BINARY_BCAST_SCALAR_IN_1, d->ldi2, d->n) * ts1);
     a.out = stage_inout(&st, p->out.primary, ext_out);
+    if ((d->flags & LIBXSMM_MELTW_FLAG_BINARY_STOCHASTIC_ROUND) != 0 && d->t_out == LIBXSMM_DATATYPE_BF8 && d->op < LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GT
+        && d->op != LIBXSMM_MELTW_TYPE_BINARY_MUL_AND_REDUCE_TO_SCALAR_OP_ADD && d->op != LIBXSMM_MELTW_TYPE_BINARY_ZIP) stage_stochastic(&st, &a, p->op.secondary, (long long)d->m * d->n);
   } else {
     const libxsmm_meltw_ternary_param* p = (const libxsmm_meltw_ternary_param*)param;
     const size_t ts1 = libxsmm_typesize((libxsmm_datatype)d->t_in1), ts2 = libxsmm_typesize((libxsmm_datatype)d->t_in2);
@@ -307,6 +333,7 @@ void xb_invoke_meltw(const xb_slot* s, const void* param) {
     else a.in2 = stage_in(&st, p->in2.primary, in_extent(d, d->flags & LIBXSMM_MELTW_FLAG_TERNARY_BCAST_ROW_IN_2, d->flags & LIBXSMM_MELTW_FLAG_TERNARY_BCAST_COL_IN_2,
                                                           d->flags & LIBXSMM_MELTW_FLAG_TERNARY_BCAST_SCALAR_IN_2, d->ldi3, d->n) * ts2);
     a.out = stage_inout(&st, p->out.primary, ((size_t)(d->n - 1) * d->ldo + d->m) * ts_out);
+    if ((d->flags & LIBXSMM_MELTW_FLAG_TERNARY_STOCHASTIC_ROUND) != 0 && d->t_out == LIBXSMM_DATATYPE_BF8) stage_stochastic(&st, &a, p->op.secondary, (long long)d->m * d->n);
   }
   if (st.failed) { xb_rt_note_error(2, "meltw: staging failed"); xb_rt_scratch_reset(); return; }
   rc = xb_meltw_launch(d, &a);

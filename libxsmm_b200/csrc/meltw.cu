@@ -28,10 +28,10 @@ __host__ __device__ inline bool is_f(int t) {
 __host__ __device__ inline int family_of(const xb_meltw_desc& d) {
   if (d.op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
     switch (d.op) {
-      case LIBXSMM_MELTW_TYPE_UNARY_IDENTITY: case LIBXSMM_MELTW_TYPE_UNARY_XOR: case LIBXSMM_MELTW_TYPE_UNARY_X2:
+      case LIBXSMM_MELTW_TYPE_UNARY_IDENTITY: case LIBXSMM_MELTW_TYPE_UNARY_XOR: case LIBXSMM_MELTW_TYPE_UNARY_X2: case LIBXSMM_MELTW_TYPE_UNARY_DUMP:
       case LIBXSMM_MELTW_TYPE_UNARY_SQRT: case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: case LIBXSMM_MELTW_TYPE_UNARY_INC:
       case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT:
-        if (d.t_in0 == LIBXSMM_DATATYPE_F64 && d.t_out == LIBXSMM_DATATYPE_F64 && d.t_comp == LIBXSMM_DATATYPE_F64) return FAM_MAP;
+        if (d.t_in0 == LIBXSMM_DATATYPE_F64 && d.t_out == LIBXSMM_DATATYPE_F64 && d.t_comp == LIBXSMM_DATATYPE_F64) return (d.op == LIBXSMM_MELTW_TYPE_UNARY_DUMP) ? FAM_NONE : FAM_MAP;
         return (is_f(d.t_in0) && is_f(d.t_out)) ? FAM_MAP : FAM_NONE;
       case LIBXSMM_MELTW_TYPE_UNARY_TANH: case LIBXSMM_MELTW_TYPE_UNARY_TANH_INV: case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID:
       case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID_INV: case LIBXSMM_MELTW_TYPE_UNARY_GELU: case LIBXSMM_MELTW_TYPE_UNARY_GELU_INV:
@@ -127,6 +127,20 @@ __device__ __forceinline__ void st_f32(void* p, long long idx, int t, float v) {
   else if (t == LIBXSMM_DATATYPE_BF8) ((unsigned char*)p)[idx] = xb_f32_to_bf8(v);
   else if (t == LIBXSMM_DATATYPE_HF8) ((unsigned char*)p)[idx] = xb_f32_to_hf8(v);
   else ((unsigned short*)p)[idx] = xb_f32_to_f16(v);
+}
+// f32 -> bf8 with a random byte added below the kept bits (libxsmm_stochastic_convert_fp32_bf8, src/libxsmm_lpflt_quant.c:332-368):
+// normal numbers only; f16-subnormal magnitudes round to nearest even, Inf/NaN pass through
+__device__ __forceinline__ unsigned char bf8_stochastic(float v, unsigned int rnd) {
+  unsigned int h = xb_f32_to_f16(v);
+  if ((h & 0x7c00u) == 0x7c00u) { if (h & 0x03ffu) h |= 0x0200u; }
+  else if ((h & 0x7c00u) == 0u) h = (h + 0x7fu + ((h >> 8) & 1u)) & 0xffffu;
+  else h = (h + rnd) & 0xffffu;
+  return (unsigned char)(h >> 8);
+}
+// store of the map kernels: element (i, j) is the (j*m + i)-th the reference visits, which selects its random byte
+__device__ __forceinline__ void st_map(const xb_meltw_desc& d, const xb_meltw_args& a, long long oi, int i, int j, float v) {
+  if (a.rnd8 != nullptr) ((unsigned char*)a.out)[oi] = bf8_stochastic(v, a.rnd8[(long long)j * d.m + i]);
+  else st_f32(a.out, oi, d.t_out, v);
 }
 // operand index with broadcast flags; which: 0,1,2 = in0,in1,in2
 __device__ __forceinline__ long long bidx(const xb_meltw_desc& d, int which, int i, int j, long long ld) {
@@ -235,7 +249,10 @@ __global__ void __launch_bounds__(256) meltw_map_kernel(const xb_meltw_desc d, c
     const long long oi = i + (long long)j * d.ldo;
     if (d.op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
       const int op = d.op;
-      if (f64) { if (act) ((double*)a.out)[oi] = unary_f64(((const double*)a.in0)[bidx(d, 0, i, j, d.ldi)], op); continue; }
+      if (f64) {
+        if (act) { const double r = unary_f64(((const double*)a.in0)[bidx(d, 0, i, j, d.ldi)], op); ((double*)a.out)[oi] = r; if (op == LIBXSMM_MELTW_TYPE_UNARY_DUMP) ((double*)a.out_aux)[oi] = r; }
+        continue;
+      }
       const float x = act ? ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0) : 0.0f;
       const bool bitm = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0;
       if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_ELU) {
@@ -253,7 +270,13 @@ __global__ void __launch_bounds__(256) meltw_map_kernel(const xb_meltw_desc d, c
         }
       } else if (op == LIBXSMM_MELTW_TYPE_UNARY_ELU_INV) {
         if (act) { const float fwd = ld_f32(a.in_aux, i + (long long)j * d.ldi, d.t_in0); st_f32(a.out, oi, d.t_out, (fwd > 0) ? x : x * (fwd + a.alpha)); }
-      } else if (act) st_f32(a.out, oi, d.t_out, unary_f32(x, op));
+      } else if (act) {
+        st_map(d, a, oi, i, j, unary_f32(x, op));
+        if (op == LIBXSMM_MELTW_TYPE_UNARY_DUMP) {                      // second copy of what was stored (:2478-2493)
+          if (a.rnd8 != nullptr) ((unsigned char*)a.out_aux)[oi] = ((unsigned char*)a.out)[oi];
+          else st_f32(a.out_aux, oi, d.t_out, x);
+        }
+      }
     } else if (d.op_class == LIBXSMM_MELTW_OPERATION_BINARY) {
       const int op = d.op;
       if (op == LIBXSMM_MELTW_TYPE_BINARY_ZIP) {
@@ -270,17 +293,17 @@ __global__ void __launch_bounds__(256) meltw_map_kernel(const xb_meltw_desc d, c
       if (op >= LIBXSMM_MELTW_TYPE_BINARY_CMP_OP_GT) mask_store(a.out, i0, j, ((d.ldo + 15) / 16) * 16, d.m, act && cmp_op(x, y, op), lane);
       else if (act) {
         const float o = (op == LIBXSMM_MELTW_TYPE_BINARY_MULADD) ? ld_f32(a.out, oi, d.t_out) : 0.0f;
-        st_f32(a.out, oi, d.t_out, binary_op<float>(x, y, o, op));
+        st_map(d, a, oi, i, j, binary_op<float>(x, y, o, op));
       }
     } else if (act) {
       if (d.op == LIBXSMM_MELTW_TYPE_TERNARY_SELECT) {
         const bool bit = mask_bit(a.in2, i, j, ((d.ldi3 + 15) / 16) * 16);
         if (f64) ((double*)a.out)[oi] = bit ? ((const double*)a.in1)[bidx(d, 1, i, j, d.ldi2)] : ((const double*)a.in0)[bidx(d, 0, i, j, d.ldi)];
-        else st_f32(a.out, oi, d.t_out, bit ? ld_f32(a.in1, bidx(d, 1, i, j, d.ldi2), d.t_in1) : ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0));
+        else st_map(d, a, oi, i, j, bit ? ld_f32(a.in1, bidx(d, 1, i, j, d.ldi2), d.t_in1) : ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0));
       } else {
         const float x = ld_f32(a.in0, bidx(d, 0, i, j, d.ldi), d.t_in0), y = ld_f32(a.in1, bidx(d, 1, i, j, d.ldi2), d.t_in1);
         const float z = ld_f32(a.in2, bidx(d, 2, i, j, d.ldi3), d.t_in2);
-        st_f32(a.out, oi, d.t_out, (d.op == LIBXSMM_MELTW_TYPE_TERNARY_MULADD) ? (z + x * y) : (y - x * z));
+        st_map(d, a, oi, i, j, (d.op == LIBXSMM_MELTW_TYPE_TERNARY_MULADD) ? (z + x * y) : (y - x * z));
       }
     }
   }
@@ -716,6 +739,20 @@ __global__ void __launch_bounds__(32) meltw_rng_kernel(unsigned int* __restrict_
   }
   state[w] = s0; state[16 + w] = s1; state[32 + w] = s2; state[48 + w] = s3;
 }
+// random bytes for stochastic rounding: element e draws from sequence e % 16 (libxsmm_lsfr_i32, src/libxsmm_lpflt_quant.c:303-330:
+// xoshiro128++ per lane, top byte of the draw); sequential per lane like the dropout generator above
+__global__ void __launch_bounds__(32) meltw_rng8_kernel(unsigned int* __restrict__ state, unsigned char* __restrict__ rnd8, long long count) {
+  const int w = threadIdx.x;
+  if (w >= 16) return;
+  unsigned int s0 = state[w], s1 = state[16 + w], s2 = state[32 + w], s3 = state[48 + w];
+  for (long long e = w; e < count; e += 16) {
+    const unsigned int sum = s0 + s3;
+    rnd8[e] = (unsigned char)((((sum << 7) | (sum >> 25)) + s0) >> 24);
+    const unsigned int t = s1 << 9;
+    s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = (s3 << 11) | (s3 >> 21);
+  }
+  state[w] = s0; state[16 + w] = s1; state[32 + w] = s2; state[48 + w] = s3;
+}
 __global__ void __launch_bounds__(256) meltw_dropout_kernel(const xb_meltw_desc d, const xb_meltw_args a) {
   const int lane = threadIdx.x & 31;
   const int chunks = (d.m + 31) / 32, gpc = (d.m + 15) / 16;
@@ -784,6 +821,10 @@ extern "C" int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
       const int n_eff = (d->op_class == LIBXSMM_MELTW_OPERATION_UNARY && d->op == LIBXSMM_MELTW_TYPE_UNARY_REPLICATE_COL_VAR) ? (int)a->n_rt : d->n;
       const long long warps = (long long)((d->m + 31) / 32) * n_eff;
       long long grid = (warps + 7) / 8; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) return 0;
+      if (a->rnd8 != nullptr) {
+        meltw_rng8_kernel<<<1, 32, 0, st>>>((unsigned int*)a->rng, a->rnd8, (long long)d->m * n_eff);
+        if (launch_done("meltw_rng8") != 0) return 1;
+      }
       meltw_map_kernel<<<(unsigned int)grid, 256, 0, st>>>(*d, *a, n_eff);
       return launch_done("meltw_map");
     }

@@ -174,6 +174,7 @@ typedef struct xb_meltw_args {
   unsigned long long off[2]; /* UNZIP: byte offset of the high halves; DECOMP_FP32_TO_BF16X2/X3: byte strides of planes 2, 3 */
   void* rng;                 /* DROPOUT: 4 x 16 words of generator state (device copy, updated by the kernel) */
   float* rnd;                /* DROPOUT: scratch for the uniform numbers, 16 per group of rows */
+  unsigned char* rnd8;       /* STOCHASTIC_ROUND to BF8: one random byte per element in the reference's visiting order (NULL: round to nearest) */
 } xb_meltw_args;
 void xb_invoke_meqn(const struct xb_slot* s, const void* param);
 void xb_meqn_release(void* work);

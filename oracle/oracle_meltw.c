@@ -51,6 +51,22 @@ static void stf(void* p, long long i, int t, float v) {
   else if (t == LIBXSMM_DATATYPE_HF8) ((uint8_t*)p)[i] = (uint8_t)e4m3_rne(v);
   else ((uint16_t*)p)[i] = oracle_f32_to_f16(v);
 }
+/* store with optional stochastic rounding (libxsmm_elementwise_store_value :299-325): only a BF8 output uses the flag. Element number e
+ * of the op (j-major, i inner) draws from generator e % 16 of the 4 x 16-word state (libxsmm_lsfr_i32, src/libxsmm_lpflt_quant.c:303-330:
+ * one xoshiro128++ step); the top byte is added to the f16 image below the 8 kept bits; f16-subnormals round to nearest even instead,
+ * Inf / NaN pass (src/libxsmm_lpflt_quant.c:332-368) */
+static void stf_rnd(void* p, long long i, int t, float v, int stochastic, uint32_t* state, long long e) {
+  if (stochastic && t == LIBXSMM_DATATYPE_BF8 && state != NULL) {
+    uint32_t* s = state + (e % 16);
+    const uint32_t sum = s[0] + s[48], draw = ((sum << 7) | (sum >> 25)) + s[0], t9 = s[16] << 9;
+    unsigned h = oracle_f32_to_f16(v);
+    s[32] ^= s[0]; s[48] ^= s[16]; s[16] ^= s[32]; s[0] ^= s[48]; s[32] ^= t9; s[48] = (s[48] << 11) | (s[48] >> 21);
+    if ((h & 0x7c00u) == 0x7c00u) { if (h & 0x3ffu) h |= 0x200u; }
+    else if ((h & 0x7c00u) == 0) h = (h + 0x7fu + ((h >> 8) & 1u)) & 0xffffu;
+    else h = (h + (draw >> 24)) & 0xffffu;
+    ((uint8_t*)p)[i] = (uint8_t)(h >> 8);
+  } else stf(p, i, t, v);
+}
 /* operand index under the broadcast flags: reference :241-272 (row-bcast -> j*ld, col-bcast -> i, scalar -> 0) */
 static long long bidx(const mdesc* d, int which, int i, int j, long long ld) {
   unsigned int row = 0, col = 0, sca = 0;
@@ -120,6 +136,7 @@ static int unary_map(const mdesc* d, const libxsmm_meltw_unary_param* p) {
                        || op == LIBXSMM_MELTW_TYPE_UNARY_ELU || op == LIBXSMM_MELTW_TYPE_UNARY_ELU_INV)) ? *(const float*)p->op.primary : 0.0f;
   int i, j;
   if (!f64 && !(is_f(d->t0) && is_f(d->to))) return 2;
+  if (f64 && op == LIBXSMM_MELTW_TYPE_UNARY_DUMP) return 2;      /* not in the reference's F64 op list (:116-138) */
   for (j = 0; j < d->n; ++j) for (i = 0; i < d->m; ++i) {
     const long long oi = i + (long long)j * d->ldo;
     if (f64) { ((double*)p->out.primary)[oi] = unary_f64(((const double*)p->in.primary)[bidx(d, 0, i, j, d->ldi)], op); continue; }
@@ -140,7 +157,12 @@ static int unary_map(const mdesc* d, const libxsmm_meltw_unary_param* p) {
           const float fwd = ldf(p->in.secondary, i + (long long)j * d->ldi, d->t0);
           stf(p->out.primary, oi, d->to, (fwd > 0) ? x : x * (fwd + alpha));
         } break;
-        default: stf(p->out.primary, oi, d->to, unary_f32(x, op));
+        default:
+          stf_rnd(p->out.primary, oi, d->to, unary_f32(x, op), (d->flags & LIBXSMM_MELTW_FLAG_UNARY_STOCHASTIC_ROUND) != 0, (uint32_t*)p->op.secondary, (long long)j * d->m + i);
+          if (op == LIBXSMM_MELTW_TYPE_UNARY_DUMP) {      /* :2478-2493: the value is stored a second time (the stochastic byte is copied) */
+            if ((d->flags & LIBXSMM_MELTW_FLAG_UNARY_STOCHASTIC_ROUND) != 0 && d->to == LIBXSMM_DATATYPE_BF8) ((uint8_t*)p->out.secondary)[oi] = ((uint8_t*)p->out.primary)[oi];
+            else stf(p->out.secondary, oi, d->to, x);
+          }
       }
     }
   }
@@ -559,7 +581,7 @@ static int binary_map(const mdesc* d, const libxsmm_meltw_binary_param* p) {
         default: return 2;
       }
       if (!is_f(d->to)) return 2;
-      stf(p->out.primary, oi, d->to, r);
+      stf_rnd(p->out.primary, oi, d->to, r, (d->flags & LIBXSMM_MELTW_FLAG_BINARY_STOCHASTIC_ROUND) != 0, (uint32_t*)p->op.secondary, (long long)j * d->m + i);
     }
   }
   return 0;
@@ -574,14 +596,16 @@ static int ternary_map(const mdesc* d, const libxsmm_meltw_ternary_param* p) {  
       const int bit = mask_get(p->in2.primary, i, j, mask_ld_of(d->ldi3));
       if (f64) ((double*)p->out.primary)[oi] = bit ? ((const double*)p->in1.primary)[bidx(d, 1, i, j, d->ldi2)] : ((const double*)p->in0.primary)[bidx(d, 0, i, j, d->ldi)];
       else if (is_f(d->t0) && is_f(d->t1) && is_f(d->to))
-        stf(p->out.primary, oi, d->to, bit ? ldf(p->in1.primary, bidx(d, 1, i, j, d->ldi2), d->t1) : ldf(p->in0.primary, bidx(d, 0, i, j, d->ldi), d->t0));
+        stf_rnd(p->out.primary, oi, d->to, bit ? ldf(p->in1.primary, bidx(d, 1, i, j, d->ldi2), d->t1) : ldf(p->in0.primary, bidx(d, 0, i, j, d->ldi), d->t0),
+                (d->flags & LIBXSMM_MELTW_FLAG_TERNARY_STOCHASTIC_ROUND) != 0, (uint32_t*)p->op.secondary, (long long)j * d->m + i);
       else return 2;
     } else if (d->op == LIBXSMM_MELTW_TYPE_TERNARY_MULADD || d->op == LIBXSMM_MELTW_TYPE_TERNARY_NMULADD) {
       float x, y, z;
       if (!(is_f(d->t0) && is_f(d->t1) && is_f(d->t2) && is_f(d->to))) return 2;
       x = ldf(p->in0.primary, bidx(d, 0, i, j, d->ldi), d->t0); y = ldf(p->in1.primary, bidx(d, 1, i, j, d->ldi2), d->t1);
       z = ldf(p->in2.primary, bidx(d, 2, i, j, d->ldi3), d->t2);
-      stf(p->out.primary, oi, d->to, (d->op == LIBXSMM_MELTW_TYPE_TERNARY_MULADD) ? (z + x * y) : (y - x * z));   /* in2 + in0*in1 ; in1 - in0*in2 */
+      stf_rnd(p->out.primary, oi, d->to, (d->op == LIBXSMM_MELTW_TYPE_TERNARY_MULADD) ? (z + x * y) : (y - x * z),   /* in2 + in0*in1 ; in1 - in0*in2 */
+              (d->flags & LIBXSMM_MELTW_FLAG_TERNARY_STOCHASTIC_ROUND) != 0, (uint32_t*)p->op.secondary, (long long)j * d->m + i);
     } else return 2;
   }
   return 0;
@@ -596,7 +620,7 @@ ORACLE_API int oracle_meltw(const int* desc, void* param, int mode) {
   if (d.m <= 0 || d.n <= 0 || param == NULL) return 1;
   if (d.op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
     switch (d.op) {
-      case LIBXSMM_MELTW_TYPE_UNARY_IDENTITY: case LIBXSMM_MELTW_TYPE_UNARY_XOR: case LIBXSMM_MELTW_TYPE_UNARY_X2: case LIBXSMM_MELTW_TYPE_UNARY_SQRT:
+      case LIBXSMM_MELTW_TYPE_UNARY_IDENTITY: case LIBXSMM_MELTW_TYPE_UNARY_XOR: case LIBXSMM_MELTW_TYPE_UNARY_X2: case LIBXSMM_MELTW_TYPE_UNARY_SQRT: case LIBXSMM_MELTW_TYPE_UNARY_DUMP:
       case LIBXSMM_MELTW_TYPE_UNARY_NEGATE: case LIBXSMM_MELTW_TYPE_UNARY_INC: case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL: case LIBXSMM_MELTW_TYPE_UNARY_RECIPROCAL_SQRT:
       case LIBXSMM_MELTW_TYPE_UNARY_TANH: case LIBXSMM_MELTW_TYPE_UNARY_TANH_INV: case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID: case LIBXSMM_MELTW_TYPE_UNARY_SIGMOID_INV:
       case LIBXSMM_MELTW_TYPE_UNARY_GELU: case LIBXSMM_MELTW_TYPE_UNARY_GELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_EXP:

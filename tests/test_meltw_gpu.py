@@ -486,3 +486,63 @@ def test_block_scaled_quantisers_bit_exact():
                 p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, hy.ctypes.data, hs.ctypes.data
                 X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
                 assert np.array_equal(hy, want) and np.array_equal(hs, wscl), (tout, "host buffers")
+
+
+def test_eight_bit_floats_stochastic_rounding_and_dump():
+    """BF8 / HF8 element types, STOCHASTIC_ROUND to BF8 (bytes and the advanced generator state) and DUMP against the reference"""
+    rng = np.random.default_rng(73)
+    m, n, ld = 70, 19, 72
+    wide = (rng.standard_normal(ld * n) * np.exp2(rng.integers(-20, 16, size=ld * n))).astype(np.float32)
+    wide[3] = np.inf; wide[7] = np.nan; wide[9] = 448.0; wide[10] = 464.0; wide[12] = 57344.0; wide[13] = 61440.0
+    allbytes = np.resize(np.arange(256, dtype=np.uint8), ld * n)
+    nbytes = {gen.F32: 4, gen.BF16: 2, gen.F16: 2, gen.BF8: 1, gen.HF8: 1}
+    for t8 in (gen.BF8, gen.HF8):
+        for name in ("IDENTITY", "X2", "RELU"):
+            op = getattr(X, "MELTW_TYPE_UNARY_" + name)
+            for tin, tout, x in ((gen.F32, t8, wide), (t8, gen.F32, allbytes), (t8, t8, allbytes), (t8, gen.BF16, allbytes)):
+                k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, tin, tout, gen.F32), 0)
+                assert k, (name, tin, tout)
+                want = np.zeros(ld * n * nbytes[tout], dtype=np.uint8)
+                q = X.MeltwUnaryParam(); q.inp.primary, q.out.primary = x.ctypes.data, want.ctypes.data
+                _ref_call(_desc(1, op, 0, m, n, ld, 0, 0, ld, tin, UNS, UNS, tout, gen.F32), q)
+                d_x, d_o = dev(x), dev(np.zeros_like(want))
+                p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary = d_x.data_ptr(), d_o.data_ptr()
+                X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+                assert np.array_equal(host(d_o, np.uint8), want), (name, tin, tout)
+    # stochastic rounding: unary, binary, ternary
+    y = rng.standard_normal(ld * n).astype(np.float32); z = rng.standard_normal(ld * n).astype(np.float32)
+    state0 = rng.integers(0, 2 ** 32, size=64, dtype=np.uint32)
+    for name in ("IDENTITY", "X2", "DUMP"):
+        op = getattr(X, "MELTW_TYPE_UNARY_" + name)
+        k = X.libxsmm_dispatch_meltw_unary(op, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, gen.F32, gen.BF8, gen.F32), X.MELTW_FLAG_UNARY_STOCHASTIC_ROUND)
+        assert k, name
+        want, wst, wdump = np.zeros(ld * n, dtype=np.uint8), state0.copy(), np.zeros(ld * n, dtype=np.uint8)
+        q = X.MeltwUnaryParam(); q.op.secondary = wst.ctypes.data; q.inp.primary, q.out.primary, q.out.secondary = wide.ctypes.data, want.ctypes.data, wdump.ctypes.data
+        _ref_call(_desc(1, op, X.MELTW_FLAG_UNARY_STOCHASTIC_ROUND, m, n, ld, 0, 0, ld, gen.F32, UNS, UNS, gen.BF8, gen.F32), q)
+        d_x, d_o, d_s, d_d = dev(wide), dev(np.zeros(ld * n, dtype=np.uint8)), dev(state0), dev(np.zeros(ld * n, dtype=np.uint8))
+        p = X.MeltwUnaryParam(); p.op.secondary = d_s.data_ptr(); p.inp.primary, p.out.primary, p.out.secondary = d_x.data_ptr(), d_o.data_ptr(), d_d.data_ptr()
+        X.MELTW_UNARY_FN(k)(C.byref(p)); X.check()
+        assert np.array_equal(host(d_o, np.uint8), want), name
+        assert np.array_equal(host(d_s, np.uint32), wst), (name, "generator state")
+        if name == "DUMP":
+            assert np.array_equal(host(d_d, np.uint8), wdump)
+    kb = X.libxsmm_dispatch_meltw_binary(X.MELTW_TYPE_BINARY_MUL, X.libxsmm_create_meltw_binary_shape(m, n, ld, ld, ld, gen.F32, gen.F32, gen.BF8, gen.F32), X.MELTW_FLAG_BINARY_STOCHASTIC_ROUND)
+    assert kb
+    want, wst = np.zeros(ld * n, dtype=np.uint8), state0.copy()
+    q = X.MeltwBinaryParam(); q.op.secondary = wst.ctypes.data; q.in0.primary, q.in1.primary, q.out.primary = wide.ctypes.data, y.ctypes.data, want.ctypes.data
+    _ref_call(_desc(2, X.MELTW_TYPE_BINARY_MUL, X.MELTW_FLAG_BINARY_STOCHASTIC_ROUND, m, n, ld, ld, 0, ld, gen.F32, gen.F32, UNS, gen.BF8, gen.F32), q)
+    hs, ho = state0.copy(), np.zeros(ld * n, dtype=np.uint8)       # host buffers all the way: state staged in and out
+    p = X.MeltwBinaryParam(); p.op.secondary = hs.ctypes.data; p.in0.primary, p.in1.primary, p.out.primary = wide.ctypes.data, y.ctypes.data, ho.ctypes.data
+    X.MELTW_BINARY_FN(kb)(C.byref(p)); X.check()
+    assert np.array_equal(ho, want) and np.array_equal(hs, wst)
+    kt = X.libxsmm_dispatch_meltw_ternary(X.MELTW_TYPE_TERNARY_MULADD, X.libxsmm_create_meltw_ternary_shape(m, n, ld, ld, ld, ld, gen.F32, gen.F32, gen.F32, gen.BF8, gen.F32), X.MELTW_FLAG_TERNARY_STOCHASTIC_ROUND)
+    assert kt
+    want, wst = np.zeros(ld * n, dtype=np.uint8), state0.copy()
+    q = X.MeltwTernaryParam(); q.op.secondary = wst.ctypes.data; q.in0.primary, q.in1.primary, q.in2.primary, q.out.primary = wide.ctypes.data, y.ctypes.data, z.ctypes.data, want.ctypes.data
+    _ref_call(_desc(3, X.MELTW_TYPE_TERNARY_MULADD, X.MELTW_FLAG_TERNARY_STOCHASTIC_ROUND, m, n, ld, ld, ld, ld, gen.F32, gen.F32, gen.F32, gen.BF8, gen.F32), q)
+    d_o, d_s = dev(np.zeros(ld * n, dtype=np.uint8)), dev(state0)
+    d_x, d_y, d_z = dev(wide), dev(y), dev(z)
+    p = X.MeltwTernaryParam(); p.op.secondary = d_s.data_ptr(); p.in0.primary, p.in1.primary, p.in2.primary, p.out.primary = d_x.data_ptr(), d_y.data_ptr(), d_z.data_ptr(), d_o.data_ptr()
+    X.MELTW_TERNARY_FN(kt)(C.byref(p)); X.check()
+    assert np.array_equal(host(d_o, np.uint8), want) and np.array_equal(host(d_s, np.uint32), wst)
+    assert not X.libxsmm_dispatch_meltw_unary(X.MELTW_TYPE_UNARY_DUMP, X.libxsmm_create_meltw_unary_shape(m, n, ld, ld, gen.F64, gen.F64, gen.F64), 0)

@@ -251,6 +251,42 @@ def test_eight_bit_float_element_types():
     both((2, X.MELTW_TYPE_BINARY_ADD, 0, m, n, ld, ld, 0, ld, gen.BF8, gen.HF8, UNS, gen.HF8, gen.F32), mkb, [y0])
 
 
+def test_stochastic_rounding_to_bf8_and_dump():
+    """STOCHASTIC_ROUND (unary, binary, ternary) with a BF8 output: bytes AND the advanced 4 x 16-word generator state; DUMP writes twice"""
+    rng = np.random.default_rng(72)
+    m, n, ld = 37, 13, 40
+    x = (rng.standard_normal(ld * n) * np.exp2(rng.integers(-18, 14, size=ld * n))).astype(np.float32)
+    x[5] = np.inf; x[6] = np.nan; x[7] = 3.0e-6; x[8] = -1.0e-7
+    y = rng.standard_normal(ld * n).astype(np.float32); z = rng.standard_normal(ld * n).astype(np.float32)
+    state0 = rng.integers(0, 2 ** 32, size=64, dtype=np.uint32)
+    o0 = np.zeros(ld * n, dtype=np.uint8)
+    for name in ("IDENTITY", "X2", "DUMP"):
+        def mk(bufs, keep):
+            p = X.MeltwUnaryParam(); p.op.secondary = bufs[1].ctypes.data
+            p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, bufs[0].ctypes.data, bufs[2].ctypes.data
+            return p
+        both((1, getattr(X, "MELTW_TYPE_UNARY_" + name), X.MELTW_FLAG_UNARY_STOCHASTIC_ROUND, m, n, ld, 0, 0, ld, gen.F32, UNS, UNS, gen.BF8, gen.F32), mk, [o0, state0, o0])
+
+    def mkb(bufs, keep):
+        p = X.MeltwBinaryParam(); p.op.secondary = bufs[1].ctypes.data
+        p.in0.primary, p.in1.primary, p.out.primary = x.ctypes.data, y.ctypes.data, bufs[0].ctypes.data
+        return p
+    both((2, X.MELTW_TYPE_BINARY_MUL, X.MELTW_FLAG_BINARY_STOCHASTIC_ROUND, m, n, ld, ld, 0, ld, gen.F32, gen.F32, UNS, gen.BF8, gen.F32), mkb, [o0, state0])
+
+    def mkt(bufs, keep):
+        p = X.MeltwTernaryParam(); p.op.secondary = bufs[1].ctypes.data
+        p.in0.primary, p.in1.primary, p.in2.primary, p.out.primary = x.ctypes.data, y.ctypes.data, z.ctypes.data, bufs[0].ctypes.data
+        return p
+    both((3, X.MELTW_TYPE_TERNARY_MULADD, X.MELTW_FLAG_TERNARY_STOCHASTIC_ROUND, m, n, ld, ld, ld, ld, gen.F32, gen.F32, gen.F32, gen.BF8, gen.F32), mkt, [o0, state0])
+    # DUMP without the flag, f32 -> bf16 (the reference has no F64 DUMP: libxsmm_fp64_unary_compute :116-138 rejects it)
+    oo = np.zeros(ld * n, dtype=np.uint16)
+
+    def mkd(bufs, keep):
+        p = X.MeltwUnaryParam(); p.inp.primary, p.out.primary, p.out.secondary = x.ctypes.data, bufs[0].ctypes.data, bufs[1].ctypes.data
+        return p
+    both((1, X.MELTW_TYPE_UNARY_DUMP, 0, m, n, ld, 0, 0, ld, gen.F32, UNS, UNS, gen.BF16, gen.F32), mkd, [oo, oo])
+
+
 def mx_inputs(rng, m, n, ld):
     """bf16 blocks that reach every branch of the block quantisers: wide exponent range, exact ties of the 4-bit code grid, all-zero
     blocks, blocks with Inf / NaN, sub-normal magnitudes"""
