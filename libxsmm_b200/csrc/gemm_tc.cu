@@ -104,6 +104,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 // SMEM matrix descriptor, SWIZZLE_128B, descriptor version 1 (Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32)
@@ -153,9 +154,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_word;
 
+  // The producer and the MMA warp run their loops with ALL lanes (every lane computes the same, provably warp-uniform values) and
+  // only the instruction itself is predicated on one elected lane: operands then sit in uniform registers. Under `if (lane == 0)`
+  // the compiler cannot know that and wraps every tcgen05.mma / TMA issue into an R2UR.BROADCAST loop (33 instructions per MMA).
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    {
+      uint32_t leader;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
       int stage = 0; uint32_t phase = 0;
       uint64_t policy = 0;
       if (P.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
@@ -174,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(bar_base + 8 * (S + stage), phase ^ 1);
             const uint32_t full = bar_base + 8 * stage;
             const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
+            if (leader) {
             mbar_expect_tx(full, (uint32_t)P.stage_bytes);
             if (P.evict_first) {
               tma_load_4d_hint(sa, &map_a, full, 0, kc * 64, (int)r, ta, policy);
@@ -184,6 +191,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, 64, kc * 64, (int)r, ta);
               tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, tb);
             }
+            }
+            __syncwarp();
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -191,9 +200,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    {
+      uint32_t leader;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
       int stage = 0; uint32_t phase = 0;                  // cursor of the next freshly loaded stage
       int run_stage = 0; uint32_t run_phase = 0;          // first stage of the run of equal set pairs this tile belongs to
+      const uint32_t hi_a = (P.sbo_a & 0x3FFFu) | (1u << 14) | (2u << 29), hi_b = (P.sbo_b & 0x3FFFu) | (1u << 14) | (2u << 29);
       for (long long i = 0; i < n_local; ++i) {
         bool reuse = false, last_of_run = true;
         if (can_hold) {
@@ -218,18 +230,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t sa = smem_base + cs * P.stage_bytes, sb = sa + P.a_bytes;
             const int krem = P.k - kc * 64;
             const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t adesc = make_desc(sa + ks * 2048, P.lbo_a, P.sbo_a);   // 16 k-rows of 128 B
-              const uint64_t bdesc = make_desc(sb + ks * 32, P.lbo_b, P.sbo_b);     // 16 k-elements inside the swizzle row
-              umma_f16(d_tmem, adesc, bdesc, P.idesc, accumulate);
-              accumulate = 1;
+            // descriptors: high word constant, low word = (address >> 4) | lbo << 16; a k-step advances A by 16 rows of 128 bytes
+            // and B by 16 elements inside the swizzled row -- one 32-bit add each per instruction
+            const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | ((P.lbo_a & 0x3FFFu) << 16), b_lo = ((sb & 0x3FFFFu) >> 4) | ((P.lbo_b & 0x3FFFu) << 16);
+            if (leader) {
+              if (ksteps == 4) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), P.idesc, ks == 0 ? accumulate : 1u);
+              } else {
+                for (int ks = 0; ks < ksteps; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), P.idesc, ks == 0 ? accumulate : 1u);
+              }
             }
-            if (last_of_run) umma_commit(bar_base + 8 * (S + cs));     // stage reusable once the MMAs of the whole run retired
+            accumulate = 1;
+            if (last_of_run && leader) umma_commit(bar_base + 8 * (S + cs));     // stage reusable once the MMAs of the whole run retired
+            __syncwarp();
             if (++cs == S) { cs = 0; cph ^= 1; }
           }
         }
         if (!reuse) { stage = cs; phase = cph; }
-        if (half == TPS - 1 || i == n_local - 1) umma_commit(bar_base + 8 * (2 * S + slot));
+        if ((half == TPS - 1 || i == n_local - 1) && leader) umma_commit(bar_base + 8 * (2 * S + slot));
+        __syncwarp();
       }
     }
   } else {

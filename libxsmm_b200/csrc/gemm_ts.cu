@@ -43,9 +43,11 @@ struct TsParams {
   char* c; long long tile_stride_c, ldc;
   int c_type, a_type, beta0, is_i8;
   int ep_mode, c_esz;           // xb_epilogue.cuh
+  int grp, mp;                  // small tiles: grp tiles share one instruction (tile g*grp + j owns rows j*mp.. and columns j*np..); grp = 1: mp = 128
+  long long groups;             // ceil(count / grp): the unit the CTAs walk
   float scf;
   uint32_t idesc;
-  int skip;                     // diagnostic (LIBXSMM_B200_TS_SKIP): 1 no C stores, 2 no MMAs, 4 no TMEM copy, 8 no TMA loads, 16 no A load, 32 no B load
+  int skip;                     // diagnostic (LIBXSMM_B200_TS_SKIP): 1 no C stores, 2 no MMAs, 4 no TMEM copy, 8 no TMA loads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,11 +97,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-// K-major SWIZZLE_128B shared-memory descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart), descriptor version 1
-__device__ __forceinline__ uint64_t make_desc_b(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
 constexpr int kTsgThreads = 320;     // 10 warps
 constexpr int MAX_S = 8, MAX_NS = 4;
 
@@ -116,7 +113,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_word = (uint32_t*)(bars + 3 * MAX_S + 2 * MAX_NS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long G = gridDim.x, b = blockIdx.x;
-  const long long n_local = (b < P.count) ? (P.count - b + G - 1) / G : 0;
+  const long long n_local = (b < P.groups) ? (P.groups - b + G - 1) / G : 0;      // groups of P.grp tiles
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
@@ -135,27 +132,28 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_word;
   const uint32_t tmem_a = tmem_base + (uint32_t)P.a_col0;
 
+  // producer and MMA warps loop with all lanes (warp-uniform values -> uniform registers); one elected lane issues (see gemm_tc.cu)
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    {
+      uint32_t leader;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
       int stage = 0; uint32_t phase = 0;
       for (long long i = 0; i < n_local; ++i) {
-        const long long t = b + i * G;
+        const long long t = (b + i * G) * P.grp;                       // first tile of the group; the boxes span P.grp tiles
         for (unsigned long long r = 0; r < P.br; ++r) {
           for (int kc = 0; kc < P.kchunks; ++kc) {
             mbar_wait(empty + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
-            if (P.skip & 8) { mbar_arrive(full + 8 * stage); if (++stage == S) { stage = 0; phase ^= 1; } continue; }
-            if (P.skip & 48) {
-              mbar_expect_tx(full + 8 * stage, (uint32_t)((P.skip & 16) ? P.np * 128 : P.m * 128));
-              if (!(P.skip & 16)) tma_load_4d(sa, &map_a, full + 8 * stage, 0, kc * 32, (int)r, (int)t);
-              if (!(P.skip & 32)) tma_load_4d(sb, &map_b, full + 8 * stage, kc * P.kc_elems, 0, (int)r, (int)t);
-              if (++stage == S) { stage = 0; phase ^= 1; }
-              continue;
+            if (leader) {
+              if (P.skip & 8) mbar_arrive(full + 8 * stage);
+              else {
+                mbar_expect_tx(full + 8 * stage, (uint32_t)P.tx_bytes);         // rows / words beyond the matrix are zero-filled and counted
+                tma_load_4d(sa, &map_a, full + 8 * stage, 0, kc * 32, (int)r, (int)t);               // m words x 32 word-rows
+                tma_load_4d(sb, &map_b, full + 8 * stage, kc * P.kc_elems, 0, (int)r, (int)t);       // 128 bytes of k x np rows
+              }
             }
-            mbar_expect_tx(full + 8 * stage, (uint32_t)P.tx_bytes);         // rows / words beyond the matrix are zero-filled and counted
-            tma_load_4d(sa, &map_a, full + 8 * stage, 0, kc * 32, (int)r, (int)t);               // m words x 32 word-rows
-            tma_load_4d(sb, &map_b, full + 8 * stage, kc * P.kc_elems, 0, (int)r, (int)t);       // 128 bytes of k x np rows
+            __syncwarp();
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -163,7 +161,9 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    {
+      uint32_t leader;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
       int stage = 0; uint32_t phase = 0;
       for (long long i = 0; i < n_local; ++i) {
         const int slot = (int)(i % NS);
@@ -180,17 +180,20 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int krem = P.k - kc * P.kc_elems;
             const int ksteps = (krem >= P.kc_elems) ? 4 : (krem + P.kinst - 1) / P.kinst;
             const uint32_t a_slot = tmem_a + (uint32_t)stage * 32u;
-            for (int ks = 0; ks < ((P.skip & 2) ? 0 : ksteps); ++ks) {
-              const uint64_t bdesc = make_desc_b(sb + ks * 32);                 // 32 bytes of k inside the swizzled 128-byte row
-              if (P.is_i8) umma_i8_ts(d_tmem, a_slot + (uint32_t)ks * 8u, bdesc, P.idesc, accumulate);
-              else umma_f16_ts(d_tmem, a_slot + (uint32_t)ks * 8u, bdesc, P.idesc, accumulate);
-              accumulate = 1;
+            // B descriptor: constant high word; low word = (address >> 4) | 1 << 16; a k-step is 32 bytes inside the swizzled row
+            const uint32_t b_lo = ((sb & 0x3FFFFu) >> 4) | (1u << 16), b_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            if (leader && !(P.skip & 2)) {
+              if (P.is_i8) { for (int ks = 0; ks < ksteps; ++ks) umma_i8_ts(d_tmem, a_slot + (uint32_t)ks * 8u, ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)ks * 2u), P.idesc, ks == 0 ? accumulate : 1u); }
+              else { for (int ks = 0; ks < ksteps; ++ks) umma_f16_ts(d_tmem, a_slot + (uint32_t)ks * 8u, ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)ks * 2u), P.idesc, ks == 0 ? accumulate : 1u); }
             }
-            umma_commit(empty + 8 * stage);                  // stage (shared memory AND its A columns) reusable once these retire
+            accumulate = 1;
+            if (leader) umma_commit(empty + 8 * stage);      // stage (shared memory AND its A columns) reusable once these retire
+            __syncwarp();
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(t_full + 8 * slot);
+        if (leader) umma_commit(t_full + 8 * slot);
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -201,15 +204,26 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int slot = (int)(i % NS);
       mbar_wait(t_full + 8 * slot, (uint32_t)((i / NS) & 1));
       tc_fence_after();
-      const bool valid = row < P.m && !(P.skip & 1);
+      // row r of the instruction belongs to tile (group * grp + r / mp), row r % mp of it, and that tile's results sit in
+      // accumulator columns (r / mp) * np ...: a warp covers 32 / mp tiles (one tcgen05.ld sequence each)
+      const int tl = row / P.mp, ri = row - tl * P.mp;
+      const long long tile = (b + i * G) * P.grp + tl;
+      const bool valid = tl < P.grp && ri < P.m && tile < P.count && !(P.skip & 1);
       const long long ldcb = P.ldc * P.c_esz;
-      char* crow = P.c + (b + i * G) * P.tile_stride_c + (long long)row * P.c_esz;
+      char* crow = P.c + tile * P.tile_stride_c + (long long)ri * P.c_esz;
       const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < P.np; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        if (c0 + 32 >= P.np) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
-        if (valid && c0 < P.n) xb_ep_store_chunk(P.ep_mode, P.beta0, v, crow + c0 * ldcb, ldcb, P.n - c0, P.scf);
+      const int wtl0 = (32 * q) / P.mp, nsub = (P.mp >= 32) ? 1 : 32 / P.mp;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int wtl = wtl0 + sub;                                     // warp-uniform tile index inside the group
+        const bool last_sub = (sub == nsub - 1) || (wtl + 1 >= P.grp);
+        if (wtl < P.grp) {
+          for (int c0 = 0; c0 < P.np; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)(wtl * P.np + c0), v);
+            if (last_sub && c0 + 32 >= P.np) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
+            if (valid && tl == wtl && c0 < P.n) xb_ep_store_chunk(P.ep_mode, P.beta0, v, crow + c0 * ldcb, ldcb, P.n - c0, P.scf);
+          }
+        } else if (sub == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }   // rows beyond the group's tiles
       }
     }
   } else {
@@ -218,7 +232,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // consecutive words (conflict-free); rows >= m read a neighbouring stage's bytes -- they only feed accumulator rows
     // that are never stored
     const int q = warp & 3, row = 32 * q + lane;
-    const int rr = (row < P.m) ? row : 0;
+    const int tl = row / P.mp, ri = row - tl * P.mp;
+    const int rr = (tl < P.grp && ri < P.m) ? tl * 32 * P.m + ri : 0;      // the raw stage is [grp][32 word-rows][m words]
     int stage = 0; uint32_t phase = 0;
     for (long long i = 0; i < n_local; ++i) {
       for (unsigned long long r = 0; r < P.br; ++r) {
@@ -294,11 +309,22 @@ extern "C" int xb_gemm_ts_launch(const xb_gemm_launch* L) {
   TsParams P; memset(&P, 0, sizeof(P));
   P.m = d.m; P.n = d.n; P.k = d.k; P.np = (d.n + 15) & ~15;
   P.kc_elems = 128 / es; P.kinst = is_i8 ? 32 : 16; P.kchunks = (d.k + P.kc_elems - 1) / P.kc_elems;
-  P.a_bytes = d.m * 128;                                       // m words x 32 word-rows
-  P.tx_bytes = P.a_bytes + P.np * 128;
-  P.stage_bytes = ((P.a_bytes + 1023) & ~1023) + P.np * 128;   // B starts 1024-byte aligned (SWIZZLE_128B atom)
+  // small tiles: grp tiles at constant stride share one instruction as a block-diagonal product -- their A rows are stacked
+  // (tile j at rows j*mp), their B columns put side by side (tile j at columns j*np); the off-diagonal blocks are computed and
+  // ignored. One TMA box per operand fetches all grp tiles (4th box dimension), one barrier round trip serves grp tiles.
+  P.grp = 1; P.mp = 128;
+  if (d.m <= 32 && L->count > 1 && ts_env_int("LIBXSMM_B200_TS_PACK", 1) != 0) {
+    P.mp = d.m <= 8 ? 8 : (d.m <= 16 ? 16 : 32);
+    P.grp = 128 / P.mp; if (P.grp > 128 / P.np) P.grp = 128 / P.np;
+    { const int ge = ts_env_int("LIBXSMM_B200_TS_GRP", 0); if (ge >= 1 && ge < P.grp) P.grp = ge; }
+    if (P.grp < 2) { P.grp = 1; P.mp = 128; }
+  }
+  P.groups = (L->count + P.grp - 1) / P.grp;
+  P.a_bytes = P.grp * d.m * 128;                               // grp x (m words x 32 word-rows)
+  P.tx_bytes = P.a_bytes + P.grp * P.np * 128;
+  P.stage_bytes = ((P.a_bytes + 1023) & ~1023) + P.grp * P.np * 128;   // B starts 1024-byte aligned (SWIZZLE_128B atom)
   P.a_bytes = (P.a_bytes + 1023) & ~1023;
-  P.slot_cols = (P.np + 31) & ~31;
+  P.slot_cols = (P.grp * P.np + 31) & ~31;
   const long long loads_per_tile = (long long)P.kchunks * (long long)br;
   int ctas = ts_env_int("LIBXSMM_B200_TS_CTAS", loads_per_tile <= 2 ? 4 : 2);
   if (ctas < 1) ctas = 1; if (ctas > 4) ctas = 4;
@@ -318,10 +344,10 @@ extern "C" int xb_gemm_ts_launch(const xb_gemm_launch* L) {
   P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0; P.is_i8 = is_i8; P.scf = L->one.scf;
   if (is_i8) {
     const uint32_t fa = (d.ta == LIBXSMM_DATATYPE_I8) ? 1u : 0u, fb = (d.tb == LIBXSMM_DATATYPE_I8) ? 1u : 0u;
-    P.idesc = (2u << 4) | (fa << 7) | (fb << 10) | ((uint32_t)(P.np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    P.idesc = (2u << 4) | (fa << 7) | (fb << 10) | ((uint32_t)((P.grp * P.np) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   } else {
     const uint32_t fmt = (d.ta == LIBXSMM_DATATYPE_BF16) ? 1u : 0u;
-    P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((P.grp * P.np) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   }
 
   const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -331,7 +357,7 @@ extern "C" int xb_gemm_ts_launch(const xb_gemm_launch* L) {
   {
     const cuuint64_t dims[4] = {(cuuint64_t)d.m, (cuuint64_t)(d.k / v), (cuuint64_t)br, (cuuint64_t)L->count};
     const cuuint64_t strides[3] = {(cuuint64_t)d.lda * 4, (d.br_type == 3) ? (cuuint64_t)d.br_stride_a : pad_a, (L->count > 1) ? (cuuint64_t)sa : pad_a};
-    const cuuint32_t box[4] = {(cuuint32_t)d.m, 32, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)d.m, 32, 1, (cuuint32_t)P.grp};
     if (CUDA_SUCCESS != enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) return xb_gemm_simt_launch(L);
   }
@@ -339,14 +365,14 @@ extern "C" int xb_gemm_ts_launch(const xb_gemm_launch* L) {
     const CUtensorMapDataType dt = is_i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (d.ta == LIBXSMM_DATATYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     const cuuint64_t dims[4] = {(cuuint64_t)d.k, (cuuint64_t)d.n, (cuuint64_t)br, (cuuint64_t)L->count};
     const cuuint64_t strides[3] = {(cuuint64_t)d.ldb * es, (d.br_type == 3) ? (cuuint64_t)d.br_stride_b : pad_b, (L->count > 1) ? (cuuint64_t)sb : pad_b};
-    const cuuint32_t box[4] = {(cuuint32_t)P.kc_elems, (cuuint32_t)P.np, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)P.kc_elems, (cuuint32_t)P.np, 1, (cuuint32_t)P.grp};
     if (CUDA_SUCCESS != enc(&map_b, dt, 4, (void*)b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) return xb_gemm_simt_launch(L);
   }
   const size_t smem = (size_t)P.stages * P.stage_bytes + 1024 + (3 * MAX_S + 2 * MAX_NS) * 8 + 64;
   static int sms = 0;
   if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  long long grid = L->count; if (grid > (long long)sms * ctas) grid = (long long)sms * ctas; if (grid < 1) grid = 1;
+  long long grid = P.groups; if (grid > (long long)sms * ctas) grid = (long long)sms * ctas; if (grid < 1) grid = 1;
   if (xb_rt_first_use_on_device(&g_ts_attr)) cudaFuncSetAttribute(gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   gemm_ts_kernel<<<(unsigned int)grid, kTsgThreads, smem, (cudaStream_t)xb_rt_stream()>>>(map_a, map_b, P);
   xb_rt_count_launch();
