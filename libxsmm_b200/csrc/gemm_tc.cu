@@ -112,7 +112,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16
 }
 
 template <int UM>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(320)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int TPS = (UM == 64) ? 2 : 1;          // tiles per TMEM slot
@@ -142,7 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
     for (int i = 0; i < S; ++i) { mbar_init(bar_base + 8 * i, 1); mbar_init(bar_base + 8 * (S + i), 1); }
-    for (int i = 0; i < NS; ++i) { mbar_init(bar_base + 8 * (2 * S + i), 1); mbar_init(bar_base + 8 * (2 * S + NS + i), 4); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_base + 8 * (2 * S + i), 1); mbar_init(bar_base + 8 * (2 * S + NS + i), (blockDim.x >> 5) - 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM: whole 512 columns (one CTA per SM)
@@ -177,7 +177,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (unsigned long long r = 0; r < P.br; ++r) {
           for (int kc = 0; kc < P.kchunks; ++kc) {
-            mbar_wait(bar_base + 8 * (S + stage), phase ^ 1);
+            if (leader) mbar_wait(bar_base + 8 * (S + stage), phase ^ 1);
+            __syncwarp();
             const uint32_t full = bar_base + 8 * stage;
             const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
             if (leader) {
@@ -206,6 +207,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0; uint32_t phase = 0;                  // cursor of the next freshly loaded stage
       int run_stage = 0; uint32_t run_phase = 0;          // first stage of the run of equal set pairs this tile belongs to
       const uint32_t hi_a = (P.sbo_a & 0x3FFFu) | (1u << 14) | (2u << 29), hi_b = (P.sbo_b & 0x3FFFu) | (1u << 14) | (2u << 29);
+      // per-stage descriptor low words: (address >> 4) | lbo << 16; the high words are constant. A k-step advances A by 16 rows of
+      // 128 bytes and B by 16 elements inside the swizzled row: one 32-bit add per operand and instruction.
+      const uint32_t stage_step = (uint32_t)P.stage_bytes >> 4;
+      const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | ((P.lbo_a & 0x3FFFu) << 16);
+      const uint32_t b_lo0 = (((smem_base + (uint32_t)P.a_bytes) & 0x3FFFFu) >> 4) | ((P.lbo_b & 0x3FFFu) << 16);
+      const uint32_t full0 = bar_base, empty0 = bar_base + 8 * S, tfull0 = bar_base + 8 * (2 * S), tempty0 = bar_base + 8 * (2 * S + NS);
+      const int nload = loads_per_tile, kchunks = P.kchunks;
+      const int ks_last = (P.k - (kchunks - 1) * 64 + 15) / 16;           // k-steps of a tile's last k-chunk (4 when k % 64 == 0)
+      const uint32_t idesc = P.idesc;
+      int slot = 0; uint32_t slot_par = 1; int half = 0;                   // TMEM slot cursor (TPS tiles per slot)
       for (long long i = 0; i < n_local; ++i) {
         bool reuse = false, last_of_run = true;
         if (can_hold) {
@@ -215,46 +226,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (!reuse) { run_stage = stage; run_phase = phase; }
         int cs = run_stage; uint32_t cph = run_phase;
-        const long long slot_seq = i / TPS; const int half = (int)(i % TPS);
-        const int slot = (int)(slot_seq % NS);
         if (half == 0) {
-          mbar_wait(bar_base + 8 * (2 * S + NS + slot), (uint32_t)(((slot_seq / NS) & 1) ^ 1));
-          tc_fence_after();
+          if (leader) mbar_wait(tempty0 + 8 * slot, slot_par);
+          __syncwarp();
         }
+        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(slot * P.slot_cols) + (half ? (16u << 16) : 0u);
         uint32_t accumulate = 0;
-        for (unsigned long long r = 0; r < P.br; ++r) {
-          for (int kc = 0; kc < P.kchunks; ++kc) {
-            if (!reuse) mbar_wait(bar_base + 8 * cs, cph);
-            tc_fence_after();
-            const uint32_t sa = smem_base + cs * P.stage_bytes, sb = sa + P.a_bytes;
-            const int krem = P.k - kc * 64;
-            const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
-            // descriptors: high word constant, low word = (address >> 4) | lbo << 16; a k-step advances A by 16 rows of 128 bytes
-            // and B by 16 elements inside the swizzled row -- one 32-bit add each per instruction
-            const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | ((P.lbo_a & 0x3FFFu) << 16), b_lo = ((sb & 0x3FFFFu) >> 4) | ((P.lbo_b & 0x3FFFu) << 16);
-            if (leader) {
-              if (ksteps == 4) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), P.idesc, ks == 0 ? accumulate : 1u);
-              } else {
-                for (int ks = 0; ks < ksteps; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), P.idesc, ks == 0 ? accumulate : 1u);
-              }
+        int kc = 0;
+        for (int l = 0; l < nload; ++l) {
+          if (!reuse) { if (leader) mbar_wait(full0 + 8 * cs, cph); __syncwarp(); tc_fence_after(); }
+          const uint32_t a_lo = a_lo0 + (uint32_t)cs * stage_step, b_lo = b_lo0 + (uint32_t)cs * stage_step;
+          const int ksteps = (kc == kchunks - 1) ? ks_last : 4;
+          if (leader) {
+            if (ksteps == 4) {
+              umma_f16(d_tmem, desc64(hi_a, a_lo), desc64(hi_b, b_lo), idesc, accumulate);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 128), desc64(hi_b, b_lo + 2), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 256), desc64(hi_b, b_lo + 4), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 384), desc64(hi_b, b_lo + 6), idesc, 1u);
+            } else {
+              for (int ks = 0; ks < ksteps; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), idesc, ks == 0 ? accumulate : 1u);
             }
-            accumulate = 1;
-            if (last_of_run && leader) umma_commit(bar_base + 8 * (S + cs));     // stage reusable once the MMAs of the whole run retired
-            __syncwarp();
-            if (++cs == S) { cs = 0; cph ^= 1; }
+            if (last_of_run) umma_commit(empty0 + 8 * cs);               // stage reusable once the MMAs of the whole run retired
           }
+          accumulate = 1;
+          if (++kc == kchunks) kc = 0;
+          if (++cs == S) { cs = 0; cph ^= 1; }
         }
         if (!reuse) { stage = cs; phase = cph; }
-        if ((half == TPS - 1 || i == n_local - 1) && leader) umma_commit(bar_base + 8 * (2 * S + slot));
+        if ((half == TPS - 1 || i == n_local - 1) && leader) umma_commit(tfull0 + 8 * slot);
         __syncwarp();
+        if (++half == TPS) { half = 0; if (++slot == NS) { slot = 0; slot_par ^= 1; } }
       }
     }
   } else {
     // ===================================== epilogue =========================================
+    // 4 or 8 epilogue warps (192 or 320 threads per CTA): warp w reads TMEM lane quadrant w % 4; with 8 warps the two warps of a
+    // quadrant take alternate 32-column chunks
     const int q = warp & 3;                         // TMEM lane quadrant this warp may read
+    const int cgrp = (warp - 2) >> 2, cstep = 32 * (((int)(blockDim.x >> 5) - 2) >> 2);
     const long long n_slots = (n_local + TPS - 1) / TPS;
     const int half = (UM == 64) ? (lane >> 4) : 0;
     const int row = (UM == 64) ? (16 * q + (lane & 15)) : (32 * q + lane);
@@ -269,10 +279,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
       const long long ldcb = P.ldc * P.c_esz;
       char* crow = valid ? ctile + (long long)row * P.c_esz : nullptr;
-      for (int c0 = 0; c0 < P.np; c0 += 32) {
+      if (32 * cgrp >= P.np) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_base + 8 * (2 * S + NS + slot)); }   // no chunk for this warp
+      for (int c0 = 32 * cgrp; c0 < P.np; c0 += cstep) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
-        if (c0 + 32 >= P.np) {                      // last read of this slot: hand it back to the MMA warp
+        if (c0 + cstep >= P.np) {                   // this warp's last read of the slot: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_base + 8 * (2 * S + NS + slot));
@@ -436,12 +447,14 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   }
   cudaStream_t stream = (cudaStream_t)xb_rt_stream();
   cudaError_t e;
+  // one CTA per SM has nothing co-resident to hide its epilogue behind: give it 8 epilogue warps instead of 4
+  const unsigned int threads = (unsigned int)env_int("LIBXSMM_B200_TC_THREADS", (ctas == 1 && P.np >= 64) ? 320 : 192) == 320u ? 320u : 192u;
   if (UM == 64) {
     if (xb_rt_first_use_on_device(&g_attr_set[0])) cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    gemm_tc_kernel<64><<<(unsigned int)grid, 192, smem, stream>>>(map_a, map_b, P);
+    gemm_tc_kernel<64><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
   } else {
     if (xb_rt_first_use_on_device(&g_attr_set[1])) cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    gemm_tc_kernel<128><<<(unsigned int)grid, 192, smem, stream>>>(map_a, map_b, P);
+    gemm_tc_kernel<128><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
   }
   xb_rt_count_launch();
   e = cudaGetLastError();

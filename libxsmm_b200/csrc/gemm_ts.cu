@@ -143,7 +143,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const long long t = (b + i * G) * P.grp;                       // first tile of the group; the boxes span P.grp tiles
         for (unsigned long long r = 0; r < P.br; ++r) {
           for (int kc = 0; kc < P.kchunks; ++kc) {
-            mbar_wait(empty + 8 * stage, phase ^ 1);
+            if (leader) mbar_wait(empty + 8 * stage, phase ^ 1);          // one lane polls, the others park at the warp barrier
+            __syncwarp();
             const uint32_t sa = smem_base + stage * P.stage_bytes, sb = sa + P.a_bytes;
             if (leader) {
               if (P.skip & 8) mbar_arrive(full + 8 * stage);
@@ -167,14 +168,18 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (long long i = 0; i < n_local; ++i) {
         const int slot = (int)(i % NS);
-        mbar_wait(t_empty + 8 * slot, (uint32_t)(((i / NS) & 1) ^ 1));
+        if (leader) mbar_wait(t_empty + 8 * slot, (uint32_t)(((i / NS) & 1) ^ 1));
+        __syncwarp();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(slot * P.slot_cols);
         uint32_t accumulate = 0;
         for (unsigned long long r = 0; r < P.br; ++r) {
           for (int kc = 0; kc < P.kchunks; ++kc) {
-            mbar_wait(full + 8 * stage, phase);              // B bytes have landed (the copy warps waited on it too)
-            mbar_wait(a_full + 8 * stage, phase);            // this stage's A words are in tensor memory
+            if (leader) {
+              mbar_wait(full + 8 * stage, phase);            // B bytes have landed (the copy warps waited on it too)
+              mbar_wait(a_full + 8 * stage, phase);          // this stage's A words are in tensor memory
+            }
+            __syncwarp();
             tc_fence_after();
             const uint32_t sb = smem_base + stage * P.stage_bytes + P.a_bytes;
             const int krem = P.k - kc * P.kc_elems;

@@ -293,7 +293,7 @@ def test_vnni_a_on_tensor_cores(types):
     ta, tb, tcomp, tc = types
     is8 = ta in (gen.I8, gen.U8)
     shapes = [(64, 64, 64, 3, 8, 0), (128, 128, 128, 0, 1, 0), (16, 16, 16, 0, 1, 0), (32, 48, 96, 3, 2, 16), (12, 20, 48 if is8 else 40, 0, 1, 0),
-              (128, 64, 256 + 32, 3, 2, 0), (64, 128, 32, 0, 1, 0), (8, 8, 16, 0, 1, 0), (24, 16, 32, 3, 3, 0), (4, 32, 64, 0, 1, 4)]   # m <= 32: several tiles per instruction
+              (128, 64, 256 + 32, 3, 2, 0), (64, 128, 32, 0, 1, 0), (8, 8, 16, 0, 1, 0), (24, 16, 32, 3, 3, 0), (4, 32, 64, 0, 1, 0)]   # m <= 32: several tiles per instruction
     for (m, n, k, br_type, br, pad) in shapes:
         for beta0 in (1, 0):
             flags = (cases.FLAG_BETA_0 if beta0 else 0) | cases.FLAG_VNNI_A
