@@ -45,12 +45,14 @@ struct TcParams {
   int c_type, a_type, beta0;
   int ep_mode, c_esz;                 // xb_epilogue.cuh
   int sets_in_smem;                   // pooled: the CTA's slice of `sets` is copied behind the barriers at start
+  int pair;                           // pooled, m <= 64: an item is TWO tiles that share B -- tile 0 in rows 0..63, tile 1 in rows 64..127 of one M=128 instruction
   uint32_t idesc;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // in 16-byte units
-  // pooled address mode (libxsmm_b200_gemm_plan over ADDRESS batch-reduce): tile p reads block-set sets[p].x of A and
-  // sets[p].y of B (4th tensor-map coordinate) and writes cptrs[p]; positions are sorted by set pair, a CTA owns a
-  // contiguous range and keeps the operands of a run of equal pairs resident in its stage ring
-  const int2* sets; char* const* cptrs;
+  // pooled address mode (libxsmm_b200_gemm_plan over ADDRESS batch-reduce): item p reads block-set sets[p].x of A (and, in pair
+  // mode, sets[p].y for its second tile) and sets[p].z of B (4th tensor-map coordinate) and writes cptrs[p] (pair mode:
+  // cptrs[2p], cptrs[2p+1], the second may be null); items are sorted by set, a CTA owns a contiguous range and keeps the
+  // operands of a run of equal items resident in its stage ring
+  const int4* sets; char* const* cptrs;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -132,9 +134,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const long long chunk = (P.count + G - 1) / G;                       // pooled: contiguous range per CTA
   const long long n_local = pooled ? ((b * chunk < P.count) ? ((P.count - b * chunk < chunk) ? P.count - b * chunk : chunk) : 0)
                                    : ((b < P.count) ? (P.count - b + G - 1) / G : 0);
-  const int2* s_sets = reinterpret_cast<const int2*>(bars + 2 * MAX_STAGES + 2 * MAX_SLOTS + 2);     // pooled: this CTA's slice of the set pairs
-  const int2* my_sets = P.sets_in_smem ? s_sets : (pooled ? P.sets + b * chunk : nullptr);
-  if (P.sets_in_smem) { int2* w = const_cast<int2*>(s_sets); for (long long i = threadIdx.x; i < n_local; i += blockDim.x) w[i] = P.sets[b * chunk + i]; }
+  const int4* s_sets = reinterpret_cast<const int4*>(bars + 2 * MAX_STAGES + 2 * MAX_SLOTS + 2);     // pooled: this CTA's slice of the items
+  const int4* my_sets = P.sets_in_smem ? s_sets : (pooled ? P.sets + b * chunk : nullptr);
+  if (P.sets_in_smem) { int4* w = const_cast<int4*>(s_sets); for (long long i = threadIdx.x; i < n_local; i += blockDim.x) w[i] = P.sets[b * chunk + i]; }
   const int loads_per_tile = (int)P.br * P.kchunks;
   const bool can_hold = pooled && loads_per_tile <= P.stages;          // a tile's operands fit the ring: equal neighbours re-use them
 
@@ -165,14 +167,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       uint64_t policy = 0;
       if (P.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      int2 prev = make_int2(-1, -1);
+      int4 prev = make_int4(-1, -1, -1, -1);
       for (long long i = 0; i < n_local; ++i) {
         const long long t = pooled ? b * chunk + i : b + i * G;
-        int ta = (int)t, tb = (int)t;
+        int ta = (int)t, ta1 = (int)t, tb = (int)t, m1 = 64;             // second 64-row box of an M=128 stage: rows 64.. of the same tile
         if (pooled) {
-          const int2 st = my_sets[i];
-          const bool same = can_hold && i > 0 && st.x == prev.x && st.y == prev.y;
-          prev = st; ta = st.x; tb = st.y;
+          const int4 st = my_sets[i];
+          const bool same = can_hold && i > 0 && st.x == prev.x && st.y == prev.y && st.z == prev.z;
+          prev = st; ta = st.x; ta1 = st.x; tb = st.z;
+          if (P.pair) { ta1 = st.y; m1 = 0; }                             // pair mode: rows 0.. of the item's second tile
           if (same) continue;                                          // operands of the previous tile are still in the ring
         }
         for (unsigned long long r = 0; r < P.br; ++r) {
@@ -185,11 +188,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_expect_tx(full, (uint32_t)P.stage_bytes);
             if (P.evict_first) {
               tma_load_4d_hint(sa, &map_a, full, 0, kc * 64, (int)r, ta, policy);
-              if (UM == 128) tma_load_4d_hint(sa + 8192, &map_a, full, 64, kc * 64, (int)r, ta, policy);
+              if (UM == 128) tma_load_4d_hint(sa + 8192, &map_a, full, m1, kc * 64, (int)r, ta1, policy);
               tma_load_4d_hint(sb, &map_b, full, kc * 64, 0, (int)r, tb, policy);
             } else {
               tma_load_4d(sa, &map_a, full, 0, kc * 64, (int)r, ta);
-              if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, 64, kc * 64, (int)r, ta);
+              if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, m1, kc * 64, (int)r, ta1);
               tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, tb);
             }
             }
@@ -220,9 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (long long i = 0; i < n_local; ++i) {
         bool reuse = false, last_of_run = true;
         if (can_hold) {
-          const int2 st = my_sets[i];
-          if (i > 0) { const int2 pv = my_sets[i - 1]; reuse = (pv.x == st.x && pv.y == st.y); }
-          if (i + 1 < n_local) { const int2 nx = my_sets[i + 1]; last_of_run = !(nx.x == st.x && nx.y == st.y); }
+          const int4 st = my_sets[i];
+          if (i > 0) { const int4 pv = my_sets[i - 1]; reuse = (pv.x == st.x && pv.y == st.y && pv.z == st.z); }
+          if (i + 1 < n_local) { const int4 nx = my_sets[i + 1]; last_of_run = !(nx.x == st.x && nx.y == st.y && nx.z == st.z); }
         }
         if (!reuse) { run_stage = stage; run_phase = phase; }
         int cs = run_stage; uint32_t cph = run_phase;
@@ -234,6 +237,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t d_tmem = tmem_base + (uint32_t)(slot * P.slot_cols) + (half ? (16u << 16) : 0u);
         uint32_t accumulate = 0;
         int kc = 0;
+        if (reuse && ks_last == 4) {
+          // the operands of this tile are already resident (same set pair as the previous tile): nothing to wait for, every k-chunk
+          // is full -- a straight run of 4 instructions per stage, descriptors advanced by adds
+          uint32_t a_lo = a_lo0 + (uint32_t)cs * stage_step, b_lo = b_lo0 + (uint32_t)cs * stage_step;
+          for (int l = 0; l < nload; ++l) {
+            if (leader) {
+              umma_f16(d_tmem, desc64(hi_a, a_lo), desc64(hi_b, b_lo), idesc, l == 0 ? 0u : 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 128), desc64(hi_b, b_lo + 2), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 256), desc64(hi_b, b_lo + 4), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 384), desc64(hi_b, b_lo + 6), idesc, 1u);
+              if (last_of_run) umma_commit(empty0 + 8 * cs);
+            }
+            a_lo += stage_step; b_lo += stage_step;
+            if (++cs == S) { cs = 0; a_lo = a_lo0; b_lo = b_lo0; }
+          }
+        } else
         for (int l = 0; l < nload; ++l) {
           if (!reuse) { if (leader) mbar_wait(full0 + 8 * cs, cph); __syncwarp(); tc_fence_after(); }
           const uint32_t a_lo = a_lo0 + (uint32_t)cs * stage_step, b_lo = b_lo0 + (uint32_t)cs * stage_step;
@@ -267,15 +286,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int cgrp = (warp - 2) >> 2, cstep = 32 * (((int)(blockDim.x >> 5) - 2) >> 2);
     const long long n_slots = (n_local + TPS - 1) / TPS;
     const int half = (UM == 64) ? (lane >> 4) : 0;
-    const int row = (UM == 64) ? (16 * q + (lane & 15)) : (32 * q + lane);
+    const int row = (UM == 64) ? (16 * q + (lane & 15)) : (P.pair ? ((32 * q + lane) & 63) : (32 * q + lane));
+    const int second = (UM == 128 && P.pair) ? (q >> 1) : 0;                 // pair mode: quadrants 2, 3 hold the item's second tile
     for (long long slot_seq = 0; slot_seq < n_slots; ++slot_seq) {
       const int slot = (int)(slot_seq % NS);
       mbar_wait(bar_base + 8 * (2 * S + slot), (uint32_t)((slot_seq / NS) & 1));
       tc_fence_after();
       const long long i = slot_seq * TPS + half;
-      const bool valid = (i < n_local) && (row < P.m);
       const long long t = pooled ? b * chunk + i : b + i * G;
-      char* ctile = pooled ? ((i < n_local) ? P.cptrs[t] : nullptr) : P.c + t * P.tile_stride_c;
+      char* ctile = pooled ? ((i < n_local) ? (P.pair ? P.cptrs[2 * t + second] : P.cptrs[t]) : nullptr) : P.c + t * P.tile_stride_c;
+      const bool valid = (i < n_local) && (row < P.m) && ctile != nullptr;
       const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
       const long long ldcb = P.ldc * P.c_esz;
       char* crow = valid ? ctile + (long long)row * P.c_esz : nullptr;
@@ -379,7 +399,7 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
     return (pool != nullptr) ? 1 : xb_gemm_simt_launch(L);
   }
 
-  const int UM = (d.m <= 64) ? 64 : 128;
+  const int UM = (d.m <= 64 && !(pool != nullptr && pool->pair)) ? 64 : 128;
   TcParams P; memset(&P, 0, sizeof(P));
   P.m = d.m; P.n = d.n; P.k = d.k;
   P.np = (UM == 64) ? ((d.n + 7) & ~7) : ((d.n + 15) & ~15);
@@ -405,7 +425,7 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   P.nslot = P.tmem_cols / P.slot_cols; if (P.nslot > 4) P.nslot = 4;
   P.evict_first = env_int("LIBXSMM_B200_TC_EVICT_FIRST", 0);
   P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
-  if (pool != nullptr) { P.sets = (const int2*)pool->sets; P.cptrs = (char* const*)pool->cptrs; }
+  if (pool != nullptr) { P.sets = (const int4*)pool->sets; P.cptrs = (char* const*)pool->cptrs; P.pair = pool->pair; }
   P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0;
   P.ep_mode = xb_ep_mode(d.ta, d.tc, &P.c_esz);
   // instruction descriptor: D=f32, A/B format, A MN-major, B K-major, N>>3, M>>4
@@ -442,7 +462,7 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   const long long tiles_per_cta_unit = (UM == 64) ? 2 : 1;
   long long grid = (L->count + tiles_per_cta_unit - 1) / tiles_per_cta_unit; if (grid > (long long)g_num_sms * ctas) grid = (long long)g_num_sms * ctas; if (grid < 1) grid = 1;
   if (pool != nullptr) {
-    const size_t sets_bytes = (size_t)((L->count + grid - 1) / grid) * sizeof(int2);
+    const size_t sets_bytes = (size_t)((L->count + grid - 1) / grid) * sizeof(int4);
     if (sets_bytes <= 16 * 1024 && smem + sets_bytes <= (size_t)(227 * 1024) / ctas) { P.sets_in_smem = 1; smem += sets_bytes; }
   }
   cudaStream_t stream = (cudaStream_t)xb_rt_stream();

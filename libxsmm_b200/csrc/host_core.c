@@ -670,11 +670,12 @@ struct libxsmm_b200_gemm_plan {
   int pooled; xb_tc_pool pool; unsigned long long br; void* d_sets; void* d_cptrs;
 };
 
+static int xb_env_flag(const char* name, int fallback) { const char* e = getenv(name); return (e != NULL && *e != 0) ? (atoi(e) != 0) : fallback; }
 typedef struct xb_pool_key { long long sa, sb; long long t; } xb_pool_key;
-static int xb_pool_key_cmp(const void* x, const void* y) {
+static int xb_pool_key_cmp(const void* x, const void* y) {      /* by set of B, then set of A: neighbours share B (pairing) and often A too */
   const xb_pool_key* a = (const xb_pool_key*)x; const xb_pool_key* b = (const xb_pool_key*)y;
-  if (a->sa != b->sa) return (a->sa < b->sa) ? -1 : 1;
   if (a->sb != b->sb) return (a->sb < b->sb) ? -1 : 1;
+  if (a->sa != b->sa) return (a->sa < b->sa) ? -1 : 1;
   return (a->t < b->t) ? -1 : (a->t > b->t);
 }
 static long long xb_gcd_ll(long long a, long long b) { while (b != 0) { const long long c = a % b; a = b; b = c; } return a; }
@@ -685,6 +686,8 @@ static int xb_plan_try_pool(libxsmm_b200_gemm_plan* plan, const xb_slot* s, cons
   unsigned long long br; long long t, blk_a = 0, blk_b = 0, set_a = 0, set_b = 0; unsigned long long r;
   uintptr_t base_a = (uintptr_t)-1, base_b = (uintptr_t)-1;
   xb_pool_key* keys; int* sets; void** cptrs; int ok = 1;
+  long long items = 0;
+  const int pair = (d->m <= 64 && count > 1 && xb_env_flag("LIBXSMM_B200_TC_PAIR", 1)) ? 1 : 0;   /* two 64-row tiles per M=128 instruction */
   if (d->br_type != 1 || g_force_simt || !xb_gemm_tc_shape_ok(d) || count > 0x7fffffffll) return 0;
   if (params[0].op.tertiary == NULL) return 0;
   br = *(const unsigned long long*)params[0].op.tertiary;
@@ -711,7 +714,7 @@ static int xb_plan_try_pool(libxsmm_b200_gemm_plan* plan, const xb_slot* s, cons
   if (set_a == 0) set_a = 16;
   if (set_b == 0) set_b = 16;
   if ((set_a % 16) != 0 || (set_b % 16) != 0) return 0;
-  keys = (xb_pool_key*)malloc((size_t)count * sizeof(*keys)); sets = (int*)malloc((size_t)count * 2 * sizeof(int)); cptrs = (void**)malloc((size_t)count * sizeof(void*));
+  keys = (xb_pool_key*)malloc((size_t)count * sizeof(*keys)); sets = (int*)malloc((size_t)count * 4 * sizeof(int)); cptrs = (void**)malloc((size_t)count * 2 * sizeof(void*));
   if (keys == NULL || sets == NULL || cptrs == NULL) { free(keys); free(sets); free(cptrs); return 0; }
   plan->pool.nsets_a = plan->pool.nsets_b = 1;
   for (t = 0; t < count; ++t) {
@@ -724,16 +727,25 @@ static int xb_plan_try_pool(libxsmm_b200_gemm_plan* plan, const xb_slot* s, cons
   }
   if (ok) {
     qsort(keys, (size_t)count, sizeof(*keys), xb_pool_key_cmp);
-    for (t = 0; t < count; ++t) { sets[2 * t] = (int)keys[t].sa; sets[2 * t + 1] = (int)keys[t].sb; cptrs[t] = params[keys[t].t].c.primary; }
-    plan->d_sets = xb_rt_device_malloc((size_t)count * 2 * sizeof(int)); plan->d_cptrs = xb_rt_device_malloc((size_t)count * sizeof(void*));
-    if (plan->d_sets == NULL || plan->d_cptrs == NULL || 0 != xb_rt_memcpy(plan->d_sets, sets, (size_t)count * 2 * sizeof(int))
-     || 0 != xb_rt_memcpy(plan->d_cptrs, cptrs, (size_t)count * sizeof(void*))) { xb_rt_device_free(plan->d_sets); xb_rt_device_free(plan->d_cptrs); plan->d_sets = plan->d_cptrs = NULL; ok = 0; }
+    /* items {set A, set A of the second tile, set B, 0}: in pair mode two neighbours with the same B set form one item (the
+     * kernel stacks them into one M=128 instruction); a tile without such a neighbour travels alone (second C pointer NULL) */
+    for (t = 0; t < count; ++items) {
+      int* it = sets + 4 * items;
+      const int two = (pair && t + 1 < count && keys[t + 1].sb == keys[t].sb) ? 1 : 0;
+      it[0] = (int)keys[t].sa; it[1] = (int)keys[t + two].sa; it[2] = (int)keys[t].sb; it[3] = 0;
+      if (pair) { cptrs[2 * items] = params[keys[t].t].c.primary; cptrs[2 * items + 1] = two ? params[keys[t + 1].t].c.primary : NULL; }
+      else cptrs[items] = params[keys[t].t].c.primary;
+      t += 1 + two;
+    }
+    plan->d_sets = xb_rt_device_malloc((size_t)items * 4 * sizeof(int)); plan->d_cptrs = xb_rt_device_malloc((size_t)items * (pair ? 2 : 1) * sizeof(void*));
+    if (plan->d_sets == NULL || plan->d_cptrs == NULL || 0 != xb_rt_memcpy(plan->d_sets, sets, (size_t)items * 4 * sizeof(int))
+     || 0 != xb_rt_memcpy(plan->d_cptrs, cptrs, (size_t)items * (pair ? 2 : 1) * sizeof(void*))) { xb_rt_device_free(plan->d_sets); xb_rt_device_free(plan->d_cptrs); plan->d_sets = plan->d_cptrs = NULL; ok = 0; }
   }
   free(keys); free(sets); free(cptrs);
   if (!ok) return 0;
   plan->pool.base_a = (const void*)base_a; plan->pool.base_b = (const void*)base_b; plan->pool.blk_a = blk_a; plan->pool.blk_b = blk_b;
-  plan->pool.set_a = set_a; plan->pool.set_b = set_b; plan->pool.sets = plan->d_sets; plan->pool.cptrs = plan->d_cptrs;
-  plan->pooled = 1; plan->br = br; plan->slot = s; plan->count = count;
+  plan->pool.set_a = set_a; plan->pool.set_b = set_b; plan->pool.sets = plan->d_sets; plan->pool.cptrs = plan->d_cptrs; plan->pool.pair = pair;
+  plan->pooled = 1; plan->br = br; plan->slot = s; plan->count = items;        /* the unit the kernel walks */
   return 1;
 }
 

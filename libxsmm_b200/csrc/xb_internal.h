@@ -158,8 +158,9 @@ int xb_gemm_tc_launch(const xb_gemm_launch* L);
 /* pooled address mode (gemm plan): block r of tile p is base + set[p]*set_stride + r*blk_stride; see gemm_tc.cu */
 typedef struct xb_tc_pool {
   const void* base_a; const void* base_b; long long blk_a, blk_b, set_a, set_b, nsets_a, nsets_b;
-  const void* sets;          /* device int2[count], sorted by (set of A, set of B) */
-  const void* cptrs;         /* device char*[count], C tile of every position */
+  const void* sets;          /* device int4[items] {set of A, set of A of the second tile, set of B, 0}, sorted */
+  const void* cptrs;         /* device char*[items] (pair: [2*items], second may be NULL): C tile(s) of every item */
+  int pair;                  /* 1: an item is two tiles (m <= 64) sharing B, stacked into one M=128 instruction */
 } xb_tc_pool;
 int xb_gemm_tc_shape_ok(const xb_gemm_desc* d);           /* everything xb_gemm_tc_supported checks except the batch-reduce mode */
 int xb_gemm_tc_launch_pooled(const xb_gemm_desc* d, const xb_tc_pool* pool, unsigned long long br, long long count);

@@ -1,17 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "=== gemm tests"; timeout -s KILL 500 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x > gpurun_out/test_gemm.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/test_gemm.log
-echo "=== meltw tests"; timeout -s KILL 300 python -m pytest tests/test_meltw_gpu.py -m gpu -q -x > gpurun_out/test_meltw.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/test_meltw.log
-echo "=== ts probe"; timeout -s KILL 300 python tools/ts_probe.py "" > gpurun_out/ts_probe.log 2>&1; cat gpurun_out/ts_probe.log
-echo "=== mode R bench"; for th in 320 192; do LIBXSMM_B200_TC_THREADS=$th timeout -s KILL 300 python bench.py --workload brgemm_r --steps 10 > gpurun_out/bench_r_$th.json 2> gpurun_out/bench_r.err; echo "threads $th rc=$?"; tail -3 gpurun_out/bench_r.err; cut -c1-330 gpurun_out/bench_r_$th.json | cut -c130-; done
-echo "=== bench"; timeout -s KILL 600 python bench.py --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; tail -3 gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench.json'))
-print('value', d['value'], 'ms', d['ms_per_step'], 'frac', d['roofline']['frac'], 'e2e', d['e2e']['value'])
-for k,v in d['also'].items():
-    if 'points' in v:
-        for p in v['points']: print(k, {a:(round(b,4) if isinstance(b,float) else b) for a,b in p.items() if a in ('type','m','ms','hbm_frac','op','n','GBps','backend','error')})
-    else: print(k, v.get('ms_per_step'), v.get('roofline',{}).get('frac'), v.get('error'))
-PY
+echo "=== gemm tests (pool, tc)"; timeout -s KILL 500 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x -k "pool or tcgen05 or tensor" > gpurun_out/test_gemm.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/test_gemm.log
+echo "=== meltw tests"; timeout -s KILL 300 python -m pytest tests/test_meltw_gpu.py -m gpu -q -x > gpurun_out/test_meltw.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/test_meltw.log
+echo "=== mode R bench"; for pr in 1 0; do LIBXSMM_B200_TC_PAIR=$pr timeout -s KILL 300 python bench.py --workload brgemm_r --steps 10 > gpurun_out/bench_r_$pr.json 2> gpurun_out/bench_r.err; echo "pair $pr rc=$?"; tail -3 gpurun_out/bench_r.err; cut -c1-330 gpurun_out/bench_r_$pr.json | cut -c130-; done
 echo "=== ncu mode R"; timeout -s KILL 400 ncu --set full --import-source on --clock-control none -k regex:gemm_tc -c 1 -o gpurun_out/prof_tc_pool -f python bench.py --workload brgemm_r --steps 5 > gpurun_out/ncu_r.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_r.log
