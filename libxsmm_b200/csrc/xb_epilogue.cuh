@@ -40,9 +40,39 @@ __device__ __forceinline__ void xb_ep_store_one(uint32_t raw, char* p, float scf
   }
 }
 
+// bf16 output, full chunk: the software RNE of xb_f32_to_bf16_rne costs ~16 instructions per value; the hardware conversion
+// (cvt.rn.bf16x2.f32, two values per instruction) gives the same bits for every zero, normal and infinite input. The two cases
+// where libxsmm_convert_f32_to_bf16_rne differs are handled explicitly: f32 denormals are flushed to signed zero first (a
+// multiply by one in .ftz mode does exactly that) and NaNs -- detected per thread, rare -- take the software path.
+template <bool BETA0>
+__device__ __forceinline__ void xb_ep_store_chunk_bf16_full(const uint32_t (&v)[32], char* p, long long ldc_bytes) {
+  float f[32];
+  bool any_nan = false;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float acc = __uint_as_float(v[j]);
+    if (!BETA0) acc += xb_bf16_to_f32(*reinterpret_cast<const unsigned short*>(p + j * ldc_bytes));
+    any_nan |= (acc != acc);
+    asm("mul.ftz.f32 %0, %1, 0f3F800000;" : "=f"(f[j]) : "f"(acc));
+  }
+  if (!any_nan) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      uint32_t two;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(two) : "f"(f[j + 1]), "f"(f[j]));      // upper half <- f[j+1], lower half <- f[j]
+      *reinterpret_cast<unsigned short*>(p) = (unsigned short)two; p += ldc_bytes;
+      *reinterpret_cast<unsigned short*>(p) = (unsigned short)(two >> 16); p += ldc_bytes;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { xb_ep_store_one<XB_EP_BF16, BETA0>(v[j], p, 0.0f); p += ldc_bytes; }     // nothing was stored yet: redo it the slow way
+  }
+}
+
 // p: address of (this thread's row, first column of the chunk); ncols: valid columns of the chunk (1..32)
 template <int MODE, bool BETA0>
 __device__ __forceinline__ void xb_ep_store_chunk_t(const uint32_t (&v)[32], char* p, long long ldc_bytes, int ncols, float scf) {
+  if (MODE == XB_EP_BF16 && ncols >= 32) { xb_ep_store_chunk_bf16_full<BETA0>(v, p, ldc_bytes); return; }
   if (ncols >= 32) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) { xb_ep_store_one<MODE, BETA0>(v[j], p, scf); p += ldc_bytes; }
