@@ -25,7 +25,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.c $(CSRC)/xb_internal.h $(CSRC)/xb_device.cuh include/l
 	@mkdir -p $(OBJDIR)
 	$(CC) $(CFLAGS) -Iinclude -x c -c $< -o $@
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/xb_internal.h $(CSRC)/xb_device.cuh $(CSRC)/xb_tma.cuh include/libxsmm.h include/libxsmm_typedefs.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/xb_internal.h $(CSRC)/xb_device.cuh $(CSRC)/xb_tma.cuh $(CSRC)/xb_epilogue.cuh include/libxsmm.h include/libxsmm_typedefs.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -Iinclude -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 
