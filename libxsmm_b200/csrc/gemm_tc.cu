@@ -321,6 +321,185 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+
+// ---- pooled mode, second form: whole operand SETS resident ----------------------------------------------------------------------
+// Mode R of the benchmark: every tile reads one of a few A block-sets and one of a few B block-sets. Items (pairs of
+// tiles that share the B set, see xb_plan_try_pool) arrive sorted by (B set, A set), so over a CTA's slice the B set changes a couple
+// of times and the A set walks upwards. This kernel keeps ONE B set and TWO A sets in shared memory (set = br x kchunks blocks):
+//   * the MMA of an item takes its rows 0..63 from one resident A set and rows 64..127 from another (or the same) one: the two
+//     64-row halves of an MN-major M=128 operand are `leading byte offset` apart, and that offset is just a descriptor field --
+//     the distance between the two buffers, or 0 when both tiles use the same set;
+//   * while the items of set s run, the producer loads the next set into the other buffer (sets are needed in first-use order,
+//     alternating buffers); a buffer is released by a tcgen05.commit after the last item that reads it;
+//   * no operand byte is fetched twice per run of equal sets and nothing is fetched per tile.
+// Roles (320 threads): warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quadrant, alternate column chunks).
+// Producer, issuer and epilogue each replay the same cheap scan over the item list to know which load a set corresponds to.
+struct PoolParams {
+  int m, n, np, k, kchunks, br, loads;      // loads = br * kchunks blocks per set
+  int b_blk;                                // bytes of one B block: np rows x 128 bytes
+  int nslot, slot_cols, tmem_cols;
+  long long count, ldc;                     // items
+  int ep_mode, c_esz, beta0;
+  uint32_t idesc, sbo_a, sbo_b, lbo_b;
+  const int4* items; char* const* cptrs;
+};
+
+__global__ void __launch_bounds__(320)
+gemm_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const PoolParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_set_bytes = (uint32_t)P.loads * 8192u, b_set_bytes = (uint32_t)P.loads * (uint32_t)P.b_blk;
+  const uint32_t sA = smem_base, sB = smem_base + 2u * a_set_bytes;
+  uint64_t* bars = (uint64_t*)(smem + 2u * a_set_bytes + b_set_bytes);
+  const uint32_t bar0 = smem_u32(bars);
+  const int NS = P.nslot;
+  // barriers: a_full[2], a_empty[2], b_full, b_empty, t_full[NS<=4], t_empty[NS<=4]
+  const uint32_t a_full = bar0, a_empty = bar0 + 16, b_full = bar0 + 32, b_empty = bar0 + 40, t_full = bar0 + 48, t_empty = bar0 + 80;
+  uint32_t* tmem_word = (uint32_t*)(bars + 14);
+  int4* s_items = reinterpret_cast<int4*>(bars + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long G = gridDim.x, b = blockIdx.x;
+  const long long chunk = (P.count + G - 1) / G;
+  const long long n_local = (b * chunk < P.count) ? ((P.count - b * chunk < chunk) ? P.count - b * chunk : chunk) : 0;
+  for (long long i = threadIdx.x; i < n_local; i += blockDim.x) s_items[i] = P.items[b * chunk + i];
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
+    mbar_init(a_full, 1); mbar_init(a_full + 8, 1); mbar_init(a_empty, 1); mbar_init(a_empty + 8, 1); mbar_init(b_full, 1); mbar_init(b_empty, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_word)), "r"((uint32_t)P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_word;
+
+  if (warp == 0) {
+    // ===================================== producer =====================================
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    int last = -1, j = -1, cur_sb = -1, jb = -1;
+    for (long long i = 0; i < n_local; ++i) {
+      const int4 it = s_items[i];
+      if (it.z != cur_sb) {                                        // new B set: the single buffer must have been released
+        cur_sb = it.z; ++jb;
+        if (leader) {
+          mbar_wait(b_empty, (uint32_t)((jb & 1) ^ 1));
+          mbar_expect_tx(b_full, b_set_bytes);
+          int l = 0;
+          for (int r = 0; r < P.br; ++r) for (int kc = 0; kc < P.kchunks; ++kc, ++l) tma_load_4d(sB + (uint32_t)l * (uint32_t)P.b_blk, &map_b, b_full, kc * 64, 0, r, it.z);
+        }
+        __syncwarp();
+      }
+      for (int h = 0; h < 2; ++h) {
+        const int s = h ? it.y : it.x;
+        if (s != last) {                                           // first use of this A set: load it into the other buffer
+          last = s; ++j;
+          const uint32_t buf = (uint32_t)(j & 1);
+          if (leader) {
+            mbar_wait(a_empty + 8 * buf, (uint32_t)(((j >> 1) & 1) ^ 1));
+            mbar_expect_tx(a_full + 8 * buf, a_set_bytes);
+            int l = 0;
+            for (int r = 0; r < P.br; ++r) for (int kc = 0; kc < P.kchunks; ++kc, ++l) tma_load_4d(sA + buf * a_set_bytes + (uint32_t)l * 8192u, &map_a, a_full + 8 * buf, 0, kc * 64, r, s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    const uint32_t hi_a = (P.sbo_a & 0x3FFFu) | (1u << 14) | (2u << 29), hi_b = (P.sbo_b & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t b_lo0 = ((sB & 0x3FFFFu) >> 4) | ((P.lbo_b & 0x3FFFu) << 16);
+    const int ks_last = (P.k - (P.kchunks - 1) * 64 + 15) / 16;
+    int last = -1, j = -1, cur_sb = -1, jb = -1, slot = 0; uint32_t slot_par = 1;
+    for (long long i = 0; i < n_local; ++i) {
+      const int4 it = s_items[i];
+      if (it.z != cur_sb) { cur_sb = it.z; ++jb; if (leader) mbar_wait(b_full, (uint32_t)(jb & 1)); __syncwarp(); }
+      if (it.x != last) { last = it.x; ++j; if (leader) mbar_wait(a_full + 8 * (j & 1), (uint32_t)((j >> 1) & 1)); __syncwarp(); }
+      const int j0 = j;
+      if (it.y != last) { last = it.y; ++j; if (leader) mbar_wait(a_full + 8 * (j & 1), (uint32_t)((j >> 1) & 1)); __syncwarp(); }
+      const int j1 = j;
+      if (leader) mbar_wait(t_empty + 8 * slot, slot_par);
+      __syncwarp();
+      tc_fence_after();
+      // rows 0..63 come from the lower of the two buffers, rows 64..127 from `lbo` bytes above it (0: the same set twice)
+      const uint32_t buf_lo = (uint32_t)(((j0 & 1) < (j1 & 1)) ? (j0 & 1) : (j1 & 1)), lbo = (uint32_t)(((j0 ^ j1) & 1) ? (a_set_bytes >> 4) : 0u);
+      const uint32_t a_lo0 = (((sA + buf_lo * a_set_bytes) & 0x3FFFFu) >> 4) | ((lbo & 0x3FFFu) << 16);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(slot * P.slot_cols);
+      if (leader) {
+        int kc = 0;
+        uint32_t a_lo = a_lo0, b_lo = b_lo0, acc = 0u;
+        for (int l = 0; l < P.loads; ++l) {
+          const int ksteps = (kc == P.kchunks - 1) ? ks_last : 4;
+          if (ksteps == 4) {
+            umma_f16(d_tmem, desc64(hi_a, a_lo), desc64(hi_b, b_lo), P.idesc, acc);
+            umma_f16(d_tmem, desc64(hi_a, a_lo + 128), desc64(hi_b, b_lo + 2), P.idesc, 1u);
+            umma_f16(d_tmem, desc64(hi_a, a_lo + 256), desc64(hi_b, b_lo + 4), P.idesc, 1u);
+            umma_f16(d_tmem, desc64(hi_a, a_lo + 384), desc64(hi_b, b_lo + 6), P.idesc, 1u);
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), P.idesc, ks == 0 ? acc : 1u);
+          }
+          acc = 1u;
+          a_lo += 8192u >> 4; b_lo += (uint32_t)P.b_blk >> 4;
+          if (++kc == P.kchunks) kc = 0;
+        }
+        umma_commit(t_full + 8 * slot);
+        // release what the next item no longer reads
+        const bool more = (i + 1 < n_local);
+        const int4 nx = more ? s_items[i + 1] : make_int4(-2, -2, -2, 0);
+        if (more) {
+          if (nx.x != it.x && nx.y != it.x) umma_commit(a_empty + 8 * (j0 & 1));
+          if (j1 != j0 && nx.x != it.y && nx.y != it.y) umma_commit(a_empty + 8 * (j1 & 1));
+          if (nx.z != it.z) umma_commit(b_empty);
+        }
+      }
+      __syncwarp();
+      if (++slot == NS) { slot = 0; slot_par ^= 1; }
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3, cgrp = (warp - 2) >> 2;
+    const int row = (32 * q + lane) & 63, upper = q >> 1;              // rows 64..127 of the instruction: TMEM lane quadrants 2, 3
+    int last = -1, j = -1, slot = 0; uint32_t slot_par = 0;
+    for (long long i = 0; i < n_local; ++i) {
+      const int4 it = s_items[i];
+      if (it.x != last) { last = it.x; ++j; }
+      const int j0 = j;
+      if (it.y != last) { last = it.y; ++j; }
+      const int j1 = j;
+      const int swapped = ((j0 & 1) > (j1 & 1)) ? 1 : 0;                // the item's first tile sits in the upper buffer: rows 64..127
+      mbar_wait(t_full + 8 * slot, slot_par);
+      tc_fence_after();
+      char* ctile = P.cptrs[2 * (b * chunk + i) + (upper ^ swapped)];
+      const bool valid = (row < P.m) && ctile != nullptr;
+      const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
+      const long long ldcb = P.ldc * P.c_esz;
+      char* crow = valid ? ctile + (long long)row * P.c_esz : nullptr;
+      if (32 * cgrp >= P.np) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
+      for (int c0 = 32 * cgrp; c0 < P.np; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        if (c0 + 64 >= P.np) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(t_empty + 8 * slot); }
+        if (valid && c0 < P.n) xb_ep_store_chunk(P.ep_mode, P.beta0, v, crow + c0 * ldcb, ldcb, P.n - c0, 0.0f);
+      }
+      if (++slot == NS) { slot = 0; slot_par ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -375,14 +554,60 @@ extern "C" int xb_gemm_tc_supported(const xb_gemm_desc* d) {
 }
 
 static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool);
+static int pool_sets_launch(const xb_gemm_desc& d, const xb_tc_pool* pool, unsigned long long br, long long items);
 extern "C" int xb_gemm_tc_launch(const xb_gemm_launch* L) { return tc_launch_common(L, nullptr); }
 extern "C" int xb_gemm_tc_launch_pooled(const xb_gemm_desc* d, const xb_tc_pool* pool, unsigned long long br, long long count) {
   xb_gemm_launch L; memset(&L, 0, sizeof(L));
   L.d = *d; L.count = count; L.br = br;
   L.a = pool->base_a; L.b = pool->base_b; L.c = (void*)pool->cptrs;        // non-null markers; the pool carries the real addressing
   L.tile_stride_a = pool->set_a; L.tile_stride_b = pool->set_b; L.tile_stride_c = 16;
+  { const int rc = pool_sets_launch(*d, pool, br, count); if (rc >= 0) return rc; }
   return tc_launch_common(&L, pool);
 }
+// resident-set form of the pooled mode (gemm_pool_kernel): returns -1 when the geometry does not fit (the caller then uses the ring form)
+unsigned long long g_pool_attr = 0ull;
+static int pool_sets_launch(const xb_gemm_desc& d, const xb_tc_pool* pool, unsigned long long br, long long items) {
+  if (!pool->pair || env_int("LIBXSMM_B200_TC_POOLSETS", 1) == 0 || tc_init_once() != 0) return -1;
+  PoolParams P; memset(&P, 0, sizeof(P));
+  const int es = 2;
+  P.m = d.m; P.n = d.n; P.k = d.k; P.np = (d.n + 15) & ~15; P.kchunks = (d.k + 63) / 64; P.br = (int)br;
+  P.loads = P.br * P.kchunks; P.b_blk = P.np * 128;
+  const size_t a_set = (size_t)P.loads * 8192, b_set = (size_t)P.loads * P.b_blk;
+  long long grid = items < g_num_sms ? items : g_num_sms; if (grid < 1) grid = 1;
+  const size_t items_bytes = (size_t)((items + grid - 1) / grid) * sizeof(int4);
+  const size_t smem = 2 * a_set + b_set + 1024 + 128 + items_bytes + 64;
+  if (br > 64 || smem > (size_t)227 * 1024 || (a_set >> 4) > 0x3FFF || d.m > 64 || P.np > 256) return -1;
+  P.slot_cols = (P.np + 31) & ~31; P.nslot = 512 / P.slot_cols; if (P.nslot > 4) P.nslot = 4; P.tmem_cols = 512;
+  P.count = items; P.ldc = d.ldc; P.ep_mode = xb_ep_mode(d.ta, d.tc, &P.c_esz); P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0;
+  const uint32_t fmt = (d.ta == LIBXSMM_DATATYPE_BF16) ? 1u : 0u;
+  P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(P.np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  P.sbo_a = 1024 >> 4; P.sbo_b = 1024 >> 4; P.lbo_b = 1;
+  P.items = (const int4*)pool->sets; P.cptrs = (char* const*)pool->cptrs;
+  const CUtensorMapDataType dt = (d.ta == LIBXSMM_DATATYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap map_a, map_b;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d.m, (cuuint64_t)d.k, (cuuint64_t)br, (cuuint64_t)pool->nsets_a};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.lda * es, (cuuint64_t)pool->blk_a, (cuuint64_t)pool->set_a};
+    const cuuint32_t box[4] = {64, 64, 1, 1};
+    if (CUDA_SUCCESS != g_encode(&map_a, dt, 4, (void*)pool->base_a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) return -1;
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)d.k, (cuuint64_t)d.n, (cuuint64_t)br, (cuuint64_t)pool->nsets_b};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.ldb * es, (cuuint64_t)pool->blk_b, (cuuint64_t)pool->set_b};
+    const cuuint32_t box[4] = {64, (cuuint32_t)P.np, 1, 1};
+    if (CUDA_SUCCESS != g_encode(&map_b, dt, 4, (void*)pool->base_b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) return -1;
+  }
+  if (xb_rt_first_use_on_device(&g_pool_attr)) cudaFuncSetAttribute(gemm_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  gemm_pool_kernel<<<(unsigned int)grid, 320, smem, (cudaStream_t)xb_rt_stream()>>>(map_a, map_b, P);
+  xb_rt_count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { xb_rt_note_error((int)e, "gemm_pool"); return (int)e; }
+  return 0;
+}
+
 static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   const xb_gemm_desc& d = L->d;
   // resolve the uniform strided form (count==1 by-value record included)

@@ -257,7 +257,11 @@ __global__ void __launch_bounds__(256) meltw_map_kernel(const xb_meltw_desc d, c
       const bool bitm = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0;
       if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_ELU) {
         float y;
-        if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU) y = __uint_as_float((x <= 0.0f) ? 0u : __float_as_uint(x));   // a select on the bits: NaN passes with its payload (no max())
+        if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU) {   // a select on the BITS, in PTX: written in C the compiler turns it into a NaN-canonicalising max
+          uint32_t yb;
+          asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, 0f00000000;\n\tselp.b32 %0, 0, %2, p;\n\t}" : "=r"(yb) : "f"(x), "r"(__float_as_uint(x)));
+          y = __uint_as_float(yb);
+        }
         else if (op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU) y = (x <= 0.0f) ? a.alpha * x : x;
         else y = (x <= 0.0f) ? a.alpha * (expf(x) - 1.0f) : x;
         if (act) st_f32(a.out, oi, d.t_out, y);

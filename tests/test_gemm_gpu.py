@@ -324,7 +324,8 @@ def test_address_mode_pool_on_tensor_cores(tc):
     runs the tcgen05 kernel (set index = tensor-map coordinate, tiles visited sorted by set pair, operands of equal neighbours
     shared through the stage ring). Every tile against the oracle called exactly like the reference (pointer arrays)."""
     rng = np.random.default_rng(98)
-    for (m, n, k, br, nsets, count) in ((64, 64, 64, 8, 5, 300), (32, 48, 64, 2, 3, 41), (128, 64, 128, 3, 4, 57), (64, 64, 64, 1, 2, 9)):
+    for (m, n, k, br, nsets, count) in ((64, 64, 64, 8, 5, 300), (32, 48, 64, 2, 3, 41), (128, 64, 128, 3, 4, 57), (64, 64, 64, 1, 2, 9),
+                                        (64, 64, 64, 2, 7, 3001), (48, 80, 96, 2, 6, 2000)):   # many items per CTA: set changes, buffer swaps, odd tails
         case = cases.GemmCase(m, n, k, gen.BF16, gen.BF16, gen.F32, tc, flags=cases.FLAG_BETA_0, br_type=1, br=br)
         blk_a, blk_b = m * k * 2, k * n * 2
         pool_a = gen.values(rng, nsets * br * m * k, gen.BF16); pool_b = gen.values(rng, nsets * br * k * n, gen.BF16)
