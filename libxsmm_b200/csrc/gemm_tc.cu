@@ -113,8 +113,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16
        | (1ull << 46) | (2ull << 61);
 }
 
-template <int UM>
-__global__ void __launch_bounds__(320)
+// WIDE = false: 192 threads, registers capped so that six CTAs share an SM (the latency-bound small-load shapes need that);
+// WIDE = true: 320 threads (eight epilogue warps) for the one-CTA-per-SM configurations
+template <int UM, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 320 : 192, WIDE ? 1 : 6)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int TPS = (UM == 64) ? 2 : 1;          // tiles per TMEM slot
@@ -433,31 +435,38 @@ gemm_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t buf_lo = (uint32_t)(((j0 & 1) < (j1 & 1)) ? (j0 & 1) : (j1 & 1)), lbo = (uint32_t)(((j0 ^ j1) & 1) ? (a_set_bytes >> 4) : 0u);
       const uint32_t a_lo0 = (((sA + buf_lo * a_set_bytes) & 0x3FFFFu) >> 4) | ((lbo & 0x3FFFu) << 16);
       const uint32_t d_tmem = tmem_base + (uint32_t)(slot * P.slot_cols);
-      if (leader) {
+      {
+        // all lanes walk the loop (uniform registers hold the descriptors), the elected lane issues
         int kc = 0;
         uint32_t a_lo = a_lo0, b_lo = b_lo0, acc = 0u;
-        for (int l = 0; l < P.loads; ++l) {
-          const int ksteps = (kc == P.kchunks - 1) ? ks_last : 4;
+        const uint32_t b_step = (uint32_t)P.b_blk >> 4, idesc = P.idesc;
+        const int loads = P.loads, kchunks = P.kchunks;
+        for (int l = 0; l < loads; ++l) {
+          const int ksteps = (kc == kchunks - 1) ? ks_last : 4;
           if (ksteps == 4) {
-            umma_f16(d_tmem, desc64(hi_a, a_lo), desc64(hi_b, b_lo), P.idesc, acc);
-            umma_f16(d_tmem, desc64(hi_a, a_lo + 128), desc64(hi_b, b_lo + 2), P.idesc, 1u);
-            umma_f16(d_tmem, desc64(hi_a, a_lo + 256), desc64(hi_b, b_lo + 4), P.idesc, 1u);
-            umma_f16(d_tmem, desc64(hi_a, a_lo + 384), desc64(hi_b, b_lo + 6), P.idesc, 1u);
+            if (leader) {
+              umma_f16(d_tmem, desc64(hi_a, a_lo), desc64(hi_b, b_lo), idesc, acc);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 128), desc64(hi_b, b_lo + 2), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 256), desc64(hi_b, b_lo + 4), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 384), desc64(hi_b, b_lo + 6), idesc, 1u);
+            }
           } else {
-            for (int ks = 0; ks < ksteps; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), P.idesc, ks == 0 ? acc : 1u);
+            for (int ks = 0; ks < ksteps; ++ks) { if (leader) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), idesc, ks == 0 ? acc : 1u); }
           }
           acc = 1u;
-          a_lo += 8192u >> 4; b_lo += (uint32_t)P.b_blk >> 4;
-          if (++kc == P.kchunks) kc = 0;
+          a_lo += 8192u >> 4; b_lo += b_step;
+          if (++kc == kchunks) kc = 0;
         }
-        umma_commit(t_full + 8 * slot);
         // release what the next item no longer reads
         const bool more = (i + 1 < n_local);
         const int4 nx = more ? s_items[i + 1] : make_int4(-2, -2, -2, 0);
-        if (more) {
-          if (nx.x != it.x && nx.y != it.x) umma_commit(a_empty + 8 * (j0 & 1));
-          if (j1 != j0 && nx.x != it.y && nx.y != it.y) umma_commit(a_empty + 8 * (j1 & 1));
-          if (nx.z != it.z) umma_commit(b_empty);
+        if (leader) {
+          umma_commit(t_full + 8 * slot);
+          if (more) {
+            if (nx.x != it.x && nx.y != it.x) umma_commit(a_empty + 8 * (j0 & 1));
+            if (j1 != j0 && nx.x != it.y && nx.y != it.y) umma_commit(a_empty + 8 * (j1 & 1));
+            if (nx.z != it.z) umma_commit(b_empty);
+          }
         }
       }
       __syncwarp();
@@ -506,7 +515,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
-unsigned long long g_attr_set[2] = {0ull, 0ull};   // MaxDynamicSharedMemorySize is a per-device attribute: one bit per device
+unsigned long long g_attr_set[4] = {0ull, 0ull, 0ull, 0ull};   // MaxDynamicSharedMemorySize is a per-device attribute: one bit per device
 
 int tc_init_once() {
   if (g_encode == nullptr) {
@@ -694,12 +703,18 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   cudaError_t e;
   // one CTA per SM has nothing co-resident to hide its epilogue behind: give it 8 epilogue warps instead of 4
   const unsigned int threads = (unsigned int)env_int("LIBXSMM_B200_TC_THREADS", (ctas == 1 && P.np >= 64) ? 320 : 192) == 320u ? 320u : 192u;
-  if (UM == 64) {
-    if (xb_rt_first_use_on_device(&g_attr_set[0])) cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    gemm_tc_kernel<64><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
+  if (UM == 64 && threads == 192u) {
+    if (xb_rt_first_use_on_device(&g_attr_set[0])) cudaFuncSetAttribute(gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    gemm_tc_kernel<64, false><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
+  } else if (UM == 64) {
+    if (xb_rt_first_use_on_device(&g_attr_set[2])) cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    gemm_tc_kernel<64, true><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
+  } else if (threads == 192u) {
+    if (xb_rt_first_use_on_device(&g_attr_set[1])) cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    gemm_tc_kernel<128, false><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
   } else {
-    if (xb_rt_first_use_on_device(&g_attr_set[1])) cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    gemm_tc_kernel<128><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
+    if (xb_rt_first_use_on_device(&g_attr_set[3])) cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    gemm_tc_kernel<128, true><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
   }
   xb_rt_count_launch();
   e = cudaGetLastError();

@@ -100,7 +100,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 constexpr int kTsgThreads = 320;     // 10 warps
 constexpr int MAX_S = 8, MAX_NS = 4;
 
-__global__ void __launch_bounds__(kTsgThreads)
+__global__ void __launch_bounds__(kTsgThreads, 3)      // <= 68 registers: three CTAs per SM for the small-tile shapes
 gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TsParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);

@@ -257,10 +257,12 @@ __global__ void __launch_bounds__(256) meltw_map_kernel(const xb_meltw_desc d, c
       const bool bitm = (d.flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0;
       if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU || op == LIBXSMM_MELTW_TYPE_UNARY_ELU) {
         float y;
-        if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU) {   // a select on the BITS, in PTX: written in C the compiler turns it into a NaN-canonicalising max
-          uint32_t yb;
-          asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, 0f00000000;\n\tselp.b32 %0, 0, %2, p;\n\t}" : "=r"(yb) : "f"(x), "r"(__float_as_uint(x)));
-          y = __uint_as_float(yb);
+        if (op == LIBXSMM_MELTW_TYPE_UNARY_RELU) {
+          // (x <= 0) ? 0 : x on the BITS with integer compares: written with a float compare (even in PTX) ptxas fuses it into
+          // FMNMX.NAN, which canonicalises a NaN's payload; the reference passes the NaN through untouched
+          const unsigned int xb = __float_as_uint(x);
+          const bool zero_it = ((int)xb <= 0) && ((xb & 0x7fffffffu) <= 0x7f800000u);
+          y = __uint_as_float(zero_it ? 0u : xb);
         }
         else if (op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU) y = (x <= 0.0f) ? a.alpha * x : x;
         else y = (x <= 0.0f) ? a.alpha * (expf(x) - 1.0f) : x;

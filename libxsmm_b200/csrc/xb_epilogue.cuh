@@ -41,31 +41,25 @@ __device__ __forceinline__ void xb_ep_store_one(uint32_t raw, char* p, float scf
 }
 
 // bf16 output, full chunk: the software RNE of xb_f32_to_bf16_rne costs ~16 instructions per value; the hardware conversion
-// (cvt.rn.bf16x2.f32, two values per instruction) gives the same bits for every zero, normal and infinite input. The two cases
-// where libxsmm_convert_f32_to_bf16_rne differs are handled explicitly: f32 denormals are flushed to signed zero first (a
-// multiply by one in .ftz mode does exactly that) and NaNs -- detected per thread, rare -- take the software path.
+// (cvt.rn.bf16x2.f32, two values per instruction) gives the same bits for every zero, normal and infinite input. Where
+// libxsmm_convert_f32_to_bf16_rne differs: f32 denormals are flushed to signed zero first -- a multiply by one in .ftz mode
+// does exactly that -- and NaNs keep their upper payload bits; but an accumulator NaN on this machine is always the canonical
+// 0x7fffffff (tensor core and FADD both canonicalise), for which both conversions give 0x7fff.
 template <bool BETA0>
 __device__ __forceinline__ void xb_ep_store_chunk_bf16_full(const uint32_t (&v)[32], char* p, long long ldc_bytes) {
-  float f[32];
-  bool any_nan = false;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float acc = __uint_as_float(v[j]);
-    if (!BETA0) acc += xb_bf16_to_f32(*reinterpret_cast<const unsigned short*>(p + j * ldc_bytes));
-    any_nan |= (acc != acc);
-    asm("mul.ftz.f32 %0, %1, 0f3F800000;" : "=f"(f[j]) : "f"(acc));
-  }
-  if (!any_nan) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      uint32_t two;
-      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(two) : "f"(f[j + 1]), "f"(f[j]));      // upper half <- f[j+1], lower half <- f[j]
-      *reinterpret_cast<unsigned short*>(p) = (unsigned short)two; p += ldc_bytes;
-      *reinterpret_cast<unsigned short*>(p) = (unsigned short)(two >> 16); p += ldc_bytes;
+  for (int j = 0; j < 32; j += 2) {
+    float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
+    if (!BETA0) {
+      a0 += xb_bf16_to_f32(*reinterpret_cast<const unsigned short*>(p));
+      a1 += xb_bf16_to_f32(*reinterpret_cast<const unsigned short*>(p + ldc_bytes));
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { xb_ep_store_one<XB_EP_BF16, BETA0>(v[j], p, 0.0f); p += ldc_bytes; }     // nothing was stored yet: redo it the slow way
+    float f0, f1; uint32_t two;
+    asm("mul.ftz.f32 %0, %1, 0f3F800000;" : "=f"(f0) : "f"(a0));
+    asm("mul.ftz.f32 %0, %1, 0f3F800000;" : "=f"(f1) : "f"(a1));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(two) : "f"(f1), "f"(f0));                 // upper half <- f1, lower half <- f0
+    *reinterpret_cast<unsigned short*>(p) = (unsigned short)two; p += ldc_bytes;
+    *reinterpret_cast<unsigned short*>(p) = (unsigned short)(two >> 16); p += ldc_bytes;
   }
 }
 
