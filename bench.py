@@ -492,7 +492,8 @@ def also_brgemm_r(X, torch, pk, args, full=False, pool_sets=64, batch=BATCH):
     """SURVEY.md 8d "mode R": the same 64^3 x 8 bf16 BRGEMM, ADDRESS batch-reduce, every tile's A block-set and B block-set drawn
     from a pool of 64 sets each (8 MB, L2-resident), C unique bf16 -- the tensor-core-bound variant of configs[1]. One step = one
     libxsmm_b200_gemm_plan_run over 65536 per-tile argument structs (the plan sorts tiles by set pair; equal neighbours share their
-    operands in shared memory). Roofline: dense bf16 tensor throughput (MEASURED_PEAKS bf16_tflops, burst: the kernel is timed alone)."""
+    operands in shared memory; pairs of tiles with the same B set share one M=128 instruction). Roofline: dense bf16 tensor throughput
+    (MEASURED_PEAKS bf16_tflops, burst: the kernel is timed alone)."""
     import numpy as np
     from oracle_ffi import oracle, run_gemm
     import gen
@@ -542,8 +543,9 @@ def also_brgemm_r(X, torch, pk, args, full=False, pool_sets=64, batch=BATCH):
     return {"metric": "batched BRGEMM GFLOP/s, mode R (bf16 64^3 br=8, address batch-reduce, operand pool of %d block-sets, C bf16 unique)" % pool_sets,
             "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "oracle_check": {"tiles": 4, "max_normf_rel": worst},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": None,
-                         "kernel": "gemm_tc_kernel<64> (pooled)", "note": "M=64 tcgen05.mma runs at half the M=128 rate: independent 64-row tiles cap at 50 % of the nominal peak "
-                         "(2.38 PFLOP/s at 1965 MHz) = 71 % of the measured cuBLAS peak"},
+                         "kernel": "gemm_pool_kernel (resident operand sets, two tiles per M=128 instruction)",
+                         "note": "a 128x64x16 tcgen05.mma costs 48 cycles (profiles/r01_umma_cost.txt: max(N/2, 32+N/4)), i.e. 67 % of the nominal "
+                                 "2.38 PFLOP/s at 1965 MHz = 95 % of the measured cuBLAS peak: the bound of this tile shape"},
             "config": {"workload": "configs[1] mode R: tiles draw their A and B block-sets from pools of %d (L2-resident); C %.0f MB per step" % (pool_sets, batch * M * N * 2 / 1e6)}}
 
 

@@ -688,28 +688,31 @@ static int xb_plan_try_pool(libxsmm_b200_gemm_plan* plan, const xb_slot* s, cons
   xb_pool_key* keys; int* sets; void** cptrs; int ok = 1;
   long long items = 0;
   const int pair = (d->m <= 64 && count > 1 && xb_env_flag("LIBXSMM_B200_TC_PAIR", 1)) ? 1 : 0;   /* two 64-row tiles per M=128 instruction */
-  if (d->br_type != 1 || g_force_simt || !xb_gemm_tc_shape_ok(d) || count > 0x7fffffffll) return 0;
+  const int offs_mode = (d->br_type == 2);       /* OFFSET batch-reduce: block r = a.primary + a.secondary[r]; same regularity test */
+#define XB_POOL_BLK(ARG, R) (offs_mode ? (uintptr_t)(ARG).primary + (uintptr_t)((const unsigned long long*)(ARG).secondary)[R] \
+                                       : (uintptr_t)((const void* const*)(ARG).primary)[R])
+  if ((d->br_type != 1 && d->br_type != 2) || g_force_simt || !xb_gemm_tc_shape_ok(d) || count > 0x7fffffffll) return 0;
   if (params[0].op.tertiary == NULL) return 0;
   br = *(const unsigned long long*)params[0].op.tertiary;
   if (br == 0 || br > 4096) return 0;
   for (t = 0; t < count && ok; ++t) {          /* pass 1: common block stride, lowest address */
     const libxsmm_gemm_param* p = &params[t];
-    const void* const* pa = (const void* const*)p->a.primary; const void* const* pb = (const void* const*)p->b.primary;
-    if (p->op.tertiary == NULL || *(const unsigned long long*)p->op.tertiary != br || pa == NULL || pb == NULL
+    const void* pa = offs_mode ? p->a.secondary : p->a.primary; const void* pb = offs_mode ? p->b.secondary : p->b.primary;   /* the host-side index arrays */
+    if (p->op.tertiary == NULL || *(const unsigned long long*)p->op.tertiary != br || pa == NULL || pb == NULL || p->a.primary == NULL || p->b.primary == NULL
      || xb_rt_ptr_kind(pa) == 1 || xb_rt_ptr_kind(pb) == 1 || xb_rt_ptr_kind(p->c.primary) == 0) { ok = 0; break; }
     for (r = 1; r < br; ++r) {
-      const long long da = (long long)((uintptr_t)pa[r] - (uintptr_t)pa[r - 1]), db = (long long)((uintptr_t)pb[r] - (uintptr_t)pb[r - 1]);
+      const long long da = (long long)(XB_POOL_BLK(p->a, r) - XB_POOL_BLK(p->a, r - 1)), db = (long long)(XB_POOL_BLK(p->b, r) - XB_POOL_BLK(p->b, r - 1));
       if (blk_a == 0) { blk_a = da; blk_b = db; }
       if (da != blk_a || db != blk_b || da <= 0 || db <= 0 || (da % 16) != 0 || (db % 16) != 0) { ok = 0; break; }
     }
-    if ((uintptr_t)pa[0] < base_a) base_a = (uintptr_t)pa[0];
-    if ((uintptr_t)pb[0] < base_b) base_b = (uintptr_t)pb[0];
+    if (XB_POOL_BLK(p->a, 0) < base_a) base_a = XB_POOL_BLK(p->a, 0);
+    if (XB_POOL_BLK(p->b, 0) < base_b) base_b = XB_POOL_BLK(p->b, 0);
   }
   if (!ok || (base_a & 15) != 0 || (base_b & 15) != 0) return 0;
   if (br == 1) { blk_a = 16; blk_b = 16; }
   for (t = 0; t < count; ++t) {                /* pass 2: set stride = gcd of the set offsets */
-    set_a = xb_gcd_ll(set_a, (long long)((uintptr_t)((const void* const*)params[t].a.primary)[0] - base_a));
-    set_b = xb_gcd_ll(set_b, (long long)((uintptr_t)((const void* const*)params[t].b.primary)[0] - base_b));
+    set_a = xb_gcd_ll(set_a, (long long)(XB_POOL_BLK(params[t].a, 0) - base_a));
+    set_b = xb_gcd_ll(set_b, (long long)(XB_POOL_BLK(params[t].b, 0) - base_b));
   }
   if (set_a == 0) set_a = 16;
   if (set_b == 0) set_b = 16;
@@ -718,8 +721,8 @@ static int xb_plan_try_pool(libxsmm_b200_gemm_plan* plan, const xb_slot* s, cons
   if (keys == NULL || sets == NULL || cptrs == NULL) { free(keys); free(sets); free(cptrs); return 0; }
   plan->pool.nsets_a = plan->pool.nsets_b = 1;
   for (t = 0; t < count; ++t) {
-    keys[t].sa = (long long)((uintptr_t)((const void* const*)params[t].a.primary)[0] - base_a) / set_a;
-    keys[t].sb = (long long)((uintptr_t)((const void* const*)params[t].b.primary)[0] - base_b) / set_b;
+    keys[t].sa = (long long)(XB_POOL_BLK(params[t].a, 0) - base_a) / set_a;
+    keys[t].sb = (long long)(XB_POOL_BLK(params[t].b, 0) - base_b) / set_b;
     keys[t].t = t;
     if (keys[t].sa >= 0x7fffffffll || keys[t].sb >= 0x7fffffffll) ok = 0;
     if (keys[t].sa + 1 > plan->pool.nsets_a) plan->pool.nsets_a = keys[t].sa + 1;
@@ -746,6 +749,7 @@ static int xb_plan_try_pool(libxsmm_b200_gemm_plan* plan, const xb_slot* s, cons
   plan->pool.base_a = (const void*)base_a; plan->pool.base_b = (const void*)base_b; plan->pool.blk_a = blk_a; plan->pool.blk_b = blk_b;
   plan->pool.set_a = set_a; plan->pool.set_b = set_b; plan->pool.sets = plan->d_sets; plan->pool.cptrs = plan->d_cptrs; plan->pool.pair = pair;
   plan->pooled = 1; plan->br = br; plan->slot = s; plan->count = items;        /* the unit the kernel walks */
+#undef XB_POOL_BLK
   return 1;
 }
 

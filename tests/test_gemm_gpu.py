@@ -358,3 +358,40 @@ def test_address_mode_pool_on_tensor_cores(tc):
         thr = 1.2e-5 if tc == gen.F32 else 5e-3
         assert gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc)) <= thr, (m, n, k, br, tc)
         X.libxsmm_b200_gemm_plan_destroy(plan)
+
+
+def test_offset_mode_pool_on_tensor_cores():
+    """OFFSET batch-reduce (block r = a.primary + a.secondary[r]) over the same kind of operand pool: recognised by the plan like the
+    ADDRESS form and run by the resident-set tcgen05 kernel"""
+    rng = np.random.default_rng(99)
+    tc = gen.BF16
+    for (m, n, k, br, nsets, count) in ((64, 64, 64, 4, 4, 777), (32, 32, 128, 2, 3, 50)):
+        case = cases.GemmCase(m, n, k, gen.BF16, gen.BF16, gen.F32, tc, flags=cases.FLAG_BETA_0, br_type=2, br=br)
+        blk_a, blk_b = m * k * 2, k * n * 2
+        pool_a = gen.values(rng, nsets * br * m * k, gen.BF16); pool_b = gen.values(rng, nsets * br * k * n, gen.BF16)
+        c0 = gen.values(rng, count * m * n, tc)
+        sa = rng.integers(0, nsets, size=count); sb = rng.integers(0, nsets, size=count)
+        kernel = dispatch(case, None)
+        assert kernel
+        d_a, d_b, d_c = dev(pool_a), dev(pool_b), dev(c0)
+        offs_a = (C.c_ulonglong * br)(*[r * blk_a for r in range(br)]); offs_b = (C.c_ulonglong * br)(*[r * blk_b for r in range(br)])
+        brv = C.c_ulonglong(br)
+        params = (X.GemmParam * count)()
+        for t in range(count):
+            params[t].op.tertiary = C.addressof(brv)
+            params[t].a.primary = d_a.data_ptr() + int(sa[t]) * br * blk_a; params[t].a.secondary = C.addressof(offs_a)
+            params[t].b.primary = d_b.data_ptr() + int(sb[t]) * br * blk_b; params[t].b.secondary = C.addressof(offs_b)
+            params[t].c.primary = d_c.data_ptr() + t * m * n * gen.TS[tc]
+        plan = X.libxsmm_b200_gemm_plan_create(kernel, params, count)
+        assert plan and X.libxsmm_b200_gemm_plan_is_pooled(plan) == 1, (m, n, k, br)
+        assert X.libxsmm_b200_gemm_plan_run(plan) == 0
+        X.check()
+        got = host(d_c, gen.NP_OF[tc])
+        want = c0.copy()
+        for t in range(count):
+            ha = (C.c_void_p * br)(*[pool_a.ctypes.data + (int(sa[t]) * br + r) * blk_a for r in range(br)])
+            hb = (C.c_void_p * br)(*[pool_b.ctypes.data + (int(sb[t]) * br + r) * blk_b for r in range(br)])
+            cv = want[t * m * n:(t + 1) * m * n]
+            assert run_gemm(oracle, case.dims, case.types, case.flags, 1, 0, 0, br, ha, hb, cv) == 0     # same blocks through the ADDRESS form of the oracle
+        assert gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc)) <= 5e-3, (m, n, k, br)
+        X.libxsmm_b200_gemm_plan_destroy(plan)

@@ -513,7 +513,8 @@ def test_eight_bit_floats_stochastic_rounding_and_dump():
                 got = host(d_o, np.uint8)
                 bad = np.nonzero(got != want)[0]
                 assert bad.size == 0, (name, tin, tout, bad[:8].tolist(), got[bad[:8]].tolist(), want[bad[:8]].tolist(), (x.view(np.uint32) if tin == gen.F32 else x)[bad[:8] // nbytes[tout]].tolist())
-    # stochastic rounding: unary, binary, ternary
+    # stochastic rounding: unary, binary, ternary (no NaN among the inputs: arithmetic on a NaN keeps the payload on x86 only)
+    wide = np.where(np.isnan(wide), np.float32(2.5), wide).astype(np.float32)
     y = rng.standard_normal(ld * n).astype(np.float32); z = rng.standard_normal(ld * n).astype(np.float32)
     state0 = rng.integers(0, 2 ** 32, size=64, dtype=np.uint32)
     for name in ("IDENTITY", "X2", "DUMP"):
