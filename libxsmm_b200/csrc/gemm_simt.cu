@@ -22,7 +22,7 @@
 
 namespace {
 
-enum { P_F64 = 0, P_F32, P_I16, P_I8_I32, P_I8_F32, P_F16_F16, P_F16_F32, P_BF16_F32, P_BF16_BF16, P_I4_I32, P_BITMAP, P_NONE };
+enum { P_F64 = 0, P_F32, P_I16, P_I8_I32, P_I8_F32, P_F16_F16, P_F16_F32, P_BF16_F32, P_BF16_BF16, P_I4_I32, P_BITMAP, P_FP8, P_NONE };
 
 __host__ __device__ inline int xb_path_of(const xb_gemm_desc& d) {
   const int a = d.ta, b = d.tb, c = d.tc, comp = d.tcomp;
@@ -51,6 +51,12 @@ __host__ __device__ inline int xb_path_of(const xb_gemm_desc& d) {
   if (a == LIBXSMM_DATATYPE_F16 && b == a && c == LIBXSMM_DATATYPE_F32 && f16comp) return P_F16_F32;
   if (a == LIBXSMM_DATATYPE_BF16 && b == a && c == LIBXSMM_DATATYPE_F32 && comp == LIBXSMM_DATATYPE_F32) return P_BF16_F32;
   if (a == LIBXSMM_DATATYPE_BF16 && b == a && c == LIBXSMM_DATATYPE_BF16 && comp == LIBXSMM_DATATYPE_F32) return P_BF16_BF16;
+  // 8-bit float A (reference :2171-2366 with a bf16 B, :2420-2630 with B and C of A's type or f32): f32 accumulate, one rounding
+  if ((a == LIBXSMM_DATATYPE_BF8 || a == LIBXSMM_DATATYPE_HF8) && comp == LIBXSMM_DATATYPE_F32 && d.fuse_colbias == 0 && d.cp_op == 0
+      && (d.flags & (LIBXSMM_GEMM_FLAG_VNNI_C | LIBXSMM_GEMM_FLAG_VNNI_B)) == 0) {
+    if (b == a && (c == LIBXSMM_DATATYPE_F32 || c == a)) return P_FP8;
+    if (b == LIBXSMM_DATATYPE_BF16 && (c == LIBXSMM_DATATYPE_F32 || c == LIBXSMM_DATATYPE_BF16)) return P_FP8;
+  }
   return P_NONE;
 }
 
@@ -340,6 +346,33 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const xb_gemm_launch L, 
           }
           if (path == P_BF16_F32) reinterpret_cast<float*>(x.c)[ci] = acc;
           else reinterpret_cast<unsigned short*>(x.c)[ci] = xb_f32_to_bf16_rne(acc);
+        } break;
+        case P_FP8: {   // reference :2420-2630 (B of A's 8-bit type: k ascending, VNNI factor 4) and :2171-2366 (bf16 B: pairs, high k first)
+          const bool b16 = (d.tb == LIBXSMM_DATATYPE_BF16), hf = (d.ta == LIBXSMM_DATATYPE_HF8);
+          const int kb = vnni_a ? (b16 ? 2 : 4) : 1;
+          float acc = 0.0f;
+          if (!beta0) {
+            if (d.tc == LIBXSMM_DATATYPE_F32) acc = ldg_as<float>(x.c, ci);
+            else if (d.tc == LIBXSMM_DATATYPE_BF16) acc = xb_bf16_to_f32(ldg_as<unsigned short>(x.c, ci));
+            else acc = hf ? xb_hf8_to_f32(ldg_as<unsigned char>(x.c, ci)) : xb_bf8_to_f32(ldg_as<unsigned char>(x.c, ci));
+          }
+          for (unsigned long long r = 0; r < x.br; ++r) {
+            const char *pa, *pb; br_ptrs(d, x, r, 1, b16 ? 2 : 1, pa, pb);
+            for (int s = 0; s < k / kb; ++s) for (int q = 0; q < kb; ++q) {
+              const int k2 = b16 ? (kb - 1 - q) : q;
+              const long long kk = (long long)s * kb + k2;
+              unsigned char ar = 0;
+              if (!trans_a) ar = ldg_as<unsigned char>(pa, s * (lda * kb) + (long long)i * kb + k2);
+              else if (!vnni_a) ar = ldg_as<unsigned char>(pa, i * lda + kk);
+              float bv;
+              if (b16) bv = xb_bf16_to_f32(trans_b ? ldg_as<unsigned short>(pb, kk * ldb + j) : ldg_as<unsigned short>(pb, j * ldb + kk));
+              else { const unsigned char bw = trans_b ? ldg_as<unsigned char>(pb, kk * ldb + j) : ldg_as<unsigned char>(pb, j * ldb + kk); bv = hf ? xb_hf8_to_f32(bw) : xb_bf8_to_f32(bw); }
+              acc = __fadd_rn(acc, __fmul_rn(hf ? xb_hf8_to_f32(ar) : xb_bf8_to_f32(ar), bv));
+            }
+          }
+          if (d.tc == LIBXSMM_DATATYPE_F32) reinterpret_cast<float*>(x.c)[ci] = acc;
+          else if (d.tc == LIBXSMM_DATATYPE_BF16) reinterpret_cast<unsigned short*>(x.c)[ci] = xb_f32_to_bf16_rne(acc);
+          else reinterpret_cast<unsigned char*>(x.c)[ci] = hf ? xb_f32_to_hf8(acc) : xb_f32_to_bf8(acc);
         } break;
         case P_I4_I32: {   // reference :1273-1321; zero point subtracted in 8-bit arithmetic, B read as unsigned bytes
           unsigned int acc = beta0 ? 0u : (unsigned int)ldg_as<int>(x.c, ci);

@@ -53,6 +53,34 @@ ORACLE_API float oracle_f16_to_f32(uint16_t h) {                                
   } else r = ((e + 112) << 23) | (m << 13);
   return bits2f(r | s);
 }
+/* 8-bit floats: bf8 (E5M2) is the high byte of an f16 (src/libxsmm_math.c:546-551, :731-746); hf8 (E4M3, bias 7, 0x7f = NaN, no Inf)
+ * converts through f16 with RNE on the 7 dropped mantissa bits (:554-584, :749-822) */
+ORACLE_API float oracle_f16_to_f32(uint16_t h);
+ORACLE_API uint16_t oracle_f32_to_f16(float f);
+ORACLE_API float oracle_bf8_to_f32(uint8_t b) { return oracle_f16_to_f32((uint16_t)((uint16_t)b << 8)); }
+ORACLE_API uint8_t oracle_f32_to_bf8(float f) {
+  unsigned h = oracle_f32_to_f16(f);
+  if ((h & 0x7c00u) == 0x7c00u) { if (h & 0x3ffu) h |= 0x200u; } else h = (h + 0x7fu + ((h >> 8) & 1u)) & 0xffffu;
+  return (uint8_t)(h >> 8);
+}
+ORACLE_API float oracle_hf8_to_f32(uint8_t b) {
+  const unsigned e = (b >> 3) & 0xfu, m = b & 7u;
+  union { uint32_t u; float f; } x;
+  float v;
+  if (e == 0xf && m == 7) { x.u = ((uint32_t)(b & 0x80u) << 24) | 0x7fc00000u; return x.f; }
+  v = (e == 0) ? ldexpf((float)m, -9) : ldexpf((float)(8 + m), (int)e - 10);
+  return (b & 0x80u) ? -v : v;
+}
+ORACLE_API uint8_t oracle_f32_to_hf8(float f) {
+  const unsigned h = oracle_f32_to_f16(f), sign = (h & 0x8000u) >> 8, e16 = (h >> 10) & 0x1fu, m16 = h & 0x3ffu;
+  unsigned e, m, r;
+  if (e16 == 0x1f || e16 > 23 || (e16 == 23 && m16 > 0x340u)) return (uint8_t)(sign | 0x7fu);
+  if (e16 < 5) return (uint8_t)sign;
+  if (e16 > 8) { r = (h & 0x7fffu) + 0x3fu + ((m16 >> 7) & 1u); e = ((r >> 10) & 0x1fu) - 8u; m = (r & 0x3ffu) >> 7; return (uint8_t)(sign | (e << 3) | m); }
+  m = ((m16 | 0x400u) >> (9 - e16)) | (((m16 & 0x7fu) + 0x7fu) >> 7);
+  m = (m + 0x3fu + ((m >> 7) & 1u)) >> 7;
+  return (uint8_t)(sign | m);
+}
 ORACLE_API uint16_t oracle_f32_to_f16(float f) {                                             /* :824-900 */
   uint32_t u = f2bits(f), s = (u & 0x80000000u) >> 16, e32 = (u >> 23) & 0xff, m32 = u & 0x7fffff, e, m;
   if (e32 == 0xff) { e = 0x1f; m = m32 ? ((m32 >> 13) | 0x200) : 0; }
@@ -175,6 +203,29 @@ static int gemm_run(const gemm_ctx* g) {
           acc += oracle_bf16_widen(ar) * oracle_bf16_widen(bw);
         } }
       if (g->tc == T_F32) ((float*)g->c)[ci] = acc; else ((uint16_t*)g->c)[ci] = oracle_f32_to_bf16(acc);
+    } else if ((g->ta == T_BF8 || g->ta == T_HF8) && g->tcomp == T_F32 && !vnni_b
+               && ((g->tb == g->ta && (g->tc == T_F32 || g->tc == g->ta)) || (g->tb == T_BF16 && (g->tc == T_F32 || g->tc == T_BF16)))) {
+      /* 8-bit float A: :2420-2630 (B of the same type: VNNI factor 4, k ascending inside a group) and :2171-2366 (bf16 B: pairs, high k
+       * first); f32 accumulation seeded from C unless beta = 0, one rounding into C's type at the end */
+      const int b16 = (g->tb == T_BF16), hf = (g->ta == T_HF8), kb = vnni_a ? (b16 ? 2 : 4) : 1;
+      int q;
+      float acc = 0.0f;
+      if (!beta0) acc = (g->tc == T_F32) ? ((float*)g->c)[ci] : (g->tc == T_BF16 ? oracle_bf16_widen(((uint16_t*)g->c)[ci])
+                                         : (hf ? oracle_hf8_to_f32(((uint8_t*)g->c)[ci]) : oracle_bf8_to_f32(((uint8_t*)g->c)[ci])));
+      for (r = 0; r < br; ++r) { br_base(g, r, &pa, &pb);
+        for (s = 0; s < k / kb; ++s) for (q = 0; q < kb; ++q) {
+          const int kq = b16 ? (kb - 1 - q) : q;
+          const long long kk = (long long)s * kb + kq;
+          uint8_t ar = 0; float bv;
+          if (!trans_a) ar = ((const uint8_t*)pa)[s * (lda * kb) + i * kb + kq];
+          else if (!vnni_a) ar = ((const uint8_t*)pa)[i * lda + kk];
+          if (b16) bv = oracle_bf16_widen(((const uint16_t*)pb)[trans_b ? (kk * ldb + j) : (j * ldb + kk)]);
+          else { const uint8_t bw = ((const uint8_t*)pb)[trans_b ? (kk * ldb + j) : (j * ldb + kk)]; bv = hf ? oracle_hf8_to_f32(bw) : oracle_bf8_to_f32(bw); }
+          acc += (hf ? oracle_hf8_to_f32(ar) : oracle_bf8_to_f32(ar)) * bv;
+        } }
+      if (g->tc == T_F32) ((float*)g->c)[ci] = acc;
+      else if (g->tc == T_BF16) ((uint16_t*)g->c)[ci] = oracle_f32_to_bf16(acc);
+      else ((uint8_t*)g->c)[ci] = hf ? oracle_f32_to_hf8(acc) : oracle_f32_to_bf8(acc);
     } else return 1;
   }
   return 0;

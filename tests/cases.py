@@ -15,8 +15,8 @@ class GemmCase:
         self.ta, self.tb, self.tcomp, self.tc = ta, tb, tcomp, tc
         self.flags, self.br_type, self.br = flags, br_type, (br if br_type else 1)
         trans_a, trans_b = bool(flags & FLAG_TRANS_A), bool(flags & FLAG_TRANS_B)
-        honours_a = ta in (gen.F64, gen.F32, gen.BF16)
-        honours_b = tb in (gen.F64, gen.F32, gen.BF16, gen.F16)
+        honours_a = ta in (gen.F64, gen.F32, gen.BF16, gen.BF8, gen.HF8)
+        honours_b = tb in (gen.F64, gen.F32, gen.BF16, gen.F16, gen.BF8, gen.HF8)
         self.rows_a = k if (trans_a and honours_a) else m          # leading extent
         self.cols_a = m if (trans_a and honours_a) else k
         self.rows_b = n if (trans_b and honours_b) else k
@@ -101,6 +101,9 @@ TUPLES = [
     (gen.U8, gen.I8, gen.I32, gen.I32), (gen.I8, gen.U8, gen.I32, gen.I32), (gen.U8, gen.U8, gen.I32, gen.I32),
     (gen.I8, gen.I8, gen.I32, gen.I32), (gen.I8, gen.I8, gen.I32, gen.F32), (gen.U8, gen.I8, gen.I32, gen.F32),
     (gen.I16, gen.I16, gen.I32, gen.I32),
+    # 8-bit float A: B and C of the same type or f32, and the mixed form with a bf16 B
+    (gen.BF8, gen.BF8, gen.F32, gen.F32), (gen.BF8, gen.BF8, gen.F32, gen.BF8), (gen.HF8, gen.HF8, gen.F32, gen.F32), (gen.HF8, gen.HF8, gen.F32, gen.HF8),
+    (gen.BF8, gen.BF16, gen.F32, gen.F32), (gen.BF8, gen.BF16, gen.F32, gen.BF16), (gen.HF8, gen.BF16, gen.F32, gen.F32), (gen.HF8, gen.BF16, gen.F32, gen.BF16),
 ]
 
 
@@ -117,6 +120,8 @@ def flag_variants(t):
         out = [FLAG_VNNI_A] if t[3] == gen.F32 else [FLAG_VNNI_A, 0]
     elif ta == gen.I16:
         out += [FLAG_VNNI_A]
+    elif ta in (gen.BF8, gen.HF8):
+        out += [FLAG_VNNI_A, FLAG_TRANS_B, FLAG_VNNI_A | FLAG_TRANS_B, FLAG_TRANS_A]
     return out
 
 

@@ -6,8 +6,8 @@ import numpy as np
 
 F64, F32, BF16, F16, I32, I16, I8, U8 = 0, 1, 2, 3, 8, 10, 12, 13
 BF8, HF8, MXBF8, MXFP4X2, NVFP4X2 = 4, 5, 14, 20, 21
-NP_OF = {F64: np.float64, F32: np.float32, BF16: np.uint16, F16: np.uint16, I32: np.int32, I16: np.int16, I8: np.int8, U8: np.uint8}
-TS = {F64: 8, F32: 4, BF16: 2, F16: 2, I32: 4, I16: 2, I8: 1, U8: 1}
+NP_OF = {F64: np.float64, F32: np.float32, BF16: np.uint16, F16: np.uint16, I32: np.int32, I16: np.int16, I8: np.int8, U8: np.uint8, 4: np.uint8, 5: np.uint8}
+TS = {F64: 8, F32: 4, BF16: 2, F16: 2, I32: 4, I16: 2, I8: 1, U8: 1, 4: 1, 5: 1}
 
 
 def f32_to_bf16_bits(x):
@@ -39,6 +39,10 @@ def values(rng, n, dtype):
         return (tenths * 40).astype(np.int16)
     if dtype == I32:
         return rng.integers(-1000, 1000, size=n).astype(np.int32)
+    if dtype == BF8:       # E5M2 = upper byte of an f16: the tenths, truncated
+        return ((tenths / 10.0).astype(np.float16).view(np.uint16) >> 8).astype(np.uint8)
+    if dtype == HF8:       # E4M3: sign, exponent 4..9 (1/8 .. 7.5), any mantissa; no NaN code
+        return ((rng.integers(0, 2, size=n) << 7) | (rng.integers(4, 10, size=n) << 3) | rng.integers(0, 8, size=n)).astype(np.uint8)
     raise ValueError(dtype)
 
 
@@ -47,6 +51,13 @@ def to_f64(arr, dtype):
         return bf16_bits_to_f32(arr).astype(np.float64)
     if dtype == F16:
         return arr.view(np.float16).astype(np.float64)
+    if dtype == BF8:
+        return (arr.astype(np.uint16) << 8).view(np.float16).astype(np.float64)
+    if dtype == HF8:
+        b = arr.astype(np.int64); e, m = (b >> 3) & 15, b & 7
+        v = np.where(e == 0, m * 2.0 ** -9, (8 + m) * np.exp2((e - 10).astype(np.float64)))
+        v = np.where((e == 15) & (m == 7), np.nan, v)
+        return np.where(b & 0x80, -v, v)
     return arr.astype(np.float64)
 
 

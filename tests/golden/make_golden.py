@@ -29,26 +29,33 @@ def crc(*arrs):
 
 
 def main():
+    """usage: make_golden.py [gemm] [sparse] [mtx]  (default: all). The sparse sections need a host whose ISA the reference's JIT can build
+    BCSC bf16 for (AVX512-BF16 / AMX: the GPU box); the GEMM section runs on any x86-64 host."""
+    import sys
+    want = set(sys.argv[1:]) or {"gemm", "sparse", "mtx"}
     assert ref is not None, "oracle/_ref/libxsmm_ref.so is missing: run `make ref` where /root/reference exists"
     out = {}
-    for i, (case, seed, count) in enumerate(G.gemm_cases()):
+    for i, (case, seed, count) in enumerate(G.gemm_cases() if "gemm" in want else []):
         ops = cases.Operands(case, seed=seed, count=count)
         out["gemm_%03d" % i] = cases.ref_result(ref, case, ops, run_gemm)
         out["gemm_%03d_crc" % i] = crc(ops.a, ops.b, ops.c0)
-    np.savez_compressed(os.path.join(HERE, "gemm.npz"), **out)
-    print("gemm.npz: %d cases" % (len(out) // 2))
+    if "gemm" in want:
+        np.savez_compressed(os.path.join(HERE, "gemm.npz"), **out)
+        print("gemm.npz: %d cases" % (len(out) // 2))
+    if "sparse" not in want and "mtx" not in want:
+        return
 
     out = {}
     for i, cfg in enumerate(G.bcsc_cases()):
         inp = G.bcsc_inputs(cfg)
         c = inp["c0"].copy()
-        G.run_bcsc(ref, cfg, inp, c)
+        assert G.run_bcsc(ref, cfg, inp, c) == 0, cfg
         out["bcsc_%02d" % i] = c
         out["bcsc_%02d_crc" % i] = crc(inp["a"], inp["bvals"], inp["colptr"], inp["rowidx"], inp["c0"])
     for i, cfg in enumerate(G.fsspmdm_cases()):
         inp = G.fsspmdm_inputs(cfg)
         c = inp["c0"].copy()
-        G.run_fsspmdm(ref, cfg, inp, c)
+        assert G.run_fsspmdm(ref, cfg, inp, c) in (0, None), cfg
         out["fsspmdm_%02d" % i] = c
         out["fsspmdm_%02d_crc" % i] = crc(inp["a"], inp["b"], inp["c0"])
     np.savez_compressed(os.path.join(HERE, "sparse.npz"), **out)

@@ -94,7 +94,9 @@ def test_dispatch_identity_registry_and_kernel_info():
 
 def test_unsupported_descriptors_return_null():
     BF8, HF8 = 4, 5
-    assert not X.libxsmm_dispatch_gemm(X.libxsmm_create_gemm_shape(16, 16, 16, 16, 16, 16, BF8, BF8, gen.F32, gen.F32), 0, 0)
+    assert X.libxsmm_dispatch_gemm(X.libxsmm_create_gemm_shape(16, 16, 16, 16, 16, 16, BF8, BF8, gen.F32, gen.F32), 0, 0)       # 8-bit float tuples are served (exact-order kernel)
+    assert not X.libxsmm_dispatch_gemm(X.libxsmm_create_gemm_shape(16, 16, 16, 16, 16, 16, BF8, HF8, gen.F32, gen.F32), 0, 0)   # mixed 8-bit operands: no reference branch
+    assert not X.libxsmm_dispatch_gemm(X.libxsmm_create_gemm_shape(16, 16, 16, 16, 16, 16, 20, gen.BF16, gen.F32, gen.F32), 0, 0)  # MXFP4 A: SURVEY 8f-2, not built
     assert not X.libxsmm_dispatch_gemm(X.libxsmm_create_gemm_shape(16, 16, 16, 8, 16, 16, gen.F32, gen.F32, gen.F32, gen.F32), 0, 0)   # lda < m
     assert not X.libxsmm_dispatch_gemm(X.libxsmm_create_gemm_shape(0, 16, 16, 16, 16, 16, gen.F32, gen.F32, gen.F32, gen.F32), 0, 0)
     # inconsistent tile-config flags (libxsmm_generator.c:154-157)
