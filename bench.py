@@ -39,9 +39,11 @@ METRIC = "batched BRGEMM GFLOP/s (bf16, m=n=k=64, br=8, batch=65536/GPU, unique 
 WORKLOAD = ("configs[1]: batched BRGEMM bf16->f32 m=n=k=64 brcount=8 batch=65536 per GPU, stride-BR, beta=0, "
             "mode S (all operands unique)")
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` captures (bytes)
-NCU_TRAFFIC = {"gemm_tc_kernel<64>": (9652.8e6, "profiles/r01_ncu_gemm_tc.txt"),
-               "sreg_kernel<float>": (622.2e6, "profiles/r01_ncu_sreg.txt"),
-               "bcsc_tc_kernel<32>": (None, "profiles/r01_ncu_bcsc_tc.txt")}
+NCU_TRAFFIC = {"gemm_tc_kernel<64>": (9673.1e6, "profiles/r02_ncu_gemm_tc.txt"),
+               "sreg_kernel<float>": (622.1e6, "profiles/r02_ncu_sreg.txt"),
+               "bcsc_ts_kernel<32,2>": (491.3e6, "profiles/r02_ncu_bcsc_ts.txt"),       # below the 537 MB of algorithmic bytes: part of C is still in L2 when the capture ends
+               "gemm_pool_kernel": (495.6e6, "profiles/r02_ncu_gemm_pool.txt"),           # C writes (537 MB algorithmic); the operand pools stay in L2
+               "gemm_ts_kernel": (745.9e6, "profiles/r02_ncu_gemm_ts_i8.txt")}
 
 
 def traffic(kernel):
@@ -542,7 +544,7 @@ def also_brgemm_r(X, torch, pk, args, full=False, pool_sets=64, batch=BATCH):
     tf = flops / (ms * 1e-3) / 1e12
     return {"metric": "batched BRGEMM GFLOP/s, mode R (bf16 64^3 br=8, address batch-reduce, operand pool of %d block-sets, C bf16 unique)" % pool_sets,
             "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "oracle_check": {"tiles": 4, "max_normf_rel": worst},
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": None,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": traffic("gemm_pool_kernel"),
                          "kernel": "gemm_pool_kernel (resident operand sets, two tiles per M=128 instruction)",
                          "note": "a 128x64x16 tcgen05.mma costs 48 cycles (profiles/r01_umma_cost.txt: max(N/2, 32+N/4)), i.e. 67 % of the nominal "
                                  "2.38 PFLOP/s at 1965 MHz = 95 % of the measured cuBLAS peak: the bound of this tile shape"},

@@ -660,8 +660,8 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   // instruction descriptor: D=f32, A/B format, A MN-major, B K-major, N>>3, M>>4
   const uint32_t fmt = (d.ta == LIBXSMM_DATATYPE_BF16) ? 1u : 0u;
   P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(P.np >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-  P.lbo_a = (uint32_t)env_int("LIBXSMM_B200_TC_LBO_A", 8192 >> 4); P.sbo_a = (uint32_t)env_int("LIBXSMM_B200_TC_SBO_A", 1024 >> 4);
-  P.lbo_b = (uint32_t)env_int("LIBXSMM_B200_TC_LBO_B", 1);         P.sbo_b = (uint32_t)env_int("LIBXSMM_B200_TC_SBO_B", 1024 >> 4);
+  // descriptor strides in 16-byte units: A (MN-major) 64-row halves 8192 bytes apart, 8-row groups of k 1024 bytes apart; B (K-major) likewise
+  P.lbo_a = 8192 >> 4; P.sbo_a = 1024 >> 4; P.lbo_b = 1; P.sbo_b = 1024 >> 4;
 
   const CUtensorMapDataType dt = (d.ta == LIBXSMM_DATATYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const cuuint32_t estr[4] = {1, 1, 1, 1};

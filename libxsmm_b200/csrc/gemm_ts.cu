@@ -344,7 +344,11 @@ extern "C" int xb_gemm_ts_launch(const xb_gemm_launch* L) {
   if (P.stages < 2) return xb_gemm_simt_launch(L);
   P.a_col0 = P.nslot * P.slot_cols;
   P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
+#if defined(XB_DIAG)   /* ablation switch of the profiling sessions: never in a release build (it makes the kernel skip work) */
   P.skip = ts_env_int("LIBXSMM_B200_TS_SKIP", 0);
+#else
+  P.skip = 0;
+#endif
   P.ep_mode = xb_ep_mode(d.ta, d.tc, &P.c_esz);
   P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0; P.is_i8 = is_i8; P.scf = L->one.scf;
   if (is_i8) {

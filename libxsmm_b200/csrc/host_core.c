@@ -282,8 +282,10 @@ static int xb_make_gemm_desc(xb_gemm_desc* d, const libxsmm_gemm_shape* shape, u
     const int is8 = (d->ta == LIBXSMM_DATATYPE_I8 || d->ta == LIBXSMM_DATATYPE_U8);
     const int is16 = (d->ta == LIBXSMM_DATATYPE_BF16 || d->ta == LIBXSMM_DATATYPE_F16 || d->ta == LIBXSMM_DATATYPE_I16);
     const int vnni_a = (d->flags & LIBXSMM_GEMM_FLAG_VNNI_A) != 0;
+    const int is_f8 = (d->ta == LIBXSMM_DATATYPE_BF8 || d->ta == LIBXSMM_DATATYPE_HF8);      /* 8-bit float A: VNNI factor 4, or 2 next to a bf16 B */
     const int honours_trans = (d->ta == LIBXSMM_DATATYPE_F64 || d->ta == LIBXSMM_DATATYPE_F32 || d->ta == LIBXSMM_DATATYPE_BF32
-                            || d->ta == LIBXSMM_DATATYPE_BF16);
+                            || d->ta == LIBXSMM_DATATYPE_BF16 || is_f8);
+    if (is_f8 && vnni_a && (trans_a || (d->k % (d->tb == LIBXSMM_DATATYPE_BF16 ? 2 : 4)) != 0)) return 0;
     if (honours_trans && trans_a) { if (d->lda < d->k) return 0; } else if (d->lda < d->m) return 0;
     if ((honours_trans || d->ta == LIBXSMM_DATATYPE_F16) && trans_b) { if (d->ldb < d->n) return 0; } else if (d->ldb < d->k) return 0;
     if (vnni_a && is8 && (d->k % 4) != 0) return 0;
@@ -372,9 +374,10 @@ static size_t xb_extent_a(const xb_gemm_desc* d) {   /* elements touched in one 
   if (d->ta == LIBXSMM_DATATYPE_I4X2 || d->ta == LIBXSMM_DATATYPE_U4X2) return (size_t)(d->k / 8 - 1) * d->lda * 4 + (size_t)d->m * 4;   /* bytes: 8 k per 4 bytes */
   const int trans_a = (d->flags & LIBXSMM_GEMM_FLAG_TRANS_A) != 0, vnni_a = (d->flags & LIBXSMM_GEMM_FLAG_VNNI_A) != 0;
   const int is8 = (d->ta == LIBXSMM_DATATYPE_I8 || d->ta == LIBXSMM_DATATYPE_U8);
-  const int v = (is8 ? 4 : 2);
+  const int is_f8 = (d->ta == LIBXSMM_DATATYPE_BF8 || d->ta == LIBXSMM_DATATYPE_HF8);
+  const int v = (is8 || (is_f8 && d->tb != LIBXSMM_DATATYPE_BF16)) ? 4 : 2;
   const int honours_trans = (d->ta == LIBXSMM_DATATYPE_F64 || d->ta == LIBXSMM_DATATYPE_F32 || d->ta == LIBXSMM_DATATYPE_BF32
-                          || d->ta == LIBXSMM_DATATYPE_BF16);
+                          || d->ta == LIBXSMM_DATATYPE_BF16 || is_f8);
   if (honours_trans && trans_a && !vnni_a) return (size_t)(d->m - 1) * d->lda + d->k;
   if ((vnni_a && d->ta != LIBXSMM_DATATYPE_F64 && d->ta != LIBXSMM_DATATYPE_F32) || (is8 && d->tc == LIBXSMM_DATATYPE_F32)) {
     return (size_t)(d->k / v - 1) * d->lda * v + (size_t)d->m * v;
@@ -385,7 +388,7 @@ static size_t xb_extent_a(const xb_gemm_desc* d) {   /* elements touched in one 
 static size_t xb_extent_b(const xb_gemm_desc* d) {
   const int trans_b = (d->flags & LIBXSMM_GEMM_FLAG_TRANS_B) != 0, vnni_b = (d->flags & LIBXSMM_GEMM_FLAG_VNNI_B) != 0;
   const int honours = (d->tb == LIBXSMM_DATATYPE_F64 || d->tb == LIBXSMM_DATATYPE_F32 || d->tb == LIBXSMM_DATATYPE_BF32
-                    || d->tb == LIBXSMM_DATATYPE_BF16 || d->tb == LIBXSMM_DATATYPE_F16);
+                    || d->tb == LIBXSMM_DATATYPE_BF16 || d->tb == LIBXSMM_DATATYPE_F16 || d->tb == LIBXSMM_DATATYPE_BF8 || d->tb == LIBXSMM_DATATYPE_HF8);
   if (honours && trans_b && vnni_b && d->tb == LIBXSMM_DATATYPE_BF16) return (size_t)(d->k / 2 - 1) * d->ldb * 2 + (size_t)d->n * 2;
   if (honours && trans_b) return (size_t)(d->k - 1) * d->ldb + d->n;
   return (size_t)(d->n - 1) * d->ldb + d->k;
