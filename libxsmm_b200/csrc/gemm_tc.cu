@@ -334,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 //   * while the items of set s run, the producer loads the next set into the other buffer (sets are needed in first-use order,
 //     alternating buffers); a buffer is released by a tcgen05.commit after the last item that reads it;
 //   * no operand byte is fetched twice per run of equal sets and nothing is fetched per tile.
-// Roles (320 threads): warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quadrant, alternate column chunks).
+// Roles (352 threads): warp 0 producer, warps 1 and 10 MMA issuers, warps 2..9 epilogue (two per TMEM lane quadrant, alternate column chunks).
 // Producer, issuer and epilogue each replay the same cheap scan over the item list to know which load a set corresponds to.
 struct PoolParams {
   int m, n, np, k, kchunks, br, loads;      // loads = br * kchunks blocks per set
@@ -344,9 +344,10 @@ struct PoolParams {
   int ep_mode, c_esz, beta0;
   uint32_t idesc, sbo_a, sbo_b, lbo_b;
   const int4* items; char* const* cptrs;
+  int issuers;                              // 1 or 2 MMA-issuing warps (warp 1 and, if 2, warp 10); items alternate between them
 };
 
-__global__ void __launch_bounds__(320)
+__global__ void __launch_bounds__(352, 1)
 gemm_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const PoolParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -368,7 +369,8 @@ gemm_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
-    mbar_init(a_full, 1); mbar_init(a_full + 8, 1); mbar_init(a_empty, 1); mbar_init(a_empty + 8, 1); mbar_init(b_full, 1); mbar_init(b_empty, 1);
+    // a buffer is released when EVERY issuing warp has committed past its last reader (tcgen05.commit only tracks the issuing thread's MMAs)
+    mbar_init(a_full, 1); mbar_init(a_full + 8, 1); mbar_init(a_empty, P.issuers); mbar_init(a_empty + 8, P.issuers); mbar_init(b_full, 1); mbar_init(b_empty, P.issuers);
     for (int i = 0; i < NS; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -413,23 +415,27 @@ gemm_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
+  } else if (warp == 1 || warp == 10) {
+    // ===================================== MMA issuer(s) =====================================
+    // One issuing thread needs ~80 cycles per tcgen05.mma here while the instruction occupies the tensor pipe for 48: with two
+    // issuing warps (items alternate, each item has its own TMEM slot) the pipe is the limit again. Both warps walk ALL items so that
+    // they observe every barrier phase and both commit every release; only the owner of an item issues its MMAs.
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
     const uint32_t hi_a = (P.sbo_a & 0x3FFFu) | (1u << 14) | (2u << 29), hi_b = (P.sbo_b & 0x3FFFu) | (1u << 14) | (2u << 29);
     const uint32_t b_lo0 = ((sB & 0x3FFFFu) >> 4) | ((P.lbo_b & 0x3FFFu) << 16);
     const int ks_last = (P.k - (P.kchunks - 1) * 64 + 15) / 16;
+    const int me = (warp == 1) ? 0 : 1, nis = P.issuers;
     int last = -1, j = -1, cur_sb = -1, jb = -1, slot = 0; uint32_t slot_par = 1;
     for (long long i = 0; i < n_local; ++i) {
       const int4 it = s_items[i];
+      const bool mine = ((int)(i % nis) == me);
       if (it.z != cur_sb) { cur_sb = it.z; ++jb; if (leader) mbar_wait(b_full, (uint32_t)(jb & 1)); __syncwarp(); }
       if (it.x != last) { last = it.x; ++j; if (leader) mbar_wait(a_full + 8 * (j & 1), (uint32_t)((j >> 1) & 1)); __syncwarp(); }
       const int j0 = j;
       if (it.y != last) { last = it.y; ++j; if (leader) mbar_wait(a_full + 8 * (j & 1), (uint32_t)((j >> 1) & 1)); __syncwarp(); }
       const int j1 = j;
-      if (leader) mbar_wait(t_empty + 8 * slot, slot_par);
-      __syncwarp();
+      if (mine) { if (leader) mbar_wait(t_empty + 8 * slot, slot_par); __syncwarp(); }
       tc_fence_after();
       // rows 0..63 come from the lower of the two buffers, rows 64..127 from `lbo` bytes above it (0: the same set twice)
       const uint32_t buf_lo = (uint32_t)(((j0 & 1) < (j1 & 1)) ? (j0 & 1) : (j1 & 1)), lbo = (uint32_t)(((j0 ^ j1) & 1) ? (a_set_bytes >> 4) : 0u);
@@ -438,6 +444,7 @@ gemm_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // measured: issuing from inside the elected lane's branch (operands in vector registers, one R2UR each) is faster here than the
       // all-lanes form used in gemm_tc_kernel (0.283 vs 0.322 ms on mode R)
       if (leader) {
+        if (mine) {
         int kc = 0;
         uint32_t a_lo = a_lo0, b_lo = b_lo0, acc = 0u;
         for (int l = 0; l < P.loads; ++l) {
@@ -455,7 +462,8 @@ gemm_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (++kc == P.kchunks) kc = 0;
         }
         umma_commit(t_full + 8 * slot);
-        // release what the next item no longer reads
+        }
+        // release what the next item no longer reads (every issuing warp arrives, whether or not this item was its own)
         const bool more = (i + 1 < n_local);
         const int4 nx = more ? s_items[i + 1] : make_int4(-2, -2, -2, 0);
         if (more) {
@@ -467,7 +475,7 @@ gemm_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
       if (++slot == NS) { slot = 0; slot_par ^= 1; }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================================== epilogue =====================================
     const int q = warp & 3, cgrp = (warp - 2) >> 2;
     const int row = (32 * q + lane) & 63, upper = q >> 1;              // rows 64..127 of the instruction: TMEM lane quadrants 2, 3
@@ -587,6 +595,7 @@ static int pool_sets_launch(const xb_gemm_desc& d, const xb_tc_pool* pool, unsig
   P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(P.np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   P.sbo_a = 1024 >> 4; P.sbo_b = 1024 >> 4; P.lbo_b = 1;
   P.items = (const int4*)pool->sets; P.cptrs = (char* const*)pool->cptrs;
+  P.issuers = (env_int("LIBXSMM_B200_TC_POOL_ISSUERS", 2) == 1) ? 1 : 2;
   const CUtensorMapDataType dt = (d.ta == LIBXSMM_DATATYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap map_a, map_b;
@@ -605,7 +614,7 @@ static int pool_sets_launch(const xb_gemm_desc& d, const xb_tc_pool* pool, unsig
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) return -1;
   }
   if (xb_rt_first_use_on_device(&g_pool_attr)) cudaFuncSetAttribute(gemm_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  gemm_pool_kernel<<<(unsigned int)grid, 320, smem, (cudaStream_t)xb_rt_stream()>>>(map_a, map_b, P);
+  gemm_pool_kernel<<<(unsigned int)grid, P.issuers == 2 ? 352 : 320, smem, (cudaStream_t)xb_rt_stream()>>>(map_a, map_b, P);
   xb_rt_count_launch();
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { xb_rt_note_error((int)e, "gemm_pool"); return (int)e; }

@@ -321,6 +321,9 @@ extern "C" int xb_gemm_ts_launch(const xb_gemm_launch* L) {
   if (d.m <= 32 && L->count > 1 && ts_env_int("LIBXSMM_B200_TS_PACK", 1) != 0) {
     P.mp = d.m <= 8 ? 8 : (d.m <= 16 ? 16 : 32);
     P.grp = 128 / P.mp; if (P.grp > 128 / P.np) P.grp = 128 / P.np;
+    // 96 accumulator columns per slot leave room for two CTAs per SM (2 x 96 + 2 x 32 TMEM columns each): measured better than one
+    // CTA with full 128-column groups (int8 32^3: 0.075 -> 0.066 ms)
+    if (P.grp * P.np > 96 && 96 / P.np >= 2) P.grp = 96 / P.np;
     { const int ge = ts_env_int("LIBXSMM_B200_TS_GRP", 0); if (ge >= 1 && ge < P.grp) P.grp = ge; }
     if (P.grp < 2) { P.grp = 1; P.mp = 128; }
   }
