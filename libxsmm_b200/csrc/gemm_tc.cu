@@ -35,7 +35,9 @@ namespace {
 
 struct TcParams {
   int m, n, k;
-  int np;                 // n rounded up to the MMA's N granularity
+  int np;                 // N of the instruction: n rounded up to the MMA's granularity (grp > 1: grp tiles side by side)
+  int grp, npt;           // small tiles (m = 16 or 32, M = 64 instruction): grp = 64 / m tiles per item, block-diagonal; npt = columns per tile
+  long long tiles;        // number of tiles (count = items = ceil(tiles / grp))
   int kchunks;            // ceil(k / 64)
   int stages, stage_bytes, a_bytes;
   int nslot, slot_cols, tmem_cols, evict_first;
@@ -48,6 +50,7 @@ struct TcParams {
   int pair;                           // pooled, m <= 64: an item is TWO tiles that share B -- tile 0 in rows 0..63, tile 1 in rows 64..127 of one M=128 instruction
   uint32_t idesc;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // in 16-byte units
+  uint32_t a_layout, a_kstep;            // A descriptor: swizzle mode bits (<< 29 of the high word) and the advance per 16 k in 16-byte units
   // pooled address mode (libxsmm_b200_gemm_plan over ADDRESS batch-reduce): item p reads block-set sets[p].x of A (and, in pair
   // mode, sets[p].y for its second tile) and sets[p].z of B (4th tensor-map coordinate) and writes cptrs[p] (pair mode:
   // cptrs[2p], cptrs[2p+1], the second may be null); items are sorted by set, a CTA owns a contiguous range and keeps the
@@ -107,6 +110,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+// 16 columns only: the last tile of a packed item must not read past its slot (TMEM beyond the CTA's allocation faults)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // SMEM matrix descriptor, SWIZZLE_128B, descriptor version 1 (Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32)
@@ -193,9 +205,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (UM == 128) tma_load_4d_hint(sa + 8192, &map_a, full, m1, kc * 64, (int)r, ta1, policy);
               tma_load_4d_hint(sb, &map_b, full, kc * 64, 0, (int)r, tb, policy);
             } else {
+              if (P.grp > 1) {      // packed small tiles: both boxes span grp tiles (4th dimension)
+                tma_load_4d(sa, &map_a, full, 0, kc * 64, (int)r, ta * P.grp);
+                tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, tb * P.grp);
+              } else {
               tma_load_4d(sa, &map_a, full, 0, kc * 64, (int)r, ta);
               if (UM == 128) tma_load_4d(sa + 8192, &map_a, full, m1, kc * 64, (int)r, ta1);
               tma_load_4d(sb, &map_b, full, kc * 64, 0, (int)r, tb);
+              }
             }
             }
             __syncwarp();
@@ -211,7 +228,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
       int stage = 0; uint32_t phase = 0;                  // cursor of the next freshly loaded stage
       int run_stage = 0; uint32_t run_phase = 0;          // first stage of the run of equal set pairs this tile belongs to
-      const uint32_t hi_a = (P.sbo_a & 0x3FFFu) | (1u << 14) | (2u << 29), hi_b = (P.sbo_b & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t hi_a = (P.sbo_a & 0x3FFFu) | (1u << 14) | (P.a_layout << 29), hi_b = (P.sbo_b & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t aks = P.a_kstep;                  // A advance per 16 k (16-byte units): 128 for the 128-byte-row layout
       // per-stage descriptor low words: (address >> 4) | lbo << 16; the high words are constant. A k-step advances A by 16 rows of
       // 128 bytes and B by 16 elements inside the swizzled row: one 32-bit add per operand and instruction.
       const uint32_t stage_step = (uint32_t)P.stage_bytes >> 4;
@@ -246,9 +264,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int l = 0; l < nload; ++l) {
             if (leader) {
               umma_f16(d_tmem, desc64(hi_a, a_lo), desc64(hi_b, b_lo), idesc, l == 0 ? 0u : 1u);
-              umma_f16(d_tmem, desc64(hi_a, a_lo + 128), desc64(hi_b, b_lo + 2), idesc, 1u);
-              umma_f16(d_tmem, desc64(hi_a, a_lo + 256), desc64(hi_b, b_lo + 4), idesc, 1u);
-              umma_f16(d_tmem, desc64(hi_a, a_lo + 384), desc64(hi_b, b_lo + 6), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + aks), desc64(hi_b, b_lo + 2), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 2 * aks), desc64(hi_b, b_lo + 4), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 3 * aks), desc64(hi_b, b_lo + 6), idesc, 1u);
               if (last_of_run) umma_commit(empty0 + 8 * cs);
             }
             a_lo += stage_step; b_lo += stage_step;
@@ -262,11 +280,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (leader) {
             if (ksteps == 4) {
               umma_f16(d_tmem, desc64(hi_a, a_lo), desc64(hi_b, b_lo), idesc, accumulate);
-              umma_f16(d_tmem, desc64(hi_a, a_lo + 128), desc64(hi_b, b_lo + 2), idesc, 1u);
-              umma_f16(d_tmem, desc64(hi_a, a_lo + 256), desc64(hi_b, b_lo + 4), idesc, 1u);
-              umma_f16(d_tmem, desc64(hi_a, a_lo + 384), desc64(hi_b, b_lo + 6), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + aks), desc64(hi_b, b_lo + 2), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 2 * aks), desc64(hi_b, b_lo + 4), idesc, 1u);
+              umma_f16(d_tmem, desc64(hi_a, a_lo + 3 * aks), desc64(hi_b, b_lo + 6), idesc, 1u);
             } else {
-              for (int ks = 0; ks < ksteps; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * 128), desc64(hi_b, b_lo + ks * 2), idesc, ks == 0 ? accumulate : 1u);
+              for (int ks = 0; ks < ksteps; ++ks) umma_f16(d_tmem, desc64(hi_a, a_lo + ks * aks), desc64(hi_b, b_lo + ks * 2), idesc, ks == 0 ? accumulate : 1u);
             }
             if (last_of_run) umma_commit(empty0 + 8 * cs);               // stage reusable once the MMAs of the whole run retired
           }
@@ -296,16 +314,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const long long i = slot_seq * TPS + half;
       const long long t = pooled ? b * chunk + i : b + i * G;
-      char* ctile = pooled ? ((i < n_local) ? (P.pair ? P.cptrs[2 * t + second] : P.cptrs[t]) : nullptr) : P.c + t * P.tile_stride_c;
-      const bool valid = (i < n_local) && (row < P.m) && ctile != nullptr;
-      const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16);
+      // packed small tiles: row r of the M=64 instruction is row r % m of tile (item * grp + r / m), whose results sit in columns
+      // (r / m) * npt ...; m is 16 or 32, so the 16 rows of a warp all belong to one tile
+      const int tl = (P.grp > 1) ? row / P.m : 0, trow = row - tl * P.m;
+      const long long tile = t * P.grp + tl;
+      char* ctile = pooled ? ((i < n_local) ? (P.pair ? P.cptrs[2 * t + second] : P.cptrs[t]) : nullptr) : P.c + tile * P.tile_stride_c;
+      const bool valid = (i < n_local) && (trow < P.m) && tile < P.tiles && ctile != nullptr;
+      const uint32_t taddr = tmem_base + (uint32_t)(slot * P.slot_cols) + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * P.npt);
       const long long ldcb = P.ldc * P.c_esz;
-      char* crow = valid ? ctile + (long long)row * P.c_esz : nullptr;
-      if (32 * cgrp >= P.np) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_base + 8 * (2 * S + NS + slot)); }   // no chunk for this warp
-      for (int c0 = 32 * cgrp; c0 < P.np; c0 += cstep) {
+      char* crow = valid ? ctile + (long long)trow * P.c_esz : nullptr;
+      if (32 * cgrp >= P.npt) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_base + 8 * (2 * S + NS + slot)); }   // no chunk for this warp
+      for (int c0 = 32 * cgrp; c0 < P.npt; c0 += cstep) {
         uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        if (c0 + cstep >= P.np) {                   // this warp's last read of the slot: hand it back to the MMA warp
+        if (P.npt - c0 <= 16) tmem_ld16(taddr + (uint32_t)c0, v); else tmem_ld32(taddr + (uint32_t)c0, v);
+        if (c0 + cstep >= P.npt) {                  // this warp's last read of the slot: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_base + 8 * (2 * S + NS + slot));
@@ -641,6 +663,15 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   TcParams P; memset(&P, 0, sizeof(P));
   P.m = d.m; P.n = d.n; P.k = d.k;
   P.np = (UM == 64) ? ((d.n + 7) & ~7) : ((d.n + 15) & ~15);
+  // small tiles (m = 16 or 32): 64 / m tiles at constant stride share one M=64 instruction as a block-diagonal product. One TMA box
+  // fetches the A blocks of all of them (each its own [64 k][m] block, the narrower swizzle modes describe exactly that), B's tiles
+  // land side by side as N. One load, one barrier round trip and one instruction chain then serve 2 or 4 tiles.
+  P.grp = 1; P.npt = P.np; P.tiles = L->count;
+  long long items = L->count;
+  if (pool == nullptr && UM == 64 && (d.m == 16 || d.m == 32) && L->count >= 8 && (64 / d.m) * P.np <= 256 && (P.np == 16 || (P.np % 32) == 0)
+      && env_int("LIBXSMM_B200_TC_PACK", 1) != 0) {          // columns per tile: 16 or a multiple of 32, so that no TMEM read leaves the item's slot
+    P.grp = 64 / d.m; P.np = P.grp * P.npt; items = (L->count + P.grp - 1) / P.grp;
+  }
   P.kchunks = (d.k + 63) / 64;
   P.a_bytes = UM * 128; P.stage_bytes = P.a_bytes + P.np * 128;
   // several independent (producer, MMA, epilogue) pipelines per SM hide each other's serial phases. Measured on B200:
@@ -662,7 +693,7 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   P.tmem_cols = tmem_for(ctas);
   P.nslot = P.tmem_cols / P.slot_cols; if (P.nslot > 4) P.nslot = 4;
   P.evict_first = env_int("LIBXSMM_B200_TC_EVICT_FIRST", 0);
-  P.br = br; P.count = L->count; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
+  P.br = br; P.count = items; P.c = c; P.tile_stride_c = sc; P.ldc = d.ldc;
   if (pool != nullptr) { P.sets = (const int4*)pool->sets; P.cptrs = (char* const*)pool->cptrs; P.pair = pool->pair; }
   P.c_type = d.tc; P.a_type = d.ta; P.beta0 = (d.flags & LIBXSMM_GEMM_FLAG_BETA_0) ? 1 : 0;
   P.ep_mode = xb_ep_mode(d.ta, d.tc, &P.c_esz);
@@ -671,6 +702,14 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(P.np >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
   // descriptor strides in 16-byte units: A (MN-major) 64-row halves 8192 bytes apart, 8-row groups of k 1024 bytes apart; B (K-major) likewise
   P.lbo_a = 8192 >> 4; P.sbo_a = 1024 >> 4; P.lbo_b = 1; P.sbo_b = 1024 >> 4;
+  P.a_layout = 2u; P.a_kstep = 2048 >> 4;                    // SWIZZLE_128B: 128-byte rows of 64 elements, 16 k rows = 2048 bytes
+  if (P.grp > 1) {
+    // packed small tiles: every tile is its own block of 64 k-rows x (m elements = 64 or 32 bytes), blocks back to back. That is the
+    // MN-major canonical layout of the 64-byte (m = 32) or 32-byte (m = 16) swizzle mode with the blocks `lbo` apart.
+    const uint32_t rowb = (uint32_t)d.m * 2u;
+    P.a_layout = (d.m == 32) ? 4u : 6u;                       // SWIZZLE_64B : SWIZZLE_32B
+    P.sbo_a = (8u * rowb) >> 4; P.lbo_a = (64u * rowb) >> 4; P.a_kstep = (16u * rowb) >> 4;
+  }
 
   const CUtensorMapDataType dt = (d.ta == LIBXSMM_DATATYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -682,15 +721,20 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
     const cuuint64_t strides[3] = {(cuuint64_t)d.lda * es, pool ? (cuuint64_t)pool->blk_a : ((d.br_type == 3) ? (cuuint64_t)d.br_stride_a : pad_a),
                                    pool ? (cuuint64_t)pool->set_a : ((L->count > 1) ? (cuuint64_t)sa : pad_a)};
     const cuuint32_t box[4] = {64, 64, 1, 1};
-    const CUresult r = g_encode(&map_a, dt, 4, (void*)a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // packed small tiles: the box spans grp tiles; inner extent m elements = the swizzle span
+    const cuuint32_t pbox[4] = {(cuuint32_t)d.m, 64, 1, (cuuint32_t)P.grp};
+    const CUresult r = (P.grp > 1)
+      ? g_encode(&map_a, dt, 4, (void*)a, dims, strides, pbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 (d.m == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+      : g_encode(&map_a, dt, 4, (void*)a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return (pool != nullptr) ? 1 : xb_gemm_simt_launch(L);
   }
   {
     const cuuint64_t dims[4] = {(cuuint64_t)d.k, (cuuint64_t)d.n, (cuuint64_t)br, (cuuint64_t)(pool ? pool->nsets_b : L->count)};
     const cuuint64_t strides[3] = {(cuuint64_t)d.ldb * es, pool ? (cuuint64_t)pool->blk_b : ((d.br_type == 3) ? (cuuint64_t)d.br_stride_b : pad_b),
                                    pool ? (cuuint64_t)pool->set_b : ((L->count > 1) ? (cuuint64_t)sb : pad_b)};
-    const cuuint32_t box[4] = {64, (cuuint32_t)P.np, 1, 1};
+    const cuuint32_t box[4] = {64, (cuuint32_t)P.npt, 1, (cuuint32_t)P.grp};     // grp > 1: the tiles of an item side by side as N
     const CUresult r = g_encode(&map_b, dt, 4, (void*)b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return (pool != nullptr) ? 1 : xb_gemm_simt_launch(L);
@@ -698,7 +742,7 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
 
   size_t smem = (size_t)P.stages * P.stage_bytes + 1024 /*align slack*/ + (2 * 16 + 2 * 8) * 8 + 64;
   const long long tiles_per_cta_unit = (UM == 64) ? 2 : 1;
-  long long grid = (L->count + tiles_per_cta_unit - 1) / tiles_per_cta_unit; if (grid > (long long)g_num_sms * ctas) grid = (long long)g_num_sms * ctas; if (grid < 1) grid = 1;
+  long long grid = (items + tiles_per_cta_unit - 1) / tiles_per_cta_unit; if (grid > (long long)g_num_sms * ctas) grid = (long long)g_num_sms * ctas; if (grid < 1) grid = 1;
   if (pool != nullptr) {
     const size_t sets_bytes = (size_t)((L->count + grid - 1) / grid) * sizeof(int4);
     if (sets_bytes <= 16 * 1024 && smem + sets_bytes <= (size_t)(227 * 1024) / ctas) { P.sets_in_smem = 1; smem += sets_bytes; }

@@ -60,7 +60,7 @@ def test_hello_host_pointers_f64_and_f32():
 
 
 TC_SHAPES = [(64, 64, 64), (64, 64, 32), (32, 64, 64), (64, 32, 64), (48, 40, 80), (128, 64, 64), (96, 128, 64),
-             (128, 128, 128), (16, 16, 16), (64, 256, 64), (64, 64, 128), (24, 72, 200)]
+             (128, 128, 128), (16, 16, 16), (64, 256, 64), (64, 64, 128), (24, 72, 200), (32, 40, 96), (16, 24, 48), (32, 128, 64)]   # m = 16 / 32: several tiles per instruction
 
 
 @pytest.mark.parametrize("ta,tc", [(gen.BF16, gen.F32), (gen.BF16, gen.BF16), (gen.F16, gen.F32), (gen.F16, gen.F16)])
@@ -395,3 +395,21 @@ def test_offset_mode_pool_on_tensor_cores():
             assert run_gemm(oracle, case.dims, case.types, case.flags, 1, 0, 0, br, ha, hb, cv) == 0     # same blocks through the ADDRESS form of the oracle
         assert gen.normf_rel(gen.to_f64(want, tc), gen.to_f64(got, tc)) <= 5e-3, (m, n, k, br)
         X.libxsmm_b200_gemm_plan_destroy(plan)
+
+
+def test_multi_device_strided_batch_from_host_buffers():
+    """libxsmm_b200_gemm_batch_strided_multi: a host-resident strided batch cut into one contiguous range per device (all visible GPUs,
+    one worker thread and stream each). On a one-GPU box this is the ndevices = 1 path."""
+    import torch
+    ndev = max(1, min(4, torch.cuda.device_count()))
+    rng = np.random.default_rng(100)
+    case = cases.GemmCase(64, 64, 64, gen.BF16, gen.BF16, gen.F32, gen.F32, flags=cases.FLAG_BETA_0, br_type=3, br=2)
+    count = 1001
+    ops = cases.Operands(case, seed=int(rng.integers(1 << 30)), count=count)
+    kernel = dispatch(case, ops)
+    assert kernel
+    a, b, c = ops.a.copy(), ops.b.copy(), ops.c0.copy()
+    rc = X.libxsmm_b200_gemm_batch_strided_multi(kernel, a.ctypes.data, b.ctypes.data, c.ctypes.data, ops.tile_a, ops.tile_b, ops.tile_c, case.br, count, ndev)
+    assert rc == 0, X.libxsmm_b200_last_error_string()
+    want = cases.ref_result(oracle, case, ops, run_gemm)
+    assert gen.normf_rel(want, c) <= 1.2e-5, ndev

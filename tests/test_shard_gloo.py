@@ -42,6 +42,17 @@ def _worker(rank, world, port, q):
         units, ms = aggregate(dist, e - b, 1.0 + rank)
         t = torch.tensor([local], dtype=torch.float64)
         dist.all_reduce(t)
+        # the strong-scaling cut of bench.py: BCSC m_blocks in groups of 4, fsspmdm columns in groups of 16; the optional gather of the
+        # C ranges (here: the ids of the units) must reassemble the whole job in order
+        for total, granule in ((8192, 4), (1000000, 16)):
+            sb, se = shard_range(total, world, rank, granule)
+            assert sb % granule == 0 and (se - sb) * world >= total - granule * world
+            size = (total + world - 1) // world + granule
+            mine = torch.full((size,), -1, dtype=torch.int64); mine[:se - sb] = torch.arange(sb, se)
+            parts = [torch.empty(size, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            whole = torch.cat([p_[p_ >= 0] for p_ in parts])
+            assert torch.equal(whole, torch.arange(total)), (total, granule)
         q.put((rank, units, ms, float(t.item())))
     finally:
         dist.destroy_process_group()

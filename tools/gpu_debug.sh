@@ -1,5 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "=== pool tests"; timeout -s KILL 400 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x -k "pool" > gpurun_out/test_gemm_gpu.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/test_gemm_gpu.log
-echo "=== mode R"; for is in 2 1 2 1; do LIBXSMM_B200_TC_POOL_ISSUERS=$is timeout -s KILL 300 python bench.py --workload brgemm_r --steps 10 > gpurun_out/bench_r_$is.json 2> gpurun_out/bench_r.err; echo "issuers $is rc=$?"; tail -2 gpurun_out/bench_r.err; cut -c130-250 gpurun_out/bench_r_$is.json; done
-echo "=== ncu mode R"; timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:gemm_pool -s 2 -c 1 -f -o gpurun_out/prof_tc_pool2 python bench.py --workload brgemm_r --steps 3 > gpurun_out/ncu_r.log 2>&1; echo "rc=$?"
+echo "=== tc tests"; timeout -s KILL 600 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x -k "tcgen05 or multi_device or plan or pipeline" > gpurun_out/test_gemm_gpu.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/test_gemm_gpu.log
+echo "=== sweep"; for pk in 1 0; do LIBXSMM_B200_TC_PACK=$pk timeout -s KILL 300 python bench.py --workload sweep --steps 10 > gpurun_out/bench_sweep_$pk.json 2> gpurun_out/bench_sweep_$pk.err; echo "pack $pk rc=$?"; tail -3 gpurun_out/bench_sweep_$pk.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_sweep_$pk.json'))
+for p in d['points']:
+    if p['type'].startswith('f16'): print({a:(round(b,4) if isinstance(b,float) else b) for a,b in p.items() if a in ('type','m','ms','hbm_frac','backend','error')})
+PY
+done
