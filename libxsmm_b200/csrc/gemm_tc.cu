@@ -127,8 +127,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16
 
 // WIDE = false: 192 threads, registers capped so that six CTAs share an SM (the latency-bound small-load shapes need that);
 // WIDE = true: 320 threads (eight epilogue warps) for the one-CTA-per-SM configurations
-template <int UM, bool WIDE>
-__global__ void __launch_bounds__(WIDE ? 320 : 192, WIDE ? 1 : 6)
+// CT = minimum co-resident CTAs the register budget must allow: 6 (56 registers, small spills) only for the shapes that really run
+// five or six CTAs per SM, 4 (80 registers, no spills) for the rest of the 192-thread configurations, 1 for the wide form
+template <int UM, bool WIDE, int CT>
+__global__ void __launch_bounds__(WIDE ? 320 : 192, CT)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int TPS = (UM == 64) ? 2 : 1;          // tiles per TMEM slot
@@ -540,7 +542,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
-unsigned long long g_attr_set[4] = {0ull, 0ull, 0ull, 0ull};   // MaxDynamicSharedMemorySize is a per-device attribute: one bit per device
+unsigned long long g_attr_set[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};   // MaxDynamicSharedMemorySize is a per-device attribute: one bit per device
 
 int tc_init_once() {
   if (g_encode == nullptr) {
@@ -751,19 +753,13 @@ static int tc_launch_common(const xb_gemm_launch* L, const xb_tc_pool* pool) {
   cudaError_t e;
   // one CTA per SM has nothing co-resident to hide its epilogue behind: give it 8 epilogue warps instead of 4
   const unsigned int threads = (unsigned int)env_int("LIBXSMM_B200_TC_THREADS", (ctas == 1 && P.np >= 64) ? 320 : 192) == 320u ? 320u : 192u;
-  if (UM == 64 && threads == 192u) {
-    if (xb_rt_first_use_on_device(&g_attr_set[0])) cudaFuncSetAttribute(gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    gemm_tc_kernel<64, false><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
-  } else if (UM == 64) {
-    if (xb_rt_first_use_on_device(&g_attr_set[2])) cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    gemm_tc_kernel<64, true><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
-  } else if (threads == 192u) {
-    if (xb_rt_first_use_on_device(&g_attr_set[1])) cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    gemm_tc_kernel<128, false><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
-  } else {
-    if (xb_rt_first_use_on_device(&g_attr_set[3])) cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    gemm_tc_kernel<128, true><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P);
-  }
+#define XB_TC_LAUNCH(SLOT, ...) do { \
+    if (xb_rt_first_use_on_device(&g_attr_set[SLOT])) cudaFuncSetAttribute(gemm_tc_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+    gemm_tc_kernel<__VA_ARGS__><<<(unsigned int)grid, threads, smem, stream>>>(map_a, map_b, P); } while (0)
+  if (threads == 320u) { if (UM == 64) XB_TC_LAUNCH(0, 64, true, 1); else XB_TC_LAUNCH(1, 128, true, 1); }
+  else if (ctas > 4)   { if (UM == 64) XB_TC_LAUNCH(2, 64, false, 6); else XB_TC_LAUNCH(3, 128, false, 6); }
+  else                 { if (UM == 64) XB_TC_LAUNCH(4, 64, false, 4); else XB_TC_LAUNCH(5, 128, false, 4); }
+#undef XB_TC_LAUNCH
   xb_rt_count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) { xb_rt_note_error((int)e, "gemm_tc"); return (int)e; }
