@@ -7,7 +7,12 @@
 // of libxsmm_ref_matmul (src/generator_gemm_reference_impl.c:2025-2170, 2367-2419) with f32
 // accumulation in tensor memory instead of a sequential scalar loop (tolerance, not bit-exact).
 //
-// Data flow per CTA (persistent, one CTA per SM, tiles assigned round-robin):
+// Kernels in this file:
+//   gemm_tc_kernel<UM, WIDE, CT>  the general form below (stride / no batch-reduce, and the ring form of pooled ADDRESS/OFFSET mode);
+//                                 1..6 CTAs per SM, chosen by the launcher from the number of loads per tile
+//   gemm_pool_kernel              pooled mode with whole operand sets resident in shared memory (mode R of the benchmark)
+//
+// Data flow per CTA of gemm_tc_kernel (persistent, tiles assigned round-robin):
 //   warp 0   TMA producer : cp.async.bulk.tensor.4d of one A k-chunk and one B k-chunk per stage,
 //                           SWIZZLE_128B, ring of STAGES stages guarded by full/empty mbarriers
 //   warp 1   MMA issuer   : one lane issues tcgen05.mma.cta_group::1.kind::f16 (K=16 per instruction)
@@ -20,7 +25,8 @@
 // SWIZZLE_128B layout directly from TMA (box inner extent 64 elements = 128 bytes).
 // For m <= 64 the M=64 instruction shape is used: its accumulator occupies lanes 0-15 of each 32-lane
 // TMEM quadrant, so two tiles share one slot (the second at lane offset 16) and one tcgen05.ld feeds
-// all 32 lanes of an epilogue warp.
+// all 32 lanes of an epilogue warp. Flat tiles with m = 16 or 32 are packed 4 or 2 per instruction (block-diagonal product, the
+// narrower swizzle modes describe the stacked A blocks); see tc_launch_common.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
