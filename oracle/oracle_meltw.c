@@ -4,9 +4,11 @@
  * src/generator_mateltwise_reference_impl.c, for the operations of SURVEY.md 8a (rows a5, a6) that the CUDA
  * library dispatches most: element-wise unary / binary / ternary maps with broadcast, the ReLU family with
  * bitmasks, compare / select / zip, row / column / to-scalar reductions (sum, sum of squares, max, min, absmax), all
- * layout transforms, gather / scatter, quantise / dequantise. Operations that are not restated return 2
- * and stay pinned by the reference itself (oracle/_ref). Pinned bit for bit against libxsmm_reference_elementwise
- * in tests/test_oracle_vs_ref.py (transcendental ops: same libm calls, so equal on the same host).
+ * layout transforms (incl. VNNI8 and the PAD forms), gather / scatter, quantise / dequantise (integer and the block-scaled MXFP4 / NVFP4 /
+ * MXBF8 formats), dropout with the reference's 16-lane generator, unzip / decomp, BF8 / HF8 element types, stochastic rounding to BF8, DUMP.
+ * Operations that are not restated return 2 and stay pinned by the reference itself (oracle/_ref). Pinned bit for bit -- outputs AND advanced
+ * generator states -- against libxsmm_reference_elementwise in tests/test_oracle_meltw.py (transcendental ops: same libm calls, so equal on the
+ * same host).
  *
  * Interface mirrors ref_meltw (oracle/ref_shim.c): desc = {op_class, op, flags, m, n, ldi, ldi2, ldi3, ldo,
  * t_in0, t_in1, t_in2, t_out, t_comp}, param = the reference's libxsmm_meltw_{unary,binary,ternary}_param.
