@@ -142,6 +142,24 @@
 #define LIBXSMM_SQRTF(A) sqrtf(A)
 #define LIBXSMM_ERFF(A) erff(A)
 #define LIBXSMM_FREXPF(A, B) frexpf(A, B)
+#define LIBXSMM_FABSF(A) fabsf(A)
+#define LIBXSMM_FABS(A) fabs(A)
+/* flag arithmetic on enumerations without C++ complaints: (type)(a | b)   (reference include/libxsmm_macros.h:650) */
+#define LIBXSMM_EOR(ENUM_TYPE, ENUM, FLAG) ((ENUM_TYPE)(((int)(ENUM)) | ((int)(FLAG))))
+/* evaluate an expression whose value is deliberately dropped (reference :1006-1013) */
+#define LIBXSMM_ELIDE_RESULT(TYPE, EXPR) do { TYPE libxsmm_b200_elided_ = (EXPR); LIBXSMM_UNUSED(libxsmm_b200_elided_); } while (0)
+#define LIBXSMM_EXPECT_ELIDE(EXPR) LIBXSMM_ELIDE_RESULT(int, EXPR)
+#define LIBXSMM_PUTENV(A) putenv(A)
+/* checked narrowing casts of the reference (include/libxsmm_macros.h:231-264): here plain casts (LP64, 32-bit blasint) */
+#define LIBXSMM_CAST_INT(VALUE) ((int)(VALUE))
+#define LIBXSMM_CAST_UINT(VALUE) ((unsigned int)(VALUE))
+#define LIBXSMM_CAST_LLONG(VALUE) ((long long)(VALUE))
+#define LIBXSMM_CAST_BLASINT(VALUE) ((libxsmm_blasint)(VALUE))
+#if defined(_OPENMP) && (201811 <= _OPENMP)
+# define LIBXSMM_OMP_MASKED _Pragma("omp masked")
+#else
+# define LIBXSMM_OMP_MASKED _Pragma("omp master")
+#endif
 #define LIBXSMM_SNPRINTF(S, N, ...) snprintf(S, N, __VA_ARGS__)
 #define LIBXSMM_PUT(ARRAY, I, V) ((ARRAY)[I] = (V))
 

@@ -99,7 +99,17 @@ LIBXSMM_API double libxsmm_dsqrt(double x);
 LIBXSMM_API float libxsmm_ssqrt(float x);
 
 /* ---- sequence generator (reference include/utils/libxsmm_math.h:17-31, src/libxsmm_rng.c): xoshiro128+ in 16 lanes -- */
+/* small math helpers of the reference's utility library (include/utils/libxsmm_math.h:54, include/libxsmm_math.h:267) */
+LIBXSMM_API float libxsmm_sexp2_i8(signed char x);      /* 2^x */
+LIBXSMM_API float libxsmm_sexp2_i8i(int x);             /* 2^x, -128 <= x <= 127 */
+LIBXSMM_API float libxsmm_nearbyintf(float x);
+LIBXSMM_API double libxsmm_nearbyint(double x);
 LIBXSMM_API void libxsmm_rng_set_seed(unsigned int seed);
+/* caller-owned generator state for DROPOUT / STOCHASTIC_ROUND kernels: 4 x 16 words, lane l seeded like libxsmm_rng_set_seed
+ * (reference include/libxsmm_math.h:222-231, src/libxsmm_rng.c:172-210) */
+LIBXSMM_API unsigned int* libxsmm_rng_create_extstate(unsigned int seed);
+LIBXSMM_API unsigned int libxsmm_rng_get_extstate_size(void);
+LIBXSMM_API void libxsmm_rng_destroy_extstate(unsigned int* stateptr);
 LIBXSMM_API void libxsmm_rng_f32_seq(float* rngs, libxsmm_blasint count);     /* uniform in [0, 1) */
 LIBXSMM_API unsigned int libxsmm_rng_u32(unsigned int n);                       /* uniform in [0, n) */
 LIBXSMM_API void libxsmm_rng_seq(void* data, size_t nbytes);
@@ -113,6 +123,8 @@ LIBXSMM_API void libxsmm_convert_bf16_f32(const libxsmm_bfloat16* in, float* out
 LIBXSMM_API void libxsmm_rne_convert_fp32_f16(const float* in, libxsmm_float16* out, size_t length);
 LIBXSMM_API void libxsmm_convert_f16_f32(const libxsmm_float16* in, float* out, size_t length);
 LIBXSMM_API void libxsmm_rne_convert_fp32_bf8(const float* in, libxsmm_bfloat8* out, size_t length);
+/* stochastic rounding with the 16-lane generator state (reference src/libxsmm_lpflt_quant.c:332-368) */
+LIBXSMM_API void libxsmm_stochastic_convert_fp32_bf8(const float* in, libxsmm_bfloat8* out, unsigned int len, void* rng_state, unsigned int start_seed_idx);
 LIBXSMM_API void libxsmm_convert_bf8_f32(const libxsmm_bfloat8* in, float* out, size_t length);
 LIBXSMM_API void libxsmm_rne_convert_fp32_hf8(const float* in, libxsmm_hfloat8* out, size_t length);
 LIBXSMM_API void libxsmm_convert_hf8_f32(const libxsmm_hfloat8* in, float* out, size_t length);

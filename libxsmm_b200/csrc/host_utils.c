@@ -257,6 +257,12 @@ LIBXSMM_API void libxsmm_matdiff_reduce(libxsmm_matdiff_info* output, const libx
   ++output->r;
 }
 
+/* ---- small math helpers (reference src/libxsmm_utils.c:218-252, src/libxsmm_math.c:980-999) --------------------------------- */
+LIBXSMM_API float libxsmm_sexp2_i8(signed char x) { return ldexpf(1.0f, (int)x); }
+LIBXSMM_API float libxsmm_sexp2_i8i(int x) { return ldexpf(1.0f, x < -128 ? -128 : (x > 127 ? 127 : x)); }
+LIBXSMM_API float libxsmm_nearbyintf(float x) { return nearbyintf(x); }
+LIBXSMM_API double libxsmm_nearbyint(double x) { return nearbyint(x); }
+
 /* ---- sequence generator ---------------------------------------------------------------------------------------- */
 static unsigned int g_rng[4][16];       /* xoshiro128+ : four state words x sixteen independent lanes */
 static int g_rng_seeded = 0;
@@ -267,9 +273,9 @@ static void xb_rng_step(unsigned int* s0, unsigned int* s1, unsigned int* s2, un
   *s3 = (*s3 << 11) | (*s3 >> 21);
 }
 
-LIBXSMM_API void libxsmm_rng_set_seed(unsigned int seed) {
-  /* lane l starts at (seed + 31-l, seed + 131-l, seed + 231-l, seed + 331-l) and is then advanced by 2^64 draws with the
-   * generator's jump polynomial, so that the lanes never overlap (reference src/libxsmm_rng.c:30-106) */
+/* lane l starts at (seed + 31-l, seed + 131-l, seed + 231-l, seed + 331-l) and is then advanced by 2^64 draws with the
+ * generator's jump polynomial, so that the lanes never overlap (reference src/libxsmm_rng.c:30-106); state[w * 16 + lane] */
+static void xb_rng_seed_lanes(unsigned int seed, unsigned int* state) {
   static const unsigned int jump[4] = { 0x8764000bu, 0xf542d2d3u, 0x6fa035c3u, 0x77f2db5bu };
   int lane, w, b;
   for (lane = 0; lane < 16; ++lane) {
@@ -279,8 +285,38 @@ LIBXSMM_API void libxsmm_rng_set_seed(unsigned int seed) {
       if (jump[w] & (1u << b)) { acc[0] ^= s[0]; acc[1] ^= s[1]; acc[2] ^= s[2]; acc[3] ^= s[3]; }
       xb_rng_step(&s[0], &s[1], &s[2], &s[3]);
     }
-    for (w = 0; w < 4; ++w) g_rng[w][lane] = acc[w];
+    for (w = 0; w < 4; ++w) state[w * 16 + lane] = acc[w];
   }
+}
+
+LIBXSMM_API unsigned int* libxsmm_rng_create_extstate(unsigned int seed) {
+  void* p = NULL;
+  if (0 != posix_memalign(&p, 64, 64 * sizeof(unsigned int))) return NULL;
+  xb_rng_seed_lanes(seed, (unsigned int*)p);
+  return (unsigned int*)p;
+}
+LIBXSMM_API unsigned int libxsmm_rng_get_extstate_size(void) { return (unsigned int)(64 * sizeof(unsigned int)); }
+LIBXSMM_API void libxsmm_rng_destroy_extstate(unsigned int* stateptr) { free(stateptr); }
+
+/* f32 -> bf8 with a random byte added below the kept bits (src/libxsmm_lpflt_quant.c:303-368): element j draws from lane
+ * (start_seed_idx + j % 16) % 16 of the caller's state (one xoshiro128++ step); f16-subnormal magnitudes round to nearest even, Inf/NaN pass */
+LIBXSMM_API void libxsmm_stochastic_convert_fp32_bf8(const float* in, libxsmm_bfloat8* out, unsigned int len, void* rng_state, unsigned int start_seed_idx) {
+  unsigned int* st = (unsigned int*)rng_state;
+  unsigned int i;
+  for (i = 0; i < len; ++i) {
+    const unsigned int lane = (start_seed_idx + (i % 16)) % 16;
+    const unsigned int sum = st[lane] + st[48 + lane], draw = ((sum << 7) | (sum >> 25)) + st[lane];
+    unsigned int h = libxsmm_convert_f32_to_f16(in[i]);
+    xb_rng_step(&st[lane], &st[16 + lane], &st[32 + lane], &st[48 + lane]);
+    if ((h & 0x7c00u) == 0x7c00u) { if (h & 0x03ffu) h |= 0x0200u; }
+    else if ((h & 0x7c00u) == 0u) h = (h + 0x7fu + ((h >> 8) & 1u)) & 0xffffu;
+    else h = (h + (draw >> 24)) & 0xffffu;
+    out[i] = (libxsmm_bfloat8)(h >> 8);
+  }
+}
+
+LIBXSMM_API void libxsmm_rng_set_seed(unsigned int seed) {
+  xb_rng_seed_lanes(seed, &g_rng[0][0]);
   srand(seed);                          /* the scalar draws below come from the C library, like the reference's */
   g_rng_seeded = 1;
 }

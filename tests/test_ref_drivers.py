@@ -26,6 +26,21 @@ DRIVERS = {
     "gemm_kernel_fused": "samples/xgemm/gemm_kernel_fused.c",
     "eltwise_unary_relu": "samples/eltwise/eltwise_unary_relu.c",
     "eltwise_unary_transform": "samples/eltwise/eltwise_unary_transform.c",
+    "eltwise_unary_simple": "samples/eltwise/eltwise_unary_simple.c",
+    "eltwise_binary_simple": "samples/eltwise/eltwise_binary_simple.c",
+    "eltwise_ternary_simple": "samples/eltwise/eltwise_ternary_simple.c",
+    "eltwise_unary_dropout": "samples/eltwise/eltwise_unary_dropout.c",
+    "eltwise_unary_gather_scatter": "samples/eltwise/eltwise_unary_gather_scatter.c",
+    "eltwise_unary_quantization": "samples/eltwise/eltwise_unary_quantization.c",
+    "eltwise_unary_quantization_to_mxbf8": "samples/eltwise/eltwise_unary_quantization_to_mxbf8.c",
+    "eltwise_unary_quantization_to_mxfp4": "samples/eltwise/eltwise_unary_quantization_to_mxfp4.c",
+    "eltwise_unary_quantization_to_nvfp4": "samples/eltwise/eltwise_unary_quantization_to_nvfp4.c",
+    "eltwise_unary_reduce": "samples/eltwise/eltwise_unary_reduce.c",
+    "equation_simple": "samples/equation/equation_simple.c",
+    "equation_relu": "samples/equation/equation_relu.c",
+    "equation_softmax": "samples/equation/equation_softmax.c",
+    "gimmik": "samples/xgemm_sparse_Ainregs/gimmik.c",
+    "gemm_kernel_parallel": "samples/xgemm/gemm_kernel_parallel.c",
 }
 
 
@@ -96,3 +111,36 @@ def test_spmm_kernel_driver_f32_and_int8():
     for types, vnni in ((("F32", "F32", "F32", "F32"), 0), (("U8", "I8", "I32", "I32"), 1)):
         p = _run("spmm_kernel", *types, 32, 128, 128, 8, 0.5, 16 if types[0] == "F32" else 32, 16, 1, 0, 0, vnni, 0, 0, 2)
         assert p.returncode == 0, (types, p.stdout[-1500:], p.stderr[-800:])
+
+
+# (driver, arguments) sets that the unmodified reference drivers accept and PASS by their own criteria on the B200
+# (profiles/r02_reference_drivers_run.txt is the log of exactly these invocations)
+ELTWISE_RUNS = [
+    ("eltwise_unary_simple", (1, 0, "F32", "F32", "F32", 37, 11, 40, 40, 0)), ("eltwise_unary_simple", (2, 0, "F32", "F32", "F32", 37, 11, 40, 40, 0)),
+    ("eltwise_unary_simple", (3, 0, "F32", "F32", "F32", 37, 11, 40, 40, 0)), ("eltwise_unary_simple", (11, 0, "F32", "F32", "F32", 37, 11, 40, 40, 0)),
+    ("eltwise_unary_simple", (1, 0, "BF16", "F32", "BF16", 64, 16, 64, 64, 0)), ("eltwise_unary_simple", (1, 0, "F32", "F32", "BF8", 64, 16, 64, 64, 0)),
+    ("eltwise_unary_simple", (1, 0, "F32", "F32", "BF8", 64, 16, 64, 64, 1)),      # rnd_mode 1: stochastic rounding with libxsmm_rng_create_extstate
+    ("eltwise_unary_simple", (1, 1, "F32", "F32", "F32", 32, 32, 32, 32, 0)),
+    ("eltwise_binary_simple", (1, 0, "F32", "F32", "F32", "F32", 37, 11, 40, 40)), ("eltwise_binary_simple", (2, 0, "F32", "F32", "F32", "F32", 37, 11, 40, 40)),
+    ("eltwise_binary_simple", (3, 0, "F32", "F32", "F32", "F32", 37, 11, 40, 40)), ("eltwise_binary_simple", (4, 0, "F32", "F32", "F32", "F32", 37, 11, 40, 40)),
+    ("eltwise_binary_simple", (1, 3, "BF16", "BF16", "F32", "BF16", 64, 16, 64, 64)),
+    ("eltwise_unary_dropout", ("F", 1, "F32", "F32", 64, 16, 64, 64)), ("eltwise_unary_dropout", ("B", 1, "F32", "F32", 64, 16, 64, 64)),
+    ("eltwise_unary_dropout", ("F", 0, "BF16", "BF16", 33, 7, 40, 40)),
+    ("eltwise_unary_gather_scatter", (64, 32, 80, 64, 0, 0, 0, 0, 1)), ("eltwise_unary_gather_scatter", (64, 32, 64, 80, 1, 1, 1, 1, 1)),
+    ("eltwise_unary_quantization", ("F32", "I8", 64, 16, 64, 64, 0, 0)), ("eltwise_unary_quantization", ("F32", "I16", 33, 7, 40, 40, 0, 1)),
+    ("eltwise_unary_quantization_to_mxbf8", (64, 16, 64, 64)), ("eltwise_unary_quantization_to_mxfp4", (64, 16, 64, 64)),
+    ("eltwise_unary_quantization_to_nvfp4", (64, 16, 64, 64)),
+    ("eltwise_unary_reduce", (64, 32, 64, 1, 0, 0, 0, "F32", 0, 0, 0, 0, 1)), ("eltwise_unary_reduce", (64, 32, 64, 1, 1, 1, 0, "F32", 0, 0, 0, 0, 1)),
+    ("eltwise_unary_reduce", (64, 32, 64, 1, 0, 0, 1, "F32", 0, 0, 1, 0, 1)),
+    ("equation_simple", (64, 32)),
+]
+
+
+@pytest.mark.gpu
+def test_eltwise_and_equation_drivers_pass_by_their_own_criteria():
+    """samples/eltwise/*.c and samples/equation/equation_simple.c: each driver computes its own scalar gold, compares with libxsmm_matdiff
+    or bit for bit (quantisers, masks) and returns EXIT_FAILURE on a mismatch"""
+    for name, args in ELTWISE_RUNS:
+        p = _run(name, *args, timeout=120)
+        assert p.returncode == 0, (name, args, p.stdout[-800:], p.stderr[-400:])
+        assert "FAILURE" not in p.stdout.upper(), (name, args, p.stdout[-800:])
