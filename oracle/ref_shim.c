@@ -393,6 +393,17 @@ REF_API void ref_rng(unsigned int seed, float* f32_seq, int n32, double* f64_seq
   for (i = 0; i < n64; ++i) f64_seq[i] = libxsmm_rng_f64();
   for (i = 0; i < nu; ++i) u32_seq[i] = libxsmm_rng_u32(u_range);
 }
+/* external generator state, stochastic bf8 conversion and the small math helpers the eltwise drivers call */
+REF_API void ref_extstate(unsigned int seed, unsigned int* out64) {
+  unsigned int* st = libxsmm_rng_create_extstate(seed);
+  memcpy(out64, st, libxsmm_rng_get_extstate_size());
+  libxsmm_rng_destroy_extstate(st);
+}
+REF_API void ref_stochastic_bf8(const float* in, unsigned char* out, unsigned int len, unsigned int* state64, unsigned int start_idx) {
+  libxsmm_stochastic_convert_fp32_bf8(in, (libxsmm_bfloat8*)out, len, state64, start_idx);
+}
+REF_API float ref_sexp2_i8i(int x) { return libxsmm_sexp2_i8i(x); }
+REF_API float ref_nearbyintf(float x) { return libxsmm_nearbyintf(x); }
 REF_API void ref_lp_convert(int which, const void* in, void* out, unsigned long long n) {
   switch (which) {
     case 0: libxsmm_rne_convert_fp32_bf8((const float*)in, (libxsmm_bfloat8*)out, (size_t)n); break;

@@ -128,6 +128,34 @@ def test_rng_conversions_and_matinit_match_reference():
         fn = getattr(L, name); fn.restype, fn.argtypes = None, [_P, _P, C.c_size_t]
         fn(src.ctypes.data, got.ctypes.data, len(src))
         assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), name
+    # external generator state (DROPOUT / STOCHASTIC_ROUND callers), stochastic bf8 conversion, 2^x and nearbyint helpers
+    ref_lib.ref_extstate.restype, ref_lib.ref_extstate.argtypes = None, [C.c_uint, _P]
+    L.libxsmm_rng_create_extstate.restype, L.libxsmm_rng_create_extstate.argtypes = C.POINTER(C.c_uint), [C.c_uint]
+    L.libxsmm_rng_destroy_extstate.restype, L.libxsmm_rng_destroy_extstate.argtypes = None, [C.POINTER(C.c_uint)]
+    L.libxsmm_rng_get_extstate_size.restype = C.c_uint
+    assert L.libxsmm_rng_get_extstate_size() == 256
+    for seed in (0, 1, 555, 0xfffffff0):
+        want = np.zeros(64, dtype=np.uint32); ref_lib.ref_extstate(seed, want.ctypes.data)
+        st = L.libxsmm_rng_create_extstate(seed)
+        got = np.ctypeslib.as_array(st, shape=(64,)).copy(); L.libxsmm_rng_destroy_extstate(st)
+        assert np.array_equal(got, want), seed
+    ref_lib.ref_stochastic_bf8.restype, ref_lib.ref_stochastic_bf8.argtypes = None, [_P, _P, C.c_uint, _P, C.c_uint]
+    L.libxsmm_stochastic_convert_fp32_bf8.restype, L.libxsmm_stochastic_convert_fp32_bf8.argtypes = None, [_P, _P, C.c_uint, _P, C.c_uint]
+    for n_, start in ((1, 0), (1, 13), (37, 5), (4016, 0)):
+        x = f[:n_].copy()
+        s_r = ((np.arange(64, dtype=np.uint64) * 2654435761 + 12345) % (2 ** 32)).astype(np.uint32); s_o = s_r.copy()
+        o_r = np.zeros(n_, dtype=np.uint8); o_o = np.zeros(n_, dtype=np.uint8)
+        ref_lib.ref_stochastic_bf8(x.ctypes.data, o_r.ctypes.data, n_, s_r.ctypes.data, start)
+        L.libxsmm_stochastic_convert_fp32_bf8(x.ctypes.data, o_o.ctypes.data, n_, s_o.ctypes.data, start)
+        assert np.array_equal(o_o, o_r) and np.array_equal(s_o, s_r), (n_, start)
+    ref_lib.ref_sexp2_i8i.restype, ref_lib.ref_sexp2_i8i.argtypes = C.c_float, [_I]
+    L.libxsmm_sexp2_i8i.restype, L.libxsmm_sexp2_i8i.argtypes = C.c_float, [_I]
+    for e in range(-128, 128):
+        assert L.libxsmm_sexp2_i8i(e) == ref_lib.ref_sexp2_i8i(e), e
+    ref_lib.ref_nearbyintf.restype, ref_lib.ref_nearbyintf.argtypes = C.c_float, [C.c_float]
+    L.libxsmm_nearbyintf.restype, L.libxsmm_nearbyintf.argtypes = C.c_float, [C.c_float]
+    for v in (0.5, 1.5, 2.5, -0.5, -1.5, 3.49999, 1e9, -7.5000001):
+        assert L.libxsmm_nearbyintf(v) == ref_lib.ref_nearbyintf(v), v
     # coprime2 and the drivers' fill macro (compiled from OUR header)
     ref_lib.ref_coprime2.restype, ref_lib.ref_coprime2.argtypes = C.c_ulonglong, [C.c_ulonglong]
     L.libxsmm_coprime2.restype, L.libxsmm_coprime2.argtypes = C.c_size_t, [C.c_size_t]
