@@ -171,6 +171,9 @@ static int check_nodes(const xb_eqn* e, int at) {
   const xb_eqn_node* nd = &e->node[at]; int c; xb_meltw_desc d;
   if (nd->type == EQ_ARG) return 0;
   for (c = 0; c < arity(nd->type); ++c) if (check_nodes(e, nd->child[c]) != 0) return 1;
+  /* a relu's bit mask has one destination, output.secondary: only the head may produce it (reference :39-56) */
+  if (at != 0 && nd->type == EQ_UNARY && (nd->flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0
+      && (nd->op == LIBXSMM_MELTW_TYPE_UNARY_RELU || nd->op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU || nd->op == LIBXSMM_MELTW_TYPE_UNARY_ELU)) return 1;
   node_desc(e, at, &d);
   return xb_meltw_supported(&d) ? 0 : 1;
 }
@@ -200,9 +203,29 @@ LIBXSMM_API libxsmm_meqn_function libxsmm_dispatch_meqn(const libxsmm_blasint id
 void xb_meqn_release(void* work) { free(work); }
 
 /* ---- evaluation --------------------------------------------------------------------------------------------------- */
-typedef struct xb_eval { const xb_eqn* e; const libxsmm_meqn_param* p; void* out_dev; int failed; } xb_eval;
+typedef struct xb_eval {
+  const xb_eqn* e; const libxsmm_meqn_param* p; void* out_dev; int failed;
+  struct { void* host; void* dev; size_t bytes; } back[4]; int nback;   /* secondary outputs staged for host callers */
+} xb_eval;
 
 static size_t span(const xb_eqn_node* nd) { return ((size_t)(nd->n - 1) * nd->ld + nd->m) * libxsmm_typesize((libxsmm_datatype)nd->dtype); }
+
+/* a secondary output (relu bit mask, dump copy): device pointers pass through, host memory is staged in and copied back at the end */
+static void* eval_aux_out(xb_eval* ev, void* user, size_t bytes) {
+  void* d;
+  if (user == NULL || bytes == 0) { ev->failed = 1; return NULL; }
+  if (xb_rt_ptr_kind(user) != 0) return user;
+  if (ev->nback >= (int)(sizeof(ev->back) / sizeof(ev->back[0]))) { ev->failed = 1; return NULL; }
+  d = xb_rt_scratch(bytes);
+  if (d == NULL) { ev->failed = 1; return NULL; }
+  xb_rt_upload(d, user, bytes);
+  ev->back[ev->nback].host = user; ev->back[ev->nback].dev = d; ev->back[ev->nback].bytes = bytes; ev->nback++;
+  return d;
+}
+static int has_bitmask_out(const xb_eqn_node* nd) {
+  return nd->type == EQ_UNARY && (nd->flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0
+      && (nd->op == LIBXSMM_MELTW_TYPE_UNARY_RELU || nd->op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU || nd->op == LIBXSMM_MELTW_TYPE_UNARY_ELU);
+}
 
 static const void* eval_node(xb_eval* ev, int at, int is_root) {
   const xb_eqn_node* nd = &ev->e->node[at];
@@ -210,13 +233,19 @@ static const void* eval_node(xb_eval* ev, int at, int is_root) {
     const void* hp = ev->p->inputs[nd->pos].primary;
     if (hp == NULL) { ev->failed = 1; return NULL; }
     if (xb_rt_ptr_kind(hp) != 0) return hp;
+    { int i;   /* host memory an earlier node of this evaluation wrote as its secondary output (softmax: DUMP -> tmp -> operand) */
+      for (i = 0; i < ev->nback; ++i) if (ev->back[i].host == hp && ev->back[i].bytes >= span(nd)) return ev->back[i].dev; }
     { void* d = xb_rt_scratch(span(nd)); if (d == NULL) { ev->failed = 1; return NULL; } xb_rt_upload(d, hp, span(nd)); return d; }
   } else {
     xb_meltw_desc d; xb_meltw_args a; void* out;
+    const void* in[3] = { NULL, NULL, NULL }; int c, pass;
     memset(&a, 0, sizeof(a));
-    a.in0 = eval_node(ev, nd->child[0], 0);
-    if (nd->type != EQ_UNARY) a.in1 = eval_node(ev, nd->child[1], 0);
-    if (nd->type == EQ_TERNARY) a.in2 = eval_node(ev, nd->child[2], 0);
+    /* operand subtrees first, plain arguments last: the reference reads an argument when the consuming node executes, i.e. after
+     * every operation below that node has run (and possibly written the argument's memory through a DUMP) */
+    for (pass = 0; pass < 2; ++pass) for (c = 0; c < arity(nd->type); ++c) {
+      if ((ev->e->node[nd->child[c]].type == EQ_ARG) == (pass == 1)) in[c] = eval_node(ev, nd->child[c], 0);
+    }
+    a.in0 = in[0]; a.in1 = in[1]; a.in2 = in[2];
     if (ev->failed) return NULL;
     out = is_root ? ev->out_dev : xb_rt_scratch(span(nd) ? span(nd) : 16);
     if (out == NULL) { ev->failed = 1; return NULL; }
@@ -228,6 +257,15 @@ static const void* eval_node(xb_eval* ev, int at, int is_root) {
         if (xb_rt_ptr_kind(op1) == 1) xb_rt_memcpy(&a.alpha, op1, sizeof(float)); else a.alpha = *(const float*)op1;
       }
     }
+    /* secondary outputs as the reference wires them (generator_matequation_reference_impl.c:39-61): the bit mask of a relu at
+     * the head goes to output.secondary, a DUMP node copies its value to its ops_args slot */
+    if (has_bitmask_out(nd)) {
+      if (!is_root) { ev->failed = 1; return NULL; }
+      a.out_aux = eval_aux_out(ev, ev->p->output.secondary, (size_t)LIBXSMM_UP(d.ldo, 16) / 8 * (size_t)d.n);
+    } else if (nd->type == EQ_UNARY && nd->op == LIBXSMM_MELTW_TYPE_UNARY_DUMP) {
+      a.out_aux = eval_aux_out(ev, (ev->p->ops_args != NULL && nd->pos >= 0) ? ev->p->ops_args[nd->pos].primary : NULL, span(nd));
+    }
+    if (ev->failed) return NULL;
     if (0 != xb_meltw_launch(&d, &a)) ev->failed = 1;
     return out;
   }
@@ -236,10 +274,10 @@ static const void* eval_node(xb_eval* ev, int at, int is_root) {
 void xb_invoke_meqn(const xb_slot* s, const void* param) {
   const xb_eqn_plan* plan = (const xb_eqn_plan*)s->u.sp.work;
   const libxsmm_meqn_param* p = (const libxsmm_meqn_param*)param;
-  xb_eval ev; void* host_out = NULL; size_t out_bytes;
+  xb_eval ev; void* host_out = NULL; size_t out_bytes; int i;
   if (plan == NULL || p == NULL || p->output.primary == NULL) return;
   out_bytes = ((size_t)(plan->out_n - 1) * plan->out_ld + plan->out_m) * libxsmm_typesize((libxsmm_datatype)plan->out_type);
-  ev.e = &plan->eqn; ev.p = p; ev.failed = 0; ev.out_dev = p->output.primary;
+  ev.e = &plan->eqn; ev.p = p; ev.failed = 0; ev.nback = 0; ev.out_dev = p->output.primary;
   if (xb_rt_ptr_kind(p->output.primary) == 0) {            /* host output: staged in and out (partial writes keep the padding) */
     host_out = p->output.primary; ev.out_dev = xb_rt_scratch(out_bytes);
     if (ev.out_dev == NULL) { xb_rt_note_error(2, "meqn: out of scratch"); return; }
@@ -248,6 +286,7 @@ void xb_invoke_meqn(const xb_slot* s, const void* param) {
   (void)eval_node(&ev, 0, 1);
   if (ev.failed) { xb_rt_note_error(2, "meqn: evaluation failed"); xb_rt_scratch_reset(); return; }
   if (host_out != NULL) xb_rt_memcpy_async(host_out, ev.out_dev, out_bytes);
+  for (i = 0; i < ev.nback; ++i) xb_rt_memcpy_async(ev.back[i].host, ev.back[i].dev, ev.back[i].bytes);
   xb_rt_sync(); xb_rt_scratch_reset();
 }
 

@@ -1,0 +1,103 @@
+/* TEST INFRASTRUCTURE ONLY -- never linked into libxsmm_b200.so.
+ *
+ * A stand-in for the CUDA side of the library (runtime.cu and the kernel launchers) so that the HOST logic above the kernels --
+ * equation trees (host_meqn.c), operand staging, dispatch rules -- can be exercised in the GPU-less build container:
+ * "device" memory is plain host memory, every elementwise launch is answered by the oracle (oracle/liboracle.so), GEMM and
+ * sparse launchers refuse. tests/test_hostsim.py links the host_*.o objects with this file into tests/c/_hostsim/libxsmm.so and
+ * runs the reference's unmodified equation drivers against it; what that validates is the order of evaluation, the shapes and
+ * leading dimensions handed to each node, and where secondary outputs land -- not any kernel. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../libxsmm_b200/csrc/xb_internal.h"
+#include "../../include/libxsmm.h"
+
+extern int oracle_meltw(const int* desc, void* param, int mode);
+
+/* ---- runtime ------------------------------------------------------------------------------------------------------------- */
+static __thread void* g_blocks[4096]; static __thread int g_nblocks = 0;
+static __thread int g_err = 0; static __thread char g_errs[256];
+static unsigned long long g_launches = 0;
+
+int xb_rt_device_count(void) { return 1; }
+int xb_rt_set_device(int ordinal) { return ordinal == 0 ? 0 : 1; }
+void xb_rt_set_stream(void* stream) { (void)stream; }
+void* xb_rt_stream(void) { return NULL; }
+void xb_rt_set_blocking(int on) { (void)on; }
+int xb_rt_blocking(void) { return 1; }
+int xb_rt_sync(void) { return 0; }
+int xb_rt_last_error(void) { const int e = g_err; g_err = 0; return e; }
+const char* xb_rt_last_error_string(void) { return g_errs; }
+void xb_rt_note_error(int code, const char* where) { g_err = code; snprintf(g_errs, sizeof(g_errs), "%s", where); fprintf(stderr, "hostsim: error %d: %s\n", code, where); }
+unsigned long long xb_rt_launch_count(void) { return g_launches; }
+void xb_rt_count_launch(void) { ++g_launches; }
+void* xb_rt_device_malloc(size_t size) { return malloc(size); }
+void xb_rt_device_free(void* p) { free(p); }
+void* xb_rt_host_malloc(size_t size) { return malloc(size); }
+void xb_rt_host_free(void* p) { free(p); }
+void* xb_rt_managed_malloc(size_t size) { return malloc(size); }
+void xb_rt_managed_free(void* p) { free(p); }
+int xb_rt_memcpy(void* dst, const void* src, size_t size) { memmove(dst, src, size); return 0; }
+int xb_rt_memcpy_async(void* dst, const void* src, size_t size) { memmove(dst, src, size); return 0; }
+int xb_rt_upload(void* dst_dev, const void* src_host, size_t size) { memmove(dst_dev, src_host, size); return 0; }
+int xb_rt_pipeline(long long nchunks, size_t max_a, size_t max_b, size_t max_c, xb_pipe_describe_fn describe, xb_pipe_launch_fn launch, void* ctx) {
+  (void)nchunks; (void)max_a; (void)max_b; (void)max_c; (void)describe; (void)launch; (void)ctx; return 1;
+}
+int xb_rt_ptr_kind(const void* p) { (void)p; return 0; }      /* every caller pointer is "pageable host": the staging paths run */
+int xb_rt_have_gpu(void) { return 1; }
+void* xb_rt_scratch(size_t bytes) {
+  void* p;
+  if (g_nblocks >= 4096) return NULL;
+  p = calloc(1, bytes ? bytes : 1);
+  if (p != NULL) g_blocks[g_nblocks++] = p;
+  return p;
+}
+void xb_rt_scratch_reset(void) { while (g_nblocks > 0) free(g_blocks[--g_nblocks]); }
+int xb_rt_current_device(void) { return 0; }
+int xb_rt_first_use_on_device(unsigned long long* mask) { const int first = (*mask & 1ull) == 0; *mask |= 1ull; return first; }
+
+/* ---- launchers ----------------------------------------------------------------------------------------------------------- */
+int xb_gemm_simt_supported(const xb_gemm_desc* d) { (void)d; return 0; }
+int xb_gemm_simt_launch(const xb_gemm_launch* L) { (void)L; return 1; }
+int xb_gemm_tc_supported(const xb_gemm_desc* d) { (void)d; return 0; }
+int xb_gemm_tc_shape_ok(const xb_gemm_desc* d) { (void)d; return 0; }
+int xb_gemm_tc_launch(const xb_gemm_launch* L) { (void)L; return 1; }
+int xb_gemm_tc_launch_pooled(const xb_gemm_desc* d, const xb_tc_pool* pool, unsigned long long br, long long count) { (void)d; (void)pool; (void)br; (void)count; return 1; }
+int xb_gemm_ts_supported(const xb_gemm_desc* d) { (void)d; return 0; }
+int xb_gemm_ts_launch(const xb_gemm_launch* L) { (void)L; return 1; }
+int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_total) { (void)d; (void)b; (void)c; (void)n_total; return 1; }
+int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const void* b, void* c, long long count, long long sa, long long sb, long long sc) {
+  (void)d; (void)a; (void)b; (void)c; (void)count; (void)sa; (void)sb; (void)sc; return 1;
+}
+int xb_bcsc_launch(xb_sparse_desc* d, const void* a, const void* b_vals, const unsigned int* colptr, const unsigned int* rowidx,
+                   unsigned long long n_blocks, unsigned int nnzb, void* c) {
+  (void)d; (void)a; (void)b_vals; (void)colptr; (void)rowidx; (void)n_blocks; (void)nnzb; (void)c; return 1;
+}
+int xb_bcsc_tc_variant(const xb_sparse_desc* d, unsigned long long n_blocks) { (void)d; (void)n_blocks; return 0; }
+void xb_bcsc_state_free(void* work) { (void)work; }
+
+/* elementwise: the oracle answers. Only the argument forms an equation node uses are mapped (operands, output, the two
+ * secondaries, the scalar of LEAKY_RELU/ELU); everything else is refused so that a test cannot pass by accident */
+int xb_meltw_supported(const xb_meltw_desc* d) { return d->m > 0 && d->n > 0; }
+int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
+  int desc[14]; int rc; float alpha = a->alpha;
+  desc[0] = d->op_class; desc[1] = d->op; desc[2] = (int)d->flags; desc[3] = d->m; desc[4] = d->n; desc[5] = d->ldi; desc[6] = d->ldi2; desc[7] = d->ldi3;
+  desc[8] = d->ldo; desc[9] = d->t_in0; desc[10] = d->t_in1; desc[11] = d->t_in2; desc[12] = d->t_out; desc[13] = d->t_comp;
+  if (a->rng != NULL || a->rnd8 != NULL || a->n_rt != 0) return 1;
+  ++g_launches;
+  if (d->op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
+    libxsmm_meltw_unary_param p; memset(&p, 0, sizeof(p));
+    p.in.primary = (void*)(uintptr_t)a->in0; p.in.secondary = (void*)(uintptr_t)a->in_aux; p.out.primary = a->out; p.out.secondary = a->out_aux; p.op.primary = &alpha;
+    rc = oracle_meltw(desc, &p, 0);
+  } else if (d->op_class == LIBXSMM_MELTW_OPERATION_BINARY) {
+    libxsmm_meltw_binary_param p; memset(&p, 0, sizeof(p));
+    p.in0.primary = (void*)(uintptr_t)a->in0; p.in1.primary = (void*)(uintptr_t)a->in1; p.out.primary = a->out;
+    rc = oracle_meltw(desc, &p, 0);
+  } else {
+    libxsmm_meltw_ternary_param p; memset(&p, 0, sizeof(p));
+    p.in0.primary = (void*)(uintptr_t)a->in0; p.in1.primary = (void*)(uintptr_t)a->in1; p.in2.primary = (void*)(uintptr_t)a->in2; p.out.primary = a->out;
+    rc = oracle_meltw(desc, &p, 0);
+  }
+  if (rc != 0) fprintf(stderr, "hostsim: the oracle does not restate class %d op %d (rc %d)\n", d->op_class, d->op, rc);
+  return rc;
+}

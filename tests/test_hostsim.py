@@ -1,0 +1,177 @@
+"""Host logic of the matrix equations (libxsmm_b200/csrc/host_meqn.c) exercised WITHOUT a GPU.
+
+The host_*.c sources are linked with tests/c/hostsim_runtime.c -- a stand-in for runtime.cu and the kernel launchers in which
+"device" memory is host memory and every elementwise launch is answered by the oracle -- into tests/c/_hostsim/libxsmm.so (test
+infrastructure, never shipped). What this checks is the part of an equation that is not a kernel: the order nodes run in, the
+shape / leading dimension / type each node is launched with, where secondary outputs land (reference
+src/generator_matequation_reference_impl.c:16-61: the bit mask of a relu at the head -> output.secondary, a DUMP node ->
+ops_args[pos].primary) and that an argument is read when its consumer runs (a DUMP below may have written it: the softmax sample).
+Kernels are validated on the GPU in test_meqn.py / test_meltw_gpu.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import gen
+import libxsmm_b200 as X          # constants and struct layouts only: every call below goes to the simulation library
+from test_meqn import EQUATIONS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "libxsmm_b200", "csrc")
+OUT = os.path.join(ROOT, "tests", "c", "_hostsim")
+DRV = os.path.join(ROOT, "tests", "c", "_drivers")
+ORACLE = os.path.join(ROOT, "oracle")
+F32, BF16 = gen.F32, gen.BF16
+HOST_C = ["host_core.c", "host_thunks.c", "host_sparse.c", "host_meltw.c", "host_utils.c", "host_meqn.c"]
+
+
+def build_sim():
+    os.makedirs(OUT, exist_ok=True)
+    if not os.path.exists(os.path.join(ORACLE, "liboracle.so")):
+        subprocess.check_call(["make", "-C", ROOT, "oracle"])
+    so = os.path.join(OUT, "libxsmm.so")
+    srcs = [os.path.join(CSRC, f) for f in HOST_C] + [os.path.join(ROOT, "tests", "c", "hostsim_runtime.c")]
+    if os.path.exists(so) and all(os.path.getmtime(s) < os.path.getmtime(so) for s in srcs + [os.path.join(CSRC, "xb_internal.h")]):
+        return so
+    cmd = ["gcc", "-O1", "-std=gnu99", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-o", so] + srcs + \
+          ["-L" + ORACLE, "-loracle", "-Wl,-rpath," + ORACLE, "-lpthread", "-ldl", "-lm"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]
+    return so
+
+
+class Sim:
+    def __init__(self):
+        self.lib = C.CDLL(build_sim())
+        I, U, P = C.c_int, C.c_uint, C.c_void_p
+        for name, res, args in (
+                ("libxsmm_meqn_create", I, []), ("libxsmm_create_meqn_arg_shape", X.MeqnArgShape, [I] * 4),
+                ("libxsmm_create_matrix_arg_attributes", X.MatrixArgAttributes, [I] * 4),
+                ("libxsmm_create_meqn_arg_metadata", X.MeqnMetadata, [I, I]), ("libxsmm_create_meqn_op_metadata", X.MeqnMetadata, [I, I]),
+                ("libxsmm_meqn_push_back_arg", I, [X.MeqnMetadata, X.MeqnArgShape, X.MatrixArgAttributes]),
+                ("libxsmm_meqn_push_back_unary_op", I, [X.MeqnMetadata, I, I, U]), ("libxsmm_meqn_push_back_binary_op", I, [X.MeqnMetadata, I, I, U]),
+                ("libxsmm_meqn_push_back_ternary_op", I, [X.MeqnMetadata, I, I, U]), ("libxsmm_dispatch_meqn", P, [I, X.MeqnArgShape])):
+            fn = getattr(self.lib, name); fn.restype = res; fn.argtypes = args
+            setattr(self, name[len("libxsmm_"):], fn)
+
+    def build(self, nodes):
+        """nodes in pre-order: ('arg', pos, m, n, ld, dtype) | ('u'|'b'|'t', op, dtype, flags[, op_arg_pos])"""
+        eq = self.meqn_create()
+        for nd in nodes:
+            if nd[0] == "arg":
+                rc = self.meqn_push_back_arg(self.create_meqn_arg_metadata(eq, nd[1]), self.create_meqn_arg_shape(*nd[2:6]), self.create_matrix_arg_attributes(0, 0, 0, 0))
+            else:
+                fn = {"u": self.meqn_push_back_unary_op, "b": self.meqn_push_back_binary_op, "t": self.meqn_push_back_ternary_op}[nd[0]]
+                rc = fn(self.create_meqn_op_metadata(eq, nd[4] if len(nd) > 4 else -1), nd[1], nd[2], nd[3])
+            assert rc == 0, nd
+        return eq
+
+    def run(self, fn, ins, out, out_secondary=None, ops=None):
+        args = (X.MatrixArg * max(1, len(ins)))()
+        for i, x in enumerate(ins):
+            args[i].primary = x.ctypes.data
+        opa = (X.MatrixOpArg * 32)()
+        for pos, buf in (ops or {}).items():
+            opa[pos].primary = buf.ctypes.data
+        p = X.MeqnParam(); p.inputs = C.addressof(args); p.ops_args = C.addressof(opa); p.output.primary = out.ctypes.data
+        if out_secondary is not None:
+            p.output.secondary = out_secondary.ctypes.data
+        X.MEQN_FN(fn)(C.byref(p))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return Sim()
+
+
+@pytest.mark.parametrize("name", sorted(EQUATIONS))
+def test_equation_patterns_on_the_simulated_device(sim, name):
+    """the four trees of test_meqn.py (chain, broadcasts, reduction, ternary) from host buffers"""
+    rng = np.random.default_rng(97)
+    for (m, n) in ((32, 16), (13, 7)):
+        nodes, in_shapes, (om, on) = EQUATIONS[name](m, n)
+        ins = [(rng.standard_normal(a * b) * 0.5).astype(np.float32) for (a, b) in in_shapes]
+        A = [x.reshape(sh[1], sh[0]).T for x, sh in zip(ins, in_shapes)]
+        exact = {"chain": lambda: np.tanh(A[0] + A[1]) * A[2], "bcast": lambda: np.maximum(A[0] * A[1] + A[2], 0),
+                 "reduce": lambda: (A[0] * A[0]).sum(1, keepdims=True, dtype=np.float32), "ternary": lambda: A[0] - np.exp(A[1]) * A[2]}[name]()
+        want = np.ascontiguousarray(exact.T.astype(np.float32)).ravel()
+        fn = sim.dispatch_meqn(sim.build(nodes), sim.create_meqn_arg_shape(om, on, om, F32))
+        assert fn, name
+        out = np.zeros(om * on, dtype=np.float32)
+        sim.run(fn, ins, out)
+        assert np.allclose(out, want, rtol=2e-5, atol=2e-5), (name, m, n, np.abs(out - want).max())
+
+
+def test_relu_at_the_head_writes_its_bit_mask_to_the_secondary_output(sim):
+    """samples/equation/equation_relu.c: relu(bitmask) over (a + b + 1) - c; mask rows are padded to 16 bits"""
+    rng = np.random.default_rng(98)
+    for (m, n, ld, odt) in ((64, 32, 64, F32), (37, 5, 40, F32), (48, 7, 48, BF16)):
+        nodes = [("u", X.MELTW_TYPE_UNARY_RELU, F32, X.MELTW_FLAG_UNARY_BITMASK_2BYTEMULT)] + \
+                ([("u", X.MELTW_TYPE_UNARY_IDENTITY, odt, 0)] if odt != F32 else []) + \
+                [("b", X.MELTW_TYPE_BINARY_SUB, F32, 0), ("u", X.MELTW_TYPE_UNARY_INC, F32, 0), ("b", X.MELTW_TYPE_BINARY_ADD, F32, 0),
+                 ("arg", 0, m, n, ld, F32), ("arg", 1, m, n, ld, F32), ("arg", 2, m, n, ld, F32)]
+        ins = [rng.standard_normal(ld * n).astype(np.float32) for _ in range(3)]
+        fn = sim.dispatch_meqn(sim.build(nodes), sim.create_meqn_arg_shape(m, n, ld, odt))
+        assert fn
+        mask_ld = (ld + 15) // 16 * 2
+        out = np.full(ld * n, 7, dtype=gen.NP_OF[odt]); mask = np.zeros(mask_ld * n, dtype=np.uint8)
+        sim.run(fn, ins, out, out_secondary=mask)
+        v = [x.reshape(n, ld)[:, :m] for x in ins]
+        pre = ((v[0] + v[1]) + np.float32(1.0)) - v[2]
+        if odt == BF16:
+            u = pre.view(np.uint32).astype(np.uint64)          # the IDENTITY below the head rounds to bf16, nearest even
+            pre = (((u + 0x7fff + ((u >> 16) & 1)) >> 16) << 16).astype(np.uint32).view(np.float32)
+        got = gen.to_f64(out, odt).reshape(n, ld)
+        assert np.array_equal(got[:, :m], np.maximum(pre, 0).astype(np.float64)), (m, n, ld, odt)
+        assert np.all(out.reshape(n, ld)[:, m:] == 7), "the padding between columns is not written"
+        bits = np.unpackbits(mask.reshape(n, mask_ld), axis=1, bitorder="little")[:, :m]
+        assert np.array_equal(bits.astype(bool), pre > 0), (m, n, ld, odt)
+
+
+def test_a_bit_mask_below_the_head_is_refused(sim):
+    nodes = [("u", X.MELTW_TYPE_UNARY_INC, F32, 0), ("u", X.MELTW_TYPE_UNARY_RELU, F32, X.MELTW_FLAG_UNARY_BITMASK_2BYTEMULT), ("arg", 0, 16, 4, 16, F32)]
+    assert not sim.dispatch_meqn(sim.build(nodes), sim.create_meqn_arg_shape(16, 4, 16, F32))
+
+
+def test_dump_feeds_an_argument_of_the_same_equation(sim):
+    """samples/equation/equation_softmax.c:527-538: out = tmp * (1 / sum(DUMP->tmp(exp(x - max(x))))) where tmp is BOTH the DUMP
+    destination (ops_args[31]) and argument 0 of the head: the argument has to be read after the subtree below ran"""
+    rng = np.random.default_rng(99)
+    m, n, ld = 24, 6, 60
+    R, Cc = X.MELTW_FLAG_UNARY_REDUCE_ROWS, X.MELTW_FLAG_UNARY_REDUCE_COLS
+    S1 = X.MELTW_FLAG_BINARY_BCAST_SCALAR_IN_1
+    nodes = [("b", X.MELTW_TYPE_BINARY_MUL, F32, S1), ("arg", 0, m, n, m, F32), ("u", X.MELTW_TYPE_UNARY_RECIPROCAL, F32, 0),
+             ("u", X.MELTW_TYPE_UNARY_REDUCE_X_OP_ADD, F32, R), ("u", X.MELTW_TYPE_UNARY_REDUCE_X_OP_ADD, F32, Cc), ("u", X.MELTW_TYPE_UNARY_DUMP, F32, 0, 31),
+             ("u", X.MELTW_TYPE_UNARY_EXP, F32, 0), ("b", X.MELTW_TYPE_BINARY_SUB, F32, S1), ("arg", 1, m, n, ld, F32),
+             ("u", X.MELTW_TYPE_UNARY_REDUCE_X_OP_MAX, F32, R), ("u", X.MELTW_TYPE_UNARY_REDUCE_X_OP_MAX, F32, Cc), ("arg", 1, m, n, ld, F32)]
+    fn = sim.dispatch_meqn(sim.build(nodes), sim.create_meqn_arg_shape(m, n, ld, F32))
+    assert fn
+    x = rng.standard_normal(ld * n).astype(np.float32)
+    tmp = np.full(m * n, np.nan, dtype=np.float32)           # stale on entry: must not be what the head multiplies
+    out = np.zeros(ld * n, dtype=np.float32)
+    sim.run(fn, [tmp, x], out, ops={31: tmp})
+    xv = x.reshape(n, ld)[:, :m].astype(np.float64)
+    e = np.exp(xv - xv.max())
+    assert np.allclose(tmp.reshape(n, m), e, rtol=1e-5, atol=1e-6)
+    assert np.allclose(out.reshape(n, ld)[:, :m], e / e.sum(), rtol=1e-5, atol=1e-7)
+    assert np.all(out.reshape(n, ld)[:, m:] == 0)
+
+
+DRIVER_RUNS = [("equation_simple", (64, 32)), ("equation_relu", (64, 32)), ("equation_relu", (64, 32, 64, 1)), ("equation_relu", (37, 9, 48, 0)),
+               ("equation_softmax", (64, 32))]
+
+
+@pytest.mark.parametrize("name,args", DRIVER_RUNS)
+def test_reference_equation_drivers_against_the_simulated_device(name, args):
+    """the reference's unmodified samples/equation/*.c (prebuilt by test_ref_drivers.build_drivers) with the simulation library
+    first on the loader's path: each driver checks itself and returns EXIT_FAILURE on a mismatch"""
+    exe = os.path.join(DRV, name)
+    if not os.path.exists(exe):
+        pytest.skip("%s was not prebuilt (no reference tree in the build container?)" % name)
+    build_sim()
+    env = dict(os.environ, LD_LIBRARY_PATH=OUT + ":" + ORACLE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS="2")
+    p = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120, env=env, cwd=DRV)
+    assert p.returncode == 0, (name, args, p.stdout[-1200:], p.stderr[-600:])
+    assert "FAILURE" not in p.stdout.upper(), (name, args, p.stdout[-1200:])
