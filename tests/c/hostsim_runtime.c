@@ -43,7 +43,9 @@ int xb_rt_upload(void* dst_dev, const void* src_host, size_t size) { memmove(dst
 int xb_rt_pipeline(long long nchunks, size_t max_a, size_t max_b, size_t max_c, xb_pipe_describe_fn describe, xb_pipe_launch_fn launch, void* ctx) {
   (void)nchunks; (void)max_a; (void)max_b; (void)max_c; (void)describe; (void)launch; (void)ctx; return 1;
 }
-int xb_rt_ptr_kind(const void* p) { (void)p; return 0; }      /* every caller pointer is "pageable host": the staging paths run */
+/* every caller pointer is "pageable host" so that the staging paths run; XB_HOSTSIM_PTR_KIND=3 ("pinned") lets the operations
+ * that insist on device-accessible operands (gather / scatter, index reductions) through */
+int xb_rt_ptr_kind(const void* p) { const char* e = getenv("XB_HOSTSIM_PTR_KIND"); (void)p; return (e != NULL) ? atoi(e) : 0; }
 int xb_rt_have_gpu(void) { return 1; }
 void* xb_rt_scratch(size_t bytes) {
   void* p;
@@ -77,25 +79,28 @@ int xb_bcsc_tc_variant(const xb_sparse_desc* d, unsigned long long n_blocks) { (
 void xb_bcsc_state_free(void* work) { (void)work; }
 
 /* elementwise: the oracle answers. Only the argument forms an equation node uses are mapped (operands, output, the two
- * secondaries, the scalar of LEAKY_RELU/ELU); everything else is refused so that a test cannot pass by accident */
+ * secondaries, the scalar of LEAKY_RELU/ELU/QUANT/DROPOUT, the generator state); run-time extents are refused */
 int xb_meltw_supported(const xb_meltw_desc* d) { return d->m > 0 && d->n > 0; }
 int xb_meltw_launch(const xb_meltw_desc* d, const xb_meltw_args* a) {
   int desc[14]; int rc; float alpha = a->alpha;
   desc[0] = d->op_class; desc[1] = d->op; desc[2] = (int)d->flags; desc[3] = d->m; desc[4] = d->n; desc[5] = d->ldi; desc[6] = d->ldi2; desc[7] = d->ldi3;
   desc[8] = d->ldo; desc[9] = d->t_in0; desc[10] = d->t_in1; desc[11] = d->t_in2; desc[12] = d->t_out; desc[13] = d->t_comp;
-  if (a->rng != NULL || a->rnd8 != NULL || a->n_rt != 0) return 1;
+  if (a->n_rt != 0) return 1;
   ++g_launches;
   if (d->op_class == LIBXSMM_MELTW_OPERATION_UNARY) {
     libxsmm_meltw_unary_param p; memset(&p, 0, sizeof(p));
     p.in.primary = (void*)(uintptr_t)a->in0; p.in.secondary = (void*)(uintptr_t)a->in_aux; p.out.primary = a->out; p.out.secondary = a->out_aux; p.op.primary = &alpha;
+    p.op.secondary = a->rng;                 /* dropout / stochastic rounding: the staged generator state, advanced in place */
+    if ((d->op == LIBXSMM_MELTW_TYPE_UNARY_QUANT || d->op == LIBXSMM_MELTW_TYPE_UNARY_DEQUANT) && a->in_aux == NULL) p.in.secondary = &alpha;   /* the scale */
     rc = oracle_meltw(desc, &p, 0);
   } else if (d->op_class == LIBXSMM_MELTW_OPERATION_BINARY) {
     libxsmm_meltw_binary_param p; memset(&p, 0, sizeof(p));
-    p.in0.primary = (void*)(uintptr_t)a->in0; p.in1.primary = (void*)(uintptr_t)a->in1; p.out.primary = a->out;
+    p.in0.primary = (void*)(uintptr_t)a->in0; p.in1.primary = (void*)(uintptr_t)a->in1; p.out.primary = a->out; p.op.secondary = a->rng;
     rc = oracle_meltw(desc, &p, 0);
   } else {
     libxsmm_meltw_ternary_param p; memset(&p, 0, sizeof(p));
     p.in0.primary = (void*)(uintptr_t)a->in0; p.in1.primary = (void*)(uintptr_t)a->in1; p.in2.primary = (void*)(uintptr_t)a->in2; p.out.primary = a->out;
+    p.op.secondary = a->rng;
     rc = oracle_meltw(desc, &p, 0);
   }
   if (rc != 0) fprintf(stderr, "hostsim: the oracle does not restate class %d op %d (rc %d)\n", d->op_class, d->op, rc);

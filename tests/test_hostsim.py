@@ -159,6 +159,15 @@ def test_dump_feeds_an_argument_of_the_same_equation(sim):
     assert np.all(out.reshape(n, ld)[:, m:] == 0)
 
 
+# valid argument sets of samples/eltwise/eltwise_ternary_simple.c (SELECT with the implicit bit mask as third input; :399-417)
+TERNARY_RUNS = [("eltwise_ternary_simple", (1, 0, "F32", "F32", "IMPLICIT", "F32", "F32", 64, 16, 64, 64)),
+                ("eltwise_ternary_simple", (1, 0, "F32", "F32", "IMPLICIT", "F32", "F32", 37, 11, 48, 40)),
+                ("eltwise_ternary_simple", (1, 0, "BF16", "BF16", "IMPLICIT", "F32", "BF16", 64, 16, 64, 64)),
+                ("eltwise_ternary_simple", (1, 1, "F32", "F32", "IMPLICIT", "F32", "F32", 64, 16, 64, 64)),
+                ("eltwise_ternary_simple", (1, 5, "F32", "F32", "IMPLICIT", "F32", "F32", 64, 16, 64, 64)),
+                ("eltwise_ternary_simple", (1, 0, "F32", "BF8", "IMPLICIT", "F32", "BF8", 64, 16, 64, 64)),
+                ("eltwise_ternary_simple", (1, 0, "F32", "F32", "IMPLICIT", "F32", "BF8", 64, 16, 64, 64, 1))]
+
 DRIVER_RUNS = [("equation_simple", (64, 32)), ("equation_relu", (64, 32)), ("equation_relu", (64, 32, 64, 1)), ("equation_relu", (37, 9, 48, 0)),
                ("equation_softmax", (64, 32))]
 
@@ -175,3 +184,24 @@ def test_reference_equation_drivers_against_the_simulated_device(name, args):
     p = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120, env=env, cwd=DRV)
     assert p.returncode == 0, (name, args, p.stdout[-1200:], p.stderr[-600:])
     assert "FAILURE" not in p.stdout.upper(), (name, args, p.stdout[-1200:])
+
+
+def test_reference_eltwise_drivers_against_the_simulated_device():
+    """every (driver, arguments) pair of test_ref_drivers.ELTWISE_RUNS (the B200 pass list) plus the ternary driver, with host operands:
+    the staging rules of host_meltw.c (extents per operation, secondary operands, generator state in and out, padding kept) against
+    the oracle's answers. Gather / scatter insist on device-accessible operands, so those runs declare the memory pinned."""
+    from test_ref_drivers import ELTWISE_RUNS
+    build_sim()
+    ran = 0
+    for name, args in ELTWISE_RUNS + TERNARY_RUNS:
+        exe = os.path.join(DRV, name)
+        if not os.path.exists(exe):
+            continue
+        env = dict(os.environ, LD_LIBRARY_PATH=OUT + ":" + ORACLE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS="2",
+                   XB_HOSTSIM_PTR_KIND="3" if "gather" in name else "0")
+        p = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120, env=env, cwd=DRV)
+        assert p.returncode == 0, (name, args, p.stdout[-1200:], p.stderr[-600:])
+        assert "FAILURE" not in p.stdout.upper(), (name, args, p.stdout[-1200:])
+        ran += 1
+    if ran == 0:
+        pytest.skip("no prebuilt drivers (no reference tree in the build container?)")

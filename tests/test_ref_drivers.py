@@ -73,6 +73,16 @@ def _run(name, *args, timeout=300):
     return subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout, env=env, cwd=OUT)
 
 
+def test_gimmik_driver_runs_on_the_utility_layer():
+    """samples/xgemm_sparse_Ainregs/gimmik.c times GiMMiK-generated C operators and takes from the library only the timer and the
+    aligned allocator (libxsmm_timer_tick/duration, libxsmm_aligned_malloc/free): it needs no device, so it runs in both tiers.
+    One CSV record per operator (60), positive rates."""
+    p = _run("gimmik", 3, timeout=120)
+    assert p.returncode == 0, (p.stdout[-400:], p.stderr[-800:])
+    rows = [ln.split(";") for ln in p.stdout.splitlines() if ln.count(";") == 2]
+    assert len(rows) == 60 and all(float(r[1]) > 0 and float(r[2]) > 0 for r in rows), p.stdout[-600:]
+
+
 @pytest.mark.gpu
 def test_hello_runs():
     """samples/hello/hello.c: dispatches one F64 13x5x7 kernel and calls it 1000 times on malloc'ed (host) matrices, C += A_i * B_i;
