@@ -2,8 +2,8 @@
  *
  * A stand-in for the CUDA side of the library (runtime.cu and the kernel launchers) so that the HOST logic above the kernels --
  * equation trees (host_meqn.c), operand staging, dispatch rules -- can be exercised in the GPU-less build container:
- * "device" memory is plain host memory, every elementwise launch is answered by the oracle (oracle/liboracle.so), GEMM and
- * sparse launchers refuse. tests/test_hostsim.py links the host_*.o objects with this file into tests/c/_hostsim/libxsmm.so and
+ * "device" memory is plain host memory, every elementwise launch and every dense GEMM tile is answered by the oracle
+ * (oracle/liboracle.so), the tensor-core and sparse launchers refuse. tests/test_hostsim.py links the host_*.o objects with this file into tests/c/_hostsim/libxsmm.so and
  * runs the reference's unmodified equation drivers against it; what that validates is the order of evaluation, the shapes and
  * leading dimensions handed to each node, and where secondary outputs land -- not any kernel. */
 #include <stdio.h>
@@ -59,8 +59,47 @@ int xb_rt_current_device(void) { return 0; }
 int xb_rt_first_use_on_device(unsigned long long* mask) { const int first = (*mask & 1ull) == 0; *mask |= 1ull; return first; }
 
 /* ---- launchers ----------------------------------------------------------------------------------------------------------- */
-int xb_gemm_simt_supported(const xb_gemm_desc* d) { (void)d; return 0; }
-int xb_gemm_simt_launch(const xb_gemm_launch* L) { (void)L; return 1; }
+/* dense GEMM: the "exact-order" backend is answered by the oracle tile by tile (strided batches, per-tile records, single calls;
+ * plain, fused colbias / relu / sigmoid, bitmap-compressed A, 4-bit A); the tensor-core backends below refuse, so a dispatch in the
+ * simulation always lands here. C re-packing (VNNI_C) is a separate elementwise pass of host_core.c, so the flag is masked. */
+extern int oracle_gemm(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a, long long stride_b,
+                       unsigned long long br, void* a, void* b, void* c, long long* offs_a, long long* offs_b, float scf, int mode);
+extern int oracle_gemm_ext(const int* dims, const int* types, unsigned int flags, int br_type, long long stride_a, long long stride_b,
+                           unsigned long long br, void* a, void* b, void* c, long long* offs_a, long long* offs_b, float scf,
+                           const int* fuse, const void* colbias, unsigned char* relu_mask);
+extern int oracle_gemm_i4(const int* dims, unsigned int flags, int br_type, long long stride_a, long long stride_b, unsigned long long br,
+                          const unsigned char* a, const unsigned char* b, int* c, const unsigned char* zpt);
+extern int oracle_gemm_bitmap(const int* dims, const int* types, unsigned int flags, const void* a, const void* b, void* c, const unsigned char* bitmap);
+
+static int sim_gemm_tile(const xb_gemm_desc* d, const xb_gemm_rec* r) {
+  const int dims[6] = { d->m, d->n, d->k, d->lda, d->ldb, d->ldc }, types[4] = { d->ta, d->tb, d->tcomp, d->tc };
+  const unsigned int flags = d->flags & ~(unsigned int)LIBXSMM_GEMM_FLAG_VNNI_C;
+  ++g_launches;
+  if ((d->flags & LIBXSMM_GEMM_FLAG_DECOMPRESS_A_VIA_BITMASK) != 0) return oracle_gemm_bitmap(dims, types, flags, r->a, r->b, r->c, (const unsigned char*)r->a_q);
+  if (d->ta == LIBXSMM_DATATYPE_I4X2 || d->ta == LIBXSMM_DATATYPE_U4X2) {
+    return oracle_gemm_i4(dims, flags, d->br_type, d->br_stride_a, d->br_stride_b, r->br, (const unsigned char*)r->a, (const unsigned char*)r->b, (int*)r->c, (const unsigned char*)r->a_q);
+  }
+  if (d->fuse_colbias != 0 || d->cp_op != 0) {
+    const int fuse[4] = { d->fuse_colbias, d->cp_op, (d->cp_flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0 && r->c_aux != NULL, 0 };
+    return oracle_gemm_ext(dims, types, flags, d->br_type, d->br_stride_a, d->br_stride_b, r->br, (void*)(uintptr_t)r->a, (void*)(uintptr_t)r->b, r->c,
+                           (long long*)(uintptr_t)r->a_aux, (long long*)(uintptr_t)r->b_aux, r->scf, fuse, r->d, (unsigned char*)r->c_aux);
+  }
+  return oracle_gemm(dims, types, flags, d->br_type, d->br_stride_a, d->br_stride_b, r->br, (void*)(uintptr_t)r->a, (void*)(uintptr_t)r->b, r->c,
+                     (long long*)(uintptr_t)r->a_aux, (long long*)(uintptr_t)r->b_aux, r->scf, 0);
+}
+int xb_gemm_simt_supported(const xb_gemm_desc* d) { return d->m > 0 && d->n > 0 && d->k > 0; }
+int xb_gemm_simt_launch(const xb_gemm_launch* L) {
+  long long t; int rc = 0;
+  if (L->recs != NULL) { for (t = 0; t < L->count && rc == 0; ++t) rc = sim_gemm_tile(&L->d, &L->recs[t]); }
+  else if (L->count == 1 && L->a == NULL) rc = sim_gemm_tile(&L->d, &L->one);
+  else for (t = 0; t < L->count && rc == 0; ++t) {
+    xb_gemm_rec r; memset(&r, 0, sizeof(r));
+    r.a = (const char*)L->a + t * L->tile_stride_a; r.b = (const char*)L->b + t * L->tile_stride_b; r.c = (char*)L->c + t * L->tile_stride_c; r.br = L->br;
+    rc = sim_gemm_tile(&L->d, &r);
+  }
+  if (rc != 0) fprintf(stderr, "hostsim: the oracle refused a GEMM tile (rc %d)\n", rc);
+  return rc;
+}
 int xb_gemm_tc_supported(const xb_gemm_desc* d) { (void)d; return 0; }
 int xb_gemm_tc_shape_ok(const xb_gemm_desc* d) { (void)d; return 0; }
 int xb_gemm_tc_launch(const xb_gemm_launch* L) { (void)L; return 1; }

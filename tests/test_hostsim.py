@@ -168,6 +168,33 @@ TERNARY_RUNS = [("eltwise_ternary_simple", (1, 0, "F32", "F32", "IMPLICIT", "F32
                 ("eltwise_ternary_simple", (1, 0, "F32", "BF8", "IMPLICIT", "F32", "BF8", 64, 16, 64, 64)),
                 ("eltwise_ternary_simple", (1, 0, "F32", "F32", "IMPLICIT", "F32", "BF8", 64, 16, 64, 64, 1))]
 
+# samples/xgemm/gemm_kernel*.c: A B Comp C  M N K LDA LDB LDC  alpha beta  alignA alignC  trA trB  vnniA vnniB vnniC  prefetch  br-kind br-count
+# br-unroll  reps  tilecfg [binary-postop unary-postop]
+def _gk(types, m, n, k, lda, ldb, ldc, beta, tra=0, trb=0, va=0, vb=0, vc=0, br="nobr", brn=1, post=()):
+    return tuple(types.split()) + (m, n, k, lda, ldb, ldc, 1, beta, 0, 0, tra, trb, va, vb, vc, "nopf", br, brn, 0, 3, 0) + tuple(post)
+
+
+GEMM_RUNS = [("hello", ())] + [("gemm_kernel", a) for a in (
+    _gk("F32 F32 F32 F32", 64, 64, 64, 64, 64, 64, 0), _gk("F32 F32 F32 F32", 37, 21, 45, 40, 48, 40, 1, trb=1, br="strdbr", brn=4),
+    _gk("F32 F32 F32 F32", 32, 32, 32, 32, 32, 32, 1, br="addrbr", brn=3), _gk("F32 F32 F32 F32", 32, 32, 32, 32, 32, 32, 0, br="offsbr", brn=3),
+    _gk("F32 F32 F32 F32", 64, 64, 64, 64, 64, 64, 0, tra=1), _gk("F64 F64 F64 F64", 13, 5, 7, 13, 7, 13, 1),
+    _gk("BF16 BF16 F32 F32", 64, 64, 64, 64, 64, 64, 1, va=1), _gk("BF16 BF16 F32 BF16", 64, 64, 64, 64, 64, 64, 0, va=1, br="strdbr", brn=2),
+    _gk("BF16 BF16 F32 BF16", 64, 64, 64, 64, 64, 64, 0, va=1, vc=1), _gk("F16 F16 F32 F32", 64, 64, 64, 64, 64, 64, 1, va=1),
+    _gk("I8 I8 I32 I32", 64, 64, 64, 64, 64, 64, 0, va=1), _gk("U8 I8 I32 I32", 64, 64, 64, 64, 64, 64, 1, va=1),
+    _gk("BF8 BF8 F32 F32", 64, 64, 64, 64, 64, 64, 1, va=1), _gk("HF8 HF8 F32 HF8", 64, 64, 64, 64, 64, 64, 0, va=1),
+    _gk("F32 F32 F32 F32", 64, 64, 64, 64, 64, 64, 0, br="spmm", brn=4), _gk("BF16 BF16 F32 BF16", 64, 64, 64, 64, 64, 64, 0, va=1, br="spmm", brn=2))] + \
+    [("gemm_kernel_fused", _gk("F32 F32 F32 F32", 64, 48, 32, 64, 32, 64, 1, post=(b, u))) for b in (0, 1) for u in (0, 1, 2, 3)] + \
+    [("gemm_kernel_fused", _gk("BF16 BF16 F32 BF16", 64, 64, 64, 64, 64, 64, 0, va=1, br="strdbr", brn=2, post=(1, 2))),
+     ("gemm_kernel_fused", _gk("BF16 BF16 F32 BF16", 64, 64, 64, 64, 64, 64, 0, va=1, vc=1, post=(1, 1))),
+     ("gemm_kernel_parallel", _gk("F32 F32 F32 F32", 64, 64, 64, 64, 64, 64, 1)),
+     ("gemm_kernel_parallel", _gk("BF16 BF16 F32 BF16", 64, 64, 64, 64, 64, 64, 0, va=1, br="strdbr", brn=2))]
+
+# samples/eltwise/eltwise_unary_relu.c [D/L/E] [F/B] [bitmask] in comp out M N ldi ldo ; eltwise_unary_transform.c op type M N ldi ldo
+MORE_ELTWISE_RUNS = [("eltwise_unary_relu", (t, fb, bm, "F32", "F32", "F32", 37, 11, 48, 40)) for t in "DLE" for fb in "FB" for bm in (0, 1)
+                     if not (fb == "B" and bm == 0 and t != "E")] + [("eltwise_unary_relu", ("D", "F", 1, "BF16", "F32", "BF16", 64, 16, 64, 64))] + \
+    [("eltwise_unary_transform", (op, "BF16", 32, 16, 32, 32)) for op in "TRSVWQFGHIXYZBCD"] + \
+    [("eltwise_unary_transform", ("T", "F32", 37, 11, 40, 16)), ("eltwise_unary_transform", ("N", "I8", 32, 16, 32, 32)), ("eltwise_unary_transform", ("M", "I8", 32, 16, 32, 32))]
+
 DRIVER_RUNS = [("equation_simple", (64, 32)), ("equation_relu", (64, 32)), ("equation_relu", (64, 32, 64, 1)), ("equation_relu", (37, 9, 48, 0)),
                ("equation_softmax", (64, 32))]
 
@@ -193,7 +220,7 @@ def test_reference_eltwise_drivers_against_the_simulated_device():
     from test_ref_drivers import ELTWISE_RUNS
     build_sim()
     ran = 0
-    for name, args in ELTWISE_RUNS + TERNARY_RUNS:
+    for name, args in ELTWISE_RUNS + TERNARY_RUNS + MORE_ELTWISE_RUNS:
         exe = os.path.join(DRV, name)
         if not os.path.exists(exe):
             continue
@@ -202,6 +229,28 @@ def test_reference_eltwise_drivers_against_the_simulated_device():
         p = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120, env=env, cwd=DRV)
         assert p.returncode == 0, (name, args, p.stdout[-1200:], p.stderr[-600:])
         assert "FAILURE" not in p.stdout.upper(), (name, args, p.stdout[-1200:])
+        ran += 1
+    if ran == 0:
+        pytest.skip("no prebuilt drivers (no reference tree in the build container?)")
+
+
+def test_reference_gemm_drivers_against_the_simulated_device():
+    """samples/hello/hello.c and samples/xgemm/gemm_kernel.c / gemm_kernel_fused.c / gemm_kernel_parallel.c: dispatch, leading-dimension rules,
+    the four batch-reduce calling conventions, staging of host A / B / C (what survives in C's padding, the relu bit mask, the bias column),
+    bitmap-compressed A ("spmm") and concurrent callers (OpenMP threads sharing one kernel) -- the GEMM half of host_core.c, with every
+    tile answered by the oracle; the drivers compare with their own gold and return EXIT_FAILURE on a mismatch"""
+    build_sim()
+    ran = 0
+    for name, args in GEMM_RUNS:
+        exe = os.path.join(DRV, name)
+        if not os.path.exists(exe):
+            continue
+        env = dict(os.environ, LD_LIBRARY_PATH=OUT + ":" + ORACLE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS="4")
+        p = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120, env=env, cwd=DRV)
+        assert p.returncode == 0, (name, args, p.stdout[-1200:], p.stderr[-600:])
+        assert "hostsim:" not in p.stderr, (name, args, p.stderr[-600:])
+        if name != "hello":
+            assert "Total Max Error 0.0000" in p.stdout, (name, args, p.stdout[-600:])
         ran += 1
     if ran == 0:
         pytest.skip("no prebuilt drivers (no reference tree in the build container?)")
