@@ -44,6 +44,11 @@ LIBXSMM_API int libxsmm_get_mmkernel_info(libxsmm_xmmfunction kernel, libxsmm_mm
 LIBXSMM_API int libxsmm_get_meltwkernel_info(libxsmm_xmeltwfunction kernel, libxsmm_meltwkernel_info* info);
 LIBXSMM_API int libxsmm_get_kernel_info(const void* kernel, libxsmm_kernel_info* info);
 LIBXSMM_API int libxsmm_get_registry_info(libxsmm_registry_info* info);
+/* enumerate the registry by kind (reference include/libxsmm.h:105-108): LIBXSMM_KERNEL_KIND_USER yields the VALUE of every entry made with
+ * libxsmm_xregister (and its key through `key`, may be NULL); the kernel kinds yield the callable of every registered handle. _next accepts
+ * an entry that was released after it was returned (tests/registry.c:133-137). NULL ends the enumeration. */
+LIBXSMM_API void* libxsmm_get_registry_begin(libxsmm_kernel_kind kind, const void** key);
+LIBXSMM_API void* libxsmm_get_registry_next(const void* regentry, const void** key);
 
 /* ---- shape/config constructors (reference include/libxsmm_generator.h:20-43) ------------------- */
 LIBXSMM_API libxsmm_gemm_shape libxsmm_create_gemm_shape(libxsmm_blasint m, libxsmm_blasint n, libxsmm_blasint k,

@@ -150,6 +150,13 @@
 #define LIBXSMM_ELIDE_RESULT(TYPE, EXPR) do { TYPE libxsmm_b200_elided_ = (EXPR); LIBXSMM_UNUSED(libxsmm_b200_elided_); } while (0)
 #define LIBXSMM_EXPECT_ELIDE(EXPR) LIBXSMM_ELIDE_RESULT(int, EXPR)
 #define LIBXSMM_PUTENV(A) putenv(A)
+/* build configuration the reference bakes into libxsmm_config.h (include/libxsmm_macros.h:17-27): kernels are always available here
+ * (LIBXSMM_JIT != 0: a dispatch that fails is an error, tests/threadsafety.c:240), no default GEMM flags, no default prefetch */
+#define LIBXSMM_JIT 1
+#define LIBXSMM_FLAGS 0
+#define LIBXSMM_PREFETCH LIBXSMM_GEMM_PREFETCH_NONE
+/* mention a loop variable that only an OpenMP pragma uses (some compilers warn otherwise); nothing to do for gcc */
+#define LIBXSMM_OMP_VAR(A)
 /* checked narrowing casts of the reference (include/libxsmm_macros.h:231-264): here plain casts (LP64, 32-bit blasint) */
 #define LIBXSMM_CAST_INT(VALUE) ((int)(VALUE))
 #define LIBXSMM_CAST_UINT(VALUE) ((unsigned int)(VALUE))

@@ -200,10 +200,18 @@ typedef enum libxsmm_gemm_flags {
   LIBXSMM_GEMM_FLAG_B200_END = 8388608
 } libxsmm_gemm_flags;
 
-/* 'N'/'T' characters to flags (reference include/libxsmm_macros.h LIBXSMM_GEMM_FLAGS) */
+/* BLAS transpose characters to flags: only 'N' / 'n' means "as is", so 'T' and the conjugate request 'C' both transpose
+ * (reference include/libxsmm_macros.h:278-281; tests/gemmflags.c is the truth table) */
+#define LIBXSMM_B200_TRANSPOSED(CH) (!('N' == (CH) || 'n' == (CH)))
 #define LIBXSMM_GEMM_FLAGS(TRANSA, TRANSB) (libxsmm_bitfield)( \
-  (('T' == (TRANSA) || 't' == (TRANSA)) ? LIBXSMM_GEMM_FLAG_TRANS_A : 0) | \
-  (('T' == (TRANSB) || 't' == (TRANSB)) ? LIBXSMM_GEMM_FLAG_TRANS_B : 0))
+  (LIBXSMM_B200_TRANSPOSED(TRANSA) ? LIBXSMM_GEMM_FLAG_TRANS_A : 0) | (LIBXSMM_B200_TRANSPOSED(TRANSB) ? LIBXSMM_GEMM_FLAG_TRANS_B : 0))
+/* the same from POINTERS to the characters, where a NULL pointer keeps the transpose bit of DEFAULT; all other bits of DEFAULT
+ * pass through (reference :283-287) */
+#define LIBXSMM_B200_PTRANS(PCH, BIT, DEFAULT) \
+  ((NULL != (const void*)(PCH)) ? (LIBXSMM_B200_TRANSPOSED(*(const char*)(PCH)) ? (BIT) : 0) : ((BIT) & (DEFAULT)))
+#define LIBXSMM_GEMM_PFLAGS(TRANSA, TRANSB, DEFAULT) (libxsmm_bitfield)( \
+  LIBXSMM_B200_PTRANS(TRANSA, LIBXSMM_GEMM_FLAG_TRANS_A, DEFAULT) | LIBXSMM_B200_PTRANS(TRANSB, LIBXSMM_GEMM_FLAG_TRANS_B, DEFAULT) | \
+  ((DEFAULT) & ~(LIBXSMM_GEMM_FLAG_TRANS_A | LIBXSMM_GEMM_FLAG_TRANS_B)))
 
 typedef enum libxsmm_gemm_prefetch_type {
   LIBXSMM_GEMM_PREFETCH_NONE = 0, LIBXSMM_GEMM_PREFETCH_AL2 = 1, LIBXSMM_GEMM_PREFETCH_BL2 = 2

@@ -219,6 +219,8 @@ libxsmm_set_verbosity = _sig("libxsmm_set_verbosity", None, [_I])
 libxsmm_get_mmkernel_info = _sig("libxsmm_get_mmkernel_info", _I, [_P, C.POINTER(MMKernelInfo)])
 libxsmm_get_kernel_info = _sig("libxsmm_get_kernel_info", _I, [_P, C.POINTER(KernelInfo)])
 libxsmm_get_registry_info = _sig("libxsmm_get_registry_info", _I, [C.POINTER(RegistryInfo)])
+libxsmm_get_registry_begin = _sig("libxsmm_get_registry_begin", _P, [_I, C.POINTER(_P)])
+libxsmm_get_registry_next = _sig("libxsmm_get_registry_next", _P, [_P, C.POINTER(_P)])
 libxsmm_create_gemm_shape = _sig("libxsmm_create_gemm_shape", GemmShape, [_I] * 10)
 libxsmm_create_gemm_batch_reduce_config = _sig("libxsmm_create_gemm_batch_reduce_config", BatchReduceConfig, [_I, _I, _I, C.c_ubyte])
 libxsmm_create_gemm_ext_unary_argops = _sig("libxsmm_create_gemm_ext_unary_argops", GemmExtUnaryArgops,

@@ -861,11 +861,28 @@ void xb_invoke(int slot, const void* param) {
 }
 
 /* ---- introspection ---------------------------------------------------------------------------------- */
+extern int xb_user_value_info(const void* value, size_t* size);      /* host_meqn.c: the user registry */
+extern int xb_user_value_release(const void* value);
+extern void* xb_user_first(const void** key);
+extern void* xb_user_next(const void* value, const void** key);
+
+static int xb_public_kind(int kind) {
+  return (kind == XB_KIND_MELTW) ? LIBXSMM_KERNEL_KIND_MELTW : ((kind == XB_KIND_MEQN) ? LIBXSMM_KERNEL_KIND_MEQN : LIBXSMM_KERNEL_KIND_MATMUL);
+}
+
 LIBXSMM_API int libxsmm_get_kernel_info(const void* kernel, libxsmm_kernel_info* info) {
   const xb_slot* s = xb_slot_of(kernel);
-  if (s == NULL || info == NULL || s->kind == XB_KIND_FREE) return 1;
+  if (info == NULL) return 1;
+  if (s == NULL) {                    /* not a thunk: the value of a user entry? (tests/registry.c:121-126) */
+    size_t size = 0;
+    if (!xb_user_value_info(kernel, &size)) return 1;
+    memset(info, 0, sizeof(*info));
+    info->kind = LIBXSMM_KERNEL_KIND_USER; info->code_size = size;
+    return 0;
+  }
+  if (s->kind == XB_KIND_FREE) return 1;
   memset(info, 0, sizeof(*info));
-  info->kind = (s->kind == XB_KIND_MELTW) ? LIBXSMM_KERNEL_KIND_MELTW : LIBXSMM_KERNEL_KIND_MATMUL;
+  info->kind = (libxsmm_kernel_kind)xb_public_kind(s->kind);
   info->nflops = s->nflops;
   info->code_size = 16;               /* one trampoline */
   info->is_reference_kernel = 0;
@@ -933,9 +950,34 @@ LIBXSMM_API int libxsmm_b200_bcsc_variant(const void* kernel, unsigned long long
   return xb_bcsc_tc_variant(&s->u.sp, n_block_columns);
 }
 
+/* enumeration by kind (reference include/libxsmm.h:105-108): user entries yield their value and key; kernel kinds yield the callable
+ * of every REGISTERED handle and the descriptor it is keyed by */
+static void* xb_registry_scan(int from, int kind, const void** key) {
+  int i; void* result = NULL;
+  pthread_mutex_lock(&g_lock);
+  for (i = from; i < XB_NTHUNKS; ++i) {
+    const xb_slot* s = &g_slots[i];
+    if (s->kind != XB_KIND_FREE && s->registered && xb_public_kind(s->kind) == kind) { result = (void*)(uintptr_t)xb_thunk(i); if (key != NULL) *key = &s->u; break; }
+  }
+  pthread_mutex_unlock(&g_lock);
+  return result;
+}
+LIBXSMM_API void* libxsmm_get_registry_begin(libxsmm_kernel_kind kind, const void** key) {
+  LIBXSMM_INIT
+  if (kind == LIBXSMM_KERNEL_KIND_USER) return xb_user_first(key);
+  return xb_registry_scan(0, (int)kind, key);
+}
+LIBXSMM_API void* libxsmm_get_registry_next(const void* regentry, const void** key) {
+  const xb_slot* s = xb_slot_of(regentry);
+  if (regentry == NULL) return NULL;
+  if (s == NULL) return xb_user_next(regentry, key);
+  return xb_registry_scan((int)(s - g_slots) + 1, xb_public_kind(s->kind), key);
+}
+
 LIBXSMM_API void libxsmm_release_kernel(const void* kernel) {
   xb_slot* s = xb_slot_of(kernel);
-  if (s == NULL || s->kind == XB_KIND_FREE) return;
+  if (s == NULL) { (void)xb_user_value_release(kernel); return; }      /* user entries are released through their value */
+  if (s->kind == XB_KIND_FREE) return;
   if (s->registered) {   /* reference src/libxsmm_main.c:3916-3921: registered kernels are not released */
     if (libxsmm_verbosity != 0) fprintf(stderr, "LIBXSMM-B200 WARNING: attempt to release a registered kernel\n");
     return;

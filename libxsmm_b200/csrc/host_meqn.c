@@ -291,8 +291,10 @@ void xb_invoke_meqn(const xb_slot* s, const void* param) {
 }
 
 /* ---- user registry: libxsmm_xregister / xdispatch / xrelease (src/libxsmm_main.c:3010-3120) --------------------------------
- * binary keys of up to LIBXSMM_DESCRIPTOR_MAXSIZE bytes; the value is copied and owned here. */
-typedef struct xb_user_entry { unsigned char key[LIBXSMM_DESCRIPTOR_MAXSIZE]; size_t key_size; void* value; size_t value_size; struct xb_user_entry* next; } xb_user_entry;
+ * binary keys of up to LIBXSMM_DESCRIPTOR_MAXSIZE bytes; the value is copied and owned here. A released entry stays in the list as
+ * a tombstone (its memory too) until the same key is registered again: tests/registry.c:133-137 walks the registry releasing each
+ * entry and then asks for the successor OF THE ENTRY IT JUST RELEASED, so the address has to stay unique and findable. */
+typedef struct xb_user_entry { unsigned char key[LIBXSMM_DESCRIPTOR_MAXSIZE]; size_t key_size; void* value; size_t value_size, capacity; int dead; struct xb_user_entry* next; } xb_user_entry;
 static xb_user_entry* g_user = NULL;
 static pthread_mutex_t g_user_lock = PTHREAD_MUTEX_INITIALIZER;
 
@@ -301,20 +303,31 @@ static xb_user_entry* user_find(const void* key, size_t key_size) {
   for (e = g_user; e != NULL; e = e->next) if (e->key_size == key_size && 0 == memcmp(e->key, key, key_size)) return e;
   return NULL;
 }
+static xb_user_entry* user_of_value(const void* value) {
+  xb_user_entry* e;
+  for (e = g_user; e != NULL; e = e->next) if (e->value == value) return e;
+  return NULL;
+}
 LIBXSMM_API void* libxsmm_xregister(const void* key, size_t key_size, size_t value_size, const void* value_init) {
   xb_user_entry* e; void* result = NULL;
   LIBXSMM_INIT
   if (key == NULL || key_size == 0 || key_size > LIBXSMM_DESCRIPTOR_MAXSIZE || value_size == 0) return NULL;
   pthread_mutex_lock(&g_user_lock);
   e = user_find(key, key_size);
-  if (e != NULL) {                       /* an existing key keeps its value unless the new one fits and an initial value is given */
+  if (e != NULL && e->dead == 0) {       /* an existing key keeps its value unless the new one fits and an initial value is given */
     if (value_size <= e->value_size) { if (value_init != NULL) memcpy(e->value, value_init, value_size); result = e->value; }
+  } else if (e != NULL) {                /* a released key comes back, with room for the new payload */
+    if (value_size > e->capacity) { void* v = realloc(e->value, value_size); if (v != NULL) { e->value = v; e->capacity = value_size; } }
+    if (value_size <= e->capacity) {
+      if (value_init != NULL) memcpy(e->value, value_init, value_size); else memset(e->value, 0, value_size);
+      e->value_size = value_size; e->dead = 0; result = e->value;
+    }
   } else {
     e = (xb_user_entry*)calloc(1, sizeof(*e));
     if (e != NULL) {
       e->value = malloc(value_size);
       if (e->value != NULL) {
-        memcpy(e->key, key, key_size); e->key_size = key_size; e->value_size = value_size;
+        memcpy(e->key, key, key_size); e->key_size = key_size; e->value_size = e->capacity = value_size;
         if (value_init != NULL) memcpy(e->value, value_init, value_size); else memset(e->value, 0, value_size);
         e->next = g_user; g_user = e; result = e->value;
       } else free(e);
@@ -327,17 +340,52 @@ LIBXSMM_API void* libxsmm_xdispatch(const void* key, size_t key_size) {
   xb_user_entry* e; void* result = NULL;
   if (key == NULL || key_size == 0 || key_size > LIBXSMM_DESCRIPTOR_MAXSIZE) return NULL;
   pthread_mutex_lock(&g_user_lock);
-  e = user_find(key, key_size); if (e != NULL) result = e->value;
+  e = user_find(key, key_size); if (e != NULL && e->dead == 0) result = e->value;
   pthread_mutex_unlock(&g_user_lock);
   return result;
 }
 LIBXSMM_API void libxsmm_xrelease(const void* key, size_t key_size) {
-  xb_user_entry **pp, *e;
+  xb_user_entry* e;
   if (key == NULL || key_size == 0) return;
   pthread_mutex_lock(&g_user_lock);
-  for (pp = &g_user; *pp != NULL; pp = &(*pp)->next) {
-    e = *pp;
-    if (e->key_size == key_size && 0 == memcmp(e->key, key, key_size)) { *pp = e->next; free(e->value); free(e); break; }
-  }
+  e = user_find(key, key_size); if (e != NULL) e->dead = 1;
   pthread_mutex_unlock(&g_user_lock);
+}
+/* what libxsmm_get_kernel_info / libxsmm_release_kernel need to know about a pointer that is not one of the thunks: is it the value
+ * of a live user entry (returns 1 and its size), and release it (reference src/libxsmm_main.c: user entries ARE released) */
+int xb_user_value_info(const void* value, size_t* size) {
+  xb_user_entry* e; int found = 0;
+  if (value == NULL) return 0;
+  pthread_mutex_lock(&g_user_lock);
+  e = user_of_value(value);
+  if (e != NULL && e->dead == 0) { found = 1; if (size != NULL) *size = e->value_size; }
+  pthread_mutex_unlock(&g_user_lock);
+  return found;
+}
+int xb_user_value_release(const void* value) {
+  xb_user_entry* e; int found = 0;
+  if (value == NULL) return 0;
+  pthread_mutex_lock(&g_user_lock);
+  e = user_of_value(value);
+  if (e != NULL && e->dead == 0) { e->dead = 1; found = 1; }
+  pthread_mutex_unlock(&g_user_lock);
+  return found;
+}
+/* enumeration of user entries: the first live entry, and the live entry after a given one (which may have been released meanwhile) */
+void* xb_user_first(const void** key) {
+  xb_user_entry* e; void* result = NULL;
+  pthread_mutex_lock(&g_user_lock);
+  for (e = g_user; e != NULL && e->dead != 0; e = e->next) {}
+  if (e != NULL) { result = e->value; if (key != NULL) *key = e->key; }
+  pthread_mutex_unlock(&g_user_lock);
+  return result;
+}
+void* xb_user_next(const void* value, const void** key) {
+  xb_user_entry* e; void* result = NULL;
+  pthread_mutex_lock(&g_user_lock);
+  e = user_of_value(value);
+  if (e != NULL) for (e = e->next; e != NULL && e->dead != 0; e = e->next) {}
+  if (e != NULL) { result = e->value; if (key != NULL) *key = e->key; }
+  pthread_mutex_unlock(&g_user_lock);
+  return result;
 }

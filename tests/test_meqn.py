@@ -52,6 +52,37 @@ def test_user_registry_roundtrip():
     assert not X.libxsmm_xdispatch(key.ctypes.data, key.size)
 
 
+def test_user_registry_enumeration_survives_release():
+    """libxsmm_get_registry_begin / _next over LIBXSMM_KERNEL_KIND_USER (reference include/libxsmm.h:105-108); the walk of
+    tests/registry.c:133-137 releases each entry and then asks for the successor of the entry it just released"""
+    USER = 3
+    keys = [np.frombuffer(bytes([7, i]) + bytes(10), dtype=np.uint8).copy() for i in range(5)]
+    vals = [np.full(4, 10 + i, dtype=np.int32) for i in range(5)]
+    for k, v in zip(keys, vals):
+        assert X.libxsmm_xregister(k.ctypes.data, k.size, v.nbytes, v.ctypes.data)
+    seen = {}
+    kp = C.c_void_p()
+    e = X.libxsmm_get_registry_begin(USER, C.byref(kp))
+    while e:
+        key = bytes(np.ctypeslib.as_array(C.cast(kp.value, C.POINTER(C.c_ubyte)), (12,)))
+        if key[0] == 7:
+            seen[key[1]] = int(np.ctypeslib.as_array(C.cast(e, C.POINTER(C.c_int)), (4,))[0])
+        info = X.KernelInfo()
+        assert X.libxsmm_get_kernel_info(e, C.byref(info)) == 0 and info.kind == USER
+        e = X.libxsmm_get_registry_next(e, C.byref(kp))
+    assert seen == {i: 10 + i for i in range(5)}
+    e = X.libxsmm_get_registry_begin(USER, None); n = 0
+    while e:
+        X.libxsmm_release_kernel(e); n += 1
+        e = X.libxsmm_get_registry_next(e, None)
+    assert n >= 5 and not X.libxsmm_get_registry_begin(USER, None)
+    assert all(not X.libxsmm_xdispatch(k.ctypes.data, k.size) for k in keys)
+    big = np.arange(64, dtype=np.int32)          # a released key comes back with a larger payload
+    p = X.libxsmm_xregister(keys[0].ctypes.data, keys[0].size, big.nbytes, big.ctypes.data)
+    assert p and np.array_equal(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int)), (64,)), big)
+    X.libxsmm_xrelease(keys[0].ctypes.data, keys[0].size)
+
+
 def test_tree_construction_is_preorder_and_bounded():
     eq = X.libxsmm_meqn_create()
     meta = X.libxsmm_create_meqn_op_metadata(eq, -1)

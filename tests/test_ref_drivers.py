@@ -41,6 +41,11 @@ DRIVERS = {
     "equation_softmax": "samples/equation/equation_softmax.c",
     "gimmik": "samples/xgemm_sparse_Ainregs/gimmik.c",
     "gemm_kernel_parallel": "samples/xgemm/gemm_kernel_parallel.c",
+    # the reference's unit tests that pin dispatch-level behaviour (threadsafety, registry, gemmflags) + matdiff
+    "ut_threadsafety": "tests/threadsafety.c",
+    "ut_registry": "tests/registry.c",
+    "ut_gemmflags": "tests/gemmflags.c",
+    "ut_matdiff": "tests/matdiff.c",
 }
 
 
@@ -81,6 +86,16 @@ def test_gimmik_driver_runs_on_the_utility_layer():
     assert p.returncode == 0, (p.stdout[-400:], p.stderr[-800:])
     rows = [ln.split(";") for ln in p.stdout.splitlines() if ln.count(";") == 2]
     assert len(rows) == 60 and all(float(r[1]) > 0 and float(r[2]) > 0 for r in rows), p.stdout[-600:]
+
+
+@pytest.mark.parametrize("name", ["ut_threadsafety", "ut_registry", "ut_gemmflags", "ut_matdiff"])
+def test_reference_unit_tests_pass(name):
+    """tests/threadsafety.c (800 random shapes <= 128 dispatched concurrently under OpenMP, libxsmm_get_mmkernel_info round trip, duplicates
+    resolve to the same handle, release), tests/registry.c (libxsmm_xregister / xdispatch / xrelease edge cases), tests/gemmflags.c (truth
+    table of LIBXSMM_GEMM_PFLAGS) and tests/matdiff.c, unmodified: dispatch is host logic, none of them launches a kernel, so they run in
+    both tiers against the real library. Each returns EXIT_SUCCESS or EXIT_FAILURE."""
+    p = _run(name, timeout=180)
+    assert p.returncode == 0, (name, p.stdout[-800:], p.stderr[-800:])
 
 
 @pytest.mark.gpu
