@@ -27,6 +27,7 @@ typedef struct xb_eqn_node {
   int pos;                      /* ARG: position in inputs[]; ops: position in ops_args[] */
   int m, n, ld;                 /* result shape (ARG: as declared) */
   int child[3];
+  int score;                    /* temporaries the subtree needs; decides which operand subtree runs first (assign_scores) */
 } xb_eqn_node;
 typedef struct xb_eqn { xb_eqn_node node[XB_EQN_NODES]; int nnodes; int used; } xb_eqn;
 typedef struct xb_eqn_plan { xb_eqn eqn; int out_m, out_n, out_ld, out_type; } xb_eqn_plan;
@@ -167,10 +168,63 @@ static void node_desc(const xb_eqn* e, int at, xb_meltw_desc* d) {
     d->t_in2 = (nd->op == LIBXSMM_MELTW_TYPE_TERNARY_SELECT) ? LIBXSMM_DATATYPE_IMPLICIT : r2->dtype;
   }
 }
+/* Order of evaluation. The reference runs, below every node, the operand subtree that needs MORE temporaries first (ties: left to
+ * right) -- a Sethi-Ullman numbering with its own twists (src/libxsmm_matrixeqn.c:323-400 scores, :745-790 visiting order). The order is
+ * observable: a DUMP node writes caller memory that another branch may read as an argument (equation_softmax.c,
+ * equation_bf16_x3_split_f32.c), so the numbering is restated here: an argument needs 0; a node over arguments only needs 1; a unary
+ * node inherits its operand's count when it may overwrite the operand's temporary and needs at least 2 otherwise; a binary node needs
+ * one more than two equally demanding operands, else the larger count, and at least 3 when it may not overwrite; a ternary node needs
+ * the largest operand count and at least 4 (3 when it reuses its third operand as output). "May overwrite" fails for IDENTITY, for
+ * layout transforms, for GEMM nodes and whenever an 8/16-bit float operand is widened to F32/F64 (:196-223). */
+static int is_narrow_float(int t) { return t == LIBXSMM_DATATYPE_BF16 || t == LIBXSMM_DATATYPE_F16 || t == LIBXSMM_DATATYPE_BF8 || t == LIBXSMM_DATATYPE_HF8; }
+static int is_wide_float(int t) { return t == LIBXSMM_DATATYPE_F32 || t == LIBXSMM_DATATYPE_F64; }
+static int is_layout_transform(int op) {
+#define XB_IS_TRANSFORM(NAME, VALUE) if (op == (VALUE)) return 0 == strncmp(#NAME, "TRANSFORM_", 10);
+  LIBXSMM_B200_UNARY_TYPES(XB_IS_TRANSFORM)
+#undef XB_IS_TRANSFORM
+  return 0;
+}
+static void assign_scores(xb_eqn* e, int at) {
+  xb_eqn_node* nd = &e->node[at]; int c, all_args = 1, top = 0, widened = 0;
+  if (nd->type == EQ_ARG) { nd->score = 0; return; }
+  for (c = 0; c < arity(nd->type); ++c) {
+    const xb_eqn_node* ch;
+    assign_scores(e, nd->child[c]);
+    ch = &e->node[nd->child[c]];
+    if (ch->type != EQ_ARG) all_args = 0;
+    if (ch->score > top) top = ch->score;
+    if (is_narrow_float(ch->dtype) && is_wide_float(nd->dtype)) widened = 1;
+  }
+  if (all_args) { nd->score = 1; return; }
+  if (nd->type == EQ_UNARY) {
+    const int in_place = !(nd->op == LIBXSMM_MELTW_TYPE_UNARY_IDENTITY || is_layout_transform(nd->op) || widened);
+    nd->score = in_place ? top : LIBXSMM_MAX(2, top);
+  } else if (nd->type == EQ_BINARY) {
+    const int l = e->node[nd->child[0]].score, r = e->node[nd->child[1]].score, need = (l == r) ? l + 1 : top;
+    const int in_place = !(nd->op == LIBXSMM_MELTW_TYPE_BINARY_MATMUL || nd->op == LIBXSMM_MELTW_TYPE_BINARY_BRGEMM || widened);
+    nd->score = in_place ? need : LIBXSMM_MAX(3, need);
+  } else {
+    nd->score = LIBXSMM_MAX((nd->flags & LIBXSMM_MELTW_FLAG_TERNARY_REUSE_IN_2_AS_OUT) ? 3 : 4, top);
+  }
+}
+
 static int check_nodes(const xb_eqn* e, int at) {
   const xb_eqn_node* nd = &e->node[at]; int c; xb_meltw_desc d;
   if (nd->type == EQ_ARG) return 0;
   for (c = 0; c < arity(nd->type); ++c) if (check_nodes(e, nd->child[c]) != 0) return 1;
+  /* declined rather than mis-evaluated: nodes without a storage type (IMPLICIT: zip / unzip trees) and operations whose extra operands
+   * this evaluator does not wire -- index arrays, bit masks or forward outputs read through in.secondary, plane offsets, generator
+   * state, run-time counts, quantiser scales (samples/equation/equation_splitSGD.c, equation_gather_*.c, equation_bf16_x3_split_f32.c) */
+  if (libxsmm_typesize((libxsmm_datatype)nd->dtype) == 0) return 1;
+  if (nd->type == EQ_UNARY) switch (nd->op) {
+    case LIBXSMM_MELTW_TYPE_UNARY_UNZIP: case LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X2: case LIBXSMM_MELTW_TYPE_UNARY_DECOMP_FP32_TO_BF16X3:
+    case LIBXSMM_MELTW_TYPE_UNARY_GATHER: case LIBXSMM_MELTW_TYPE_UNARY_SCATTER: case LIBXSMM_MELTW_TYPE_UNARY_REPLICATE_COL_VAR:
+    case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_ADD: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_MAX: case LIBXSMM_MELTW_TYPE_UNARY_REDUCE_COLS_IDX_OP_MIN:
+    case LIBXSMM_MELTW_TYPE_UNARY_DROPOUT: case LIBXSMM_MELTW_TYPE_UNARY_DROPOUT_INV: case LIBXSMM_MELTW_TYPE_UNARY_QUANT: case LIBXSMM_MELTW_TYPE_UNARY_DEQUANT:
+    case LIBXSMM_MELTW_TYPE_UNARY_RELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU_INV: case LIBXSMM_MELTW_TYPE_UNARY_ELU_INV:
+      return 1;
+    default: if ((nd->flags & LIBXSMM_MELTW_FLAG_UNARY_STOCHASTIC_ROUND) != 0) return 1;
+  }
   /* a relu's bit mask has one destination, output.secondary: only the head may produce it (reference :39-56) */
   if (at != 0 && nd->type == EQ_UNARY && (nd->flags & LIBXSMM_MELTW_FLAG_UNARY_BITMASK_2BYTEMULT) != 0
       && (nd->op == LIBXSMM_MELTW_TYPE_UNARY_RELU || nd->op == LIBXSMM_MELTW_TYPE_UNARY_LEAKY_RELU || nd->op == LIBXSMM_MELTW_TYPE_UNARY_ELU)) return 1;
@@ -192,6 +246,7 @@ LIBXSMM_API libxsmm_meqn_function libxsmm_dispatch_meqn(const libxsmm_blasint id
     if ((long long)out_shape.m * out_shape.n != (long long)root->m * root->n) { free(plan); return NULL; }
   }
   if (check_nodes(&plan->eqn, 0) != 0) { free(plan); return NULL; }
+  assign_scores(&plan->eqn, 0);
   plan->out_m = root->m; plan->out_n = root->n; plan->out_ld = out_shape.ld; plan->out_type = (int)out_shape.type;
   slot = xb_host_slot_alloc(XB_KIND_MEQN, 0);
   if (slot < 0) { free(plan); return NULL; }
@@ -238,13 +293,15 @@ static const void* eval_node(xb_eval* ev, int at, int is_root) {
     { void* d = xb_rt_scratch(span(nd)); if (d == NULL) { ev->failed = 1; return NULL; } xb_rt_upload(d, hp, span(nd)); return d; }
   } else {
     xb_meltw_desc d; xb_meltw_args a; void* out;
-    const void* in[3] = { NULL, NULL, NULL }; int c, pass;
+    const void* in[3] = { NULL, NULL, NULL }; int c, k, order[3] = { 0, 1, 2 };
     memset(&a, 0, sizeof(a));
-    /* operand subtrees first, plain arguments last: the reference reads an argument when the consuming node executes, i.e. after
-     * every operation below that node has run (and possibly written the argument's memory through a DUMP) */
-    for (pass = 0; pass < 2; ++pass) for (c = 0; c < arity(nd->type); ++c) {
-      if ((ev->e->node[nd->child[c]].type == EQ_ARG) == (pass == 1)) in[c] = eval_node(ev, nd->child[c], 0);
+    /* the more demanding operand subtree first, ties left to right (assign_scores); plain arguments score 0, so they are read last:
+     * the reference reads an argument when the consuming node executes, after every operation below that node has run (and possibly
+     * written the argument's memory through a DUMP) */
+    for (c = 1; c < arity(nd->type); ++c) for (k = c; k > 0 && ev->e->node[nd->child[order[k]]].score > ev->e->node[nd->child[order[k - 1]]].score; --k) {
+      const int t = order[k]; order[k] = order[k - 1]; order[k - 1] = t;
     }
+    for (c = 0; c < arity(nd->type); ++c) in[order[c]] = eval_node(ev, nd->child[order[c]], 0);
     a.in0 = in[0]; a.in1 = in[1]; a.in2 = in[2];
     if (ev->failed) return NULL;
     out = is_root ? ev->out_dev : xb_rt_scratch(span(nd) ? span(nd) : 16);

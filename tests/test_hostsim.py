@@ -195,8 +195,41 @@ MORE_ELTWISE_RUNS = [("eltwise_unary_relu", (t, fb, bm, "F32", "F32", "F32", 37,
     [("eltwise_unary_transform", (op, "BF16", 32, 16, 32, 32)) for op in "TRSVWQFGHIXYZBCD"] + \
     [("eltwise_unary_transform", ("T", "F32", 37, 11, 40, 16)), ("eltwise_unary_transform", ("N", "I8", 32, 16, 32, 32)), ("eltwise_unary_transform", ("M", "I8", 32, 16, 32, 32))]
 
+def test_the_more_demanding_operand_subtree_runs_first(sim):
+    """out = (a - tmp) - (a*a + DUMP->tmp(a + 1)): the right operand of the head needs two temporaries, the left one, so the reference runs
+    the right one first (src/libxsmm_matrixeqn.c:323-400, 745-790) and the left branch sees the tmp this very call produced"""
+    m, n = 20, 6
+    nodes = [("b", X.MELTW_TYPE_BINARY_SUB, F32, 0),
+             ("b", X.MELTW_TYPE_BINARY_SUB, F32, 0), ("arg", 0, m, n, m, F32), ("arg", 1, m, n, m, F32),
+             ("b", X.MELTW_TYPE_BINARY_ADD, F32, 0), ("u", X.MELTW_TYPE_UNARY_X2, F32, 0), ("arg", 0, m, n, m, F32),
+             ("u", X.MELTW_TYPE_UNARY_DUMP, F32, 0, 3), ("u", X.MELTW_TYPE_UNARY_INC, F32, 0), ("arg", 0, m, n, m, F32)]
+    fn = sim.dispatch_meqn(sim.build(nodes), sim.create_meqn_arg_shape(m, n, m, F32))
+    assert fn
+    a = np.random.default_rng(5).standard_normal(m * n).astype(np.float32)
+    tmp = np.full(m * n, 1e30, dtype=np.float32); out = np.zeros(m * n, dtype=np.float32)
+    sim.run(fn, [a, tmp], out, ops={3: tmp})
+    assert np.array_equal(tmp, a + np.float32(1))
+    assert np.allclose(out, (a - tmp) - (a * a + tmp), rtol=1e-6, atol=1e-6)
+
+
+def test_trees_with_unwired_operands_are_declined(sim):
+    """nodes without a storage type (zip / unzip trees of equation_splitSGD.c) and operations that read index arrays, masks, generator state
+    or scales through operands the evaluator does not wire (equation_gather_*.c) must not dispatch"""
+    bad = [[("u", X.MELTW_TYPE_UNARY_UNZIP, X.DATATYPE_IMPLICIT, 0), ("arg", 0, 16, 4, 16, F32)],
+           [("u", X.MELTW_TYPE_UNARY_INC, F32, 0), ("b", X.MELTW_TYPE_BINARY_ADD, X.DATATYPE_IMPLICIT, 0), ("arg", 0, 16, 4, 16, F32), ("arg", 1, 16, 4, 16, F32)],
+           [("u", X.MELTW_TYPE_UNARY_GATHER, F32, 0), ("arg", 0, 16, 4, 16, F32)],
+           [("u", X.MELTW_TYPE_UNARY_RELU_INV, F32, 0), ("arg", 0, 16, 4, 16, F32)],
+           [("u", X.MELTW_TYPE_UNARY_DROPOUT, F32, 0), ("arg", 0, 16, 4, 16, F32)],
+           [("u", X.MELTW_TYPE_UNARY_INC, F32, 0), ("u", X.MELTW_TYPE_UNARY_QUANT, gen.I8, 0), ("arg", 0, 16, 4, 16, F32)]]
+    for nodes in bad:
+        assert not sim.dispatch_meqn(sim.build(nodes), sim.create_meqn_arg_shape(16, 4, 16, F32)), nodes
+
+
 DRIVER_RUNS = [("equation_simple", (64, 32)), ("equation_relu", (64, 32)), ("equation_relu", (64, 32, 64, 1)), ("equation_relu", (37, 9, 48, 0)),
-               ("equation_softmax", (64, 32))]
+               ("equation_softmax", (64, 32)), ("equation_simple_layernorm", ()),
+               # two DUMP nodes, one of them feeding an argument of a SHALLOWER branch: passes only with the reference's visiting order
+               # (the operand subtree that needs more temporaries first). Without arguments the driver overruns its own buffers.
+               ("equation_bf16_x3_split_f32", (32, 16, 40)), ("equation_bf16_x3_split_f32", (64, 7, 64))]
 
 
 @pytest.mark.parametrize("name,args", DRIVER_RUNS)

@@ -39,6 +39,8 @@ DRIVERS = {
     "equation_simple": "samples/equation/equation_simple.c",
     "equation_relu": "samples/equation/equation_relu.c",
     "equation_softmax": "samples/equation/equation_softmax.c",
+    "equation_simple_layernorm": "samples/equation/equation_simple_layernorm.c",
+    "equation_bf16_x3_split_f32": "samples/equation/equation_bf16_x3_split_f32.c",
     "gimmik": "samples/xgemm_sparse_Ainregs/gimmik.c",
     "gemm_kernel_parallel": "samples/xgemm/gemm_kernel_parallel.c",
     # the reference's unit tests that pin dispatch-level behaviour (threadsafety, registry, gemmflags) + matdiff
