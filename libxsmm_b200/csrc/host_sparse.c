@@ -228,12 +228,20 @@ void xb_invoke_sparse(const xb_slot* s, const libxsmm_gemm_param* p) {
   const size_t ts = libxsmm_typesize((libxsmm_datatype)d->ta), tsc = libxsmm_typesize((libxsmm_datatype)d->tc);
   int staged = 0, rc = 0;
   void* c_host = NULL; void* c_dev = NULL; size_t c_bytes = 0;
+  size_t c_pitch = 0, c_width = 0, c_rows = 0;   /* non-zero: the staged C is a column block of a wider matrix (see XB_KIND_SREG) */
   switch (d->kind) {
     case XB_KIND_SREG: {   /* a=NULL, b=B, c=C covering max_N columns (src/libxsmm_fsspmdm.c:491-515) */
       const size_t bb = ((size_t)(d->k - 1) * d->ldb + d->max_n) * ts; c_bytes = ((size_t)(d->m - 1) * d->ldc + d->max_n) * ts;
       const void* b = xb_dev_in(p->b.primary, bb, &staged);
       c_dev = p->c.primary;
-      if (xb_rt_ptr_kind(p->c.primary) == 0) { c_host = p->c.primary; c_dev = xb_rt_scratch(c_bytes); if (c_dev) xb_rt_upload(c_dev, c_host, c_bytes); staged = 1; }
+      if (xb_rt_ptr_kind(p->c.primary) == 0) {
+        c_host = p->c.primary; c_dev = xb_rt_scratch(c_bytes); staged = 1;
+        /* A handle narrower than the rows of C (max_N < ldc) owns a column block, and callers run the blocks of one C concurrently
+         * (samples/xgemm_sparse_Ainregs/pyfr_driver_asp_reg.c:381-392, omp parallel for over l_n_block): only the m x max_N block may
+         * travel -- the contiguous span would carry the neighbours' columns out stale and back over their results */
+        if (d->max_n < d->ldc) { c_pitch = (size_t)d->ldc * ts; c_width = (size_t)d->max_n * ts; c_rows = (size_t)d->m; }
+        if (c_dev != NULL) { if (c_rows != 0) xb_rt_memcpy2d_async(c_dev, c_host, c_pitch, c_width, c_rows); else xb_rt_upload(c_dev, c_host, c_bytes); }
+      }
       if (b == NULL || c_dev == NULL) { rc = 2; break; }
       rc = xb_sreg_launch(d, b, c_dev, d->max_n);
     } break;
@@ -282,7 +290,7 @@ void xb_invoke_sparse(const xb_slot* s, const libxsmm_gemm_param* p) {
     default: break;
   }
   if (rc != 0) { xb_rt_note_error(rc, "invoke_sparse"); xb_rt_scratch_reset(); return; }
-  if (c_host != NULL) xb_rt_memcpy_async(c_host, c_dev, c_bytes);
+  if (c_host != NULL) { if (c_rows != 0) xb_rt_memcpy2d_async(c_host, c_dev, c_pitch, c_width, c_rows); else xb_rt_memcpy_async(c_host, c_dev, c_bytes); }
   if (staged || xb_rt_blocking()) { xb_rt_sync(); xb_rt_scratch_reset(); }
 }
 

@@ -120,6 +120,13 @@ int xb_rt_memcpy_async(void* dst, const void* src, size_t size) {
   return 0;
 }
 int xb_rt_upload(void* dst_dev, const void* src_host, size_t size) { return xb_rt_memcpy_async(dst_dev, src_host, size); }
+// `rows` pieces of `width` bytes, `pitch` bytes apart on both sides, on the thread's stream: a column block of a wider row-major matrix
+int xb_rt_memcpy2d_async(void* dst, const void* src, size_t pitch, size_t width, size_t rows) {
+  if (width == 0 || rows == 0) return 0;
+  const cudaError_t e = cudaMemcpy2DAsync(dst, pitch, src, pitch, width, rows, cudaMemcpyDefault, tls.stream);
+  if (e != cudaSuccess) { xb_rt_note_error((int)e, "memcpy2d_async"); return (int)e; }
+  return 0;
+}
 
 int xb_rt_ptr_kind(const void* p) {
   if (p == nullptr) return 0;

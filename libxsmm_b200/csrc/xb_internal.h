@@ -130,6 +130,7 @@ void* xb_rt_managed_malloc(size_t size);
 void xb_rt_managed_free(void* p);
 int xb_rt_memcpy(void* dst, const void* src, size_t size);           /* blocking, any direction */
 int xb_rt_memcpy_async(void* dst, const void* src, size_t size);     /* on the thread's stream */
+int xb_rt_memcpy2d_async(void* dst, const void* src, size_t pitch, size_t width, size_t rows);   /* same pitch on both sides, any direction */
 /* chunked host<->device pipeline (three streams, two staging slots); `launch` runs with the thread's stream switched
  * to the pipeline's compute stream and must only enqueue work */
 typedef struct xb_pipe_chunk {

@@ -3,7 +3,7 @@
  * A stand-in for the CUDA side of the library (runtime.cu and the kernel launchers) so that the HOST logic above the kernels --
  * equation trees (host_meqn.c), operand staging, dispatch rules -- can be exercised in the GPU-less build container:
  * "device" memory is plain host memory, every elementwise launch and every dense GEMM tile is answered by the oracle
- * (oracle/liboracle.so), the tensor-core and sparse launchers refuse. tests/test_hostsim.py links the host_*.o objects with this file into tests/c/_hostsim/libxsmm.so and
+ * (oracle/liboracle.so), fsspmdm runs the library's own direct loop on the host, the tensor-core and packed / block-sparse launchers refuse. tests/test_hostsim.py links the host_*.o objects with this file into tests/c/_hostsim/libxsmm.so and
  * runs the reference's unmodified equation drivers against it; what that validates is the order of evaluation, the shapes and
  * leading dimensions handed to each node, and where secondary outputs land -- not any kernel. */
 #include <stdio.h>
@@ -39,6 +39,9 @@ void* xb_rt_managed_malloc(size_t size) { return malloc(size); }
 void xb_rt_managed_free(void* p) { free(p); }
 int xb_rt_memcpy(void* dst, const void* src, size_t size) { memmove(dst, src, size); return 0; }
 int xb_rt_memcpy_async(void* dst, const void* src, size_t size) { memmove(dst, src, size); return 0; }
+int xb_rt_memcpy2d_async(void* dst, const void* src, size_t pitch, size_t width, size_t rows) {
+  size_t r; for (r = 0; r < rows; ++r) memmove((char*)dst + r * pitch, (const char*)src + r * pitch, width); return 0;
+}
 int xb_rt_upload(void* dst_dev, const void* src_host, size_t size) { memmove(dst_dev, src_host, size); return 0; }
 int xb_rt_pipeline(long long nchunks, size_t max_a, size_t max_b, size_t max_c, xb_pipe_describe_fn describe, xb_pipe_launch_fn launch, void* ctx) {
   (void)nchunks; (void)max_a; (void)max_b; (void)max_c; (void)describe; (void)launch; (void)ctx; return 1;
@@ -106,7 +109,30 @@ int xb_gemm_tc_launch(const xb_gemm_launch* L) { (void)L; return 1; }
 int xb_gemm_tc_launch_pooled(const xb_gemm_desc* d, const xb_tc_pool* pool, unsigned long long br, long long count) { (void)d; (void)pool; (void)br; (void)count; return 1; }
 int xb_gemm_ts_supported(const xb_gemm_desc* d) { (void)d; return 0; }
 int xb_gemm_ts_launch(const xb_gemm_launch* L) { (void)L; return 1; }
-int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_total) { (void)d; (void)b; (void)c; (void)n_total; return 1; }
+/* fsspmdm: C[row][col] (= or +=) sum over the row's non-zeros of value * B[column][col], entries as host_sparse.c stores them
+ * ({value, 512 * column}); the accumulation order per element is the row order, like the library's direct kernel */
+int xb_sreg_launch(const xb_sparse_desc* d, const void* b, void* c, long long n_total) {
+  const int f64 = (d->ta == LIBXSMM_DATATYPE_F64); int row; long long col; unsigned int z;
+  ++g_launches;
+  for (row = 0; row < d->m; ++row) for (col = 0; col < n_total; ++col) {
+    if (f64) {
+      double acc = 0, *dst = (double*)c + (size_t)row * d->ldc + col;
+      for (z = d->d_ptr[row]; z < d->d_ptr[row + 1]; ++z) {
+        const char* e = (const char*)d->d_val + (size_t)z * 16;
+        acc += *(const double*)e * ((const double*)b)[(size_t)(*(const unsigned int*)(e + 8) >> 9) * d->ldb + col];
+      }
+      *dst = d->beta0 ? acc : (*dst + acc);
+    } else {
+      float acc = 0, *dst = (float*)c + (size_t)row * d->ldc + col;
+      for (z = d->d_ptr[row]; z < d->d_ptr[row + 1]; ++z) {
+        const char* e = (const char*)d->d_val + (size_t)z * 8;
+        acc += *(const float*)e * ((const float*)b)[(size_t)(*(const unsigned int*)(e + 4) >> 9) * d->ldb + col];
+      }
+      *dst = d->beta0 ? acc : (*dst + acc);
+    }
+  }
+  return 0;
+}
 int xb_packed_sp_launch(const xb_sparse_desc* d, const void* a, const void* b, void* c, long long count, long long sa, long long sb, long long sc) {
   (void)d; (void)a; (void)b; (void)c; (void)count; (void)sa; (void)sb; (void)sc; return 1;
 }

@@ -287,3 +287,20 @@ def test_reference_gemm_drivers_against_the_simulated_device():
         ran += 1
     if ran == 0:
         pytest.skip("no prebuilt drivers (no reference tree in the build container?)")
+
+
+@pytest.mark.parametrize("mtx", ["pyfr_p1_tet_m6-sp.mtx", "pyfr_p3_hex_m6-sp.mtx"])
+def test_pyfr_driver_concurrent_column_blocks_from_pageable_memory(mtx):
+    """samples/xgemm_sparse_Ainregs/pyfr_driver_asp_reg.c runs the 48-column blocks of one C under `omp parallel for`. In the simulation
+    every pointer counts as pageable host memory, so each call stages its operands: only the m x max_N block of C may travel (a contiguous
+    span would carry the neighbours' columns back stale -- the fault this test found). The sparse product itself is the library's direct
+    loop restated in tests/c/hostsim_runtime.c."""
+    exe = os.path.join(DRV, "pyfr_driver_asp_reg")
+    if not os.path.exists(exe):
+        pytest.skip("pyfr_driver_asp_reg was not prebuilt (no reference tree in the build container?)")
+    build_sim()
+    env = dict(os.environ, LD_LIBRARY_PATH=OUT + ":" + ORACLE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS="4")
+    p = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "mtx", mtx), "480", "2"], capture_output=True, text=True, timeout=180, env=env, cwd=DRV)
+    assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-600:])
+    lines = [ln for ln in p.stdout.splitlines() if "(libxsmm vs. gold)" in ln]
+    assert len(lines) == 2 and all(float(ln.split("abs=")[1].split()[0]) < 1e-6 for ln in lines), p.stdout[-1500:]
