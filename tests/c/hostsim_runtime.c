@@ -43,8 +43,25 @@ int xb_rt_memcpy2d_async(void* dst, const void* src, size_t pitch, size_t width,
   size_t r; for (r = 0; r < rows; ++r) memmove((char*)dst + r * pitch, (const char*)src + r * pitch, width); return 0;
 }
 int xb_rt_upload(void* dst_dev, const void* src_host, size_t size) { memmove(dst_dev, src_host, size); return 0; }
+/* the chunked host<->device pipeline, serialised: describe a chunk, copy its operands in (C only when the kernel reads it), launch,
+ * copy C out -- the staging buffers are poisoned first so that a chunk that relies on bytes it did not ask for shows up */
 int xb_rt_pipeline(long long nchunks, size_t max_a, size_t max_b, size_t max_c, xb_pipe_describe_fn describe, xb_pipe_launch_fn launch, void* ctx) {
-  (void)nchunks; (void)max_a; (void)max_b; (void)max_c; (void)describe; (void)launch; (void)ctx; return 1;
+  char *da = (char*)malloc(max_a ? max_a : 1), *db = (char*)malloc(max_b ? max_b : 1), *dc = (char*)malloc(max_c ? max_c : 1);
+  long long i; int rc = 0;
+  if (da == NULL || db == NULL || dc == NULL) { free(da); free(db); free(dc); return 2; }
+  for (i = 0; i < nchunks && rc == 0; ++i) {
+    xb_pipe_chunk ch; memset(&ch, 0, sizeof(ch));
+    describe(ctx, i, &ch);
+    if (ch.bytes_a > max_a || ch.bytes_b > max_b || ch.bytes_c > max_c) { rc = 3; break; }
+    memset(da, 0xa5, max_a); memset(db, 0xa5, max_b); memset(dc, 0xa5, max_c);
+    if (ch.bytes_a) memcpy(da, ch.host_a, ch.bytes_a);
+    if (ch.bytes_b) memcpy(db, ch.host_b, ch.bytes_b);
+    if (ch.copy_c_in && ch.bytes_c) memcpy(dc, ch.host_c, ch.bytes_c);
+    rc = launch(ctx, &ch, da, db, dc);
+    if (rc == 0 && ch.bytes_c) memcpy(ch.host_c, dc, ch.bytes_c);
+  }
+  free(da); free(db); free(dc);
+  return rc;
 }
 /* every caller pointer is "pageable host" so that the staging paths run; XB_HOSTSIM_PTR_KIND=3 ("pinned") lets the operations
  * that insist on device-accessible operands (gather / scatter, index reductions) through */

@@ -304,3 +304,38 @@ def test_pyfr_driver_concurrent_column_blocks_from_pageable_memory(mtx):
     assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-600:])
     lines = [ln for ln in p.stdout.splitlines() if "(libxsmm vs. gold)" in ln]
     assert len(lines) == 2 and all(float(ln.split("abs=")[1].split()[0]) < 1e-6 for ln in lines), p.stdout[-1500:]
+
+
+def test_host_resident_strided_batch_through_the_chunked_pipeline(sim):
+    """libxsmm_b200_gemm_batch_strided on HOST buffers -- the call bench.py's `e2e` leg makes: host_core.c cuts the batch into chunks (A, B, C
+    extents per chunk, C copied in only when it is read, the last chunk shorter) and a three-stage pipeline moves them. Here the pipeline is
+    serial and its staging buffers are poisoned between chunks; the chunk budget is forced to its minimum (1 MB) so that three chunks with a ragged tail
+    occur. Stride batch-reduce (br = 3), beta = 1 and beta = 0, padded leading dimensions."""
+    lib = sim.lib
+    I, U, P, LL, ULL = C.c_int, C.c_uint, C.c_void_p, C.c_longlong, C.c_ulonglong
+    lib.libxsmm_create_gemm_shape.restype = X.GemmShape; lib.libxsmm_create_gemm_shape.argtypes = [I] * 10
+    lib.libxsmm_create_gemm_batch_reduce_config.restype = X.BatchReduceConfig; lib.libxsmm_create_gemm_batch_reduce_config.argtypes = [I, I, I, C.c_ubyte]
+    lib.libxsmm_dispatch_brgemm.restype = P; lib.libxsmm_dispatch_brgemm.argtypes = [X.GemmShape, U, U, X.BatchReduceConfig]
+    lib.libxsmm_b200_gemm_batch_strided.restype = I; lib.libxsmm_b200_gemm_batch_strided.argtypes = [P, P, P, P, LL, LL, LL, ULL, LL]
+    rng = np.random.default_rng(11)
+    m, n, k, lda, ldb, ldc, br, count = 12, 7, 9, 16, 10, 14, 3, 800      # 2960 bytes per tile: 354 tiles per 1 MB chunk -> 354 + 354 + 92
+    for beta0 in (0, 1):
+        a = rng.standard_normal((count, br, k, lda)).astype(np.float32)      # column-major tiles: [k][lda], rows 0..m-1 used
+        b = rng.standard_normal((count, br, n, ldb)).astype(np.float32)
+        c = rng.standard_normal((count, n, ldc)).astype(np.float32); c0 = c.copy()
+        shape = lib.libxsmm_create_gemm_shape(m, n, k, lda, ldb, ldc, F32, F32, F32, F32)
+        cfg = lib.libxsmm_create_gemm_batch_reduce_config(X.GEMM_BATCH_REDUCE_STRIDE, k * lda * 4, n * ldb * 4, 0)
+        fn = lib.libxsmm_dispatch_brgemm(shape, X.GEMM_FLAG_BETA_0 if beta0 else 0, 0, cfg)
+        assert fn
+        os.environ["LIBXSMM_B200_CHUNK_MB"] = "1"
+        try:
+            rc = lib.libxsmm_b200_gemm_batch_strided(fn, a.ctypes.data, b.ctypes.data, c.ctypes.data, a[0].nbytes, b[0].nbytes, c[0].nbytes, br, count)
+        finally:
+            os.environ.pop("LIBXSMM_B200_CHUNK_MB", None)
+        assert rc == 0, rc
+        for t in range(count):
+            acc = np.zeros((n, m), dtype=np.float64) if beta0 else c0[t, :, :m].astype(np.float64)
+            for r in range(br):
+                acc += b[t, r, :, :k].astype(np.float64) @ a[t, r, :, :m].astype(np.float64)        # C^T[n][m] = B^T[n][k] A^T[k][m]
+            assert np.allclose(c[t, :, :m], acc, rtol=1e-5, atol=1e-5), (beta0, t)
+            assert np.array_equal(c[t, :, m:], c0[t, :, m:]), "padding rows of C survive"
